@@ -1,0 +1,108 @@
+// Symmetric-heap layout of one rank's parameter store.
+//
+// Every rank allocates ONE heap with the SAME layout; peers map each other's heaps
+// (POSIX shm on CPU, CUDA-IPC/NVLink on B200), so any per-key or per-slot field of
+// any rank is `heap[rank] + offset`. This replaces the reference's
+// vector<unique_ptr<Parameter>> + 16384 mutexes (coloc_kv_server_handle.h:122-152,
+// :1069-1083) and its Addressbook (addressbook.h:30-176): the ownership directory
+// `dir[key]` is fully replicated on every rank and updated by the relocating owner
+// with peer stores, so there is no home-node forwarding.
+#pragma once
+#include "base.h"
+#include "atomics.h"
+
+namespace adapm {
+
+struct ClassInfo {
+  uint32_t len;         // values per row
+  uint32_t cap;         // slots of this class per rank
+  uint32_t slot_begin;  // first global slot id of this class
+  uint32_t pad;
+  uint64_t rows_off;    // Val[cap][len]   current value (owner: main copy; replica: base + local delta)
+  uint64_t base_off;    // Val[cap][len]   replica sync state ("state at last sync")
+  uint64_t free_off;    // int32[cap]      free-slot stack
+};
+
+struct Layout {
+  int64_t num_keys;
+  int32_t world;
+  int32_t num_classes;
+  int32_t workers;       // local workers per rank
+  uint32_t total_slots;
+  uint32_t val_bytes;    // sizeof(Val)
+  uint32_t pad;
+  uint64_t off_dir;        // uint8[num_keys]   owner rank of each key (replicated directory)
+  uint64_t off_slot_of;    // int32[num_keys]   local slot of a key, -1 = not resident
+  uint64_t off_key_class;  // uint8[num_keys]   length class (only if num_classes > 1)
+  uint64_t off_meta;       // uint32[S]         state | peer | seq
+  uint64_t off_version;    // uint32[S]         owner: #pushes applied
+  uint64_t off_ver_seen;   // uint32[S]         replica: owner version at last refresh
+  uint64_t off_want;       // uint64[S]         owner: ranks that requested the key this round
+  uint64_t off_slot_key;   // int64[S]
+  uint64_t off_intent_end; // int64[S*workers]  end clock of the local intents
+  uint64_t off_flags;      // uint8[S]
+  uint64_t off_free_top;   // int32[MAX_CLASSES]
+  uint64_t off_counters;   // uint64[C_NUM_COUNTERS]
+  uint64_t off_retry;      // IntentRec[retry_cap] x2 + counts (deferred intents)
+  uint32_t retry_cap;
+  uint32_t pad2;
+  ClassInfo cls[MAX_CLASSES];
+  uint64_t heap_bytes;
+};
+
+struct IntentRec {
+  int64_t key;
+  int64_t end;
+  int32_t worker;
+  int32_t pad;
+};
+
+// The execution context handed to every kernel / CPU loop (by value).
+struct Ctx {
+  Layout L;
+  int32_t rank;
+  int32_t technique;    // MgmtTechniques
+  char* heap[MAX_RANKS];
+};
+
+template <class T> ADAPM_HD T* at(const Ctx& c, int r, uint64_t off) {
+  return reinterpret_cast<T*>(c.heap[r] + off);
+}
+ADAPM_HD uint8_t* dir_of(const Ctx& c, int r) { return at<uint8_t>(c, r, c.L.off_dir); }
+ADAPM_HD int32_t* slot_of(const Ctx& c, int r) { return at<int32_t>(c, r, c.L.off_slot_of); }
+ADAPM_HD uint32_t* meta_of(const Ctx& c, int r) { return at<uint32_t>(c, r, c.L.off_meta); }
+ADAPM_HD uint32_t* version_of(const Ctx& c, int r) { return at<uint32_t>(c, r, c.L.off_version); }
+ADAPM_HD uint32_t* ver_seen_of(const Ctx& c, int r) { return at<uint32_t>(c, r, c.L.off_ver_seen); }
+ADAPM_HD uint64_t* want_of(const Ctx& c, int r) { return at<uint64_t>(c, r, c.L.off_want); }
+ADAPM_HD int64_t* slot_key_of(const Ctx& c, int r) { return at<int64_t>(c, r, c.L.off_slot_key); }
+ADAPM_HD int64_t* intent_end_of(const Ctx& c, int r) { return at<int64_t>(c, r, c.L.off_intent_end); }
+ADAPM_HD uint8_t* flags_of(const Ctx& c, int r) { return at<uint8_t>(c, r, c.L.off_flags); }
+ADAPM_HD int32_t* free_top_of(const Ctx& c, int r) { return at<int32_t>(c, r, c.L.off_free_top); }
+ADAPM_HD uint64_t* counters_of(const Ctx& c, int r) { return at<uint64_t>(c, r, c.L.off_counters); }
+
+ADAPM_HD int class_of_key(const Ctx& c, Key k) {
+  if (c.L.num_classes == 1) return 0;
+  return at<uint8_t>(c, c.rank, c.L.off_key_class)[k];
+}
+ADAPM_HD int class_of_slot(const Ctx& c, uint32_t slot) {
+  int k = 0;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int i = 1; i < MAX_CLASSES; ++i)
+    if (i < c.L.num_classes && slot >= c.L.cls[i].slot_begin) k = i;
+  return k;
+}
+template <class Val> ADAPM_HD Val* row_ptr(const Ctx& c, int r, int cls, uint32_t slot) {
+  const ClassInfo& ci = c.L.cls[cls];
+  return reinterpret_cast<Val*>(c.heap[r] + ci.rows_off) + (size_t)(slot - ci.slot_begin) * ci.len;
+}
+template <class Val> ADAPM_HD Val* base_ptr(const Ctx& c, int r, int cls, uint32_t slot) {
+  const ClassInfo& ci = c.L.cls[cls];
+  return reinterpret_cast<Val*>(c.heap[r] + ci.base_off) + (size_t)(slot - ci.slot_begin) * ci.len;
+}
+ADAPM_HD void count(const Ctx& c, int which, uint64_t n = 1) {
+  mem::red_add(counters_of(c, c.rank) + which, n);
+}
+
+}  // namespace adapm

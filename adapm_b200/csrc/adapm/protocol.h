@@ -1,0 +1,582 @@
+// The parameter-management protocol, written once for host and device.
+//
+// Every function here is a per-key / per-slot step executed by a "group" of lanes:
+// one CPU thread (HostGroup) or one 32-wide warp (WarpGroup, see cuda/group.cuh).
+// The CPU executor and the sm_100a kernels both instantiate this file, so the CPU
+// contract tests exercise the exact state machine that runs on B200.
+//
+// What it replaces in the reference (studied, not copied):
+//   worker fast path       coloc_kv_worker.h:120-318, coloc_kv_server_handle.h:346-478
+//   intent registration    coloc_kv_server_handle.h:484-532, sync_manager.h:257-286
+//   replica delta / drop   coloc_kv_server_handle.h:601-662         (phase A)
+//   relocate-vs-replicate  sync_manager.h:553-739                   (phase B)
+//   refresh / upgrade      coloc_kv_server_handle.h:776-840         (phase C)
+// Instead of SYNC / SYNC_FORWARD / response messages, a sync round is three passes
+// over the slots separated by barriers; all cross-rank traffic is peer loads,
+// stores and reductions. Relocation is made exact without locks by a grace period
+// (all worker kernels that may have read the old directory have drained) between
+// the ownership announcement (phase B) and the transfer (phase C).
+#pragma once
+#include "layout.h"
+
+namespace adapm {
+
+struct HostGroup {
+  ADAPM_HD int lane() const { return 0; }
+  ADAPM_HD int size() const { return 1; }
+  ADAPM_HD bool any(bool p) const { return p; }
+  ADAPM_HD void sync() const {}
+  ADAPM_HD uint32_t bcast(uint32_t v) const { return v; }
+  ADAPM_HD int32_t bcast(int32_t v) const { return v; }
+  ADAPM_HD uint64_t bcast(uint64_t v) const { return v; }
+  ADAPM_HD double sum(double v) const { return v; }
+};
+
+constexpr int kMaxAttempts = 1 << 16;
+
+enum LocKind : int { LOC_FAIL = 0, LOC_DIRECT = 1, LOC_SUM3 = 2 };
+
+template <class Val> struct PullLoc {
+  int kind;
+  bool local;               // served from this rank's memory only
+  const Val* row;           // DIRECT: the row; SUM3: target row
+  const Val* base;          // SUM3: target base
+  const Val* row2;          // SUM3: source (old owner) row
+  const uint32_t* meta_ptr; // SUM3: seqlock word to re-validate
+  uint32_t meta_val;
+};
+
+template <class Val> struct PushLoc {
+  Val* row;          // nullptr on failure
+  uint32_t* version; // owner version counter to bump (nullptr for replica pushes)
+  uint8_t* flag;     // replica dirty flag (nullptr otherwise)
+  bool local;
+  int owner;
+};
+
+// ---------------------------------------------------------------------------------------
+// locate: where does a Pull of `key` read from?   (all lanes compute the same result)
+template <class Val, class G>
+ADAPM_HD PullLoc<Val> locate_pull(const Ctx& c, const G& g, Key key, bool local_only) {
+  PullLoc<Val> r;
+  r.kind = LOC_FAIL; r.local = false; r.row = nullptr; r.base = nullptr; r.row2 = nullptr;
+  r.meta_ptr = nullptr; r.meta_val = 0;
+  const int me = c.rank;
+  const int cls = class_of_key(c, key);
+  for (int attempt = 0; attempt < kMaxAttempts; ++attempt) {
+    int32_t s = g.bcast(g.lane() == 0 ? mem::ld_relaxed(slot_of(c, me) + key) : 0);
+    if (s >= 0) {
+      uint32_t m = g.bcast(g.lane() == 0 ? mem::ld_acquire(meta_of(c, me) + s) : 0u);
+      uint32_t st = meta_state(m);
+      if (st == S_OWNED || st == S_REPLICA) {
+        r.kind = LOC_DIRECT; r.local = true; r.row = row_ptr<Val>(c, me, cls, s);
+        return r;
+      }
+      if (st == S_INCOMING && !local_only) {
+        int src = (int)meta_peer(m);
+        // while INCOMING, ver_seen holds the source's slot id (written by the old owner in phase B)
+        int32_t ss = (int32_t)g.bcast(g.lane() == 0 ? mem::ld_relaxed(ver_seen_of(c, me) + s) : 0u);
+        if (ss >= 0) {
+          r.kind = LOC_SUM3; r.local = false;
+          r.row = row_ptr<Val>(c, me, cls, s); r.base = base_ptr<Val>(c, me, cls, s);
+          r.row2 = row_ptr<Val>(c, src, cls, ss);
+          r.meta_ptr = meta_of(c, me) + s; r.meta_val = m;
+          return r;
+        }
+      }
+      if (st == S_FINALIZING && !local_only) { mem::cpu_relax(); continue; }
+      // REPLICA_PENDING / OUTGOING / DEAD / DROPPING: not usable locally
+    }
+    if (local_only) return r;
+    int o = (int)g.bcast((uint32_t)(g.lane() == 0 ? mem::ld_relaxed(dir_of(c, me) + key) : 0));
+    if (o == me) { mem::cpu_relax(); continue; }  // directory in flux
+    bool retry = false;
+    for (int hop = 0; hop < 4; ++hop) {
+      int32_t ps = g.bcast(g.lane() == 0 ? mem::ld_relaxed(slot_of(c, o) + key) : 0);
+      if (ps < 0) { retry = true; break; }
+      uint32_t pm = g.bcast(g.lane() == 0 ? mem::ld_acquire(meta_of(c, o) + ps) : 0u);
+      uint32_t pst = meta_state(pm);
+      if (pst == S_OWNED) {
+        r.kind = LOC_DIRECT; r.local = false; r.row = row_ptr<Val>(c, o, cls, ps);
+        return r;
+      }
+      if (pst == S_INCOMING) {
+        int src = (int)meta_peer(pm);
+        int32_t ss = (int32_t)g.bcast(g.lane() == 0 ? mem::ld_relaxed(ver_seen_of(c, o) + ps) : 0u);
+        if (ss < 0) { retry = true; break; }
+        r.kind = LOC_SUM3; r.local = false;
+        r.row = row_ptr<Val>(c, o, cls, ps); r.base = base_ptr<Val>(c, o, cls, ps);
+        r.row2 = row_ptr<Val>(c, src, cls, ss);
+        r.meta_ptr = meta_of(c, o) + ps; r.meta_val = pm;
+        return r;
+      }
+      if (pst == S_OUTGOING || pst == S_DEAD) { o = (int)meta_peer(pm); if (o == me) { retry = true; break; } continue; }
+      retry = true; break;  // FINALIZING or a stale directory entry
+    }
+    if (retry) { mem::cpu_relax(); continue; }
+  }
+  return r;
+}
+
+// Copy the located row into `out` (len values). Returns false if a SUM3 read raced with the
+// finalize step and must be retried by the caller.
+template <class Val, class G>
+ADAPM_HD bool read_row(const G& g, const PullLoc<Val>& loc, Val* out, uint32_t len) {
+  if (loc.kind == LOC_DIRECT) {
+    for (uint32_t i = g.lane(); i < len; i += g.size()) out[i] = mem::ld_relaxed(loc.row + i);
+    return true;
+  }
+  for (uint32_t i = g.lane(); i < len; i += g.size())
+    out[i] = mem::ld_relaxed(loc.row + i) - mem::ld_relaxed(loc.base + i) + mem::ld_relaxed(loc.row2 + i);
+  mem::fence();
+  uint32_t m2 = g.bcast(g.lane() == 0 ? mem::ld_acquire(loc.meta_ptr) : 0u);
+  return m2 == loc.meta_val;
+}
+
+template <class Val, class G>
+ADAPM_HD bool pull_key(const Ctx& c, const G& g, Key key, Val* out, bool local_only, bool* was_local) {
+  const uint32_t len = c.L.cls[class_of_key(c, key)].len;
+  for (int attempt = 0; attempt < kMaxAttempts; ++attempt) {
+    PullLoc<Val> loc = locate_pull<Val>(c, g, key, local_only);
+    if (loc.kind == LOC_FAIL) return false;
+    if (read_row(g, loc, out, len)) {
+      if (was_local) *was_local = loc.local;
+      return true;
+    }
+    mem::cpu_relax();
+  }
+  return false;
+}
+
+// ---------------------------------------------------------------------------------------
+// locate: where does a Push (additive) of `key` go?
+template <class Val, class G>
+ADAPM_HD PushLoc<Val> locate_push(const Ctx& c, const G& g, Key key) {
+  PushLoc<Val> r;
+  r.row = nullptr; r.version = nullptr; r.flag = nullptr; r.local = false; r.owner = -1;
+  const int me = c.rank;
+  const int cls = class_of_key(c, key);
+  for (int attempt = 0; attempt < kMaxAttempts; ++attempt) {
+    int32_t s = g.bcast(g.lane() == 0 ? mem::ld_relaxed(slot_of(c, me) + key) : 0);
+    if (s >= 0) {
+      uint32_t st = meta_state(g.bcast(g.lane() == 0 ? mem::ld_acquire(meta_of(c, me) + s) : 0u));
+      if (st == S_OWNED || st == S_INCOMING || st == S_FINALIZING) {
+        r.row = row_ptr<Val>(c, me, cls, s); r.version = version_of(c, me) + s;
+        r.local = true; r.owner = me;
+        return r;
+      }
+      if (st == S_REPLICA) {
+        r.row = row_ptr<Val>(c, me, cls, s); r.flag = flags_of(c, me) + s;
+        r.local = true; r.owner = -1;
+        return r;
+      }
+    }
+    int o = (int)g.bcast((uint32_t)(g.lane() == 0 ? mem::ld_relaxed(dir_of(c, me) + key) : 0));
+    if (o == me) { mem::cpu_relax(); continue; }
+    int32_t ps = g.bcast(g.lane() == 0 ? mem::ld_relaxed(slot_of(c, o) + key) : 0);
+    if (ps < 0) { mem::cpu_relax(); continue; }
+    uint32_t pst = meta_state(g.bcast(g.lane() == 0 ? mem::ld_acquire(meta_of(c, o) + ps) : 0u));
+    // OWNED / INCOMING / FINALIZING accept adds; OUTGOING still accepts adds until the grace
+    // period of the announcing round has passed (we are inside it, or we would see the new dir).
+    // REPLICA / REPLICA_PENDING with dir == o happens for a moment when the directory store
+    // overtakes the INCOMING store: the row is the accumulator of the incoming owner -> valid.
+    if (pst == S_FREE || pst == S_DEAD || pst == S_DROPPING) { mem::cpu_relax(); continue; }
+    r.row = row_ptr<Val>(c, o, cls, ps); r.version = version_of(c, o) + ps;
+    r.local = false; r.owner = o;
+    return r;
+  }
+  return r;
+}
+
+template <class Val, class G>
+ADAPM_HD bool push_key(const Ctx& c, const G& g, Key key, const Val* vals, bool* was_local) {
+  const uint32_t len = c.L.cls[class_of_key(c, key)].len;
+  PushLoc<Val> loc = locate_push<Val>(c, g, key);
+  if (!loc.row) return false;
+  for (uint32_t i = g.lane(); i < len; i += g.size()) mem::red_add(loc.row + i, vals[i]);
+  if (g.lane() == 0) {
+    if (loc.version) mem::red_add(loc.version, 1u);
+    if (loc.flag) mem::st_relaxed(loc.flag, (uint8_t)(mem::ld_relaxed(loc.flag) | F_DIRTY));
+  }
+  if (was_local) *was_local = loc.local;
+  return true;
+}
+
+// Set (assignment) goes to the owner's row. Mirrors the reference's `set` flag of Push
+// (coloc_kv_worker.h:223-239, coloc_kv_server_handle.h:404-415); on a replica the reference
+// only asserts, we route the store to the owner and re-base the local replica.
+template <class Val, class G>
+ADAPM_HD bool set_key(const Ctx& c, const G& g, Key key, const Val* vals, bool* was_local) {
+  const int me = c.rank;
+  const int cls = class_of_key(c, key);
+  const uint32_t len = c.L.cls[cls].len;
+  for (int attempt = 0; attempt < kMaxAttempts; ++attempt) {
+    int32_t s = g.bcast(g.lane() == 0 ? mem::ld_relaxed(slot_of(c, me) + key) : 0);
+    uint32_t st = S_FREE;
+    if (s >= 0) st = meta_state(g.bcast(g.lane() == 0 ? mem::ld_acquire(meta_of(c, me) + s) : 0u));
+    if (st == S_OWNED) {
+      Val* row = row_ptr<Val>(c, me, cls, s);
+      for (uint32_t i = g.lane(); i < len; i += g.size()) mem::st_relaxed(row + i, vals[i]);
+      if (g.lane() == 0) mem::red_add(version_of(c, me) + s, 1u);
+      if (was_local) *was_local = true;
+      return true;
+    }
+    if (st == S_INCOMING || st == S_FINALIZING) { mem::cpu_relax(); continue; }  // wait for the transfer
+    int o = (int)g.bcast((uint32_t)(g.lane() == 0 ? mem::ld_relaxed(dir_of(c, me) + key) : 0));
+    if (o == me) { mem::cpu_relax(); continue; }
+    int32_t ps = g.bcast(g.lane() == 0 ? mem::ld_relaxed(slot_of(c, o) + key) : 0);
+    if (ps < 0) { mem::cpu_relax(); continue; }
+    uint32_t pst = meta_state(g.bcast(g.lane() == 0 ? mem::ld_acquire(meta_of(c, o) + ps) : 0u));
+    if (pst != S_OWNED) { mem::cpu_relax(); continue; }
+    Val* row = row_ptr<Val>(c, o, cls, ps);
+    for (uint32_t i = g.lane(); i < len; i += g.size()) mem::st_relaxed(row + i, vals[i]);
+    if (g.lane() == 0) mem::red_add(version_of(c, o) + ps, 1u);
+    if (st == S_REPLICA) {  // keep the local replica coherent with the assignment
+      Val* lrow = row_ptr<Val>(c, me, cls, s);
+      Val* lbase = base_ptr<Val>(c, me, cls, s);
+      for (uint32_t i = g.lane(); i < len; i += g.size()) {
+        mem::st_relaxed(lrow + i, vals[i]);
+        mem::st_relaxed(lbase + i, vals[i]);
+      }
+    }
+    if (was_local) *was_local = false;
+    return true;
+  }
+  return false;
+}
+
+// ---------------------------------------------------------------------------------------
+// helpers for the sync round
+ADAPM_HD bool intent_active(const Ctx& c, uint32_t s, const Clock* clocks) {
+  const int64_t* ie = intent_end_of(c, c.rank) + (size_t)s * c.L.workers;
+  for (int w = 0; w < c.L.workers; ++w)
+    if (mem::ld_relaxed(ie + w) > clocks[w]) return true;
+  return false;
+}
+
+ADAPM_HD void atomic_max_i64(int64_t* p, int64_t v) {
+#if defined(__CUDA_ARCH__)
+  atomicMax((long long*)p, (long long)v);
+#else
+  int64_t old = __atomic_load_n(p, __ATOMIC_RELAXED);
+  while (old < v && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+#endif
+}
+ADAPM_HD int32_t cas_i32(int32_t* p, int32_t expect, int32_t desired) {
+#if defined(__CUDA_ARCH__)
+  return atomicCAS_system(p, expect, desired);
+#else
+  __atomic_compare_exchange_n(p, &expect, desired, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE);
+  return expect;
+#endif
+}
+
+ADAPM_HD int32_t alloc_slot(const Ctx& c, int cls) {
+  int32_t* top = free_top_of(c, c.rank) + cls;
+  int32_t idx = mem::fetch_add(top, (int32_t)-1) - 1;
+  if (idx < 0) { mem::fetch_add(top, (int32_t)1); return -1; }
+  const int32_t* stack = at<int32_t>(c, c.rank, c.L.cls[cls].free_off);
+  return mem::ld_relaxed(stack + idx);
+}
+ADAPM_HD void free_slot(const Ctx& c, int cls, int32_t slot) {
+  int32_t* top = free_top_of(c, c.rank) + cls;
+  int32_t idx = mem::fetch_add(top, (int32_t)1);
+  int32_t* stack = at<int32_t>(c, c.rank, c.L.cls[cls].free_off);
+  mem::st_relaxed(stack + idx, slot);
+}
+
+// Register one intent record (phase A, step 1). Executed by ONE lane.
+// Returns 0 = registered, 1 = deferred to the next round, 2 = dropped (expired / no memory).
+template <class Val>
+ADAPM_HD int register_intent(const Ctx& c, const IntentRec& rec, const Clock* clocks) {
+  const int me = c.rank;
+  const Key key = rec.key;
+  if (rec.end <= clocks[rec.worker]) return 2;  // already expired
+  int32_t s = mem::ld_relaxed(slot_of(c, me) + key);
+  bool claimed = false;
+  if (s >= 0) {
+    // a relocation source slot (OUTGOING/DEAD) no longer represents the key on this rank:
+    // the key gets a fresh placeholder, the old row stays readable until it is recycled
+    uint32_t st0 = meta_state(mem::ld_acquire(meta_of(c, me) + s));
+    if (st0 == S_OUTGOING || st0 == S_DEAD) {
+      int32_t prev = cas_i32(slot_of(c, me) + key, s, -2);
+      if (prev != s) return 1;
+      claimed = true;
+      s = -1;
+    }
+  }
+  if (s == -1) {
+    // claim the key so that concurrent records for the same key do not allocate twice
+    if (!claimed) {
+      int32_t prev = cas_i32(slot_of(c, me) + key, -1, -2);
+      if (prev != -1) return 1;
+    }
+    const int cls = class_of_key(c, key);
+    int32_t ns = alloc_slot(c, cls);
+    if (ns < 0) { mem::st_relaxed(slot_of(c, me) + key, (int32_t)-1); count(c, C_ALLOC_FAIL); return 2; }
+    const uint32_t len = c.L.cls[cls].len;
+    Val* row = row_ptr<Val>(c, me, cls, ns);
+    Val* base = base_ptr<Val>(c, me, cls, ns);
+    for (uint32_t i = 0; i < len; ++i) { mem::st_relaxed(row + i, (Val)0); mem::st_relaxed(base + i, (Val)0); }
+    int64_t* ie = intent_end_of(c, me) + (size_t)ns * c.L.workers;
+    for (int w = 0; w < c.L.workers; ++w) mem::st_relaxed(ie + w, (int64_t)0);
+    mem::st_relaxed(ie + rec.worker, rec.end);
+    mem::st_relaxed(slot_key_of(c, me) + ns, (int64_t)key);
+    mem::st_relaxed(version_of(c, me) + ns, 0u);
+    mem::st_relaxed(ver_seen_of(c, me) + ns, 0xffffffffu);
+    mem::st_relaxed(want_of(c, me) + ns, (uint64_t)0);
+    mem::st_relaxed(flags_of(c, me) + ns, (uint8_t)0);
+    uint32_t m = mem::ld_relaxed(meta_of(c, me) + ns);
+    mem::fence();
+    mem::st_release(meta_of(c, me) + ns, meta_next(m, S_REPLICA_PENDING, 0));
+    mem::st_release(slot_of(c, me) + key, ns);
+    return 0;
+  }
+  if (s < 0) return 1;  // being allocated by a concurrent record
+  uint32_t st = meta_state(mem::ld_acquire(meta_of(c, me) + s));
+  if (st == S_OWNED || st == S_REPLICA || st == S_REPLICA_PENDING || st == S_INCOMING) {
+    atomic_max_i64(intent_end_of(c, me) + (size_t)s * c.L.workers + rec.worker, rec.end);
+    return 0;
+  }
+  return 1;  // OUTGOING / DEAD / DROPPING / FINALIZING: retry after the slot is recycled
+}
+
+struct RoundParams {
+  Clock clocks[MAX_LOCAL_WORKERS];
+  double threshold;   // sys.sync.threshold: -1 all, 0 non-zero, >0 L2 norm, inf = never
+  int32_t sweep;      // ignore dirty hints / versions (guaranteed propagation)
+  int32_t pad;
+};
+
+// Phase A, step 2: visit one non-owned slot: ship the replica delta to the owner, decide
+// whether the replica is still needed, request a refresh.
+template <class Val, class G>
+ADAPM_HD void phase_a_slot(const Ctx& c, const G& g, uint32_t s, const RoundParams& rp) {
+  const int me = c.rank;
+  uint32_t* mp = meta_of(c, me) + s;
+  uint32_t m = g.bcast(g.lane() == 0 ? mem::ld_acquire(mp) : 0u);
+  uint32_t st = meta_state(m);
+  if (st != S_REPLICA && st != S_REPLICA_PENDING) return;
+  const Key key = (Key)g.bcast((uint64_t)(g.lane() == 0 ? (uint64_t)mem::ld_relaxed(slot_key_of(c, me) + s) : 0));
+  const int cls = class_of_key(c, key);
+  const uint32_t len = c.L.cls[cls].len;
+  const bool active = g.bcast((uint32_t)(g.lane() == 0 ? (intent_active(c, s, rp.clocks) ? 1u : 0u) : 0u)) != 0;
+  const int o = (int)g.bcast((uint32_t)(g.lane() == 0 ? mem::ld_relaxed(dir_of(c, me) + key) : 0));
+  int32_t ps = -1;
+  if (o != me) ps = g.bcast(g.lane() == 0 ? mem::ld_relaxed(slot_of(c, o) + key) : 0);
+  if (ps < 0) { if (g.lane() == 0) count(c, C_PROTOCOL_ERRORS); return; }
+  uint8_t* fl = flags_of(c, me) + s;
+  if (st == S_REPLICA) {
+    uint8_t f = (uint8_t)g.bcast((uint32_t)(g.lane() == 0 ? mem::ld_relaxed(fl) : 0));
+    bool consider = (f & F_DIRTY) || rp.sweep || !active;
+    bool never = rp.threshold > 1e300;  // inf: replicas never synchronise (except on drop)
+    if (consider && (!never || !active)) {
+      Val* row = row_ptr<Val>(c, me, cls, s);
+      Val* base = base_ptr<Val>(c, me, cls, s);
+      bool ship = true;
+      if (rp.threshold > 0 && active && !rp.sweep) {
+        double acc = 0;
+        for (uint32_t i = g.lane(); i < len; i += g.size()) {
+          double d = (double)(mem::ld_relaxed(row + i) - mem::ld_relaxed(base + i));
+          acc += d * d;
+        }
+        acc = g.sum(acc);
+        ship = acc >= rp.threshold * rp.threshold;
+      }
+      if (ship) {
+        if (g.lane() == 0) mem::st_relaxed(fl, (uint8_t)(f & ~F_DIRTY));
+        mem::fence();
+        Val* orow = row_ptr<Val>(c, o, cls, ps);
+        bool nz = false;
+        for (uint32_t i = g.lane(); i < len; i += g.size()) {
+          Val v = mem::ld_relaxed(row + i);
+          Val d = v - mem::ld_relaxed(base + i);
+          if (d != (Val)0 || rp.threshold < 0) {
+            if (d != (Val)0) mem::red_add(orow + i, d);
+            mem::st_relaxed(base + i, v);
+            nz = nz || (d != (Val)0);
+          }
+        }
+        nz = g.any(nz);
+        if (nz && g.lane() == 0) {
+          uint32_t old = mem::fetch_add(version_of(c, o) + ps, 1u);
+          uint32_t* vs = ver_seen_of(c, me) + s;
+          if (mem::ld_relaxed(vs) == old) mem::st_relaxed(vs, old + 1);
+          count(c, C_DELTAS_SHIPPED);
+        }
+      }
+    }
+  }
+  if (!active) {
+    if (g.lane() == 0) {
+      mem::st_relaxed(fl, (uint8_t)(mem::ld_relaxed(fl) & ~F_REQUESTED));
+      mem::st_release(mp, meta_next(m, S_DROPPING, 0));
+    }
+    return;
+  }
+  if (g.lane() == 0) {
+    mem::fetch_or(want_of(c, o) + ps, (uint64_t)1 << me);
+    mem::st_relaxed(fl, (uint8_t)(mem::ld_relaxed(fl) | F_REQUESTED));
+  }
+}
+
+// Phase B: the owner decides relocate vs replicate for one owned slot (ONE lane).
+// Decision rule = reference sync_manager.h:615-641: relocate iff no worker on the owner and no
+// other node has intent; the technique switch forces one side.
+ADAPM_HD void phase_b_slot(const Ctx& c, uint32_t s, const RoundParams& rp) {
+  const int me = c.rank;
+  uint64_t* wp = want_of(c, me) + s;
+  if (mem::ld_relaxed(wp) == 0) return;
+  uint32_t* mp = meta_of(c, me) + s;
+  uint32_t m = mem::ld_acquire(mp);
+  uint64_t mask = mem::exchange(wp, (uint64_t)0);
+  if (meta_state(m) != S_OWNED || mask == 0) return;
+  mask &= ~((uint64_t)1 << me);
+  if (mask == 0) return;
+  const Key key = mem::ld_relaxed(slot_key_of(c, me) + s);
+  bool relocate;
+  if (c.technique == (int)MgmtTechniques::REPLICATION_ONLY) relocate = false;
+  else if (c.technique == (int)MgmtTechniques::RELOCATION_ONLY) relocate = true;
+  else {
+    int pc = 0; for (uint64_t t = mask; t; t &= t - 1) ++pc;
+    relocate = (pc == 1) && !intent_active(c, s, rp.clocks);
+  }
+  if (!relocate) return;
+  int dst = 0; while (!((mask >> dst) & 1)) ++dst;
+  int32_t ds = mem::ld_relaxed(slot_of(c, dst) + key);
+  if (ds < 0) { count(c, C_PROTOCOL_ERRORS); return; }
+  uint32_t* dmp = meta_of(c, dst) + ds;
+  uint32_t dm = mem::ld_acquire(dmp);
+  uint32_t dst_state = meta_state(dm);
+  if (dst_state != S_REPLICA && dst_state != S_REPLICA_PENDING) return;
+  mem::st_relaxed(ver_seen_of(c, dst) + ds, (uint32_t)s);  // source slot id for SUM3 readers / finalize
+  mem::fence();
+  mem::st_release(dmp, meta_next(dm, S_INCOMING, (uint32_t)me));
+  mem::st_release(mp, meta_next(m, S_OUTGOING, (uint32_t)dst));
+  mem::fence();
+  for (int r = 0; r < c.L.world; ++r) mem::st_relaxed(dir_of(c, r) + key, (uint8_t)dst);
+  count(c, C_RELOCATIONS);
+}
+
+// Phase C: transfers, refreshes, drops.  (after the grace period)
+template <class Val, class G>
+ADAPM_HD void phase_c_slot(const Ctx& c, const G& g, uint32_t s, const RoundParams& rp) {
+  const int me = c.rank;
+  uint32_t* mp = meta_of(c, me) + s;
+  uint32_t m = g.bcast(g.lane() == 0 ? mem::ld_acquire(mp) : 0u);
+  uint32_t st = meta_state(m);
+  if (st == S_FREE || st == S_OWNED) return;
+  const Key key = (Key)g.bcast((uint64_t)(g.lane() == 0 ? (uint64_t)mem::ld_relaxed(slot_key_of(c, me) + s) : 0));
+  const int cls = class_of_key(c, key);
+  const uint32_t len = c.L.cls[cls].len;
+  uint8_t* fl = flags_of(c, me) + s;
+  if (st == S_INCOMING) {
+    const int src = (int)meta_peer(m);
+    int32_t ss = (int32_t)g.bcast(g.lane() == 0 ? mem::ld_relaxed(ver_seen_of(c, me) + s) : 0u);
+    if (ss < 0) { if (g.lane() == 0) count(c, C_PROTOCOL_ERRORS); return; }
+    uint32_t m1 = meta_next(m, S_FINALIZING, (uint32_t)src);
+    if (g.lane() == 0) mem::st_release(mp, m1);
+    mem::fence(); g.sync();
+    Val* row = row_ptr<Val>(c, me, cls, s);
+    Val* base = base_ptr<Val>(c, me, cls, s);
+    const Val* srow = row_ptr<Val>(c, src, cls, ss);
+    for (uint32_t i = g.lane(); i < len; i += g.size()) {
+      Val S = mem::ld_relaxed(srow + i);
+      Val b = mem::ld_relaxed(base + i);
+      if (S != b) mem::red_add(row + i, (Val)(S - b));
+      mem::st_relaxed(base + i, (Val)0);
+    }
+    mem::fence(); g.sync();
+    if (g.lane() == 0) {
+      uint32_t sv = mem::ld_relaxed(version_of(c, src) + ss);
+      mem::red_add(version_of(c, me) + s, sv + 1u);
+      mem::st_relaxed(ver_seen_of(c, me) + s, 0xffffffffu);
+      mem::st_relaxed(fl, (uint8_t)0);
+      mem::st_release(mp, meta_next(m1, S_OWNED, 0));
+    }
+    return;
+  }
+  if (st == S_REPLICA || st == S_REPLICA_PENDING) {
+    uint8_t f = (uint8_t)g.bcast((uint32_t)(g.lane() == 0 ? mem::ld_relaxed(fl) : 0));
+    if (!(f & F_REQUESTED)) return;
+    if (g.lane() == 0) mem::st_relaxed(fl, (uint8_t)(f & ~F_REQUESTED));
+    if (c.technique == (int)MgmtTechniques::RELOCATION_ONLY) return;
+    const int o = (int)g.bcast((uint32_t)(g.lane() == 0 ? mem::ld_relaxed(dir_of(c, me) + key) : 0));
+    if (o == me) return;
+    int32_t ps = g.bcast(g.lane() == 0 ? mem::ld_relaxed(slot_of(c, o) + key) : 0);
+    if (ps < 0) return;
+    uint32_t pm = g.bcast(g.lane() == 0 ? mem::ld_acquire(meta_of(c, o) + ps) : 0u);
+    if (meta_state(pm) != S_OWNED) return;  // owner is mid-relocation: ask again next round
+    uint32_t v = g.bcast(g.lane() == 0 ? mem::ld_acquire(version_of(c, o) + ps) : 0u);
+    uint32_t seen = g.bcast(g.lane() == 0 ? mem::ld_relaxed(ver_seen_of(c, me) + s) : 0u);
+    if (st == S_REPLICA && v == seen && !rp.sweep) return;
+    Val* row = row_ptr<Val>(c, me, cls, s);
+    Val* base = base_ptr<Val>(c, me, cls, s);
+    const Val* orow = row_ptr<Val>(c, o, cls, ps);
+    for (uint32_t i = g.lane(); i < len; i += g.size()) {
+      Val S = mem::ld_relaxed(orow + i);
+      Val b = mem::ld_relaxed(base + i);
+      if (S != b) { mem::red_add(row + i, (Val)(S - b)); mem::st_relaxed(base + i, S); }
+    }
+    mem::fence(); g.sync();
+    if (g.lane() == 0) {
+      mem::st_relaxed(ver_seen_of(c, me) + s, v);
+      count(c, C_REFRESHES);
+      if (st == S_REPLICA_PENDING) {
+        mem::st_release(mp, meta_next(m, S_REPLICA, 0));
+        count(c, C_REPLICA_SETUPS);
+      }
+    }
+    return;
+  }
+  if (st == S_DROPPING) {
+    const int o = (int)g.bcast((uint32_t)(g.lane() == 0 ? mem::ld_relaxed(dir_of(c, me) + key) : 0));
+    int32_t ps = -1;
+    if (o != me) ps = g.bcast(g.lane() == 0 ? mem::ld_relaxed(slot_of(c, o) + key) : 0);
+    if (ps >= 0) {
+      Val* row = row_ptr<Val>(c, me, cls, s);
+      Val* base = base_ptr<Val>(c, me, cls, s);
+      Val* orow = row_ptr<Val>(c, o, cls, ps);
+      bool nz = false;
+      for (uint32_t i = g.lane(); i < len; i += g.size()) {
+        Val d = mem::ld_relaxed(row + i) - mem::ld_relaxed(base + i);
+        if (d != (Val)0) { mem::red_add(orow + i, d); nz = true; }
+      }
+      nz = g.any(nz);
+      if (nz && g.lane() == 0) mem::red_add(version_of(c, o) + ps, 1u);
+    } else if (g.lane() == 0) {
+      count(c, C_PROTOCOL_ERRORS);
+    }
+    mem::fence(); g.sync();
+    if (g.lane() == 0) {
+      mem::st_release(slot_of(c, me) + key, (int32_t)-1);
+      mem::st_release(mp, meta_next(m, S_FREE, 0));
+      free_slot(c, cls, (int32_t)s);
+      count(c, C_REPLICA_DROPS);
+    }
+    return;
+  }
+  if (st == S_OUTGOING) {
+    if (g.lane() == 0) mem::st_release(mp, meta_next(m, S_DEAD, meta_peer(m)));
+    return;
+  }
+  if (st == S_DEAD) {
+    if (g.lane() == 0) {
+      // the key may already have a fresh slot on this rank (it was requested back)
+      cas_i32(slot_of(c, me) + key, (int32_t)s, (int32_t)-1);
+      mem::st_release(mp, meta_next(m, S_FREE, 0));
+      free_slot(c, cls, (int32_t)s);
+    }
+    return;
+  }
+}
+
+// Is `key` usable from local memory right now (owned or usable replica)?  (PullIfLocal / local sampling)
+ADAPM_HD bool is_local(const Ctx& c, Key key) {
+  int32_t s = mem::ld_relaxed(slot_of(c, c.rank) + key);
+  if (s < 0) return false;
+  uint32_t st = meta_state(mem::ld_acquire(meta_of(c, c.rank) + s));
+  return st == S_OWNED || st == S_REPLICA;
+}
+
+}  // namespace adapm

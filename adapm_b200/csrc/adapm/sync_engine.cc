@@ -1,0 +1,227 @@
+// SyncEngine: one background thread per rank that drives the sync rounds.
+//
+// A round (all ranks in lock-step, separated by control-plane barriers):
+//   0. publish stop/sweep flags, barrier, agree on stop/sweep
+//   1. act on intents whose start clock falls into the estimated window (ActionTimer),
+//      i.e. create placeholder replicas                     [register_intents]
+//   2. phase A: replicas ship deltas to owners, expired replicas start dropping,
+//      live replicas request a refresh                      [barrier]
+//   3. phase B: owners decide relocate vs replicate and announce new owners
+//      in every rank's directory                            [barrier]
+//   4. grace period: all worker ops that may have used the old directory drain [barrier]
+//   5. phase C: relocation transfers, replica refreshes, drops
+// Reference equivalent: SyncManager::thread/startSync/ProcessSyncMessage
+// (sync_manager.h:291-382,452-520,544-799); message round trips became barriers.
+#include "node.h"
+
+#include <sstream>
+
+namespace adapm {
+
+SyncEngine::SyncEngine(Server* server)
+    : server_(server),
+      timer_(server->options().workers, server->options().timing_initial_estimate, server->options().timing_autotune,
+             server->options().timing_smoothing_factor, server->options().timing_buffer_quantile),
+      heaps_(server->options().workers) {}
+
+SyncEngine::~SyncEngine() {
+  if (thread_.joinable()) {
+    try { request_stop_and_join(); } catch (...) {}
+  }
+}
+
+void SyncEngine::start() {
+  started_ = true;
+  if (server_->num_servers() == 1) return;  // nothing to synchronise
+  last_run_ = std::chrono::steady_clock::now();
+  thread_ = std::thread([this] {
+    try {
+      loop();
+    } catch (const std::exception& e) {
+      ALOG("[adapm] rank " << server_->my_rank() << " sync thread died: " << e.what());
+      server_->control()->sync_barrier.broken.store(1);
+      server_->control()->node_barrier.broken.store(1);
+      server_->control()->worker_barrier.broken.store(1);
+    }
+  });
+}
+
+void SyncEngine::request_stop_and_join() {
+  if (!thread_.joinable()) return;
+  server_->my_control().stop_requested.store(1, std::memory_order_release);
+  thread_.join();
+}
+
+void SyncEngine::enqueue(FutureIntent&& fi) {
+  std::lock_guard<std::mutex> lk(in_mu_);
+  incoming_.push_back(std::move(fi));
+}
+
+uint64_t SyncEngine::rounds_done() const {
+  return server_->my_control().rounds_done.load(std::memory_order_acquire);
+}
+
+void SyncEngine::wait_sync() {
+  if (server_->num_servers() == 1) return;
+  RankControl& rc = server_->my_control();
+  const uint64_t target = rc.rounds_done.load(std::memory_order_acquire) + 2;
+  // ask for (at least) two guaranteed-propagation rounds
+  int32_t cur = rc.sweep_requested.load();
+  while (cur < 2 && !rc.sweep_requested.compare_exchange_weak(cur, 2)) {}
+  auto t0 = std::chrono::steady_clock::now();
+  int spins = 0;
+  while (rc.rounds_done.load(std::memory_order_acquire) < target) {
+    if (++spins < 50) std::this_thread::yield();
+    else std::this_thread::sleep_for(std::chrono::microseconds(50));
+    if ((spins & 4095) == 0) {
+      double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      ADAPM_CHECK(el < server_->options().wait_timeout_s, "watchdog: WaitSync timed out (sync thread or a peer is dead)");
+      ADAPM_CHECK(!server_->control()->sync_barrier.broken.load(), "WaitSync: sync barrier broken by a failed peer");
+    }
+  }
+}
+
+void SyncEngine::collect_intents(const std::vector<Clock>& clocks, const std::vector<Clock>& windows) {
+  {
+    std::lock_guard<std::mutex> lk(in_mu_);
+    while (!incoming_.empty()) {
+      FutureIntent fi = std::move(incoming_.front());
+      incoming_.pop_front();
+      ++intents_seen_;
+      heaps_[fi.worker].push(std::move(fi));
+    }
+  }
+  recs_.clear();
+  recs_.swap(deferred_);  // retry what could not be registered last round
+  for (size_t w = 0; w < heaps_.size(); ++w) {
+    auto& h = heaps_[w];
+    const Clock clk = clocks[w];
+    if (clk == WORKER_FINISHED) { while (!h.empty()) h.pop(); continue; }
+    const Clock horizon = (windows[w] >= WINDOW_MAX || clk > CLOCK_MAX - windows[w]) ? CLOCK_MAX : clk + windows[w];
+    while (!h.empty() && h.top().start <= horizon) {
+      const FutureIntent& fi = h.top();
+      if (fi.end > clk) {
+        for (Key k : *fi.keys) {
+          IntentRec r;
+          r.key = k; r.end = fi.end; r.worker = (int32_t)w; r.pad = 0;
+          recs_.push_back(r);
+          if (server_->tracing() && (server_->trace_all_ || server_->traced_.count(k))) server_->trace(k, TraceEvent::INTENT_START);
+        }
+      }
+      h.pop();
+    }
+  }
+}
+
+void SyncEngine::round(bool sweep) {
+  const Options& opt = server_->options();
+  Backend& be = server_->backend();
+  ControlBlock* ctl = server_->control();
+  const int world = opt.world;
+  const double to = opt.wait_timeout_s;
+
+  std::vector<Clock> clocks = server_->worker_clocks();
+  std::vector<Clock> windows(clocks.size(), WINDOW_MAX);
+  if (opt.time_intent_actions) windows = timer_.estimate_windows_and_tune(clocks, round_no_);
+
+  RoundParams rp;
+  memset(&rp, 0, sizeof(rp));
+  for (size_t w = 0; w < clocks.size(); ++w) rp.clocks[w] = clocks[w];
+  rp.threshold = opt.sync_threshold;
+  rp.sweep = sweep ? 1 : 0;
+
+  sw_register_.resume();
+  collect_intents(clocks, windows);
+  if (!recs_.empty()) {
+    status_.assign(recs_.size(), 0);
+    be.register_intents(recs_.data(), recs_.size(), rp, status_.data());
+    for (size_t i = 0; i < recs_.size(); ++i) {
+      if (status_[i] == 1) deferred_.push_back(recs_[i]);
+      else if (status_[i] == 0) ++recs_registered_;
+    }
+  }
+  sw_register_.stop();
+
+  sw_phase_a_.resume();
+  be.phase_a(rp);
+  be.round_fence();
+  sw_phase_a_.stop();
+  sw_barriers_.resume(); ctl->sync_barrier.wait(world, to, "sync round: after phase A"); sw_barriers_.stop();
+
+  sw_phase_b_.resume();
+  be.phase_b(rp);
+  be.round_fence();
+  sw_phase_b_.stop();
+  sw_barriers_.resume(); ctl->sync_barrier.wait(world, to, "sync round: after phase B"); sw_barriers_.stop();
+
+  sw_grace_.resume();
+  be.grace();
+  sw_grace_.stop();
+  sw_barriers_.resume(); ctl->sync_barrier.wait(world, to, "sync round: grace"); sw_barriers_.stop();
+
+  sw_phase_c_.resume();
+  be.phase_c(rp);
+  be.round_fence();
+  sw_phase_c_.stop();
+}
+
+void SyncEngine::loop() {
+  const Options& opt = server_->options();
+  ControlBlock* ctl = server_->control();
+  RankControl& rc = server_->my_control();
+  const int world = opt.world;
+  sw_total_.start();
+  for (;;) {
+    // ---- pacing (reference wait_none / wait_period / wait_interval, sync_manager.h:385-411)
+    sw_pausing_.resume();
+    const bool urgent = rc.sweep_requested.load() > 0 || rc.stop_requested.load() > 0;
+    if (round_no_ > 0 && !urgent) {
+      if (opt.sync_pause_ms > 0) {
+        std::this_thread::sleep_for(std::chrono::milliseconds(opt.sync_pause_ms));
+      } else if (opt.sync_max_per_sec > 0) {
+        auto target = last_run_ + std::chrono::nanoseconds((int64_t)(1e9 / opt.sync_max_per_sec));
+        if (std::chrono::steady_clock::now() < target) std::this_thread::sleep_until(target);
+      }
+    }
+    last_run_ = std::chrono::steady_clock::now();
+    sw_pausing_.stop();
+
+    // ---- agree on stop / sweep
+    rc.snap_stop.store(rc.stop_requested.load(std::memory_order_acquire));
+    rc.snap_sweep.store(rc.sweep_requested.load(std::memory_order_acquire) > 0 ? 1 : 0);
+    sw_barriers_.resume();
+    ctl->sync_barrier.wait(world, opt.wait_timeout_s, "sync round: start");
+    sw_barriers_.stop();
+    bool all_stop = true, any_sweep = false;
+    for (int r = 0; r < world; ++r) {
+      all_stop = all_stop && ctl->ranks[r].snap_stop.load() != 0;
+      any_sweep = any_sweep || ctl->ranks[r].snap_sweep.load() != 0;
+    }
+    if (all_stop) break;
+    if (opt.sweep_period > 0 && round_no_ % (uint64_t)opt.sweep_period == 0) any_sweep = true;
+
+    round(any_sweep);
+
+    if (rc.snap_sweep.load()) {
+      int32_t cur = rc.sweep_requested.load();
+      while (cur > 0 && !rc.sweep_requested.compare_exchange_weak(cur, cur - 1)) {}
+    }
+    ++round_no_;
+    rc.rounds_done.fetch_add(1, std::memory_order_acq_rel);
+  }
+  sw_total_.stop();
+}
+
+std::string SyncEngine::report() const {
+  std::ostringstream os;
+  double tot = sw_total_.elapsed_s();
+  os << "[rank " << server_->my_rank() << "] sync: " << round_no_ << " rounds in " << tot << "s ("
+     << (tot > 0 ? round_no_ / tot : 0) << "/s), intents " << intents_seen_ << " (" << recs_registered_
+     << " key registrations), clocks/round estimate " << timer_.avg_estimate() << "; time: pausing "
+     << sw_pausing_.elapsed_s() << "s, register " << sw_register_.elapsed_s() << "s, phaseA "
+     << sw_phase_a_.elapsed_s() << "s, phaseB " << sw_phase_b_.elapsed_s() << "s, grace " << sw_grace_.elapsed_s()
+     << "s, phaseC " << sw_phase_c_.elapsed_s() << "s, barriers " << sw_barriers_.elapsed_s() << "s";
+  return os.str();
+}
+
+}  // namespace adapm

@@ -1,0 +1,163 @@
+// Python bindings of the core (pybind11 only: tensors cross the boundary as raw
+// addresses, so the extension does not depend on a particular torch ABI). The
+// torch/numpy-facing API with the reference's method names (bindings/bindings.cc:79-374)
+// lives in adapm_b200/__init__.py on top of these classes.
+#include <pybind11/functional.h>
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include "adapm/node.h"
+
+namespace py = pybind11;
+using namespace adapm;
+
+namespace adapm { namespace cudaops { void bind(py::module_& m); } }
+
+namespace {
+
+template <class T> T* ptr(uintptr_t a) { return reinterpret_cast<T*>(a); }
+
+Options make_options(const std::map<std::string, std::string>& kv) {
+  Options o;
+  for (auto& p : kv) ADAPM_CHECK(o.set(p.first, p.second), "unknown option '" << p.first << "'");
+  return o;
+}
+
+IoDesc make_io(bool on_device, uintptr_t stream) {
+  IoDesc io;
+  io.on_device = on_device;
+  io.has_stream = on_device;
+  io.stream = reinterpret_cast<void*>(stream);
+  return io;
+}
+
+}  // namespace
+
+PYBIND11_MODULE(_C, m) {
+  m.doc() = "adapm_b200 native core";
+  py::register_exception<adapm::Error>(m, "AdapmError", PyExc_RuntimeError);
+
+  m.attr("LOCAL") = (int)LOCAL;
+  m.attr("CLOCK_MAX") = (int64_t)CLOCK_MAX;
+  m.attr("MAX_RANKS") = (int)MAX_RANKS;
+  m.def("cuda_available", [] { return cudamem::available(); });
+  m.def("cuda_device_count", [] { return cudamem::available() ? cudamem::device_count() : 0; });
+  m.def("poisson_quantile", &poisson_quantile);
+
+  py::class_<KeyDistribution, std::shared_ptr<KeyDistribution>>(m, "KeyDistribution")
+      .def_readonly("name", &KeyDistribution::name)
+      .def_readonly("min_key", &KeyDistribution::min_key)
+      .def_readonly("max_key", &KeyDistribution::max_key);
+  m.def("uniform_distribution", &make_uniform_distribution);
+  m.def("log_uniform_distribution", &make_log_uniform_distribution);
+  m.def("alias_distribution", [](uintptr_t weights_f64, int64_t n, Key first, Key stride) {
+    return make_alias_distribution(ptr<const double>(weights_f64), n, first, stride);
+  });
+  m.def("callback_distribution", [](py::function fn, Key mn, Key mx) {
+    auto f = std::make_shared<py::function>(std::move(fn));
+    return make_callback_distribution([f]() { py::gil_scoped_acquire g; return (*f)().cast<Key>(); }, mn, mx);
+  });
+
+  py::class_<Server, std::shared_ptr<Server>>(m, "Server")
+      .def(py::init([](const std::map<std::string, std::string>& opts, int64_t num_keys, uint32_t uniform_len,
+                       uintptr_t lens_i64, int64_t n_lens) {
+             Options o = make_options(opts);
+             ValueSpec spec;
+             spec.num_keys = num_keys;
+             spec.uniform_len = uniform_len;
+             if (n_lens > 0) {
+               ADAPM_CHECK(n_lens == num_keys, "value_lengths has " << n_lens << " entries but num_keys is " << num_keys);
+               const int64_t* l = ptr<const int64_t>(lens_i64);
+               spec.lens.resize(n_lens);
+               for (int64_t i = 0; i < n_lens; ++i) { ADAPM_CHECK(l[i] > 0, "value length must be positive"); spec.lens[i] = (uint32_t)l[i]; }
+             }
+             py::gil_scoped_release rel;
+             return std::make_shared<Server>(o, spec);
+           }),
+           py::arg("options"), py::arg("num_keys"), py::arg("uniform_len"), py::arg("lens_ptr") = 0, py::arg("n_lens") = 0)
+      .def("enable_sampling_support", &Server::enable_sampling_support, py::arg("distribution"), py::arg("scheme") = "",
+           py::arg("with_replacement") = -1)
+      .def("barrier", &Server::barrier, py::call_guard<py::gil_scoped_release>())
+      .def("shutdown", &Server::shutdown, py::call_guard<py::gil_scoped_release>())
+      .def("my_rank", &Server::my_rank)
+      .def("num_servers", &Server::num_servers)
+      .def("num_workers", &Server::num_workers)
+      .def("num_keys", &Server::num_keys)
+      .def("get_len", &Server::get_len)
+      .def("owner_of", &Server::owner_of)
+      .def("home_of", &Server::home_of)
+      .def("is_local", &Server::is_local)
+      .def("counters", &Server::counters)
+      .def("stats_string", &Server::stats_string)
+      .def("reset_stats", &Server::reset_stats)
+      .def("sync_rounds", [](Server& s) { return s.sync().rounds_done(); })
+      .def("sync_report", [](Server& s) { return s.sync().report(); })
+      .def("worker_clocks", &Server::worker_clocks)
+      .def("is_cuda", [](Server& s) { return s.backend().is_cuda(); })
+      .def("val_bytes", [](Server& s) { return s.backend().ctx().L.val_bytes; })
+      .def("heap_bytes", [](Server& s) { return s.backend().ctx().L.heap_bytes; })
+      .def("total_slots", [](Server& s) { return s.backend().ctx().L.total_slots; })
+      .def("dtype", [](Server& s) { return s.options().dtype; })
+      .def("device", [](Server& s) { return s.fabric().device(); })
+      .def("peek", [](Server& s, const std::vector<Key>& keys) {
+        std::vector<uint8_t> st(keys.size()), ow(keys.size());
+        s.backend().peek_states(keys.data(), keys.size(), st.data(), ow.data());
+        std::vector<std::pair<int, int>> out;
+        for (size_t i = 0; i < keys.size(); ++i) out.emplace_back((int)st[i], (int)ow[i]);
+        return out;
+      })
+      .def("sampling_stats", [](Server& s) {
+        std::map<std::string, uint64_t> m;
+        if (s.sampling()) { m["checks"] = s.sampling()->local_checks(); m["pulls"] = s.sampling()->local_pulls(); }
+        return m;
+      })
+      .def("backend_handle", [](Server& s) { return (uintptr_t)&s.backend(); });
+
+  py::class_<Worker, std::shared_ptr<Worker>>(m, "Worker")
+      .def(py::init([](int customer_id, std::shared_ptr<Server> server) {
+             return std::make_shared<Worker>(customer_id, *server);
+           }),
+           py::keep_alive<1, 3>())
+      .def("pull", [](Worker& w, uintptr_t keys, size_t n, uintptr_t vals, bool on_device, uintptr_t stream) {
+             return w.Pull(ptr<const Key>(keys), n, ptr<void>(vals), make_io(on_device, stream));
+           }, py::call_guard<py::gil_scoped_release>())
+      .def("push", [](Worker& w, uintptr_t keys, size_t n, uintptr_t vals, bool set, bool on_device, uintptr_t stream) {
+             return w.Push(ptr<const Key>(keys), n, ptr<const void>(vals), set, make_io(on_device, stream));
+           }, py::call_guard<py::gil_scoped_release>())
+      .def("pull_if_local", [](Worker& w, Key key, uintptr_t vals) { return w.PullIfLocal(key, ptr<void>(vals)); },
+           py::call_guard<py::gil_scoped_release>())
+      .def("intent", [](Worker& w, uintptr_t keys, size_t n, Clock start, Clock end) {
+             return w.Intent(ptr<const Key>(keys), n, start, end);
+           }, py::call_guard<py::gil_scoped_release>())
+      .def("advance_clock", &Worker::advanceClock)
+      .def("current_clock", &Worker::currentClock)
+      .def("prepare_sample", &Worker::PrepareSample, py::call_guard<py::gil_scoped_release>())
+      .def("pull_sample", [](Worker& w, SampleID id, uintptr_t keys, size_t n, uintptr_t vals) {
+             return w.PullSample(id, ptr<Key>(keys), n, ptr<void>(vals));
+           }, py::call_guard<py::gil_scoped_release>())
+      .def("finish_sample", &Worker::FinishSample)
+      .def("wait", &Worker::Wait, py::call_guard<py::gil_scoped_release>())
+      .def("is_finished", &Worker::IsFinished)
+      .def("wait_all", &Worker::WaitAll, py::call_guard<py::gil_scoped_release>())
+      .def("wait_sync", &Worker::WaitSync, py::call_guard<py::gil_scoped_release>())
+      .def("barrier", &Worker::Barrier, py::call_guard<py::gil_scoped_release>())
+      .def("begin_setup", &Worker::BeginSetup, py::call_guard<py::gil_scoped_release>())
+      .def("end_setup", &Worker::EndSetup, py::call_guard<py::gil_scoped_release>())
+      .def("reset_stats", &Worker::ResetStats)
+      .def("finalize", &Worker::Finalize, py::call_guard<py::gil_scoped_release>())
+      .def("get_len", &Worker::GetLen)
+      .def("num_keys", &Worker::GetNumKeys)
+      .def("total_len", [](Worker& w, uintptr_t keys, size_t n) { return w.total_len(ptr<const Key>(keys), n); })
+      .def("id", &Worker::id)
+      .def("worker_id", &Worker::worker_id)
+      .def("locality", [](Worker& w) {
+        std::map<std::string, uint64_t> m;
+        m["pull_ops"] = w.num_pull_ops; m["pull_ops_local"] = w.num_pull_ops_local;
+        m["push_ops"] = w.num_push_ops; m["push_ops_local"] = w.num_push_ops_local;
+        m["pull_params"] = w.num_pull_params; m["pull_params_local"] = w.num_pull_params_local;
+        m["push_params"] = w.num_push_params; m["push_params_local"] = w.num_push_params_local;
+        return m;
+      });
+
+  adapm::cudaops::bind(m);
+}

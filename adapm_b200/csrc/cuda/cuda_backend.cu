@@ -1,0 +1,566 @@
+// Generic parameter-manager kernels for sm_100a and their host driver.
+//
+// Kernel inventory (SURVEY 2.5 numbering):
+//   K1  pull_kernel        batched gather: in-kernel directory lookup, local HBM rows or
+//                          NVLink peer loads in the same kernel
+//   K2  push_kernel        batched scatter-add / set: local or peer reductions (REDG over NVLink)
+//   K3  phase_a_kernel     replica delta extract + reduce to owner (+ L2-norm threshold, K5)
+//   K6  phase_b_kernel     owner-side relocate/replicate decision + directory broadcast
+//   K4  phase_c_kernel     replica refresh / relocation transfer / drop
+//       register_kernel    intent registration (placeholder replicas)
+#include "cuda_backend.h"
+
+#include <cstring>
+#include <sstream>
+
+#include "pm_kernels.cuh"
+
+namespace adapm {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarpsPerBlock = kThreads / 32;
+
+__global__ void init_uniform_kernel(const __grid_constant__ Ctx c) {
+  const int me = c.rank;
+  const int64_t K = c.L.num_keys;
+  const int world = c.L.world;
+  uint8_t* dir = dir_of(c, me);
+  int32_t* so = slot_of(c, me);
+  uint32_t* meta = meta_of(c, me);
+  int64_t* skey = slot_key_of(c, me);
+  for (int64_t key = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; key < K; key += (int64_t)gridDim.x * blockDim.x) {
+    int home = (int)(key % world);
+    dir[key] = (uint8_t)home;
+    if (home == me) {
+      uint32_t s = (uint32_t)(key / world);
+      so[key] = (int32_t)s;
+      meta[s] = meta_make(S_OWNED, 0, 1);
+      skey[s] = key;
+    } else {
+      so[key] = -1;
+    }
+  }
+  // free stack: slots [n_home, cap) in ascending pop order
+  const int64_t n_home = K / world + ((K % world) > me ? 1 : 0);
+  const int64_t cap = c.L.cls[0].cap;
+  int32_t* stack = at<int32_t>(c, me, c.L.cls[0].free_off);
+  const int64_t n_free = cap - n_home;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_free; i += (int64_t)gridDim.x * blockDim.x)
+    stack[i] = (int32_t)(cap - 1 - i);
+  if (blockIdx.x == 0 && threadIdx.x == 0) free_top_of(c, me)[0] = (int32_t)n_free;
+}
+
+// ------------------------------------------------------------------------------ K1
+__global__ void __launch_bounds__(kThreads)
+pull_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ keys, size_t n, float* __restrict__ out,
+            const int64_t* __restrict__ offsets, uint32_t uniform_len, int local_only, uint8_t* ok,
+            unsigned long long* result) {
+  WarpGroup g;
+  const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  unsigned nl = 0, nr = 0, nf = 0;
+  for (size_t i = warp; i < n; i += nwarps) {
+    const Key key = keys[i];
+    float* o = out + (offsets ? (size_t)offsets[i] : i * (size_t)uniform_len);
+    bool good = false, local = false;
+    if (key >= 0 && key < c.L.num_keys) {
+      const uint32_t len = c.L.cls[class_of_key(c, key)].len;
+      // fast path: directly readable row, 16-byte vectorised
+      for (int attempt = 0; attempt < 1024 && !good; ++attempt) {
+        PullLoc<float> loc = locate_pull<float>(c, g, key, local_only != 0);
+        if (loc.kind == LOC_FAIL) break;
+        if (loc.kind == LOC_DIRECT && (len & 3u) == 0 && ((((uintptr_t)loc.row) | ((uintptr_t)o)) & 15u) == 0) {
+          for (uint32_t j = g.lane() * 4; j < len; j += 128) {
+            float4 v = dev::ld_row4(loc.row + j);
+            *reinterpret_cast<float4*>(o + j) = v;
+          }
+          good = true;
+        } else {
+          good = read_row(g, loc, o, len);
+        }
+        local = loc.local;
+      }
+    }
+    if (ok && g.lane() == 0) ok[i] = good ? 1 : 0;
+    if (!good) ++nf; else if (local) ++nl; else ++nr;
+  }
+  if (g.lane() == 0) {
+    if (result) {
+      if (nl) atomicAdd(result + 0, (unsigned long long)nl);
+      if (nr) atomicAdd(result + 1, (unsigned long long)nr);
+      if (nf) atomicAdd(result + 2, (unsigned long long)nf);
+    }
+    uint64_t* cn = counters_of(c, c.rank);
+    if (nl) atomicAdd((unsigned long long*)(cn + C_PULL_LOCAL), (unsigned long long)nl);
+    if (nr) atomicAdd((unsigned long long*)(cn + C_PULL_REMOTE), (unsigned long long)nr);
+    if (nf) atomicAdd((unsigned long long*)(cn + C_PROTOCOL_ERRORS), (unsigned long long)nf);
+  }
+}
+
+// ------------------------------------------------------------------------------ K2
+__global__ void __launch_bounds__(kThreads)
+push_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ keys, size_t n, const float* __restrict__ vals,
+            const int64_t* __restrict__ offsets, uint32_t uniform_len, int set, unsigned long long* result) {
+  WarpGroup g;
+  const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  unsigned nl = 0, nr = 0, nf = 0;
+  for (size_t i = warp; i < n; i += nwarps) {
+    const Key key = keys[i];
+    const float* v = vals + (offsets ? (size_t)offsets[i] : i * (size_t)uniform_len);
+    bool good = false, local = false;
+    if (key >= 0 && key < c.L.num_keys) {
+      if (set) {
+        good = set_key<float>(c, g, key, v, &local);
+      } else {
+        const uint32_t len = c.L.cls[class_of_key(c, key)].len;
+        PushLoc<float> loc = locate_push<float>(c, g, key);
+        if (loc.row) {
+          if ((len & 3u) == 0 && ((((uintptr_t)loc.row) | ((uintptr_t)v)) & 15u) == 0) {
+            for (uint32_t j = g.lane() * 4; j < len; j += 128)
+              dev::red_row4(loc.row + j, *reinterpret_cast<const float4*>(v + j));
+          } else {
+            for (uint32_t j = g.lane(); j < len; j += 32) mem::red_add(loc.row + j, v[j]);
+          }
+          if (g.lane() == 0) {
+            if (loc.version) mem::red_add(loc.version, 1u);
+            if (loc.flag) mem::st_relaxed(loc.flag, (uint8_t)(mem::ld_relaxed(loc.flag) | F_DIRTY));
+          }
+          good = true;
+          local = loc.local;
+        }
+      }
+    }
+    if (!good) ++nf; else if (local) ++nl; else ++nr;
+  }
+  if (g.lane() == 0) {
+    if (result) {
+      if (nl) atomicAdd(result + 0, (unsigned long long)nl);
+      if (nr) atomicAdd(result + 1, (unsigned long long)nr);
+      if (nf) atomicAdd(result + 2, (unsigned long long)nf);
+    }
+    uint64_t* cn = counters_of(c, c.rank);
+    if (nl) atomicAdd((unsigned long long*)(cn + C_PUSH_LOCAL), (unsigned long long)nl);
+    if (nr) atomicAdd((unsigned long long*)(cn + C_PUSH_REMOTE), (unsigned long long)nr);
+    if (nf) atomicAdd((unsigned long long*)(cn + C_PROTOCOL_ERRORS), (unsigned long long)nf);
+  }
+}
+
+__global__ void peek_kernel(const __grid_constant__ Ctx c, const Key* keys, size_t n, uint8_t* state_out, uint8_t* owner_out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Key k = keys[i];
+  int32_t s = mem::ld_relaxed(slot_of(c, c.rank) + k);
+  state_out[i] = s >= 0 ? (uint8_t)meta_state(mem::ld_acquire(meta_of(c, c.rank) + s)) : (uint8_t)S_FREE;
+  owner_out[i] = mem::ld_relaxed(dir_of(c, c.rank) + k);
+}
+
+// ------------------------------------------------------------------------------ sync round
+__global__ void register_kernel(const __grid_constant__ Ctx c, const IntentRec* recs, size_t n, RoundParams rp, uint8_t* status) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int st = register_intent<float>(c, recs[i], rp.clocks);
+  status[i] = (uint8_t)st;
+  if (st == 0) count(c, C_INTENTS_REGISTERED);
+  else if (st == 1) count(c, C_INTENTS_DEFERRED);
+}
+
+// Each warp scans 32 slots at a time and then processes the interesting ones cooperatively.
+template <int PHASE>
+__global__ void __launch_bounds__(kThreads) phase_ac_kernel(const __grid_constant__ Ctx c, RoundParams rp) {
+  WarpGroup g;
+  const uint32_t S = c.L.total_slots;
+  const uint32_t* meta = meta_of(c, c.rank);
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t s0 = warp * 32; s0 < S; s0 += nwarps * 32) {
+    uint32_t s = s0 + g.lane();
+    bool hit = false;
+    if (s < S) {
+      uint32_t st = meta_state(__ldcg(meta + s));
+      if (PHASE == 0) hit = (st == S_REPLICA || st == S_REPLICA_PENDING);
+      else hit = (st != S_FREE && st != S_OWNED);
+    }
+    unsigned mask = __ballot_sync(0xffffffffu, hit);
+    while (mask) {
+      int b = __ffs(mask) - 1;
+      mask &= mask - 1;
+      if (PHASE == 0) phase_a_slot<float>(c, g, s0 + b, rp);
+      else phase_c_slot<float>(c, g, s0 + b, rp);
+      __syncwarp();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) phase_b_kernel(const __grid_constant__ Ctx c, RoundParams rp) {
+  const uint32_t S = c.L.total_slots;
+  const uint64_t* want = want_of(c, c.rank);
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x)
+    if (__ldcg(want + s) != 0) phase_b_slot(c, s, rp);
+}
+
+}  // namespace
+
+// =============================================================================== host side
+void CudaBackend::use_device() const { ADAPM_CUDA_CHECK(cudaSetDevice(device_)); }
+
+CudaBackend::CudaBackend(const Options& opt, const Layout& L, std::shared_ptr<Fabric> fabric) : fabric_(fabric) {
+  memset(&ctx_, 0, sizeof(ctx_));
+  ctx_.L = L;
+  ctx_.rank = opt.rank;
+  ctx_.technique = (int)opt.techniques;
+  fabric_->allocate_heaps(L.heap_bytes);
+  device_ = fabric_->device();
+  use_device();
+  for (int r = 0; r < L.world; ++r) ctx_.heap[r] = fabric_->heap(r);
+  cudaDeviceProp prop;
+  ADAPM_CUDA_CHECK(cudaGetDeviceProperties(&prop, device_));
+  num_sms_ = prop.multiProcessorCount;
+  int lo = 0, hi = 0;
+  ADAPM_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  ADAPM_CUDA_CHECK(cudaStreamCreateWithPriority(&sync_stream_, cudaStreamNonBlocking, hi));
+  worker_streams_.resize(opt.workers);
+  for (int w = 0; w < opt.workers; ++w) {
+    ADAPM_CUDA_CHECK(cudaStreamCreateWithFlags(&worker_streams_[w], cudaStreamNonBlocking));
+    tracked_.insert(worker_streams_[w]);
+    staging_.emplace_back(new Staging());
+  }
+}
+
+CudaBackend::~CudaBackend() {
+  cudaSetDevice(device_);
+  cudaDeviceSynchronize();
+  for (auto& st : staging_) { if (st->host) cudaFreeHost(st->host); if (st->dev) cudaFree(st->dev); }
+  if (sync_staging_.host) cudaFreeHost(sync_staging_.host);
+  if (sync_staging_.dev) cudaFree(sync_staging_.dev);
+  for (auto& kv : tickets_) cudaEventDestroy(kv.second);
+  for (auto e : event_pool_) cudaEventDestroy(e);
+  for (auto s : worker_streams_) cudaStreamDestroy(s);
+  if (sync_stream_) cudaStreamDestroy(sync_stream_);
+}
+
+void CudaBackend::ensure_staging(Staging& st, size_t bytes) {
+  if (st.bytes >= bytes) return;
+  size_t nb = std::max<size_t>(bytes * 2, 1 << 20);
+  if (st.host) { ADAPM_CUDA_CHECK(cudaFreeHost(st.host)); st.host = nullptr; }
+  if (st.dev) { ADAPM_CUDA_CHECK(cudaFree(st.dev)); st.dev = nullptr; }
+  ADAPM_CUDA_CHECK(cudaMallocHost((void**)&st.host, nb));
+  ADAPM_CUDA_CHECK(cudaMalloc((void**)&st.dev, nb));
+  st.bytes = nb;
+}
+
+void CudaBackend::init_store(const std::vector<uint8_t>& key_class) {
+  use_device();
+  const Layout& L = ctx_.L;
+  const int me = ctx_.rank;
+  if (L.num_classes == 1) {
+    init_uniform_kernel<<<num_sms_ * 4, 256, 0, sync_stream_>>>(ctx_);
+    ADAPM_CUDA_CHECK(cudaGetLastError());
+  } else {
+    // multi-class: build the tables on the host (cold path) and upload
+    std::vector<uint8_t> dir(L.num_keys);
+    std::vector<int32_t> so(L.num_keys, -1);
+    std::vector<uint32_t> meta(L.total_slots, 0);
+    std::vector<int64_t> skey(L.total_slots, 0);
+    std::vector<uint32_t> next(L.num_classes);
+    for (int k = 0; k < L.num_classes; ++k) next[k] = L.cls[k].slot_begin;
+    key_len_.resize(L.num_keys);
+    for (int64_t key = 0; key < L.num_keys; ++key) {
+      int home = (int)(key % L.world);
+      dir[key] = (uint8_t)home;
+      key_len_[key] = L.cls[key_class[key]].len;
+      if (home == me) {
+        uint32_t s = next[key_class[key]]++;
+        so[key] = (int32_t)s;
+        meta[s] = meta_make(S_OWNED, 0, 1);
+        skey[s] = key;
+      }
+    }
+    char* h = ctx_.heap[me];
+    ADAPM_CUDA_CHECK(cudaMemcpy(h + L.off_dir, dir.data(), dir.size(), cudaMemcpyHostToDevice));
+    ADAPM_CUDA_CHECK(cudaMemcpy(h + L.off_slot_of, so.data(), so.size() * 4, cudaMemcpyHostToDevice));
+    ADAPM_CUDA_CHECK(cudaMemcpy(h + L.off_key_class, key_class.data(), key_class.size(), cudaMemcpyHostToDevice));
+    ADAPM_CUDA_CHECK(cudaMemcpy(h + L.off_meta, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice));
+    ADAPM_CUDA_CHECK(cudaMemcpy(h + L.off_slot_key, skey.data(), skey.size() * 8, cudaMemcpyHostToDevice));
+    int32_t tops[MAX_CLASSES] = {0};
+    for (int k = 0; k < L.num_classes; ++k) {
+      std::vector<int32_t> stack;
+      uint32_t end = L.cls[k].slot_begin + L.cls[k].cap;
+      for (uint32_t s = end; s-- > next[k];) stack.push_back((int32_t)s);
+      tops[k] = (int32_t)stack.size();
+      if (!stack.empty())
+        ADAPM_CUDA_CHECK(cudaMemcpy(h + L.cls[k].free_off, stack.data(), stack.size() * 4, cudaMemcpyHostToDevice));
+    }
+    ADAPM_CUDA_CHECK(cudaMemcpy(h + L.off_free_top, tops, sizeof(tops), cudaMemcpyHostToDevice));
+  }
+  ADAPM_CUDA_CHECK(cudaStreamSynchronize(sync_stream_));
+  ADAPM_CUDA_CHECK(cudaDeviceSynchronize());
+  fabric_->node_barrier("init_store");
+}
+
+void CudaBackend::track_stream(cudaStream_t s) {
+  std::lock_guard<std::mutex> lk(streams_mu_);
+  tracked_.insert(s);
+}
+
+uint64_t CudaBackend::record_ticket(cudaStream_t s) {
+  cudaEvent_t ev;
+  {
+    std::lock_guard<std::mutex> lk(tickets_mu_);
+    if (!event_pool_.empty()) { ev = event_pool_.back(); event_pool_.pop_back(); }
+    else ADAPM_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  }
+  ADAPM_CUDA_CHECK(cudaEventRecord(ev, s));
+  std::lock_guard<std::mutex> lk(tickets_mu_);
+  uint64_t t = next_ticket_++;
+  tickets_[t] = ev;
+  return t;
+}
+
+void CudaBackend::wait_ticket(uint64_t t) {
+  cudaEvent_t ev;
+  {
+    std::lock_guard<std::mutex> lk(tickets_mu_);
+    auto it = tickets_.find(t);
+    if (it == tickets_.end()) return;
+    ev = it->second;
+  }
+  ADAPM_CUDA_CHECK(cudaEventSynchronize(ev));
+  std::lock_guard<std::mutex> lk(tickets_mu_);
+  auto it = tickets_.find(t);
+  if (it != tickets_.end()) { event_pool_.push_back(it->second); tickets_.erase(it); }
+}
+
+bool CudaBackend::ticket_done(uint64_t t) {
+  std::lock_guard<std::mutex> lk(tickets_mu_);
+  auto it = tickets_.find(t);
+  if (it == tickets_.end()) return true;
+  cudaError_t e = cudaEventQuery(it->second);
+  if (e == cudaErrorNotReady) return false;
+  ADAPM_CUDA_CHECK(e);
+  event_pool_.push_back(it->second);
+  tickets_.erase(it);
+  return true;
+}
+
+void CudaBackend::wait_worker(int worker) {
+  use_device();
+  ADAPM_CUDA_CHECK(cudaStreamSynchronize(worker_streams_[worker]));
+  std::vector<cudaStream_t> ss;
+  {
+    std::lock_guard<std::mutex> lk(streams_mu_);
+    ss.assign(tracked_.begin(), tracked_.end());
+  }
+  for (auto s : ss) ADAPM_CUDA_CHECK(cudaStreamSynchronize(s));
+}
+
+static inline int grid_for_warps(size_t n_items, int num_sms) {
+  size_t blocks = (n_items + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  size_t cap = (size_t)num_sms * 8;
+  return (int)std::max<size_t>(1, std::min(blocks, cap));
+}
+
+uint64_t CudaBackend::pull(int worker, const Key* keys, size_t n, void* vals, bool local_only, uint8_t* ok,
+                           OpResult* res, const IoDesc& io) {
+  use_device();
+  if (n == 0) { if (res) *res = OpResult(); return 0; }
+  const Layout& L = ctx_.L;
+  const bool uniform = L.num_classes == 1;
+  if (io.on_device) {
+    ADAPM_CHECK(uniform, "device-pointer pull needs a uniform value length (use host tensors for mixed lengths)");
+    cudaStream_t s = resolve_stream(worker, io);
+    pull_kernel<<<grid_for_warps(n, num_sms_), kThreads, 0, s>>>(ctx_, keys, n, (float*)vals, nullptr, L.cls[0].len,
+                                                                 local_only ? 1 : 0, ok, nullptr);
+    ADAPM_CUDA_CHECK(cudaGetLastError());
+    return record_ticket(s);
+  }
+  // host pointers: stage through pinned memory on the worker's stream, synchronous
+  Staging& st = *staging_[worker];
+  std::lock_guard<std::mutex> lk(st.mu);
+  cudaStream_t s = worker_streams_[worker];
+  const size_t o_keys = 0;
+  const size_t o_offs = align_up(o_keys + n * 8, 256);
+  const size_t o_res = align_up(o_offs + n * 8, 256);
+  const size_t o_ok = align_up(o_res + 64, 256);
+  const size_t o_vals = align_up(o_ok + n, 256);
+  // rows are concatenated in key order, so for mixed lengths the output offsets are a prefix sum
+  // over the key lengths (host mirror of the class table, built in init_store)
+  size_t bytes_vals;
+  std::vector<int64_t> prefix;
+  if (uniform) bytes_vals = n * (size_t)L.cls[0].len * 4;
+  else {
+    prefix.resize(n);
+    size_t acc = 0;
+    for (size_t i = 0; i < n; ++i) {
+      ADAPM_CHECK(keys[i] >= 0 && keys[i] < L.num_keys, "[ERROR] Pull key " << keys[i] << ", which is outside the configured key range [0," << L.num_keys << ")");
+      prefix[i] = (int64_t)acc;
+      acc += (size_t)key_len_[keys[i]];
+    }
+    bytes_vals = acc * 4;
+  }
+  ensure_staging(st, o_vals + bytes_vals + 256);
+  memcpy(st.host + o_keys, keys, n * 8);
+  if (!uniform) memcpy(st.host + o_offs, prefix.data(), n * 8);
+  memset(st.host + o_res, 0, 64);
+  ADAPM_CUDA_CHECK(cudaMemcpyAsync(st.dev, st.host, o_ok, cudaMemcpyHostToDevice, s));
+  pull_kernel<<<grid_for_warps(n, num_sms_), kThreads, 0, s>>>(
+      ctx_, (const Key*)(st.dev + o_keys), n, (float*)(st.dev + o_vals), uniform ? nullptr : (const int64_t*)(st.dev + o_offs),
+      L.cls[0].len, local_only ? 1 : 0, (uint8_t*)(st.dev + o_ok), (unsigned long long*)(st.dev + o_res));
+  ADAPM_CUDA_CHECK(cudaGetLastError());
+  ADAPM_CUDA_CHECK(cudaMemcpyAsync(st.host + o_res, st.dev + o_res, (o_vals - o_res) + bytes_vals, cudaMemcpyDeviceToHost, s));
+  ADAPM_CUDA_CHECK(cudaStreamSynchronize(s));
+  const unsigned long long* r = (const unsigned long long*)(st.host + o_res);
+  if (res) { res->n_local = r[0]; res->n_remote = r[1]; res->n_failed = r[2]; }
+  if (ok) memcpy(ok, st.host + o_ok, n);
+  // copy only rows that were actually read (local_only misses leave garbage)
+  memcpy(vals, st.host + o_vals, bytes_vals);
+  return 0;
+}
+
+uint64_t CudaBackend::push(int worker, const Key* keys, size_t n, const void* vals, bool set, OpResult* res,
+                           const IoDesc& io) {
+  use_device();
+  if (n == 0) { if (res) *res = OpResult(); return 0; }
+  const Layout& L = ctx_.L;
+  const bool uniform = L.num_classes == 1;
+  if (io.on_device) {
+    ADAPM_CHECK(uniform, "device-pointer push needs a uniform value length (use host tensors for mixed lengths)");
+    cudaStream_t s = resolve_stream(worker, io);
+    push_kernel<<<grid_for_warps(n, num_sms_), kThreads, 0, s>>>(ctx_, keys, n, (const float*)vals, nullptr, L.cls[0].len,
+                                                                 set ? 1 : 0, nullptr);
+    ADAPM_CUDA_CHECK(cudaGetLastError());
+    return record_ticket(s);
+  }
+  Staging& st = *staging_[worker];
+  std::lock_guard<std::mutex> lk(st.mu);
+  cudaStream_t s = worker_streams_[worker];
+  std::vector<int64_t> prefix;
+  size_t bytes_vals;
+  if (uniform) bytes_vals = n * (size_t)L.cls[0].len * 4;
+  else {
+    prefix.resize(n);
+    size_t acc = 0;
+    for (size_t i = 0; i < n; ++i) {
+      ADAPM_CHECK(keys[i] >= 0 && keys[i] < L.num_keys, "[ERROR] Push key " << keys[i] << ", which is outside the configured key range [0," << L.num_keys << ")");
+      prefix[i] = (int64_t)acc;
+      acc += (size_t)key_len_[keys[i]];
+    }
+    bytes_vals = acc * 4;
+  }
+  const size_t o_keys = 0;
+  const size_t o_offs = align_up(o_keys + n * 8, 256);
+  const size_t o_res = align_up(o_offs + n * 8, 256);
+  const size_t o_vals = align_up(o_res + 64, 256);
+  ensure_staging(st, o_vals + bytes_vals + 256);
+  memcpy(st.host + o_keys, keys, n * 8);
+  if (!uniform) memcpy(st.host + o_offs, prefix.data(), n * 8);
+  memset(st.host + o_res, 0, 64);
+  memcpy(st.host + o_vals, vals, bytes_vals);
+  ADAPM_CUDA_CHECK(cudaMemcpyAsync(st.dev, st.host, o_vals + bytes_vals, cudaMemcpyHostToDevice, s));
+  push_kernel<<<grid_for_warps(n, num_sms_), kThreads, 0, s>>>(
+      ctx_, (const Key*)(st.dev + o_keys), n, (const float*)(st.dev + o_vals), uniform ? nullptr : (const int64_t*)(st.dev + o_offs),
+      L.cls[0].len, set ? 1 : 0, (unsigned long long*)(st.dev + o_res));
+  ADAPM_CUDA_CHECK(cudaGetLastError());
+  ADAPM_CUDA_CHECK(cudaMemcpyAsync(st.host + o_res, st.dev + o_res, 64, cudaMemcpyDeviceToHost, s));
+  ADAPM_CUDA_CHECK(cudaStreamSynchronize(s));
+  const unsigned long long* r = (const unsigned long long*)(st.host + o_res);
+  if (res) { res->n_local = r[0]; res->n_remote = r[1]; res->n_failed = r[2]; }
+  return 0;
+}
+
+void CudaBackend::peek_states(const Key* keys, size_t n, uint8_t* state_out, uint8_t* owner_out) {
+  use_device();
+  if (n == 0) return;
+  std::lock_guard<std::mutex> lk(sync_staging_.mu);
+  const size_t o_st = align_up(n * 8, 256), o_ow = align_up(o_st + n, 256);
+  ensure_staging(sync_staging_, o_ow + n + 256);
+  Staging& st = sync_staging_;
+  memcpy(st.host, keys, n * 8);
+  cudaStream_t s = worker_streams_[0];
+  ADAPM_CUDA_CHECK(cudaMemcpyAsync(st.dev, st.host, n * 8, cudaMemcpyHostToDevice, s));
+  peek_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(ctx_, (const Key*)st.dev, n, (uint8_t*)(st.dev + o_st), (uint8_t*)(st.dev + o_ow));
+  ADAPM_CUDA_CHECK(cudaGetLastError());
+  ADAPM_CUDA_CHECK(cudaMemcpyAsync(st.host + o_st, st.dev + o_st, o_ow + n - o_st, cudaMemcpyDeviceToHost, s));
+  ADAPM_CUDA_CHECK(cudaStreamSynchronize(s));
+  memcpy(state_out, st.host + o_st, n);
+  memcpy(owner_out, st.host + o_ow, n);
+}
+
+bool CudaBackend::key_is_local(Key k) {
+  uint8_t st, ow;
+  peek_states(&k, 1, &st, &ow);
+  return st == S_OWNED || st == S_REPLICA;
+}
+
+void CudaBackend::register_intents(const IntentRec* recs, size_t n, const RoundParams& rp, uint8_t* status) {
+  use_device();
+  if (n == 0) return;
+  std::lock_guard<std::mutex> lk(sync_staging_.mu);
+  const size_t o_st = align_up(n * sizeof(IntentRec), 256);
+  ensure_staging(sync_staging_, o_st + n + 256);
+  Staging& st = sync_staging_;
+  memcpy(st.host, recs, n * sizeof(IntentRec));
+  ADAPM_CUDA_CHECK(cudaMemcpyAsync(st.dev, st.host, n * sizeof(IntentRec), cudaMemcpyHostToDevice, sync_stream_));
+  register_kernel<<<(int)((n + 255) / 256), 256, 0, sync_stream_>>>(ctx_, (const IntentRec*)st.dev, n, rp, (uint8_t*)(st.dev + o_st));
+  ADAPM_CUDA_CHECK(cudaGetLastError());
+  ADAPM_CUDA_CHECK(cudaMemcpyAsync(st.host + o_st, st.dev + o_st, n, cudaMemcpyDeviceToHost, sync_stream_));
+  ADAPM_CUDA_CHECK(cudaStreamSynchronize(sync_stream_));
+  memcpy(status, st.host + o_st, n);
+}
+
+void CudaBackend::phase_a(const RoundParams& rp) {
+  use_device();
+  phase_ac_kernel<0><<<num_sms_ * 2, kThreads, 0, sync_stream_>>>(ctx_, rp);
+  ADAPM_CUDA_CHECK(cudaGetLastError());
+}
+void CudaBackend::phase_b(const RoundParams& rp) {
+  use_device();
+  phase_b_kernel<<<num_sms_ * 2, kThreads, 0, sync_stream_>>>(ctx_, rp);
+  ADAPM_CUDA_CHECK(cudaGetLastError());
+}
+void CudaBackend::phase_c(const RoundParams& rp) {
+  use_device();
+  phase_ac_kernel<1><<<num_sms_ * 2, kThreads, 0, sync_stream_>>>(ctx_, rp);
+  ADAPM_CUDA_CHECK(cudaGetLastError());
+}
+void CudaBackend::round_fence() {
+  use_device();
+  ADAPM_CUDA_CHECK(cudaStreamSynchronize(sync_stream_));
+}
+
+void CudaBackend::grace() {
+  use_device();
+  std::vector<cudaStream_t> ss;
+  {
+    std::lock_guard<std::mutex> lk(streams_mu_);
+    ss.assign(tracked_.begin(), tracked_.end());
+  }
+  // One event per stream: everything enqueued before this point (which may have read the old
+  // directory) must have finished before the relocation transfers start.
+  std::vector<cudaEvent_t> evs(ss.size());
+  for (size_t i = 0; i < ss.size(); ++i) {
+    ADAPM_CUDA_CHECK(cudaEventCreateWithFlags(&evs[i], cudaEventDisableTiming));
+    ADAPM_CUDA_CHECK(cudaEventRecord(evs[i], ss[i]));
+  }
+  for (size_t i = 0; i < ss.size(); ++i) {
+    ADAPM_CUDA_CHECK(cudaEventSynchronize(evs[i]));
+    cudaEventDestroy(evs[i]);
+  }
+}
+
+void CudaBackend::read_counters(uint64_t* out) {
+  use_device();
+  ADAPM_CUDA_CHECK(cudaMemcpy(out, ctx_.heap[ctx_.rank] + ctx_.L.off_counters, C_NUM_COUNTERS * 8, cudaMemcpyDeviceToHost));
+}
+void CudaBackend::reset_counters() {
+  use_device();
+  ADAPM_CUDA_CHECK(cudaMemset(ctx_.heap[ctx_.rank] + ctx_.L.off_counters, 0, C_NUM_COUNTERS * 8));
+}
+
+std::unique_ptr<Backend> make_cuda_backend(const Options& opt, const Layout& L, std::shared_ptr<Fabric> fabric) {
+  return std::unique_ptr<Backend>(new CudaBackend(opt, L, fabric));
+}
+
+}  // namespace adapm

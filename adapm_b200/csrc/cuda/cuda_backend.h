@@ -1,0 +1,85 @@
+// CudaBackend: the B200 executor of the protocol. One instance per rank = per GPU.
+// Heaps are cudaMalloc'ed and peer-mapped (CUDA IPC across processes, peer access inside
+// one process); every kernel receives the Ctx by value and dereferences peer heaps
+// directly, so Pull = NVLink loads, Push = NVLink reductions (REDG), directory updates =
+// NVLink stores - all issued from inside the kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <mutex>
+#include <set>
+#include <unordered_map>
+
+#include "../adapm/store.h"
+
+namespace adapm {
+
+class CudaBackend : public Backend {
+ public:
+  CudaBackend(const Options& opt, const Layout& L, std::shared_ptr<Fabric> fabric);
+  ~CudaBackend() override;
+
+  const Ctx& ctx() const override { return ctx_; }
+  bool is_cuda() const override { return true; }
+  void init_store(const std::vector<uint8_t>& key_class) override;
+
+  uint64_t pull(int worker, const Key* keys, size_t n, void* vals, bool local_only, uint8_t* ok, OpResult* res,
+                const IoDesc& io) override;
+  uint64_t push(int worker, const Key* keys, size_t n, const void* vals, bool set, OpResult* res,
+                const IoDesc& io) override;
+  void wait_ticket(uint64_t t) override;
+  bool ticket_done(uint64_t t) override;
+  void wait_worker(int worker) override;
+  bool key_is_local(Key k) override;
+  void peek_states(const Key* keys, size_t n, uint8_t* state_out, uint8_t* owner_out) override;
+
+  void register_intents(const IntentRec* recs, size_t n, const RoundParams& rp, uint8_t* status) override;
+  void phase_a(const RoundParams& rp) override;
+  void phase_b(const RoundParams& rp) override;
+  void phase_c(const RoundParams& rp) override;
+  void round_fence() override;
+  void grace() override;
+  void read_counters(uint64_t* out) override;
+  void reset_counters() override;
+
+  // ---- used by the fused application kernels (cuda/ops_*.cu)
+  int device() const { return device_; }
+  cudaStream_t worker_stream(int w) const { return worker_streams_[w]; }
+  cudaStream_t sync_stream() const { return sync_stream_; }
+  void track_stream(cudaStream_t s);            // streams that launch kernels touching the store
+  uint64_t record_ticket(cudaStream_t s);       // completion ticket for work enqueued so far on s
+  cudaStream_t resolve_stream(int worker, const IoDesc& io) {
+    cudaStream_t s = io.has_stream ? (cudaStream_t)io.stream : worker_streams_[worker];
+    track_stream(s);
+    return s;
+  }
+  int num_sms() const { return num_sms_; }
+
+ private:
+  struct Staging {
+    char* host = nullptr;
+    char* dev = nullptr;
+    size_t bytes = 0;
+    std::mutex mu;
+  };
+  void ensure_staging(Staging& st, size_t bytes);
+  void use_device() const;
+
+  std::shared_ptr<Fabric> fabric_;
+  Ctx ctx_;
+  int device_ = 0;
+  int num_sms_ = 148;
+  cudaStream_t sync_stream_ = nullptr;
+  std::vector<cudaStream_t> worker_streams_;
+  std::vector<std::unique_ptr<Staging>> staging_;  // per worker
+  Staging sync_staging_;
+  std::mutex streams_mu_;
+  std::set<cudaStream_t> tracked_;
+  std::mutex tickets_mu_;
+  std::unordered_map<uint64_t, cudaEvent_t> tickets_;
+  std::vector<cudaEvent_t> event_pool_;
+  uint64_t next_ticket_ = 1;
+  std::vector<uint32_t> key_len_;   // host mirror of per-key lengths (mixed-length stores only)
+};
+
+}  // namespace adapm
