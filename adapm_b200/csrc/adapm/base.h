@@ -49,8 +49,10 @@ enum class MgmtTechniques : int { ALL = 0, REPLICATION_ONLY = 1, RELOCATION_ONLY
 //   DROPPING         replica whose intent expired; freed after the grace period
 enum SlotState : uint32_t {
   S_FREE = 0, S_OWNED = 1, S_REPLICA_PENDING = 2, S_REPLICA = 3, S_INCOMING = 4,
-  S_FINALIZING = 5, S_OUTGOING = 6, S_DEAD = 7, S_DROPPING = 8
+  S_FINALIZING = 5, S_OUTGOING = 6, S_DEAD = 7, S_DROPPING = 8,
+  S_INCOMING_REPLICA = 9   // INCOMING whose slot was a usable replica: local reads keep working
 };
+ADAPM_HD bool state_is_incoming(uint32_t st) { return st == 4u || st == 9u; }
 
 // meta word: state | peer<<8 | seq<<16   (seq bumps on every transition; seqlock for readers)
 ADAPM_HD uint32_t meta_make(uint32_t state, uint32_t peer, uint32_t seq) {

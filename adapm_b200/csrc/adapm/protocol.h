@@ -68,7 +68,9 @@ ADAPM_HD PullLoc<Val> locate_pull(const Ctx& c, const G& g, Key key, bool local_
     if (s >= 0) {
       uint32_t m = g.bcast(g.lane() == 0 ? mem::ld_acquire(meta_of(c, me) + s) : 0u);
       uint32_t st = meta_state(m);
-      if (st == S_OWNED || st == S_REPLICA) {
+      if (st == S_OWNED || st == S_REPLICA || st == S_INCOMING_REPLICA) {
+        // INCOMING_REPLICA: the slot was a usable replica when the owner handed the key over;
+        // until the transfer is finalized it keeps serving local reads with replica semantics
         r.kind = LOC_DIRECT; r.local = true; r.row = row_ptr<Val>(c, me, cls, s);
         return r;
       }
@@ -100,7 +102,7 @@ ADAPM_HD PullLoc<Val> locate_pull(const Ctx& c, const G& g, Key key, bool local_
         r.kind = LOC_DIRECT; r.local = false; r.row = row_ptr<Val>(c, o, cls, ps);
         return r;
       }
-      if (pst == S_INCOMING) {
+      if (state_is_incoming(pst)) {
         int src = (int)meta_peer(pm);
         int32_t ss = (int32_t)g.bcast(g.lane() == 0 ? mem::ld_relaxed(ver_seen_of(c, o) + ps) : 0u);
         if (ss < 0) { retry = true; break; }
@@ -160,7 +162,7 @@ ADAPM_HD PushLoc<Val> locate_push(const Ctx& c, const G& g, Key key) {
     int32_t s = g.bcast(g.lane() == 0 ? mem::ld_relaxed(slot_of(c, me) + key) : 0);
     if (s >= 0) {
       uint32_t st = meta_state(g.bcast(g.lane() == 0 ? mem::ld_acquire(meta_of(c, me) + s) : 0u));
-      if (st == S_OWNED || st == S_INCOMING || st == S_FINALIZING) {
+      if (st == S_OWNED || state_is_incoming(st) || st == S_FINALIZING) {
         r.row = row_ptr<Val>(c, me, cls, s); r.version = version_of(c, me) + s;
         r.local = true; r.owner = me;
         return r;
@@ -221,7 +223,7 @@ ADAPM_HD bool set_key(const Ctx& c, const G& g, Key key, const Val* vals, bool* 
       if (was_local) *was_local = true;
       return true;
     }
-    if (st == S_INCOMING || st == S_FINALIZING) { mem::cpu_relax(); continue; }  // wait for the transfer
+    if (state_is_incoming(st) || st == S_FINALIZING) { mem::cpu_relax(); continue; }  // wait for the transfer
     int o = (int)g.bcast((uint32_t)(g.lane() == 0 ? mem::ld_relaxed(dir_of(c, me) + key) : 0));
     if (o == me) { mem::cpu_relax(); continue; }
     int32_t ps = g.bcast(g.lane() == 0 ? mem::ld_relaxed(slot_of(c, o) + key) : 0);
@@ -334,7 +336,7 @@ ADAPM_HD int register_intent(const Ctx& c, const IntentRec& rec, const Clock* cl
   }
   if (s < 0) return 1;  // being allocated by a concurrent record
   uint32_t st = meta_state(mem::ld_acquire(meta_of(c, me) + s));
-  if (st == S_OWNED || st == S_REPLICA || st == S_REPLICA_PENDING || st == S_INCOMING) {
+  if (st == S_OWNED || st == S_REPLICA || st == S_REPLICA_PENDING || state_is_incoming(st)) {
     atomic_max_i64(intent_end_of(c, me) + (size_t)s * c.L.workers + rec.worker, rec.end);
     return 0;
   }
@@ -451,7 +453,7 @@ ADAPM_HD void phase_b_slot(const Ctx& c, uint32_t s, const RoundParams& rp) {
   if (dst_state != S_REPLICA && dst_state != S_REPLICA_PENDING) return;
   mem::st_relaxed(ver_seen_of(c, dst) + ds, (uint32_t)s);  // source slot id for SUM3 readers / finalize
   mem::fence();
-  mem::st_release(dmp, meta_next(dm, S_INCOMING, (uint32_t)me));
+  mem::st_release(dmp, meta_next(dm, dst_state == S_REPLICA ? S_INCOMING_REPLICA : S_INCOMING, (uint32_t)me));
   mem::st_release(mp, meta_next(m, S_OUTGOING, (uint32_t)dst));
   mem::fence();
   for (int r = 0; r < c.L.world; ++r) mem::st_relaxed(dir_of(c, r) + key, (uint8_t)dst);
@@ -470,7 +472,7 @@ ADAPM_HD void phase_c_slot(const Ctx& c, const G& g, uint32_t s, const RoundPara
   const int cls = class_of_key(c, key);
   const uint32_t len = c.L.cls[cls].len;
   uint8_t* fl = flags_of(c, me) + s;
-  if (st == S_INCOMING) {
+  if (state_is_incoming(st)) {
     const int src = (int)meta_peer(m);
     int32_t ss = (int32_t)g.bcast(g.lane() == 0 ? mem::ld_relaxed(ver_seen_of(c, me) + s) : 0u);
     if (ss < 0) { if (g.lane() == 0) count(c, C_PROTOCOL_ERRORS); return; }
@@ -576,7 +578,7 @@ ADAPM_HD bool is_local(const Ctx& c, Key key) {
   int32_t s = mem::ld_relaxed(slot_of(c, c.rank) + key);
   if (s < 0) return false;
   uint32_t st = meta_state(mem::ld_acquire(meta_of(c, c.rank) + s));
-  return st == S_OWNED || st == S_REPLICA;
+  return st == S_OWNED || st == S_REPLICA || st == S_INCOMING_REPLICA;
 }
 
 }  // namespace adapm

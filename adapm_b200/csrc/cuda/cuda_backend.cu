@@ -491,7 +491,7 @@ void CudaBackend::peek_states(const Key* keys, size_t n, uint8_t* state_out, uin
 bool CudaBackend::key_is_local(Key k) {
   uint8_t st, ow;
   peek_states(&k, 1, &st, &ow);
-  return st == S_OWNED || st == S_REPLICA;
+  return st == S_OWNED || st == S_REPLICA || st == S_INCOMING_REPLICA;
 }
 
 void CudaBackend::register_intents(const IntentRec* recs, size_t n, const RoundParams& rp, uint8_t* status) {

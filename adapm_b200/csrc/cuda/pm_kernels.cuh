@@ -55,7 +55,7 @@ __device__ __forceinline__ float* local_row_or_null(const Ctx& c, Key key, uint3
   uint32_t st = meta_state(mem::ld_acquire(meta_of(c, c.rank) + s));
   if (state_out) *state_out = st;
   if (slot_out) *slot_out = s;
-  if (st == S_OWNED || st == S_REPLICA) return row_ptr<float>(c, c.rank, class_of_key(c, key), (uint32_t)s);
+  if (st == S_OWNED || st == S_REPLICA || st == S_INCOMING_REPLICA) return row_ptr<float>(c, c.rank, class_of_key(c, key), (uint32_t)s);
   return nullptr;
 }
 

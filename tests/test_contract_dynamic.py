@@ -1,0 +1,111 @@
+"""Dynamic allocation + set operation contracts.
+
+Assertions ported from the reference's tests/test_dynamic_allocation.cc:25-107 (no update is
+lost or duplicated while a hot key relocates / replicates under fully asynchronous pushes)
+and tests/test_set_operation.cc:27-131 (Set then additive pushes with occasional intents).
+"""
+import random
+
+import pytest
+import torch
+
+from harness import run_cluster
+
+RUNS = 6000
+
+
+def _dyn_worker(kv, server, wid):
+    kv.barrier()
+    rng = random.Random(wid * 31 + 7)
+    keys = torch.tensor([9])
+    vals1 = torch.tensor([1, 2], dtype=server.dtype)
+    vals2 = torch.zeros(2, dtype=server.dtype)
+    ts = []
+    for _ in range(RUNS):
+        if rng.randrange(50) == 0:
+            c = kv.current_clock()
+            kv.intent(keys, c + 10, c + 40)
+        ts.append(kv.push(keys, vals1, True))
+        ts.append(kv.pull(keys, vals2, True))
+        kv.advance_clock()
+    for t in ts:
+        kv.wait(t)
+    kv.wait_sync()
+    kv.barrier()
+    kv.wait_sync()
+    out = None
+    if wid == 0:
+        v = torch.zeros(2, dtype=server.dtype)
+        kv.wait(kv.pull(keys, v))
+        out = v.tolist()
+    kv.wait_sync()
+    kv.finalize()
+    return out
+
+
+@pytest.mark.parametrize("mode,technique", [("threads", "all"), ("procs", "all"), ("threads", "replication_only"),
+                                            ("threads", "relocation_only")])
+def test_dynamic_allocation(mode, technique):
+    world, workers = 3, 2
+    res = run_cluster(_dyn_worker, world=world, workers=workers, mode=mode, value_lengths=2, num_keys=20, dtype="int64",
+                      options={"sys.techniques": technique})
+    got = res[0][0]
+    total = world * workers * RUNS
+    assert got == [total, 2 * total], f"lost or duplicated updates: {got} != {[total, 2 * total]}"
+    moved = sum(r["counters"]["relocations"] + r["counters"]["replica_setups"] for r in res.values())
+    assert moved > 0, "the hot key never relocated or replicated - the test did not exercise the adaptive path"
+    assert all(r["counters"]["protocol_errors"] == 0 for r in res.values())
+
+
+def _set_worker(kv, server, wid):
+    num_workers = server.num_servers() * 2
+    kv.barrier()
+    rng = random.Random(5)
+    keys = torch.tensor([9])
+    errors = []
+    ts, ts_pull = [], []
+    vals2 = torch.zeros(2, dtype=server.dtype)
+    correct = torch.zeros(2, dtype=server.dtype)
+    for check in range(12):
+        if wid == 0:
+            correct = torch.tensor([rng.randrange(1 << 20), rng.randrange(1 << 20)], dtype=server.dtype)
+            kv.wait(kv.set(keys, correct))
+            t = torch.zeros(2, dtype=server.dtype)
+            kv.wait(kv.pull(keys, t))
+            if not torch.equal(t, correct):
+                errors.append(f"run {check}: initial check failed: {t.tolist()} != {correct.tolist()}")
+            kv.advance_clock()
+        kv.barrier()
+        for run in range(100):
+            if run % 100 == 0:
+                kv.intent(keys, kv.current_clock() + 10)
+            ts.append(kv.push(keys, torch.tensor([wid, wid * 2], dtype=server.dtype), True))
+            ts_pull.append(kv.pull(keys, vals2, True))
+            kv.advance_clock()
+        for _ in range(10):
+            kv.advance_clock()
+        for t in ts + ts_pull:
+            kv.wait(t)
+        ts, ts_pull = [], []
+        kv.wait_sync(); kv.barrier()
+        kv.wait_sync(); kv.barrier()
+        if wid == 0:
+            t = torch.zeros(2, dtype=server.dtype)
+            kv.wait(kv.pull(keys, t))
+            for w in range(num_workers):
+                correct[0] += w * 100
+                correct[1] += w * 2 * 100
+            if not torch.equal(t, correct):
+                errors.append(f"run {check}: end check failed: {t.tolist()} != {correct.tolist()}")
+        kv.barrier()
+    kv.waitall()
+    kv.barrier()
+    kv.finalize()
+    return errors
+
+
+@pytest.mark.parametrize("mode", ["threads", "procs"])
+def test_set_operation(mode):
+    res = run_cluster(_set_worker, world=4, workers=2, mode=mode, value_lengths=2, num_keys=20, dtype="int64")
+    errs = [e for r in res.values() for k, v in r.items() if k != "counters" for e in v]
+    assert not errs, "\n".join(errs)
