@@ -88,6 +88,8 @@ std::shared_ptr<KeyDistribution> make_uniform_distribution(Key min, Key max);
 std::shared_ptr<KeyDistribution> make_log_uniform_distribution(Key min, Key max);
 std::shared_ptr<KeyDistribution> make_alias_distribution(const double* weights, int64_t n, Key first_key, Key key_stride);
 std::shared_ptr<KeyDistribution> make_callback_distribution(std::function<Key()> fn, Key min, Key max);
+// Walker/Vose alias table: prob[i] in [0,1], alias[i] in [0,n)  (shared with the device sampler)
+void build_alias_table(const double* weights, int64_t n, float* prob, int32_t* alias);
 
 class Sampling {
  public:

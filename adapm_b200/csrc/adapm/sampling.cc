@@ -43,21 +43,7 @@ class AliasDist : public KeyDistribution {
   AliasDist(const double* w, int64_t n, Key first, Key stride) : n_(n), first_(first), stride_(stride), prob_(n), alias_(n), u_(0.0, 1.0) {
     name = "alias";
     if (stride == 1) { min_key = first; max_key = first + n; }
-    double sum = 0;
-    for (int64_t i = 0; i < n; ++i) sum += w[i];
-    ADAPM_CHECK(sum > 0, "alias table: weights sum to zero");
-    std::vector<double> p(n);
-    std::vector<int64_t> small, large;
-    for (int64_t i = 0; i < n; ++i) { p[i] = w[i] * n / sum; (p[i] < 1.0 ? small : large).push_back(i); }
-    while (!small.empty() && !large.empty()) {
-      int64_t s = small.back(); small.pop_back();
-      int64_t l = large.back(); large.pop_back();
-      prob_[s] = (float)p[s]; alias_[s] = (int32_t)l;
-      p[l] = p[l] + p[s] - 1.0;
-      (p[l] < 1.0 ? small : large).push_back(l);
-    }
-    for (int64_t i : large) { prob_[i] = 1.f; alias_[i] = (int32_t)i; }
-    for (int64_t i : small) { prob_[i] = 1.f; alias_[i] = (int32_t)i; }
+    build_alias_table(w, n, prob_.data(), alias_.data());
   }
   Key draw(std::mt19937_64& rng) override {
     int64_t i = (int64_t)(u_(rng) * n_);
@@ -86,6 +72,24 @@ class CallbackDist : public KeyDistribution {
 };
 
 }  // namespace
+
+void build_alias_table(const double* w, int64_t n, float* prob, int32_t* alias) {
+  double sum = 0;
+  for (int64_t i = 0; i < n; ++i) sum += w[i];
+  ADAPM_CHECK(sum > 0, "alias table: weights sum to zero");
+  std::vector<double> p(n);
+  std::vector<int64_t> small, large;
+  for (int64_t i = 0; i < n; ++i) { p[i] = w[i] * n / sum; (p[i] < 1.0 ? small : large).push_back(i); }
+  while (!small.empty() && !large.empty()) {
+    int64_t s = small.back(); small.pop_back();
+    int64_t l = large.back(); large.pop_back();
+    prob[s] = (float)p[s]; alias[s] = (int32_t)l;
+    p[l] = p[l] + p[s] - 1.0;
+    (p[l] < 1.0 ? small : large).push_back(l);
+  }
+  for (int64_t i : large) { prob[i] = 1.f; alias[i] = (int32_t)i; }
+  for (int64_t i : small) { prob[i] = 1.f; alias[i] = (int32_t)i; }
+}
 
 std::shared_ptr<KeyDistribution> make_uniform_distribution(Key mn, Key mx) {
   ADAPM_CHECK(mx > mn, "uniform distribution needs max > min");

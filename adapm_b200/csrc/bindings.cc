@@ -53,6 +53,9 @@ PYBIND11_MODULE(_C, m) {
   m.def("alias_distribution", [](uintptr_t weights_f64, int64_t n, Key first, Key stride) {
     return make_alias_distribution(ptr<const double>(weights_f64), n, first, stride);
   });
+  m.def("build_alias_table", [](uintptr_t weights_f64, int64_t n, uintptr_t prob_f32, uintptr_t alias_i32) {
+    build_alias_table(ptr<const double>(weights_f64), n, ptr<float>(prob_f32), ptr<int32_t>(alias_i32));
+  }, py::call_guard<py::gil_scoped_release>());
   m.def("callback_distribution", [](py::function fn, Key mn, Key mx) {
     auto f = std::make_shared<py::function>(std::move(fn));
     return make_callback_distribution([f]() { py::gil_scoped_acquire g; return (*f)().cast<Key>(); }, mn, mx);

@@ -203,6 +203,11 @@ __global__ void __launch_bounds__(kThreads) phase_b_kernel(const __grid_constant
 
 }  // namespace
 
+std::atomic<uint64_t>& kernel_launch_counter() {
+  static std::atomic<uint64_t> c{0};
+  return c;
+}
+
 // =============================================================================== host side
 void CudaBackend::use_device() const { ADAPM_CUDA_CHECK(cudaSetDevice(device_)); }
 
@@ -257,7 +262,8 @@ void CudaBackend::init_store(const std::vector<uint8_t>& key_class) {
   const int me = ctx_.rank;
   if (L.num_classes == 1) {
     init_uniform_kernel<<<num_sms_ * 4, 256, 0, sync_stream_>>>(ctx_);
-    ADAPM_CUDA_CHECK(cudaGetLastError());
+    ADAPM_COUNT_LAUNCH();
+  ADAPM_CUDA_CHECK(cudaGetLastError());
   } else {
     // multi-class: build the tables on the host (cold path) and upload
     std::vector<uint8_t> dir(L.num_keys);
@@ -373,7 +379,8 @@ uint64_t CudaBackend::pull(int worker, const Key* keys, size_t n, void* vals, bo
     cudaStream_t s = resolve_stream(worker, io);
     pull_kernel<<<grid_for_warps(n, num_sms_), kThreads, 0, s>>>(ctx_, keys, n, (float*)vals, nullptr, L.cls[0].len,
                                                                  local_only ? 1 : 0, ok, nullptr);
-    ADAPM_CUDA_CHECK(cudaGetLastError());
+    ADAPM_COUNT_LAUNCH();
+  ADAPM_CUDA_CHECK(cudaGetLastError());
     return record_ticket(s);
   }
   // host pointers: stage through pinned memory on the worker's stream, synchronous
@@ -408,6 +415,7 @@ uint64_t CudaBackend::pull(int worker, const Key* keys, size_t n, void* vals, bo
   pull_kernel<<<grid_for_warps(n, num_sms_), kThreads, 0, s>>>(
       ctx_, (const Key*)(st.dev + o_keys), n, (float*)(st.dev + o_vals), uniform ? nullptr : (const int64_t*)(st.dev + o_offs),
       L.cls[0].len, local_only ? 1 : 0, (uint8_t*)(st.dev + o_ok), (unsigned long long*)(st.dev + o_res));
+  ADAPM_COUNT_LAUNCH();
   ADAPM_CUDA_CHECK(cudaGetLastError());
   ADAPM_CUDA_CHECK(cudaMemcpyAsync(st.host + o_res, st.dev + o_res, (o_vals - o_res) + bytes_vals, cudaMemcpyDeviceToHost, s));
   ADAPM_CUDA_CHECK(cudaStreamSynchronize(s));
@@ -430,7 +438,8 @@ uint64_t CudaBackend::push(int worker, const Key* keys, size_t n, const void* va
     cudaStream_t s = resolve_stream(worker, io);
     push_kernel<<<grid_for_warps(n, num_sms_), kThreads, 0, s>>>(ctx_, keys, n, (const float*)vals, nullptr, L.cls[0].len,
                                                                  set ? 1 : 0, nullptr);
-    ADAPM_CUDA_CHECK(cudaGetLastError());
+    ADAPM_COUNT_LAUNCH();
+  ADAPM_CUDA_CHECK(cudaGetLastError());
     return record_ticket(s);
   }
   Staging& st = *staging_[worker];
@@ -462,6 +471,7 @@ uint64_t CudaBackend::push(int worker, const Key* keys, size_t n, const void* va
   push_kernel<<<grid_for_warps(n, num_sms_), kThreads, 0, s>>>(
       ctx_, (const Key*)(st.dev + o_keys), n, (const float*)(st.dev + o_vals), uniform ? nullptr : (const int64_t*)(st.dev + o_offs),
       L.cls[0].len, set ? 1 : 0, (unsigned long long*)(st.dev + o_res));
+  ADAPM_COUNT_LAUNCH();
   ADAPM_CUDA_CHECK(cudaGetLastError());
   ADAPM_CUDA_CHECK(cudaMemcpyAsync(st.host + o_res, st.dev + o_res, 64, cudaMemcpyDeviceToHost, s));
   ADAPM_CUDA_CHECK(cudaStreamSynchronize(s));
@@ -481,6 +491,7 @@ void CudaBackend::peek_states(const Key* keys, size_t n, uint8_t* state_out, uin
   cudaStream_t s = worker_streams_[0];
   ADAPM_CUDA_CHECK(cudaMemcpyAsync(st.dev, st.host, n * 8, cudaMemcpyHostToDevice, s));
   peek_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(ctx_, (const Key*)st.dev, n, (uint8_t*)(st.dev + o_st), (uint8_t*)(st.dev + o_ow));
+  ADAPM_COUNT_LAUNCH();
   ADAPM_CUDA_CHECK(cudaGetLastError());
   ADAPM_CUDA_CHECK(cudaMemcpyAsync(st.host + o_st, st.dev + o_st, o_ow + n - o_st, cudaMemcpyDeviceToHost, s));
   ADAPM_CUDA_CHECK(cudaStreamSynchronize(s));
@@ -504,6 +515,7 @@ void CudaBackend::register_intents(const IntentRec* recs, size_t n, const RoundP
   memcpy(st.host, recs, n * sizeof(IntentRec));
   ADAPM_CUDA_CHECK(cudaMemcpyAsync(st.dev, st.host, n * sizeof(IntentRec), cudaMemcpyHostToDevice, sync_stream_));
   register_kernel<<<(int)((n + 255) / 256), 256, 0, sync_stream_>>>(ctx_, (const IntentRec*)st.dev, n, rp, (uint8_t*)(st.dev + o_st));
+  ADAPM_COUNT_LAUNCH();
   ADAPM_CUDA_CHECK(cudaGetLastError());
   ADAPM_CUDA_CHECK(cudaMemcpyAsync(st.host + o_st, st.dev + o_st, n, cudaMemcpyDeviceToHost, sync_stream_));
   ADAPM_CUDA_CHECK(cudaStreamSynchronize(sync_stream_));
@@ -513,16 +525,19 @@ void CudaBackend::register_intents(const IntentRec* recs, size_t n, const RoundP
 void CudaBackend::phase_a(const RoundParams& rp) {
   use_device();
   phase_ac_kernel<0><<<num_sms_ * 2, kThreads, 0, sync_stream_>>>(ctx_, rp);
+  ADAPM_COUNT_LAUNCH();
   ADAPM_CUDA_CHECK(cudaGetLastError());
 }
 void CudaBackend::phase_b(const RoundParams& rp) {
   use_device();
   phase_b_kernel<<<num_sms_ * 2, kThreads, 0, sync_stream_>>>(ctx_, rp);
+  ADAPM_COUNT_LAUNCH();
   ADAPM_CUDA_CHECK(cudaGetLastError());
 }
 void CudaBackend::phase_c(const RoundParams& rp) {
   use_device();
   phase_ac_kernel<1><<<num_sms_ * 2, kThreads, 0, sync_stream_>>>(ctx_, rp);
+  ADAPM_COUNT_LAUNCH();
   ADAPM_CUDA_CHECK(cudaGetLastError());
 }
 void CudaBackend::round_fence() {

@@ -14,6 +14,10 @@
 
 namespace adapm {
 
+// number of kernels this library launched in this process (bench.py reports it as gpu_launches)
+std::atomic<uint64_t>& kernel_launch_counter();
+#define ADAPM_COUNT_LAUNCH() (::adapm::kernel_launch_counter().fetch_add(1, std::memory_order_relaxed))
+
 class CudaBackend : public Backend {
  public:
   CudaBackend(const Options& opt, const Layout& L, std::shared_ptr<Fabric> fabric);

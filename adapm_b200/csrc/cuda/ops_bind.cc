@@ -1,4 +1,5 @@
-// Python bindings of the fused application kernels.
+// Python bindings of the fused application kernels. Tensors are passed as raw device
+// addresses (see adapm_b200/ops/__init__.py for the torch-facing wrappers).
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
@@ -9,8 +10,29 @@ namespace py = pybind11;
 namespace adapm {
 namespace cudaops {
 
+namespace {
+template <class T> T* ptr(uintptr_t a) { return reinterpret_cast<T*>(a); }
+CudaBackend& backend_of(uintptr_t handle) {
+  Backend* b = reinterpret_cast<Backend*>(handle);
+  ADAPM_CHECK(b && b->is_cuda(), "this op needs a server with backend='cuda'");
+  return *static_cast<CudaBackend*>(b);
+}
+}  // namespace
+
 void bind(py::module_& m) {
-  (void)m;
+  m.def("sgns_step", [](uintptr_t be, uintptr_t stream, uintptr_t centers, uintptr_t contexts, uintptr_t negatives,
+                        int n_pairs, int neg, int d, float alpha, uintptr_t loss, uintptr_t stats) {
+    sgns_step(backend_of(be), (cudaStream_t)stream, ptr<const Key>(centers), ptr<const Key>(contexts),
+              ptr<const Key>(negatives), n_pairs, neg, d, alpha, ptr<float>(loss), ptr<unsigned long long>(stats));
+  });
+  m.def("sample_keys", [](uintptr_t be, uintptr_t stream, int kind, uintptr_t prob, uintptr_t alias, int64_t n_table,
+                          Key first, Key stride, uintptr_t out, int64_t n, uint64_t seed, bool local_only, int max_tries,
+                          uintptr_t stats) {
+    sample_keys(backend_of(be), (cudaStream_t)stream, kind, ptr<const float>(prob), ptr<const int32_t>(alias), n_table,
+                first, stride, ptr<Key>(out), n, seed, local_only, max_tries, ptr<unsigned long long>(stats));
+  });
+  m.def("kernel_launches", [] { return kernel_launch_counter().load(); });
+  m.def("track_stream", [](uintptr_t be, uintptr_t stream) { backend_of(be).track_stream((cudaStream_t)stream); });
 }
 
 }  // namespace cudaops

@@ -1,0 +1,247 @@
+"""word2vec skip-gram with negative sampling (SGNS) + AdaGrad on the parameter manager.
+
+Behavioural parity with the reference application ``apps/word2vec.cc``:
+
+* keys: ``syn0[w] = 2w``, ``syn1[w] = 2w + 1`` (word2vec.cc:83-105); row = ``[embedding | AdaGrad]``
+  of ``2 * embed_dim`` floats (word2vec.cc:1101);
+* per (center, context) pair: 1 positive + ``negative`` negative targets, sigmoid saturating at
+  ``|f| > 6``, worker-side AdaGrad using the pulled accumulator (word2vec.cc:420-429,682-745);
+* negatives ~ unigram^0.75 (word2vec.cc:125-144) through ``PrepareSample/PullSample`` semantics
+  (``sampling.scheme``: ``local`` rejects non-resident keys, ``naive``/``preloc`` use the drawn keys);
+* intent: the keys of a future batch are signalled ``read_ahead`` clocks ahead (word2vec.cc:563-606),
+  one clock per batch instead of one per sentence;
+* init: syn0 ~ U(-0.5, 0.5)/d, syn1 = 0, accumulators 1e-6 (word2vec.cc:805-831);
+* checkpoint: ``"<vocab> <dim>\\n"`` then per word ``"<word> "`` + ``dim`` raw float32 + ``"\\n"``
+  (word2vec.cc:367-416).
+
+B200-first differences: the per-pair loop of the reference is one batched kernel
+(``ops.sgns_step``) that fuses pull, scoring, AdaGrad and push over local HBM / NVLink peers.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .. import LOCAL
+
+
+@dataclass
+class Word2VecConfig:
+    vocab_size: int = 1_000_000
+    embed_dim: int = 300
+    negative: int = 25
+    window: int = 5
+    starting_alpha: float = 0.025
+    neg_power: float = 0.75
+    batch_pairs: int = 32768
+    read_ahead: int = 4              # batches of look-ahead for intent signalling
+    sampling_scheme: str = "local"   # local | naive | preloc
+    signal_intent: bool = True
+    model_seed: int = 134827
+    zipf_exponent: float = 1.0       # synthetic corpus skew
+
+    @property
+    def row_len(self) -> int:
+        return 2 * self.embed_dim
+
+    @property
+    def num_keys(self) -> int:
+        return 2 * self.vocab_size
+
+    @property
+    def updates_per_pair(self) -> int:
+        # 1 (syn0) + (negative + 1) (syn1) additive row updates, BASELINE.md section 3
+        return 1 + (self.negative + 1)
+
+
+def syn0_key(w):
+    return 2 * w
+
+
+def syn1_key(w):
+    return 2 * w + 1
+
+
+def zipf_counts(vocab_size: int, exponent: float = 1.0, total: float = 1e9) -> np.ndarray:
+    """Word frequencies of a synthetic corpus with the named vocabulary size (rank-frequency Zipf)."""
+    r = np.arange(1, vocab_size + 1, dtype=np.float64)
+    p = r ** (-exponent)
+    p /= p.sum()
+    return np.maximum(1.0, p * total)
+
+
+class SyntheticPairs:
+    """Synthetic (center, context) pair stream: both words ~ Zipf(vocab). Deterministic per
+    (seed, rank, step); batches are produced in pinned host memory like a real data loader."""
+
+    def __init__(self, cfg: Word2VecConfig, counts: np.ndarray, rank: int, seed: int = 1, pin: bool = False):
+        self.cfg, self.rank, self.seed = cfg, rank, seed
+        p = counts / counts.sum()
+        self.cdf = np.cumsum(p)
+        self.cdf[-1] = 1.0
+        self.pin = pin
+
+    def batch(self, step: int):
+        rng = np.random.default_rng([self.seed, self.rank, step])
+        B = self.cfg.batch_pairs
+        u = rng.random(2 * B)
+        w = np.searchsorted(self.cdf, u, side="right").astype(np.int64)
+        np.clip(w, 0, self.cfg.vocab_size - 1, out=w)
+        t = torch.from_numpy(np.stack([syn0_key(w[:B]), syn1_key(w[B:])]))  # [2, B] keys
+        if self.pin:
+            t = t.pin_memory()
+        return t
+
+
+class Word2Vec:
+    def __init__(self, server, worker, cfg: Word2VecConfig, counts: Optional[np.ndarray] = None):
+        self.server, self.worker, self.cfg = server, worker, cfg
+        self.counts = counts if counts is not None else zipf_counts(cfg.vocab_size, cfg.zipf_exponent)
+        assert len(self.counts) == cfg.vocab_size
+        self.cuda = server.backend == "cuda"
+        self.alpha = cfg.starting_alpha
+        self.step_no = 0
+        weights = np.power(self.counts, cfg.neg_power)
+        if self.cuda:
+            from ..ops import DeviceSampler
+
+            # negatives are syn1 keys: first key 1, stride 2
+            self.sampler = DeviceSampler(server, weights=torch.from_numpy(weights), first_key=1, key_stride=2)
+            dev = server.device
+            self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+            self.stats = torch.zeros(4, dtype=torch.int64, device=dev)
+            self._neg = torch.empty(cfg.batch_pairs * cfg.negative, dtype=torch.int64, device=dev)
+            self._keys_dev = torch.empty(2, cfg.batch_pairs, dtype=torch.int64, device=dev)
+        else:
+            w = torch.from_numpy(weights)
+            self._neg_cdf = torch.cumsum(w / w.sum(), 0)
+            self._gen = torch.Generator().manual_seed(cfg.model_seed + 17 * server.my_rank())
+
+    # ------------------------------------------------------------------ model init
+    def init_model(self, chunk: int = 1 << 16) -> None:
+        """Each rank initialises the keys it is home for (set, not push, so re-runs are idempotent)."""
+        cfg, world, rank = self.cfg, self.server.num_servers(), self.server.my_rank()
+        d = cfg.embed_dim
+        dev = self.server.device
+        gen = torch.Generator(device=dev.type if dev.type == "cuda" else "cpu").manual_seed(cfg.model_seed + rank)
+        self.worker.begin_setup()
+        keys_all = torch.arange(rank, cfg.num_keys, world, dtype=torch.int64)
+        for i in range(0, keys_all.numel(), chunk):
+            k = keys_all[i:i + chunk].to(dev)
+            rows = torch.empty(k.numel(), 2 * d, dtype=torch.float32, device=dev)
+            rows[:, d:] = 1e-6
+            emb = (torch.rand(k.numel(), d, generator=gen, device=dev, dtype=torch.float32) - 0.5) / d
+            is_syn0 = (k % 2 == 0).view(-1, 1)
+            rows[:, :d] = torch.where(is_syn0, emb, torch.zeros_like(emb))
+            self.worker.set(k, rows.view(-1))
+        self.worker.waitall()
+        self.worker.end_setup()
+
+    # ------------------------------------------------------------------ intent
+    def signal_intent(self, keys_host: torch.Tensor, clock: int) -> None:
+        """keys_host: [2, B] (syn0 keys, syn1 keys) of a future batch (CPU tensor)."""
+        if not self.cfg.signal_intent or self.server.num_servers() == 1:
+            return
+        self.worker.intent(keys_host.view(-1), clock, clock + 1)
+
+    # ------------------------------------------------------------------ one training step
+    def step(self, keys_host: torch.Tensor) -> torch.Tensor:
+        """Runs one batch. ``keys_host``: [2, B] int64 CPU tensor (pinned for the e2e path).
+        Returns the device tensor that accumulates the summed loss (read it with ``.item()``/copy)."""
+        cfg = self.cfg
+        if self.cuda:
+            from ..ops import sgns_step
+
+            self._keys_dev.copy_(keys_host, non_blocking=True)  # H2D of this step's inputs
+            local_only = cfg.sampling_scheme == "local" and self.server.num_servers() > 1
+            seed = (cfg.model_seed * 1000003 + self.server.my_rank() * 7919 + self.step_no) & 0xFFFFFFFFFFFF
+            self.sampler.sample(self._neg.numel(), seed, local_only=local_only, out=self._neg)
+            sgns_step(self.server, self._keys_dev[0], self._keys_dev[1], self._neg, cfg.embed_dim, self.alpha,
+                      self.loss, self.stats)
+            self.step_no += 1
+            return self.loss
+        return self._step_cpu(keys_host)
+
+    # reference-semantics step through the public Pull/Push API (CPU backend; also the numerics oracle)
+    def _step_cpu(self, keys_host: torch.Tensor) -> torch.Tensor:
+        cfg, kv, d = self.cfg, self.worker, self.cfg.embed_dim
+        centers, contexts = keys_host[0], keys_host[1]
+        B = centers.numel()
+        u = torch.rand(B * cfg.negative, generator=self._gen, dtype=torch.float64)
+        negw = torch.searchsorted(self._neg_cdf, u).clamp_(max=cfg.vocab_size - 1)
+        negs = syn1_key(negw).view(B, cfg.negative)
+        loss = sgns_reference_step(kv, centers, contexts, negs, d, self.alpha)
+        self.step_no += 1
+        return torch.tensor([loss], dtype=torch.float32)
+
+    def set_alpha(self, progress: float) -> None:
+        """Linear decay like the reference (word2vec.cc:551-559)."""
+        self.alpha = max(self.cfg.starting_alpha * (1.0 - progress), self.cfg.starting_alpha * 1e-4)
+
+    # ------------------------------------------------------------------ checkpoint
+    def write_checkpoint(self, path: str, words=None, write_syn1: bool = False, chunk: int = 1 << 15) -> None:
+        """Binary word2vec format of the reference (word2vec.cc:367-416); rank 0 pulls the model."""
+        cfg, d = self.cfg, self.cfg.embed_dim
+        self.worker.wait_sync()
+        if self.server.my_rank() != 0:
+            return
+
+        def dump(fn, key_fn):
+            with open(fn, "wb") as f:
+                f.write(f"{cfg.vocab_size} {d}\n".encode())
+                for i in range(0, cfg.vocab_size, chunk):
+                    w = torch.arange(i, min(cfg.vocab_size, i + chunk), dtype=torch.int64)
+                    vals = torch.empty(w.numel() * 2 * d, dtype=torch.float32)
+                    self.worker.wait(self.worker.pull(key_fn(w), vals))
+                    emb = vals.view(-1, 2 * d)[:, :d].contiguous().numpy()
+                    for j in range(w.numel()):
+                        word = words[i + j] if words is not None else f"w{i + j}"
+                        f.write(word.encode() + b" ")
+                        f.write(emb[j].tobytes())
+                        f.write(b"\n")
+
+        dump(path, syn0_key)
+        if write_syn1:
+            dump(path + ".syn1", syn1_key)
+
+
+def sgns_reference_step(kv, centers: torch.Tensor, contexts: torch.Tensor, negatives: torch.Tensor, d: int,
+                        alpha: float) -> float:
+    """Plain PyTorch fp32 SGNS step through Pull/Push with the reference's exact update rule.
+    All pairs read the state at the start of the step (the batched-kernel semantics)."""
+    B = centers.numel()
+    neg = negatives.shape[1]
+    tk = torch.cat([contexts.view(B, 1), negatives], 1)            # [B, 1+neg] target keys
+    r0 = torch.empty(B * 2 * d, dtype=torch.float32)
+    kv.wait(kv.pull(centers, r0))
+    r1 = torch.empty(B * (1 + neg) * 2 * d, dtype=torch.float32)
+    kv.wait(kv.pull(tk.reshape(-1), r1))
+    r0 = r0.view(B, 2 * d)
+    r1 = r1.view(B, 1 + neg, 2 * d)
+    e0, a0 = r0[:, :d], r0[:, d:]
+    e1, a1 = r1[:, :, :d], r1[:, :, d:]
+    label = torch.zeros(B, 1 + neg)
+    label[:, 0] = 1
+    f = (e0.unsqueeze(1) * e1).sum(-1)
+    sig = torch.sigmoid(f)
+    g = label - sig
+    g = torch.where(f > 6, label - 1, g)
+    g = torch.where(f < -6, label, g)
+    valid = torch.ones(B, 1 + neg, dtype=torch.bool)
+    valid[:, 1:] = negatives != contexts.view(B, 1)                 # negatives equal to the target are skipped
+    g = g * valid
+    grad0 = (g.unsqueeze(-1) * e1).sum(1)
+    grad1 = g.unsqueeze(-1) * e0.unsqueeze(1)
+    u1a = grad1 * grad1
+    u1e = alpha * grad1 / torch.sqrt(a1 + u1a)
+    u0a = grad0 * grad0
+    u0e = alpha * grad0 / torch.sqrt(a0 + u0a)
+    sel = valid.reshape(-1)
+    kv.wait(kv.push(tk.reshape(-1)[sel], torch.cat([u1e, u1a], -1).view(-1, 2 * d)[sel].contiguous().view(-1)))
+    kv.wait(kv.push(centers, torch.cat([u0e, u0a], -1).contiguous().view(-1)))
+    z = torch.where(label > 0.5, f, -f).clamp(-6, 6)
+    return float((torch.log1p(torch.exp(-z)) * valid).sum())

@@ -1,0 +1,89 @@
+"""Torch-facing wrappers of the hand-written sm_100a kernels (csrc/cuda/ops_*.cu).
+
+All ops take CUDA tensors, run on the current CUDA stream and operate directly on the
+parameter store of a ``Server`` with ``backend='cuda'`` (local HBM and NVLink-mapped peers).
+They fail loudly when the native extension or a CUDA device is missing - there is no eager
+fallback on a GPU box.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from .. import _C
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _i64(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not (t.is_cuda and t.dtype == torch.int64 and t.is_contiguous()):
+        raise TypeError(f"{name} must be a contiguous CUDA int64 tensor")
+    return t
+
+
+def sgns_step(server, centers: torch.Tensor, contexts: torch.Tensor, negatives: torch.Tensor, embed_dim: int,
+              alpha: float, loss: torch.Tensor, stats: Optional[torch.Tensor] = None) -> None:
+    """Fused word2vec SGNS step (pull + score + AdaGrad + push) on ``server``'s store.
+
+    ``centers``/``contexts``: [B] syn0 / syn1 keys; ``negatives``: [B, neg] syn1 keys;
+    ``loss``: float32[1] accumulated (+=) with the summed logistic loss;
+    ``stats``: optional int64[4] accumulated with (local rows, remote rows, slow-path rows, updates).
+    """
+    _i64(centers, "centers"); _i64(contexts, "contexts"); _i64(negatives, "negatives")
+    B = centers.numel()
+    neg = negatives.numel() // max(B, 1)
+    if contexts.numel() != B or negatives.numel() != B * neg:
+        raise ValueError("contexts must have B entries and negatives B*neg entries")
+    if not (loss.is_cuda and loss.dtype == torch.float32):
+        raise TypeError("loss must be a CUDA float32 tensor")
+    _C.sgns_step(server._impl.backend_handle(), _stream(centers), centers.data_ptr(), contexts.data_ptr(),
+                 negatives.data_ptr(), B, neg, int(embed_dim), float(alpha), loss.data_ptr(),
+                 stats.data_ptr() if stats is not None else 0)
+
+
+class DeviceSampler:
+    """Key sampler on the GPU: alias table (any weights, e.g. unigram^0.75), uniform or log-uniform.
+
+    ``local_only=True`` implements the reference's *local* sampling scheme (sampling.h:361-446):
+    draws are rejected until the key is resident in this GPU's HBM (owned or usable replica).
+    """
+
+    def __init__(self, server, *, weights: Optional[torch.Tensor] = None, distribution: str = "alias",
+                 first_key: int = 0, key_stride: int = 1, num_keys: Optional[int] = None):
+        self.server = server
+        self.first_key, self.key_stride = int(first_key), int(key_stride)
+        dev = server.device
+        if weights is not None:
+            w = torch.as_tensor(weights, dtype=torch.float64).contiguous().cpu()
+            n = w.numel()
+            prob = torch.empty(n, dtype=torch.float32)
+            alias = torch.empty(n, dtype=torch.int32)
+            _C.build_alias_table(w.data_ptr(), n, prob.data_ptr(), alias.data_ptr())
+            self.kind, self.n = 0, n
+            self.prob, self.alias = prob.to(dev), alias.to(dev)
+        else:
+            if num_keys is None:
+                raise ValueError("num_keys is required for uniform / log-uniform sampling")
+            self.kind = {"uniform": 1, "log-uniform": 2}[distribution]
+            self.n = int(num_keys)
+            self.prob = torch.zeros(1, dtype=torch.float32, device=dev)
+            self.alias = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.stats = torch.zeros(2, dtype=torch.int64, device=dev)  # (residency checks, give-ups)
+
+    def sample(self, n: int, seed: int, local_only: bool = False, out: Optional[torch.Tensor] = None,
+               max_tries: int = 64) -> torch.Tensor:
+        if out is None:
+            out = torch.empty(n, dtype=torch.int64, device=self.server.device)
+        _i64(out, "out")
+        _C.sample_keys(self.server._impl.backend_handle(), _stream(out), self.kind, self.prob.data_ptr(),
+                       self.alias.data_ptr(), self.n, self.first_key, self.key_stride, out.data_ptr(), out.numel(),
+                       int(seed) & 0xFFFFFFFFFFFFFFFF, bool(local_only), int(max_tries), self.stats.data_ptr())
+        return out
+
+
+def track_current_stream(server) -> None:
+    """Tell the sync engine that kernels touching the store run on the current CUDA stream."""
+    _C.track_stream(server._impl.backend_handle(), torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,273 @@
+#!/usr/bin/env python
+"""Headline benchmark: word2vec SGNS updates/s on the intent-driven parameter manager.
+
+    python bench.py --gpus N --steps K --warmup W [--impl native|reference|nccl] [--config word2vec]
+
+Metric (BASELINE.json / BASELINE.md section 3): *updates/s*, an update = one (key,row) additive
+update applied at the key's current owner; word2vec SGNS applies ``1 + (negative + 1)`` updates per
+(center, context) pair. Config #2 of BASELINE.json: 1M-word vocabulary, d = 300, fp32 rows
+``[embedding | AdaGrad]`` (2 400 B), negative = 25 (reference default, apps/word2vec.cc:1037),
+Intent look-ahead + local PullSample. Synthetic Zipf corpus, random-init weights.
+
+Two numbers are measured back to back after W warm-up steps, both with CUDA events on the
+launching stream bracketed by barrier + synchronize, max over ranks:
+
+* ``value``     device-resident inputs, K steps of {sampler kernel, fused SGNS kernel};
+* ``e2e.value`` the public-API loop a user writes: every step copies that step's key batch from
+                pinned host memory (H2D), signals intent for a future batch, advances the clock,
+                runs the step and copies the loss back to pinned host memory (D2H).
+
+For N > 1 launch with torchrun (one rank per GPU); weak scaling (fixed pairs per GPU per step).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference", "nccl"])
+    ap.add_argument("--config", default="word2vec", choices=["word2vec"])
+    ap.add_argument("--vocab", type=int, default=1_000_000)
+    ap.add_argument("--dim", type=int, default=300)
+    ap.add_argument("--negative", type=int, default=25)
+    ap.add_argument("--batch-pairs", type=int, default=32768)
+    ap.add_argument("--read-ahead", type=int, default=4)
+    ap.add_argument("--sampling", default="local", choices=["local", "naive"])
+    ap.add_argument("--techniques", default="all")
+    ap.add_argument("--no-intent", action="store_true")
+    ap.add_argument("--sync-per-sec", type=float, default=1000)
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.p = gpu_index, None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                      stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            out = self.p.communicate(timeout=5)[0]
+        except Exception:
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def reference_arm(args):
+    # The reference (alexrenz/AdaPM) is a CPU-only C++14 project that needs libzmq, protobuf-lite,
+    # Boost and Eigen headers; none is present in this offline image and pip cannot install it
+    # (no setup.py at the root; bindings/setup.py fails compiling against missing zmq.h). See DESIGN.md.
+    print(json.dumps({"impl": "reference", "unavailable":
+                      "alexrenz/AdaPM needs libzmq+protobuf+Boost+Eigen (absent offline); it has no GPU path at all"}))
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            sys.exit("bench.py --gpus N with N>1 must be launched with torch.distributed.run (one rank per GPU)")
+        args.gpus = world
+    if not torch.cuda.is_available():
+        sys.exit("bench.py needs a CUDA device")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize()
+
+    if args.impl == "nccl":
+        from adapm_b200.parallel.nccl_baseline import run_nccl_word2vec
+
+        return run_nccl_word2vec(args, rank, world, local_rank)
+
+    import adapm_b200 as ad
+    from adapm_b200 import _C
+    from adapm_b200.models.word2vec import SyntheticPairs, Word2Vec, Word2VecConfig, zipf_counts
+
+    cfg = Word2VecConfig(vocab_size=args.vocab, embed_dim=args.dim, negative=args.negative,
+                         batch_pairs=args.batch_pairs, read_ahead=args.read_ahead, sampling_scheme=args.sampling,
+                         signal_intent=not args.no_intent)
+    server = ad.Server(cfg.row_len, num_keys=cfg.num_keys, num_threads=1, rank=rank, world=world, backend="cuda",
+                       fabric="shm" if world > 1 else "inproc", device=local_rank,
+                       options={"sys.techniques": args.techniques, "sys.sync.max_per_sec": args.sync_per_sec})
+    worker = ad.Worker(0, server)
+    counts = zipf_counts(cfg.vocab_size, cfg.zipf_exponent)
+    model = Word2Vec(server, worker, cfg, counts)
+    model.init_model()
+    data = SyntheticPairs(cfg, counts, rank, seed=1)
+
+    K, W, RA = args.steps, args.warmup, cfg.read_ahead
+    total_steps = W + K            # e2e loop
+    # data loader: pre-read all batches into pinned host memory (the reference reads sentences ahead too)
+    batches = [data.batch(s).pin_memory() for s in range(total_steps + RA + 1)]
+    loss_host = torch.zeros(total_steps + 1, dtype=torch.float32).pin_memory()
+    stream = torch.cuda.current_stream()
+
+    def e2e_step(s):
+        if s + RA < len(batches):
+            model.signal_intent(batches[s + RA], worker.current_clock() + RA)
+        model.loss.zero_()
+        model.step(batches[s])                                         # H2D copy + sampler + fused step
+        loss_host[s:s + 1].copy_(model.loss, non_blocking=True)        # D2H read of the step result
+        worker.advance_clock()
+
+    # ---------------- warm-up (also lets the sync engine localise the first batches)
+    for s in range(RA):
+        model.signal_intent(batches[s], worker.current_clock() + s)
+    if world > 1:
+        worker.wait_sync()
+    for s in range(W):
+        e2e_step(s)
+    barrier()
+
+    # ---------------- e2e timed region
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _C.kernel_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for s in range(W, W + K):
+        e2e_step(s)
+    ev1.record(stream)
+    barrier()
+    e2e_ms = ev0.elapsed_time(ev1)
+    launches_e2e = _C.kernel_launches() - launches0
+
+    # ---------------- device-resident timed region (inputs already on the device)
+    dev_batches = [b.to(dev) for b in batches[:K]]
+    torch.cuda.synchronize()
+    from adapm_b200.ops import sgns_step
+
+    def dev_step(i):
+        kb = dev_batches[i]
+        seed = 77000 + i * 131 + rank
+        model.sampler.sample(model._neg.numel(), seed, local_only=(cfg.sampling_scheme == "local" and world > 1),
+                             out=model._neg)
+        sgns_step(server, kb[0], kb[1], model._neg, cfg.embed_dim, model.alpha, model.loss, model.stats)
+
+    for i in range(min(3, K)):
+        dev_step(i)
+    barrier()
+    launches1 = _C.kernel_launches()
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev2.record(stream)
+    for i in range(K):
+        dev_step(i)
+    ev3.record(stream)
+    barrier()
+    dev_ms = ev2.elapsed_time(ev3)
+    launches_dev = _C.kernel_launches() - launches1
+    clocks = sampler.stop() if rank == 0 else None
+
+    # max over ranks
+    t = torch.tensor([e2e_ms, dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms, dev_ms = t.tolist()
+    stats = model.stats.tolist()
+    counters = server.counters()
+
+    updates_per_step = world * cfg.batch_pairs * cfg.updates_per_pair
+    value = updates_per_step * K / (dev_ms * 1e-3)
+    e2e_value = updates_per_step * K / (e2e_ms * 1e-3)
+    h2d = cfg.batch_pairs * 2 * 8
+    if rank == 0:
+        bytes_per_update = 2 * cfg.row_len * 4  # read row + reduce row
+        try:
+            peaks = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")))
+            hbm = peaks["hbm_gbs"]
+            denom = "measured"
+        except Exception:
+            hbm, denom = 6650.0, "fallback"
+        out = {
+            "metric": "word2vec SGNS updates/sec (device-timed, max over ranks)",
+            "value": value, "unit": "updates/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp32", "data": "synthetic", "impl": "native",
+            "config": {"model": "word2vec SGNS 1M-vocab d=300 (rows = [embedding|AdaGrad], 2400 B fp32)",
+                       "vocab": cfg.vocab_size, "embed_dim": cfg.embed_dim, "negative": cfg.negative,
+                       "global_batch": world * cfg.batch_pairs, "batch_pairs_per_gpu": cfg.batch_pairs,
+                       "seq_len": None, "updates_per_pair": cfg.updates_per_pair,
+                       "parallelism": f"pm{world} (key-sharded store, intent-driven relocation/replication)",
+                       "sampling": cfg.sampling_scheme, "intent_read_ahead": RA,
+                       "l2": "inputs larger than L2: 4.8 GB table per model, fresh random batch every step",
+                       "note": "reference dtype is float32 (apps/word2vec.cc:40); rows stay fp32 for exact additive updates"},
+            "e2e": {"value": e2e_value, "unit": "updates/s", "ms_per_step": e2e_ms / K,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches_dev), "gpu_launches_e2e": int(launches_e2e),
+            "clocks": clocks,
+            "roofline": {"hbm_bytes_per_update": bytes_per_update,
+                         "achieved_hbm_gbs_per_gpu": value / world * bytes_per_update / 1e9,
+                         "fraction_of_hbm_peak": value / world * bytes_per_update / 1e9 / hbm, "peak": denom},
+            "locality": {"rows_local": stats[0], "rows_remote": stats[1], "rows_slow_path": stats[2]},
+            "pm": {k: counters[k] for k in ("relocations", "replica_setups", "replica_drops", "refreshes",
+                                            "deltas_shipped", "sync_rounds", "protocol_errors")},
+            "loss_last": float(loss_host[W + K - 1]) / max(1, cfg.batch_pairs * (cfg.negative + 1)),
+        }
+        print(json.dumps(out))
+    worker.finalize()
+    server.shutdown()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

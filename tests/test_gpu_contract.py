@@ -1,0 +1,50 @@
+"""The CPU contract tests re-run on the CUDA backend: several logical ranks share one GPU
+(inproc fabric), so the full relocation/replication protocol runs through the sm_100a kernels
+with peer pointers that happen to live on the same device."""
+import pytest
+
+from harness import run_cluster
+import test_contract_dynamic as dyn
+import test_contract_locality as loc
+import test_contract_many_keys as mk
+
+pytestmark = pytest.mark.gpu
+
+
+def _errs(res):
+    return [e for r in res.values() for k, v in r.items() if k != "counters" for e in v]
+
+
+def test_locality_api_cuda():
+    res = run_cluster(loc._worker, world=3, workers=loc.NUM_LOCAL, mode="threads", value_lengths=1, num_keys=12,
+                      dtype="float32", backend="cuda")
+    assert not _errs(res), "\n".join(_errs(res))
+
+
+@pytest.mark.parametrize("technique", ["all", "replication_only", "relocation_only"])
+def test_dynamic_allocation_cuda(technique):
+    world, workers = 3, 2
+    res = run_cluster(dyn._dyn_worker, world=world, workers=workers, mode="threads", value_lengths=2, num_keys=20,
+                      dtype="float32", backend="cuda", options={"sys.techniques": technique})
+    total = world * workers * dyn.RUNS
+    assert res[0][0] == [total, 2 * total], f"lost or duplicated updates: {res[0][0]}"
+    assert all(r["counters"]["protocol_errors"] == 0 for r in res.values())
+    moved = sum(r["counters"]["relocations"] + r["counters"]["replica_setups"] for r in res.values())
+    assert moved > 0
+
+
+@pytest.mark.parametrize("technique", ["all", "replication_only", "relocation_only"])
+def test_many_key_operations_cuda(technique):
+    res = run_cluster(mk._worker, world=4, workers=2, mode="threads", value_lengths=mk.VPK, num_keys=mk.NUM_KEYS,
+                      dtype="float32", backend="cuda", options={"sys.techniques": technique})
+    errs = _errs(res)
+    if technique == "relocation_only":
+        errs = [e for e in errs if "were not local" not in e]
+    assert not errs, "\n".join(errs)
+    assert all(r["counters"]["protocol_errors"] == 0 for r in res.values())
+
+
+def test_set_operation_cuda():
+    res = run_cluster(dyn._set_worker, world=4, workers=2, mode="threads", value_lengths=2, num_keys=20,
+                      dtype="float32", backend="cuda")
+    assert not _errs(res), "\n".join(_errs(res))

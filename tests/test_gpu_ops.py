@@ -1,0 +1,168 @@
+"""Numerics of the hand-written sm_100a kernels against plain PyTorch fp32 references."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def cluster1():
+    import adapm_b200 as ad
+
+    made = []
+
+    def make(row_len, num_keys, **kw):
+        s = ad.Server(row_len, num_keys=num_keys, num_threads=1, rank=0, world=1, backend="cuda", fabric="inproc",
+                      job=f"ops{len(made)}_{np.random.randint(1 << 30)}", device=0, **kw)
+        w = ad.Worker(0, s)
+        made.append((s, w))
+        return s, w
+
+    yield make
+    for s, w in made:
+        w.finalize()
+        s.shutdown()
+
+
+def test_extension_is_native():
+    from adapm_b200 import _C
+
+    assert _C.cuda_available()
+    assert _C.__file__.endswith(".so") and "adapm_b200" in _C.__file__
+
+
+def test_pull_push_set_device_and_host_paths(cluster1):
+    server, kv = cluster1(64, 1000)
+    dev = server.device
+    g = torch.Generator().manual_seed(0)
+    keys = torch.randperm(1000, generator=g)[:300]
+    vals = torch.randn(300, 64, generator=g)
+    # host path set, device path pull
+    kv.set(keys, vals.clone().view(-1))
+    out = torch.empty(300 * 64, device=dev)
+    kv.wait(kv.pull(keys.to(dev), out, True))
+    torch.testing.assert_close(out.cpu().view(300, 64), vals)
+    # device path push (with duplicate keys: additive), host path pull
+    dk = torch.cat([keys[:100], keys[:100]]).to(dev)
+    dv = torch.ones(200, 64, device=dev) * 0.5
+    kv.wait(kv.push(dk, dv.view(-1), True))
+    out2 = torch.empty(300 * 64)
+    kv.pull(keys, out2)
+    ref = vals.clone()
+    ref[:100] += 1.0
+    torch.testing.assert_close(out2.view(300, 64), ref)
+    assert kv.pull_if_local(int(keys[0]), torch.empty(64))
+
+
+def test_mixed_value_lengths(cluster1):
+    lens = torch.full((50,), 8, dtype=torch.int64)
+    lens[10] = 20
+    lens[40] = 4
+    server, kv = cluster1(lens, 50)
+    keys = torch.tensor([3, 10, 40, 7])
+    vals = torch.arange(8 + 20 + 4 + 8, dtype=torch.float32)
+    kv.push(keys, vals)
+    out = torch.zeros_like(vals)
+    kv.pull(keys, out)
+    torch.testing.assert_close(out, vals)
+    assert kv.get_key_size(10) == 20 and kv.get_key_size(40) == 4
+
+
+@pytest.mark.parametrize("d,neg", [(300, 25), (128, 5), (64, 40), (512, 3)])
+def test_sgns_step_matches_pytorch_reference(cluster1, d, neg):
+    """Distinct keys per batch -> every row is touched by exactly one pair-target, so the batched kernel and the
+    PyTorch fp32 formula must agree (AdaGrad with the pulled accumulator, |f|>6 saturation, negative==target skip)."""
+    from adapm_b200.ops import sgns_step
+
+    B = 64
+    n_keys = 2 * (B * (neg + 2) + 10)
+    server, kv = cluster1(2 * d, n_keys)
+    dev = server.device
+    g = torch.Generator().manual_seed(d * 1000 + neg)
+    rows = torch.empty(n_keys, 2 * d)
+    rows[:, :d] = torch.randn(n_keys, d, generator=g) * 0.3
+    rows[:, d:] = torch.rand(n_keys, d, generator=g) + 1e-3
+    allk = torch.arange(n_keys)
+    kv.set(allk, rows.clone().view(-1))
+    perm = torch.randperm(n_keys // 2, generator=g)
+    centers = 2 * perm[:B]
+    tw = perm[B:B + B * (neg + 1)].view(B, neg + 1)
+    contexts = 2 * tw[:, 0] + 1
+    negatives = 2 * tw[:, 1:] + 1
+    negatives[0, 0] = contexts[0]  # exercises the "negative == positive target" skip
+    alpha = 0.05
+    loss = torch.zeros(1, device=dev)
+    stats = torch.zeros(4, dtype=torch.int64, device=dev)
+    sgns_step(server, centers.to(dev), contexts.to(dev), negatives.contiguous().to(dev), d, alpha, loss, stats)
+    torch.cuda.synchronize()
+    got = torch.empty(n_keys * 2 * d)
+    kv.pull(allk, got)
+    got = got.view(n_keys, 2 * d)
+
+    # ---- reference
+    ref = rows.clone()
+    e0, a0 = rows[centers, :d], rows[centers, d:]
+    tk = torch.cat([contexts.view(B, 1), negatives], 1)
+    e1, a1 = rows[tk][:, :, :d], rows[tk][:, :, d:]
+    label = torch.zeros(B, neg + 1); label[:, 0] = 1
+    f = (e0.unsqueeze(1) * e1).sum(-1)
+    gr = label - torch.sigmoid(f)
+    gr = torch.where(f > 6, label - 1, gr)
+    gr = torch.where(f < -6, label, gr)
+    valid = torch.ones(B, neg + 1, dtype=torch.bool)
+    valid[:, 1:] = negatives != contexts.view(B, 1)
+    gr = gr * valid
+    grad0 = (gr.unsqueeze(-1) * e1).sum(1)
+    grad1 = gr.unsqueeze(-1) * e0.unsqueeze(1)
+    ref[centers, :d] += alpha * grad0 / torch.sqrt(a0 + grad0 ** 2)
+    ref[centers, d:] += grad0 ** 2
+    upd_e = alpha * grad1 / torch.sqrt(a1 + grad1 ** 2)
+    upd_a = grad1 ** 2
+    for b in range(B):
+        for t in range(neg + 1):
+            if valid[b, t]:
+                ref[tk[b, t], :d] += upd_e[b, t]
+                ref[tk[b, t], d:] += upd_a[b, t]
+    torch.testing.assert_close(got, ref, rtol=2e-4, atol=2e-5)
+    z = torch.where(label > 0.5, f, -f).clamp(-6, 6)
+    ref_loss = (torch.log1p(torch.exp(-z)) * valid).sum()
+    torch.testing.assert_close(loss.cpu()[0], ref_loss, rtol=1e-3, atol=1e-3)
+    s = stats.tolist()
+    assert s[1] == 0 and s[2] == 0 and s[3] == int(valid.sum()) + B
+
+
+def test_device_sampler_distribution(cluster1):
+    from adapm_b200.ops import DeviceSampler
+
+    server, kv = cluster1(8, 2000)
+    w = torch.tensor([1.0, 2.0, 3.0, 4.0, 0.0, 10.0])
+    s = DeviceSampler(server, weights=w, first_key=1, key_stride=2)
+    out = s.sample(600_000, seed=123)
+    torch.cuda.synchronize()
+    assert int(out.min()) >= 1 and int(out.max()) <= 11 and bool(((out - 1) % 2 == 0).all())
+    freq = torch.bincount((out - 1) // 2, minlength=6).double() / out.numel()
+    torch.testing.assert_close(freq, (w / w.sum()).double(), atol=3e-3, rtol=0)
+    u = DeviceSampler(server, distribution="uniform", first_key=100, num_keys=50)
+    o2 = u.sample(100_000, seed=5)
+    assert int(o2.min()) == 100 and int(o2.max()) == 149
+    # different seeds give different streams, same seed is reproducible
+    assert not torch.equal(s.sample(1000, seed=1), s.sample(1000, seed=2))
+    assert torch.equal(s.sample(1000, seed=9), s.sample(1000, seed=9))
+
+
+def test_word2vec_training_reduces_loss(cluster1):
+    from adapm_b200.models.word2vec import SyntheticPairs, Word2Vec, Word2VecConfig, zipf_counts
+
+    cfg = Word2VecConfig(vocab_size=5000, embed_dim=64, negative=5, batch_pairs=2048)
+    server, kv = cluster1(cfg.row_len, cfg.num_keys)
+    counts = zipf_counts(cfg.vocab_size)
+    model = Word2Vec(server, kv, cfg, counts)
+    model.init_model()
+    data = SyntheticPairs(cfg, counts, 0)
+    losses = []
+    for s in range(30):
+        model.loss.zero_()
+        model.step(data.batch(s % 3))
+        losses.append(model.loss.item())
+    assert losses[-1] < 0.9 * losses[0]
