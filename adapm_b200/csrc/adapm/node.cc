@@ -219,16 +219,8 @@ bool Worker::PullIfLocal(Key key, void* vals) {
 int Worker::Intent(const Key* keys, size_t n, Clock start, Clock end) {
   if (end == 0) end = start + 1;
   if (server_.num_servers() == 1 || n == 0) return LOCAL;  // single node: nothing to manage
-  auto uniq = std::make_shared<std::vector<Key>>();
-  uniq->reserve(n);
-  if (n == 1) {
-    uniq->push_back(keys[0]);
-  } else {
-    std::unordered_set<Key> seen;
-    seen.reserve(n * 2);
-    for (size_t i = 0; i < n; ++i)
-      if (seen.insert(keys[i]).second) uniq->push_back(keys[i]);
-  }
+  // Copy only: duplicates are removed by the sync thread (off the worker's critical path).
+  auto uniq = std::make_shared<std::vector<Key>>(keys, keys + n);
   for (Key k : *uniq)
     ADAPM_CHECK(k >= 0 && k < server_.num_keys(), "[ERROR] Intent key " << k << " is outside the configured key range");
   FutureIntent fi;

@@ -14,6 +14,7 @@
 // (sync_manager.h:291-382,452-520,544-799); message round trips became barriers.
 #include "node.h"
 
+#include <algorithm>
 #include <sstream>
 
 namespace adapm {
@@ -101,7 +102,14 @@ void SyncEngine::collect_intents(const std::vector<Clock>& clocks, const std::ve
     while (!h.empty() && h.top().start <= horizon) {
       const FutureIntent& fi = h.top();
       if (fi.end > clk) {
-        for (Key k : *fi.keys) {
+        // the reference dedupes in Intent() (coloc_kv_worker.h:394-401); here it happens off the
+        // worker thread, once per batch
+        std::vector<Key>& ks = *fi.keys;
+        if (ks.size() > 1) {
+          std::sort(ks.begin(), ks.end());
+          ks.erase(std::unique(ks.begin(), ks.end()), ks.end());
+        }
+        for (Key k : ks) {
           IntentRec r;
           r.key = k; r.end = fi.end; r.worker = (int32_t)w; r.pad = 0;
           recs_.push_back(r);

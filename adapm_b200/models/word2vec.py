@@ -43,6 +43,7 @@ class Word2VecConfig:
     signal_intent: bool = True
     model_seed: int = 134827
     zipf_exponent: float = 1.0       # synthetic corpus skew
+    max_inflight: int = 2            # steps the host may run ahead of the GPU (bounds the sync grace period)
 
     @property
     def row_len(self) -> int:
@@ -115,7 +116,9 @@ class Word2Vec:
             self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
             self.stats = torch.zeros(4, dtype=torch.int64, device=dev)
             self._neg = torch.empty(cfg.batch_pairs * cfg.negative, dtype=torch.int64, device=dev)
-            self._keys_dev = torch.empty(2, cfg.batch_pairs, dtype=torch.int64, device=dev)
+            self._keys_dev = [torch.empty(2, cfg.batch_pairs, dtype=torch.int64, device=dev)
+                              for _ in range(max(1, cfg.max_inflight) + 1)]
+            self._events = [None] * len(self._keys_dev)
         else:
             w = torch.from_numpy(weights)
             self._neg_cdf = torch.cumsum(w / w.sum(), 0)
@@ -156,12 +159,18 @@ class Word2Vec:
         if self.cuda:
             from ..ops import sgns_step
 
-            self._keys_dev.copy_(keys_host, non_blocking=True)  # H2D of this step's inputs
+            slot = self.step_no % len(self._keys_dev)
+            if self._events[slot] is not None:
+                self._events[slot].synchronize()   # bounded run-ahead: at most max_inflight steps queued
+            kd = self._keys_dev[slot]
+            kd.copy_(keys_host, non_blocking=True)  # H2D of this step's inputs
             local_only = cfg.sampling_scheme == "local" and self.server.num_servers() > 1
             seed = (cfg.model_seed * 1000003 + self.server.my_rank() * 7919 + self.step_no) & 0xFFFFFFFFFFFF
             self.sampler.sample(self._neg.numel(), seed, local_only=local_only, out=self._neg)
-            sgns_step(self.server, self._keys_dev[0], self._keys_dev[1], self._neg, cfg.embed_dim, self.alpha,
-                      self.loss, self.stats)
+            sgns_step(self.server, kd[0], kd[1], self._neg, cfg.embed_dim, self.alpha, self.loss, self.stats)
+            ev = self._events[slot] or torch.cuda.Event()
+            ev.record()
+            self._events[slot] = ev
             self.step_no += 1
             return self.loss
         return self._step_cpu(keys_host)

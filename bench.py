@@ -33,8 +33,8 @@ import time
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="native", choices=["native", "reference", "nccl"])
     ap.add_argument("--config", default="word2vec", choices=["word2vec"])
     ap.add_argument("--vocab", type=int, default=1_000_000)
@@ -62,7 +62,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                       "-lms", "20", "-i", str(self.idx)], stdout=subprocess.PIPE,
                                       stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.p = None
@@ -153,7 +153,19 @@ def main():
     K, W, RA = args.steps, args.warmup, cfg.read_ahead
     total_steps = W + K            # e2e loop
     # data loader: pre-read all batches into pinned host memory (the reference reads sentences ahead too)
-    batches = [data.batch(s).pin_memory() for s in range(total_steps + RA + 1)]
+    RING = 64  # distinct pinned batches, cycled (64 x 32768 pairs x 27 rows touch far more than L2 holds)
+    ring = [data.batch(s).pin_memory() for s in range(min(RING, total_steps + RA + 1))]
+
+    class _Batches:
+        def __len__(self):
+            return total_steps + RA + 1
+
+        def __getitem__(self, i):
+            if isinstance(i, slice):
+                return [ring[j % len(ring)] for j in range(*i.indices(len(self)))]
+            return ring[i % len(ring)]
+
+    batches = _Batches()
     loss_host = torch.zeros(total_steps + 1, dtype=torch.float32).pin_memory()
     stream = torch.cuda.current_stream()
 
@@ -190,7 +202,8 @@ def main():
     launches_e2e = _C.kernel_launches() - launches0
 
     # ---------------- device-resident timed region (inputs already on the device)
-    dev_batches = [b.to(dev) for b in batches[:K]]
+    dev_ring = [b.to(dev) for b in ring]
+    dev_batches = [dev_ring[i % len(dev_ring)] for i in range(K)]
     torch.cuda.synchronize()
     from adapm_b200.ops import sgns_step
 
@@ -247,7 +260,7 @@ def main():
                        "seq_len": None, "updates_per_pair": cfg.updates_per_pair,
                        "parallelism": f"pm{world} (key-sharded store, intent-driven relocation/replication)",
                        "sampling": cfg.sampling_scheme, "intent_read_ahead": RA,
-                       "l2": "inputs larger than L2: 4.8 GB table per model, fresh random batch every step",
+                       "l2": "inputs larger than L2: 4.8 GB table; a ring of 64 distinct random batches (56M row touches) is cycled",
                        "note": "reference dtype is float32 (apps/word2vec.cc:40); rows stay fp32 for exact additive updates"},
             "e2e": {"value": e2e_value, "unit": "updates/s", "ms_per_step": e2e_ms / K,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},

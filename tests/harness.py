@@ -28,6 +28,10 @@ def _rank_main(rank, world, workers, fn, server_kwargs, job, fabric, out, setup_
     results = {}
     try:
         value_lengths = server_kwargs.pop("value_lengths")
+        if server_kwargs.get("backend") == "cuda" and fabric == "shm":
+            import torch as _t
+
+            server_kwargs["device"] = rank % _t.cuda.device_count()
         server = ad.Server(value_lengths, rank=rank, world=world, num_threads=workers, job=job, fabric=fabric,
                            **server_kwargs)
         if setup_fn is not None:
@@ -68,7 +72,8 @@ def run_cluster(fn, world, workers, mode="threads", setup_fn=None, timeout=300, 
         assert not any(t.is_alive() for t in ths), "cluster timed out"
         res = out
     else:
-        ctx = mp.get_context("fork")
+        # CUDA contexts do not survive fork(): GPU ranks are spawned, one device per rank
+        ctx = mp.get_context("spawn" if server_kwargs.get("backend") == "cuda" else "fork")
         q = ctx.Queue()
         ps = [ctx.Process(target=_rank_main, args=(r, world, workers, fn, dict(server_kwargs), job, "shm", q, setup_fn))
               for r in range(world)]

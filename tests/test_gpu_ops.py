@@ -141,7 +141,7 @@ def test_device_sampler_distribution(cluster1):
     out = s.sample(600_000, seed=123)
     torch.cuda.synchronize()
     assert int(out.min()) >= 1 and int(out.max()) <= 11 and bool(((out - 1) % 2 == 0).all())
-    freq = torch.bincount((out - 1) // 2, minlength=6).double() / out.numel()
+    freq = torch.bincount((out - 1) // 2, minlength=6).double().cpu() / out.numel()
     torch.testing.assert_close(freq, (w / w.sum()).double(), atol=3e-3, rtol=0)
     u = DeviceSampler(server, distribution="uniform", first_key=100, num_keys=50)
     o2 = u.sample(100_000, seed=5)
