@@ -40,7 +40,8 @@ struct Layout {
   uint64_t off_want;       // uint64[S]         owner: ranks that requested the key this round
   uint64_t off_slot_key;   // int64[S]
   uint64_t off_intent_end; // int64[S*workers]  end clock of the local intents
-  uint64_t off_flags;      // uint8[S]
+  uint64_t off_flags;      // uint8[S]          F_REQUESTED (sync thread only)
+  uint64_t off_dirty;      // uint8[S]          replica got local pushes since the last delta ship (blind store 1)
   uint64_t off_free_top;   // int32[MAX_CLASSES]
   uint64_t off_counters;   // uint64[C_NUM_COUNTERS]
   uint64_t off_retry;      // IntentRec[retry_cap] x2 + counts (deferred intents)
@@ -77,6 +78,7 @@ ADAPM_HD uint64_t* want_of(const Ctx& c, int r) { return at<uint64_t>(c, r, c.L.
 ADAPM_HD int64_t* slot_key_of(const Ctx& c, int r) { return at<int64_t>(c, r, c.L.off_slot_key); }
 ADAPM_HD int64_t* intent_end_of(const Ctx& c, int r) { return at<int64_t>(c, r, c.L.off_intent_end); }
 ADAPM_HD uint8_t* flags_of(const Ctx& c, int r) { return at<uint8_t>(c, r, c.L.off_flags); }
+ADAPM_HD uint8_t* dirty_of(const Ctx& c, int r) { return at<uint8_t>(c, r, c.L.off_dirty); }
 ADAPM_HD int32_t* free_top_of(const Ctx& c, int r) { return at<int32_t>(c, r, c.L.off_free_top); }
 ADAPM_HD uint64_t* counters_of(const Ctx& c, int r) { return at<uint64_t>(c, r, c.L.off_counters); }
 

@@ -168,7 +168,7 @@ ADAPM_HD PushLoc<Val> locate_push(const Ctx& c, const G& g, Key key) {
         return r;
       }
       if (st == S_REPLICA) {
-        r.row = row_ptr<Val>(c, me, cls, s); r.flag = flags_of(c, me) + s;
+        r.row = row_ptr<Val>(c, me, cls, s); r.flag = dirty_of(c, me) + s;
         r.local = true; r.owner = -1;
         return r;
       }
@@ -198,7 +198,7 @@ ADAPM_HD bool push_key(const Ctx& c, const G& g, Key key, const Val* vals, bool*
   for (uint32_t i = g.lane(); i < len; i += g.size()) mem::red_add(loc.row + i, vals[i]);
   if (g.lane() == 0) {
     if (loc.version) mem::red_add(loc.version, 1u);
-    if (loc.flag) mem::st_relaxed(loc.flag, (uint8_t)(mem::ld_relaxed(loc.flag) | F_DIRTY));
+    if (loc.flag) mem::st_relaxed(loc.flag, (uint8_t)1);
   }
   if (was_local) *was_local = loc.local;
   return true;
@@ -328,6 +328,7 @@ ADAPM_HD int register_intent(const Ctx& c, const IntentRec& rec, const Clock* cl
     mem::st_relaxed(ver_seen_of(c, me) + ns, 0xffffffffu);
     mem::st_relaxed(want_of(c, me) + ns, (uint64_t)0);
     mem::st_relaxed(flags_of(c, me) + ns, (uint8_t)0);
+    mem::st_relaxed(dirty_of(c, me) + ns, (uint8_t)0);
     uint32_t m = mem::ld_relaxed(meta_of(c, me) + ns);
     mem::fence();
     mem::st_release(meta_of(c, me) + ns, meta_next(m, S_REPLICA_PENDING, 0));
@@ -369,8 +370,9 @@ ADAPM_HD void phase_a_slot(const Ctx& c, const G& g, uint32_t s, const RoundPara
   if (ps < 0) { if (g.lane() == 0) count(c, C_PROTOCOL_ERRORS); return; }
   uint8_t* fl = flags_of(c, me) + s;
   if (st == S_REPLICA) {
-    uint8_t f = (uint8_t)g.bcast((uint32_t)(g.lane() == 0 ? mem::ld_relaxed(fl) : 0));
-    bool consider = (f & F_DIRTY) || rp.sweep || !active;
+    uint8_t* dp = dirty_of(c, me) + s;
+    uint8_t f = (uint8_t)g.bcast((uint32_t)(g.lane() == 0 ? mem::ld_relaxed(dp) : 0));
+    bool consider = (f != 0) || rp.sweep || !active;
     bool never = rp.threshold > 1e300;  // inf: replicas never synchronise (except on drop)
     if (consider && (!never || !active)) {
       Val* row = row_ptr<Val>(c, me, cls, s);
@@ -386,7 +388,7 @@ ADAPM_HD void phase_a_slot(const Ctx& c, const G& g, uint32_t s, const RoundPara
         ship = acc >= rp.threshold * rp.threshold;
       }
       if (ship) {
-        if (g.lane() == 0) mem::st_relaxed(fl, (uint8_t)(f & ~F_DIRTY));
+        if (g.lane() == 0) mem::st_relaxed(dp, (uint8_t)0);
         mem::fence();
         Val* orow = row_ptr<Val>(c, o, cls, ps);
         bool nz = false;

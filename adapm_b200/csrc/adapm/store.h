@@ -98,6 +98,7 @@ inline Layout build_layout(const ValueSpec& spec, const Options& opt, std::vecto
   L.off_slot_key = take((uint64_t)L.total_slots * 8);
   L.off_intent_end = take((uint64_t)L.total_slots * 8 * L.workers);
   L.off_flags = take((uint64_t)L.total_slots);
+  L.off_dirty = take((uint64_t)L.total_slots);
   L.off_free_top = take(MAX_CLASSES * 4);
   L.off_counters = take(C_NUM_COUNTERS * 8);
   for (int c = 0; c < L.num_classes; ++c) {

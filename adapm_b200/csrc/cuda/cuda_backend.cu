@@ -126,7 +126,7 @@ push_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ keys, size_t 
           }
           if (g.lane() == 0) {
             if (loc.version) mem::red_add(loc.version, 1u);
-            if (loc.flag) mem::st_relaxed(loc.flag, (uint8_t)(mem::ld_relaxed(loc.flag) | F_DIRTY));
+            if (loc.flag) mem::st_relaxed(loc.flag, (uint8_t)1);
           }
           good = true;
           local = loc.local;

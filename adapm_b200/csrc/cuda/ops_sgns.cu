@@ -50,10 +50,17 @@ __device__ __forceinline__ Target resolve_fast(const Ctx& c, Key key, unsigned* 
       return t;
     }
     if (st == S_REPLICA) {
-      t.row = row_ptr<float>(c, me, 0, (uint32_t)s); t.flag = flags_of(c, me) + s; ++*n_local;
+      t.row = row_ptr<float>(c, me, 0, (uint32_t)s); t.flag = dirty_of(c, me) + s; ++*n_local;
       return t;
     }
-    return t;  // transitional: slow path
+    if (st == S_INCOMING_REPLICA) {
+      // being upgraded from replica to owner: reads keep replica semantics, adds go to the
+      // (accumulating) local row
+      t.row = row_ptr<float>(c, me, 0, (uint32_t)s); t.version = version_of(c, me) + s; ++*n_local;
+      return t;
+    }
+    if (st == S_INCOMING || st == S_FINALIZING) return t;  // needs the 3-way read: slow path
+    // REPLICA_PENDING / OUTGOING / DEAD / DROPPING: not usable locally -> go to the owner
   }
   if (c.L.world == 1) return t;
   int o = (int)__ldcg(dir_of(c, me) + key);
@@ -257,7 +264,7 @@ sgns_step_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ centers,
       }
       if (lane == 0) {
         if (t_ver) mem::red_add(t_ver, 1u);
-        if (t_flag) *t_flag = (uint8_t)(*t_flag | F_DIRTY);
+        if (t_flag) *t_flag = (uint8_t)1;
       }
       ++n_upd;
     }
@@ -316,7 +323,7 @@ sgns_step_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ centers,
       }
       if (lane == 0) {
         if (c_ver) mem::red_add(c_ver, 1u);
-        if (c_flag) *c_flag = (uint8_t)(*c_flag | F_DIRTY);
+        if (c_flag) *c_flag = (uint8_t)1;
       }
       ++n_upd;
     }

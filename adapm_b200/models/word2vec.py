@@ -164,9 +164,7 @@ class Word2Vec:
                 self._events[slot].synchronize()   # bounded run-ahead: at most max_inflight steps queued
             kd = self._keys_dev[slot]
             kd.copy_(keys_host, non_blocking=True)  # H2D of this step's inputs
-            local_only = cfg.sampling_scheme == "local" and self.server.num_servers() > 1
-            seed = (cfg.model_seed * 1000003 + self.server.my_rank() * 7919 + self.step_no) & 0xFFFFFFFFFFFF
-            self.sampler.sample(self._neg.numel(), seed, local_only=local_only, out=self._neg)
+            self.sample_negatives()
             sgns_step(self.server, kd[0], kd[1], self._neg, cfg.embed_dim, self.alpha, self.loss, self.stats)
             ev = self._events[slot] or torch.cuda.Event()
             ev.record()
@@ -174,6 +172,30 @@ class Word2Vec:
             self.step_no += 1
             return self.loss
         return self._step_cpu(keys_host)
+
+    def sample_negatives(self) -> torch.Tensor:
+        """PrepareSample/PullSample on the device: draws batch_pairs*negative syn1 keys; the ``local``
+        scheme rejects keys that are not resident in this GPU's HBM."""
+        cfg = self.cfg
+        local_only = cfg.sampling_scheme == "local" and self.server.num_servers() > 1
+        seed = (cfg.model_seed * 1000003 + self.server.my_rank() * 7919 + self.step_no) & 0xFFFFFFFFFFFF
+        return self.sampler.sample(self._neg.numel(), seed, local_only=local_only, out=self._neg)
+
+    def step_resident(self, keys_dev: torch.Tensor) -> torch.Tensor:
+        """Same as step() for a key batch that already lives on the device."""
+        from ..ops import sgns_step
+
+        cfg = self.cfg
+        slot = self.step_no % len(self._events)
+        if self._events[slot] is not None:
+            self._events[slot].synchronize()
+        self.sample_negatives()
+        sgns_step(self.server, keys_dev[0], keys_dev[1], self._neg, cfg.embed_dim, self.alpha, self.loss, self.stats)
+        ev = self._events[slot] or torch.cuda.Event()
+        ev.record()
+        self._events[slot] = ev
+        self.step_no += 1
+        return self.loss
 
     # reference-semantics step through the public Pull/Push API (CPU backend; also the numerics oracle)
     def _step_cpu(self, keys_host: torch.Tensor) -> torch.Tensor:

@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--techniques", default="all")
     ap.add_argument("--no-intent", action="store_true")
     ap.add_argument("--sync-per-sec", type=float, default=1000)
+    ap.add_argument("--profile", action="store_true", help="also report per-kernel device times")
     return ap.parse_args()
 
 
@@ -151,7 +152,7 @@ def main():
     data = SyntheticPairs(cfg, counts, rank, seed=1)
 
     K, W, RA = args.steps, args.warmup, cfg.read_ahead
-    total_steps = W + K            # e2e loop
+    total_steps = W + 2 * K + 64   # e2e loop + device-resident loop (+ profiling)
     # data loader: pre-read all batches into pinned host memory (the reference reads sentences ahead too)
     RING = 64  # distinct pinned batches, cycled (64 x 32768 pairs x 27 rows touch far more than L2 holds)
     ring = [data.batch(s).pin_memory() for s in range(min(RING, total_steps + RA + 1))]
@@ -169,12 +170,21 @@ def main():
     loss_host = torch.zeros(total_steps + 1, dtype=torch.float32).pin_memory()
     stream = torch.cuda.current_stream()
 
-    def e2e_step(s):
+    dev_ring = [b.to(dev) for b in ring]
+    from adapm_b200.ops import sgns_step
+
+    def train_step(s, resident):
+        """One training step through the public API. resident=False: this step's key batch is copied
+        from pinned host memory (H2D) and the loss is copied back (D2H); resident=True: the batch is
+        already on the device and the loss stays there. Everything else is identical."""
         if s + RA < len(batches):
             model.signal_intent(batches[s + RA], worker.current_clock() + RA)
         model.loss.zero_()
-        model.step(batches[s])                                         # H2D copy + sampler + fused step
-        loss_host[s:s + 1].copy_(model.loss, non_blocking=True)        # D2H read of the step result
+        if resident:
+            model.step_resident(dev_ring[s % len(dev_ring)])
+        else:
+            model.step(batches[s])                                       # H2D copy + sampler + fused step
+            loss_host[s:s + 1].copy_(model.loss, non_blocking=True)      # D2H read of the step result
         worker.advance_clock()
 
     # ---------------- warm-up (also lets the sync engine localise the first batches)
@@ -183,51 +193,63 @@ def main():
     if world > 1:
         worker.wait_sync()
     for s in range(W):
-        e2e_step(s)
+        train_step(s, False)
     barrier()
 
-    # ---------------- e2e timed region
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+
+    # ---------------- e2e timed region
     launches0 = _C.kernel_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record(stream)
     for s in range(W, W + K):
-        e2e_step(s)
+        train_step(s, False)
     ev1.record(stream)
     barrier()
     e2e_ms = ev0.elapsed_time(ev1)
     launches_e2e = _C.kernel_launches() - launches0
 
-    # ---------------- device-resident timed region (inputs already on the device)
-    dev_ring = [b.to(dev) for b in ring]
-    dev_batches = [dev_ring[i % len(dev_ring)] for i in range(K)]
-    torch.cuda.synchronize()
-    from adapm_b200.ops import sgns_step
-
-    def dev_step(i):
-        kb = dev_batches[i]
-        seed = 77000 + i * 131 + rank
-        model.sampler.sample(model._neg.numel(), seed, local_only=(cfg.sampling_scheme == "local" and world > 1),
-                             out=model._neg)
-        sgns_step(server, kb[0], kb[1], model._neg, cfg.embed_dim, model.alpha, model.loss, model.stats)
-
-    for i in range(min(3, K)):
-        dev_step(i)
+    # ---------------- device-resident timed region (same loop, inputs already on the device)
+    for s in range(W + K, W + K + 3):
+        train_step(s, True)
     barrier()
     launches1 = _C.kernel_launches()
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev2.record(stream)
-    for i in range(K):
-        dev_step(i)
+    for s in range(W + K + 3, W + 2 * K + 3):
+        train_step(s, True)
     ev3.record(stream)
     barrier()
     dev_ms = ev2.elapsed_time(ev3)
     launches_dev = _C.kernel_launches() - launches1
     clocks = sampler.stop() if rank == 0 else None
+
+    # ---------------- optional: per-kernel device times (outside the timed regions)
+    prof = None
+    if args.profile:
+        evs = []
+        for s in range(W + 2 * K + 3, W + 2 * K + 3 + 40):
+            a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            if s + RA < len(batches):
+                model.signal_intent(batches[s + RA], worker.current_clock() + RA)
+            kb = dev_ring[s % len(dev_ring)]
+            a.record(stream)
+            model.sample_negatives()
+            b.record(stream)
+            sgns_step(server, kb[0], kb[1], model._neg, cfg.embed_dim, model.alpha, model.loss, model.stats)
+            c.record(stream)
+            worker.advance_clock()
+            evs.append((a, b, c))
+            if len(evs) % 2 == 0:
+                c.synchronize()
+        torch.cuda.synchronize()
+        prof = {"sampler_ms": statistics.mean(a.elapsed_time(b) for a, b, c in evs),
+                "sgns_ms": statistics.mean(b.elapsed_time(c) for a, b, c in evs),
+                "sgns_ms_max": max(b.elapsed_time(c) for a, b, c in evs)}
 
     # max over ranks
     t = torch.tensor([e2e_ms, dev_ms], dtype=torch.float64, device=dev)
@@ -272,6 +294,8 @@ def main():
             "locality": {"rows_local": stats[0], "rows_remote": stats[1], "rows_slow_path": stats[2]},
             "pm": {k: counters[k] for k in ("relocations", "replica_setups", "replica_drops", "refreshes",
                                             "deltas_shipped", "sync_rounds", "protocol_errors")},
+            "profile": prof,
+            "sync_report": server._impl.sync_report() if world > 1 else None,
             "loss_last": float(loss_host[W + K - 1]) / max(1, cfg.batch_pairs * (cfg.negative + 1)),
         }
         print(json.dumps(out))
