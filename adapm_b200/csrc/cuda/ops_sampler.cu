@@ -37,6 +37,15 @@ __device__ __forceinline__ Key draw_key(int kind, const float* __restrict__ prob
   return first + j * stride;
 }
 
+// Residency probe with plain (L2-cached) loads: a momentarily stale answer only costs one more
+// draw or one remote access, so no acquire/system-scope ordering is needed here.
+__device__ __forceinline__ bool resident_weak(const Ctx& c, Key k) {
+  int32_t s = __ldcg(slot_of(c, c.rank) + k);
+  if (s < 0) return false;
+  uint32_t st = meta_state(__ldcg(meta_of(c, c.rank) + s));
+  return st == S_OWNED || st == S_REPLICA || st == S_INCOMING_REPLICA;
+}
+
 __global__ void sample_kernel(const __grid_constant__ Ctx c, int kind, const float* __restrict__ prob,
                               const int32_t* __restrict__ alias, int64_t n_table, Key first, Key stride,
                               Key* __restrict__ out, int64_t n, uint64_t seed, int local_only, int max_tries,
@@ -51,7 +60,7 @@ __global__ void sample_kernel(const __grid_constant__ Ctx c, int kind, const flo
       k = draw_key(kind, prob, alias, n_table, first, stride, h);
       if (!local_only) break;
       ++checks;
-      if (is_local(c, k)) break;
+      if (resident_weak(c, k)) break;
       if (++t >= max_tries) { ++misses; break; }  // give up: the row will be fetched over NVLink
     }
     out[i] = k;

@@ -67,7 +67,7 @@ __device__ __forceinline__ Target resolve_fast(const Ctx& c, Key key, unsigned* 
   if (o == me) return t;
   int32_t ps = mem::ld_relaxed(slot_of(c, o) + key);     // NVLink load
   if (ps < 0) return t;
-  uint32_t pst = meta_state(mem::ld_acquire(meta_of(c, o) + ps));
+  uint32_t pst = meta_state(mem::ld_relaxed(meta_of(c, o) + ps));
   if (pst != S_OWNED) return t;
   t.row = row_ptr<float>(c, o, 0, (uint32_t)ps); t.version = version_of(c, o) + ps; ++*n_remote;
   return t;
