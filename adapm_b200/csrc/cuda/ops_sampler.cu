@@ -65,9 +65,16 @@ __global__ void sample_kernel(const __grid_constant__ Ctx c, int kind, const flo
     }
     out[i] = k;
   }
-  if (stats) {
-    if (checks) atomicAdd(stats + 0, (unsigned long long)checks);
-    if (misses) atomicAdd(stats + 1, (unsigned long long)misses);
+  if (stats) {  // one atomic per warp, not per thread (same-address atomics serialise in L2)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      checks += __shfl_xor_sync(0xffffffffu, checks, o);
+      misses += __shfl_xor_sync(0xffffffffu, misses, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      if (checks) atomicAdd(stats + 0, (unsigned long long)checks);
+      if (misses) atomicAdd(stats + 1, (unsigned long long)misses);
+    }
   }
 }
 

@@ -205,8 +205,10 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record(stream)
+    t_host0 = time.perf_counter()
     for s in range(W, W + K):
         train_step(s, False)
+    host_ms = (time.perf_counter() - t_host0) * 1e3 / K
     ev1.record(stream)
     barrier()
     e2e_ms = ev0.elapsed_time(ev1)
@@ -294,7 +296,7 @@ def main():
             "locality": {"rows_local": stats[0], "rows_remote": stats[1], "rows_slow_path": stats[2]},
             "pm": {k: counters[k] for k in ("relocations", "replica_setups", "replica_drops", "refreshes",
                                             "deltas_shipped", "sync_rounds", "protocol_errors")},
-            "profile": prof,
+            "profile": prof, "host_loop_ms_per_step": host_ms,
             "sync_report": server._impl.sync_report() if world > 1 else None,
             "loss_last": float(loss_host[W + K - 1]) / max(1, cfg.batch_pairs * (cfg.negative + 1)),
         }
