@@ -106,8 +106,10 @@ class Server:
     ) -> None:
         with _setup_lock:
             cfg = dict(_setup)
-        world = world if world is not None else _env_int("WORLD_SIZE", "DMLC_NUM_SERVER", default=1)
-        rank = rank if rank is not None else _env_int("RANK", "DMLC_RANK", default=0)
+        world = world if world is not None else _env_int("WORLD_SIZE", "OMPI_COMM_WORLD_SIZE", "PMI_SIZE", "SLURM_NTASKS",
+                                                         "DMLC_NUM_SERVER", default=1)
+        rank = rank if rank is not None else _env_int("RANK", "OMPI_COMM_WORLD_RANK", "PMI_RANK", "SLURM_PROCID",
+                                                      "DMLC_RANK", default=0)
         if backend is None:
             backend = os.environ.get("ADAPM_BACKEND") or ("cuda" if (_C.cuda_available() and dtype == "float32") else "cpu")
         if fabric is None:
@@ -117,7 +119,7 @@ class Server:
         if device is not None:
             opts["device"] = device
         elif backend == "cuda":
-            lr = _env_int("LOCAL_RANK")
+            lr = _env_int("LOCAL_RANK", "OMPI_COMM_WORLD_LOCAL_RANK", "SLURM_LOCALID")
             if lr is not None and fabric == "shm":
                 opts["device"] = lr % max(1, _C.cuda_device_count())
         if cfg["techniques"]:

@@ -167,16 +167,17 @@ __global__ void register_kernel(const __grid_constant__ Ctx c, const IntentRec* 
   else if (st == 1) count(c, C_INTENTS_DEFERRED);
 }
 
-// Each warp scans 32 slots at a time and then processes the interesting ones cooperatively.
+// Phase A / C run as two kernels: (1) a streaming scan over the slot states compacts the slots that
+// need work into a worklist (replica slots are allocated contiguously, so a static slot->warp mapping
+// would leave most warps idle), (2) one warp per worklist item, grid-strided, so that the long
+// dependent-load chains of many slots overlap.
 template <int PHASE>
-__global__ void __launch_bounds__(kThreads) phase_ac_kernel(const __grid_constant__ Ctx c, RoundParams rp) {
-  WarpGroup g;
+__global__ void __launch_bounds__(kThreads) phase_scan_kernel(const __grid_constant__ Ctx c, uint32_t* __restrict__ worklist,
+                                                              unsigned int* __restrict__ count) {
   const uint32_t S = c.L.total_slots;
   const uint32_t* meta = meta_of(c, c.rank);
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t s0 = warp * 32; s0 < S; s0 += nwarps * 32) {
-    uint32_t s = s0 + g.lane();
+  const int lane = threadIdx.x & 31;
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < ((S + 31u) & ~31u); s += gridDim.x * blockDim.x) {
     bool hit = false;
     if (s < S) {
       uint32_t st = meta_state(__ldcg(meta + s));
@@ -184,13 +185,28 @@ __global__ void __launch_bounds__(kThreads) phase_ac_kernel(const __grid_constan
       else hit = (st != S_FREE && st != S_OWNED);
     }
     unsigned mask = __ballot_sync(0xffffffffu, hit);
-    while (mask) {
-      int b = __ffs(mask) - 1;
-      mask &= mask - 1;
-      if (PHASE == 0) phase_a_slot<float>(c, g, s0 + b, rp);
-      else phase_c_slot<float>(c, g, s0 + b, rp);
-      __syncwarp();
+    if (mask) {
+      unsigned base = 0;
+      if (lane == 0) base = atomicAdd(count, (unsigned)__popc(mask));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (hit) worklist[base + __popc(mask & ((1u << lane) - 1u))] = s;
     }
+  }
+}
+
+template <int PHASE>
+__global__ void __launch_bounds__(kThreads) phase_work_kernel(const __grid_constant__ Ctx c, RoundParams rp,
+                                                              const uint32_t* __restrict__ worklist,
+                                                              const unsigned int* __restrict__ count) {
+  WarpGroup g;
+  const unsigned n = *count;
+  const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (unsigned i = warp; i < n; i += nwarps) {
+    const uint32_t s = worklist[i];
+    if (PHASE == 0) phase_a_slot<float>(c, g, s, rp);
+    else phase_c_slot<float>(c, g, s, rp);
+    __syncwarp();
   }
 }
 
@@ -232,6 +248,8 @@ CudaBackend::CudaBackend(const Options& opt, const Layout& L, std::shared_ptr<Fa
     tracked_.insert(worker_streams_[w]);
     staging_.emplace_back(new Staging());
   }
+  ADAPM_CUDA_CHECK(cudaMalloc((void**)&worklist_, (size_t)(L.total_slots + 32) * sizeof(uint32_t)));
+  ADAPM_CUDA_CHECK(cudaMalloc((void**)&work_count_, 64));
 }
 
 CudaBackend::~CudaBackend() {
@@ -240,6 +258,8 @@ CudaBackend::~CudaBackend() {
   for (auto& st : staging_) { if (st->host) cudaFreeHost(st->host); if (st->dev) cudaFree(st->dev); }
   if (sync_staging_.host) cudaFreeHost(sync_staging_.host);
   if (sync_staging_.dev) cudaFree(sync_staging_.dev);
+  if (worklist_) cudaFree(worklist_);
+  if (work_count_) cudaFree(work_count_);
   for (auto& kv : tickets_) cudaEventDestroy(kv.second);
   for (auto e : event_pool_) cudaEventDestroy(e);
   for (auto s : worker_streams_) cudaStreamDestroy(s);
@@ -524,7 +544,10 @@ void CudaBackend::register_intents(const IntentRec* recs, size_t n, const RoundP
 
 void CudaBackend::phase_a(const RoundParams& rp) {
   use_device();
-  phase_ac_kernel<0><<<num_sms_ * 2, kThreads, 0, sync_stream_>>>(ctx_, rp);
+  ADAPM_CUDA_CHECK(cudaMemsetAsync(work_count_, 0, sizeof(unsigned int), sync_stream_));
+  phase_scan_kernel<0><<<num_sms_ * 2, kThreads, 0, sync_stream_>>>(ctx_, worklist_, work_count_);
+  ADAPM_COUNT_LAUNCH();
+  phase_work_kernel<0><<<num_sms_ * 4, kThreads, 0, sync_stream_>>>(ctx_, rp, worklist_, work_count_);
   ADAPM_COUNT_LAUNCH();
   ADAPM_CUDA_CHECK(cudaGetLastError());
 }
@@ -536,7 +559,10 @@ void CudaBackend::phase_b(const RoundParams& rp) {
 }
 void CudaBackend::phase_c(const RoundParams& rp) {
   use_device();
-  phase_ac_kernel<1><<<num_sms_ * 2, kThreads, 0, sync_stream_>>>(ctx_, rp);
+  ADAPM_CUDA_CHECK(cudaMemsetAsync(work_count_, 0, sizeof(unsigned int), sync_stream_));
+  phase_scan_kernel<1><<<num_sms_ * 2, kThreads, 0, sync_stream_>>>(ctx_, worklist_, work_count_);
+  ADAPM_COUNT_LAUNCH();
+  phase_work_kernel<1><<<num_sms_ * 4, kThreads, 0, sync_stream_>>>(ctx_, rp, worklist_, work_count_);
   ADAPM_COUNT_LAUNCH();
   ADAPM_CUDA_CHECK(cudaGetLastError());
 }

@@ -83,6 +83,8 @@ class CudaBackend : public Backend {
   std::unordered_map<uint64_t, cudaEvent_t> tickets_;
   std::vector<cudaEvent_t> event_pool_;
   uint64_t next_ticket_ = 1;
+  uint32_t* worklist_ = nullptr;       // slots that need work in the current phase (device)
+  unsigned int* work_count_ = nullptr;
   std::vector<uint32_t> key_len_;   // host mirror of per-key lengths (mixed-length stores only)
 };
 
