@@ -16,5 +16,15 @@ void sample_keys(CudaBackend& be, cudaStream_t stream, int kind, const float* pr
                  int64_t n_table, Key first, Key stride, Key* out, int64_t n, uint64_t seed, bool local_only,
                  int max_tries, unsigned long long* stats);
 
+// knowledge-graph embeddings, ComplEx: fused pull + score + BCE/L2 gradient + AdaGrad + push (ops_kge.cu)
+void kge_complex_step(CudaBackend& be, cudaStream_t stream, const Key* subj, const Key* rel, const Key* obj,
+                      const float* labels, int n_calls, int nh, float eta, float gamma_e, float gamma_r, float* loss_out,
+                      unsigned long long* stats);
+
+// matrix factorisation: fused pull + error + L2 + AdaGrad + push (ops_mf.cu)
+void mf_step(CudaBackend& be, cudaStream_t stream, const Key* row_keys, const Key* col_keys, const float* xs,
+             const int* row_nnz, const int* col_nnz, int n, int rank, float eps, float lambda, float* loss_out,
+             unsigned long long* stats);
+
 }  // namespace cudaops
 }  // namespace adapm

@@ -31,6 +31,18 @@ void bind(py::module_& m) {
     sample_keys(backend_of(be), (cudaStream_t)stream, kind, ptr<const float>(prob), ptr<const int32_t>(alias), n_table,
                 first, stride, ptr<Key>(out), n, seed, local_only, max_tries, ptr<unsigned long long>(stats));
   });
+  m.def("kge_complex_step", [](uintptr_t be, uintptr_t stream, uintptr_t s, uintptr_t r, uintptr_t o, uintptr_t labels,
+                               int n, int nh, float eta, float gamma_e, float gamma_r, uintptr_t loss, uintptr_t stats) {
+    kge_complex_step(backend_of(be), (cudaStream_t)stream, ptr<const Key>(s), ptr<const Key>(r), ptr<const Key>(o),
+                     ptr<const float>(labels), n, nh, eta, gamma_e, gamma_r, ptr<float>(loss),
+                     ptr<unsigned long long>(stats));
+  });
+  m.def("mf_step", [](uintptr_t be, uintptr_t stream, uintptr_t rows, uintptr_t cols, uintptr_t xs, uintptr_t rn,
+                      uintptr_t cn, int n, int rank, float eps, float lambda, uintptr_t loss, uintptr_t stats) {
+    mf_step(backend_of(be), (cudaStream_t)stream, ptr<const Key>(rows), ptr<const Key>(cols), ptr<const float>(xs),
+            ptr<const int>(rn), ptr<const int>(cn), n, rank, eps, lambda, ptr<float>(loss),
+            ptr<unsigned long long>(stats));
+  });
   m.def("kernel_launches", [] { return kernel_launch_counter().load(); });
   m.def("track_stream", [](uintptr_t be, uintptr_t stream) { backend_of(be).track_stream((cudaStream_t)stream); });
 }

@@ -1,0 +1,223 @@
+// Fused knowledge-graph-embedding training step (ComplEx) for sm_100a: Pull(s, r, o) + score +
+// BCE gradient + L2 + AdaGrad + Push(s, r, o) in one kernel over local HBM / NVLink peers
+// (SURVEY K1 + K8 + K9 + K2 + K14).
+//
+// Semantics = the reference's Model::train with the ComplEx score
+// (apps/knowledge_graph_embeddings.cc:437-531, :832-858, :415-435):
+//   score = sum_i  r_re s_re o_re + r_re s_im o_im + r_im s_re o_im - r_im s_im o_re
+//   dl    = sigmoid(score) - [positive]
+//   d_x   = dl * dscore/dx  (+ gamma * x for positives)
+//   push(x, [-eta * d_x / sqrt(acc_x + d_x^2) | d_x^2])        for x in {s, r, o}
+// Row layout [embedding(nh) | AdaGrad(nh)], embedding = [real(nh/2) | imag(nh/2)].
+// One warp per training call; the three directory lookups are issued by three lanes at once.
+#include <cuda_runtime.h>
+
+#include "ops.h"
+#include "pm_kernels.cuh"
+
+namespace adapm {
+namespace cudaops {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ float4 f4_mul(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+__device__ __forceinline__ float4 f4_fma(float4 a, float4 b, float4 c) {
+  return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w));
+}
+__device__ __forceinline__ float4 f4_sub(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+__device__ __forceinline__ float f4_hsum(float4 a) { return a.x + a.y + a.z + a.w; }
+
+// g = dl * d + (reg ? gamma * x : 0); returns AdaGrad update pair and issues the reductions.
+__device__ __forceinline__ void adagrad_push4(float* emb_ptr, float* acc_ptr, float4 d, float4 x, float dl, float gamma,
+                                              float eta) {
+  float4 g = make_float4(fmaf(gamma, x.x, dl * d.x), fmaf(gamma, x.y, dl * d.y), fmaf(gamma, x.z, dl * d.z),
+                         fmaf(gamma, x.w, dl * d.w));
+  float4 a = dev::ld_row4(acc_ptr);
+  float4 ua = f4_mul(g, g);
+  float4 ue = make_float4(-eta * g.x * rsqrtf(a.x + ua.x), -eta * g.y * rsqrtf(a.y + ua.y),
+                          -eta * g.z * rsqrtf(a.z + ua.z), -eta * g.w * rsqrtf(a.w + ua.w));
+  dev::red_row4(emb_ptr, ue);
+  dev::red_row4(acc_ptr, ua);
+}
+
+// scalar generic path (any nh; also used when a row is in a transitional state): rows staged in smem
+__device__ __noinline__ float kge_call_generic(const Ctx& c, Key ks, Key kr, Key ko, float label, int nh, float eta,
+                                               float gamma_e, float gamma_r, float* stage, bool* applied) {
+  const int lane = threadIdx.x & 31;
+  float* S = stage; float* R = stage + 2 * nh; float* O = stage + 4 * nh;
+  *applied = false;
+  if (!dev::slow_pull(c, ks, S) || !dev::slow_pull(c, kr, R) || !dev::slow_pull(c, ko, O)) return 0.f;
+  const int H = nh / 2;
+  float sc = 0.f;
+  for (int i = lane; i < H; i += 32)
+    sc += R[i] * S[i] * O[i] + R[i] * S[H + i] * O[H + i] + R[H + i] * S[i] * O[H + i] - R[H + i] * S[H + i] * O[i];
+  sc = dev::warp_sum(sc);
+  const float dl = 1.f / (1.f + __expf(-sc)) - label;
+  const float ge = label > 0.5f ? gamma_e : 0.f, gr = label > 0.5f ? gamma_r : 0.f;
+  for (int i = lane; i < H; i += 32) {
+    float sre = S[i], sim = S[H + i], rre = R[i], rim = R[H + i], ore = O[i], oim = O[H + i];
+    float d[6] = {rre * ore + rim * oim, rre * oim - rim * ore, sre * ore + sim * oim,
+                  sre * oim - sim * ore, rre * sre - rim * sim, rre * sim + rim * sre};
+    float x[6] = {sre, sim, rre, rim, ore, oim};
+    float gm[6] = {ge, ge, gr, gr, ge, ge};
+    float* rows[6] = {S, S, R, R, O, O};
+    int off[6] = {i, H + i, i, H + i, i, H + i};
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      float g = dl * d[q] + gm[q] * x[q];
+      float a = rows[q][nh + off[q]];
+      float ua = g * g;
+      rows[q][off[q]] = -eta * g * rsqrtf(a + ua);
+      rows[q][nh + off[q]] = ua;
+    }
+  }
+  __syncwarp();
+  bool ok = dev::slow_push(c, ks, S);
+  ok = dev::slow_push(c, kr, R) && ok;
+  ok = dev::slow_push(c, ko, O) && ok;
+  *applied = ok;
+  float z = label > 0.5f ? sc : -sc;
+  return __logf(1.f + __expf(-fminf(fmaxf(z, -30.f), 30.f)));
+}
+
+// VPLH = float4 vectors per lane per half-embedding (nh/8 float4 per half); VPLH = 0 -> generic only
+template <int VPLH>
+__global__ void __launch_bounds__(kThreads, 2)
+kge_step_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ subj, const Key* __restrict__ rel,
+                const Key* __restrict__ obj, const float* __restrict__ labels, int n_calls, int nh, float eta,
+                float gamma_e, float gamma_r, float* __restrict__ loss_out, unsigned long long* __restrict__ stats) {
+  extern __shared__ float smem_f[];  // generic path: per warp 6*nh floats
+  const int lane = threadIdx.x & 31;
+  const int warp_in_block = threadIdx.x >> 5;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  float* stage = smem_f + (size_t)warp_in_block * 6 * nh;
+  const int H = nh >> 1;
+  const int nvh = H >> 2;
+  float loss_acc = 0.f;
+  unsigned n_local = 0, n_remote = 0, n_slow = 0, n_upd = 0;
+
+  for (int p = warp; p < n_calls; p += nwarps) {
+    const Key ks = subj[p], kr = rel[p], ko = obj[p];
+    const float label = labels[p];
+    dev::Target t;
+    t.row = nullptr; t.version = nullptr; t.flag = nullptr;
+    if (VPLH > 0 && lane < 3) {
+      Key k = lane == 0 ? ks : (lane == 1 ? kr : ko);
+      t = dev::resolve_fast(c, k, class_of_key(c, k), &n_local, &n_remote);
+    }
+    float* ps = (float*)__shfl_sync(0xffffffffu, (unsigned long long)t.row, 0);
+    float* pr = (float*)__shfl_sync(0xffffffffu, (unsigned long long)t.row, 1);
+    float* po = (float*)__shfl_sync(0xffffffffu, (unsigned long long)t.row, 2);
+    if (VPLH == 0 || !ps || !pr || !po) {
+      ++n_slow;
+      bool applied;
+      loss_acc += kge_call_generic(c, ks, kr, ko, label, nh, eta, gamma_e, gamma_r, stage, &applied);
+      if (applied) n_upd += 3;
+      continue;
+    }
+    constexpr int V = VPLH > 0 ? VPLH : 1;
+    float4 sre[V], sim[V], rre[V], rim[V], ore[V], oim[V];
+    float sc = 0.f;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const int j = lane + 32 * v;
+      const bool in = j < nvh;
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      sre[v] = in ? dev::ld_row4(ps + 4 * j) : z; sim[v] = in ? dev::ld_row4(ps + H + 4 * j) : z;
+      rre[v] = in ? dev::ld_row4(pr + 4 * j) : z; rim[v] = in ? dev::ld_row4(pr + H + 4 * j) : z;
+      ore[v] = in ? dev::ld_row4(po + 4 * j) : z; oim[v] = in ? dev::ld_row4(po + H + 4 * j) : z;
+    }
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      float4 a = f4_fma(sre[v], ore[v], f4_mul(sim[v], oim[v]));   // s_re o_re + s_im o_im
+      float4 b = f4_sub(f4_mul(sre[v], oim[v]), f4_mul(sim[v], ore[v]));  // s_re o_im - s_im o_re
+      sc += f4_hsum(f4_fma(rre[v], a, f4_mul(rim[v], b)));
+    }
+    sc = dev::warp_sum(sc);
+    const float dl = 1.f / (1.f + __expf(-sc)) - label;
+    const bool pos = label > 0.5f;
+    const float ge = pos ? gamma_e : 0.f, gr = pos ? gamma_r : 0.f;
+    {
+      float z = pos ? sc : -sc;
+      loss_acc += __logf(1.f + __expf(-fminf(fmaxf(z, -30.f), 30.f)));
+    }
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const int j = lane + 32 * v;
+      if (j < nvh) {
+        // gradients of the trilinear score (reference score_grad)
+        float4 ds_re = f4_fma(rre[v], ore[v], f4_mul(rim[v], oim[v]));
+        float4 ds_im = f4_sub(f4_mul(rre[v], oim[v]), f4_mul(rim[v], ore[v]));
+        float4 dr_re = f4_fma(sre[v], ore[v], f4_mul(sim[v], oim[v]));
+        float4 dr_im = f4_sub(f4_mul(sre[v], oim[v]), f4_mul(sim[v], ore[v]));
+        float4 do_re = f4_sub(f4_mul(rre[v], sre[v]), f4_mul(rim[v], sim[v]));
+        float4 do_im = f4_fma(rre[v], sim[v], f4_mul(rim[v], sre[v]));
+        adagrad_push4(ps + 4 * j, ps + nh + 4 * j, ds_re, sre[v], dl, ge, eta);
+        adagrad_push4(ps + H + 4 * j, ps + nh + H + 4 * j, ds_im, sim[v], dl, ge, eta);
+        adagrad_push4(pr + 4 * j, pr + nh + 4 * j, dr_re, rre[v], dl, gr, eta);
+        adagrad_push4(pr + H + 4 * j, pr + nh + H + 4 * j, dr_im, rim[v], dl, gr, eta);
+        adagrad_push4(po + 4 * j, po + nh + 4 * j, do_re, ore[v], dl, ge, eta);
+        adagrad_push4(po + H + 4 * j, po + nh + H + 4 * j, do_im, oim[v], dl, ge, eta);
+      }
+    }
+    if (lane < 3) dev::mark_pushed(t);
+    n_upd += 3;
+  }
+
+  __syncwarp();
+  if (lane == 0 && loss_out) atomicAdd(loss_out, loss_acc);
+  unsigned sl = n_local, sr = n_remote;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sl += __shfl_xor_sync(0xffffffffu, sl, o);
+    sr += __shfl_xor_sync(0xffffffffu, sr, o);
+  }
+  if (lane == 0 && stats) {
+    if (sl) atomicAdd(stats + 0, (unsigned long long)sl);
+    if (sr) atomicAdd(stats + 1, (unsigned long long)sr);
+    if (n_slow) atomicAdd(stats + 2, (unsigned long long)n_slow);
+    if (n_upd) atomicAdd(stats + 3, (unsigned long long)n_upd);
+  }
+}
+
+}  // namespace
+
+// n_calls training calls (s[i], r[i], o[i], label[i]); entity and relation rows must be 2*nh floats.
+void kge_complex_step(CudaBackend& be, cudaStream_t stream, const Key* subj, const Key* rel, const Key* obj,
+                      const float* labels, int n_calls, int nh, float eta, float gamma_e, float gamma_r, float* loss_out,
+                      unsigned long long* stats) {
+  if (n_calls == 0) return;
+  ADAPM_CHECK(nh % 2 == 0, "ComplEx needs an even embedding size");
+  be.track_stream(stream);
+  const Ctx& c = be.ctx();
+  const int warps_per_block = kThreads / 32;
+  int blocks = std::min((n_calls + warps_per_block - 1) / warps_per_block, be.num_sms() * 8);
+  size_t smem = (size_t)warps_per_block * 6 * nh * sizeof(float);
+  ADAPM_CHECK(smem <= 200 * 1024, "kge_complex_step: embedding size too large for the staging buffer");
+  const int nvh = nh / 8;
+  int vplh = (nh % 8 == 0) ? (nvh + 31) / 32 : 0;
+  if (vplh > 2) vplh = 0;
+#define ADAPM_LAUNCH_KGE(V)                                                                                    \
+  do {                                                                                                         \
+    static bool attr_set = false;                                                                              \
+    if (!attr_set) {                                                                                           \
+      cudaFuncSetAttribute(kge_step_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);       \
+      attr_set = true;                                                                                         \
+    }                                                                                                          \
+    kge_step_kernel<V><<<blocks, kThreads, smem, stream>>>(c, subj, rel, obj, labels, n_calls, nh, eta, gamma_e, \
+                                                           gamma_r, loss_out, stats);                          \
+  } while (0)
+  switch (vplh) {
+    case 1: ADAPM_LAUNCH_KGE(1); break;
+    case 2: ADAPM_LAUNCH_KGE(2); break;
+    default: ADAPM_LAUNCH_KGE(0); break;
+  }
+  ADAPM_COUNT_LAUNCH();
+  ADAPM_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace cudaops
+}  // namespace adapm

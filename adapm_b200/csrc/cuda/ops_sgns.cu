@@ -30,53 +30,11 @@ namespace {
 constexpr int kThreads = 256;
 constexpr float kMaxExp = 6.0f;
 
-struct Target {
-  float* row;        // emb at row[0..d), acc at row[d..2d); nullptr -> needs the slow path
-  uint32_t* version; // owner version counter (may be remote) or nullptr
-  uint8_t* flag;     // replica dirty flag or nullptr
-};
+using dev::Target;
+using dev::warp_sum;
 
-// Single-lane fast path: resolves a key to a directly usable row (local owned / local replica /
-// remote owned). Anything in a transitional state returns row == nullptr.
 __device__ __forceinline__ Target resolve_fast(const Ctx& c, Key key, unsigned* n_local, unsigned* n_remote) {
-  Target t;
-  t.row = nullptr; t.version = nullptr; t.flag = nullptr;
-  const int me = c.rank;
-  int32_t s = __ldcg(slot_of(c, me) + key);
-  if (s >= 0) {
-    uint32_t st = meta_state(__ldcg(meta_of(c, me) + s));
-    if (st == S_OWNED) {
-      t.row = row_ptr<float>(c, me, 0, (uint32_t)s); t.version = version_of(c, me) + s; ++*n_local;
-      return t;
-    }
-    if (st == S_REPLICA) {
-      t.row = row_ptr<float>(c, me, 0, (uint32_t)s); t.flag = dirty_of(c, me) + s; ++*n_local;
-      return t;
-    }
-    if (st == S_INCOMING_REPLICA) {
-      // being upgraded from replica to owner: reads keep replica semantics, adds go to the
-      // (accumulating) local row
-      t.row = row_ptr<float>(c, me, 0, (uint32_t)s); t.version = version_of(c, me) + s; ++*n_local;
-      return t;
-    }
-    if (st == S_INCOMING || st == S_FINALIZING) return t;  // needs the 3-way read: slow path
-    // REPLICA_PENDING / OUTGOING / DEAD / DROPPING: not usable locally -> go to the owner
-  }
-  if (c.L.world == 1) return t;
-  int o = (int)__ldcg(dir_of(c, me) + key);
-  if (o == me) return t;
-  int32_t ps = mem::ld_relaxed(slot_of(c, o) + key);     // NVLink load
-  if (ps < 0) return t;
-  uint32_t pst = meta_state(mem::ld_relaxed(meta_of(c, o) + ps));
-  if (pst != S_OWNED) return t;
-  t.row = row_ptr<float>(c, o, 0, (uint32_t)ps); t.version = version_of(c, o) + ps; ++*n_remote;
-  return t;
-}
-
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
+  return dev::resolve_fast(c, key, 0, n_local, n_remote);
 }
 
 // ---- slow path (key in a transitional protocol state: INCOMING, FINALIZING, ...). Rare, so it is
@@ -112,19 +70,8 @@ __device__ __noinline__ float slow_target(const Ctx& c, Key tkey, float label, f
   return __logf(1.f + __expf(-z));
 }
 
-__device__ __noinline__ bool slow_pull(const Ctx& c, Key key, float* stage) {
-  WarpGroup g;
-  bool ok = pull_key<float>(c, g, key, stage, false, nullptr);
-  __syncwarp();
-  return ok;
-}
-__device__ __noinline__ bool slow_push(const Ctx& c, Key key, const float* stage) {
-  WarpGroup g;
-  __syncwarp();
-  bool ok = push_key<float>(c, g, key, stage, nullptr);
-  __syncwarp();
-  return ok;
-}
+using dev::slow_pull;
+using dev::slow_push;
 
 // VPL = float4 vectors per lane covering d floats: VPL = ceil(d / 128)
 template <int VPL, int MINB>

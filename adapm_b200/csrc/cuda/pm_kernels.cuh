@@ -59,5 +59,70 @@ __device__ __forceinline__ float* local_row_or_null(const Ctx& c, Key key, uint3
   return nullptr;
 }
 
+// A key resolved to a directly usable row. `row == nullptr` means the key is in a transitional
+// protocol state and must go through the generic (out-of-line) path.
+struct Target {
+  float* row;
+  uint32_t* version;  // owner version counter (may be remote) or nullptr
+  uint8_t* flag;      // replica dirty byte or nullptr
+};
+
+// Single-lane fast path: local owned / local replica / local incoming-replica / remote owned.
+__device__ __forceinline__ Target resolve_fast(const Ctx& c, Key key, int cls, unsigned* n_local, unsigned* n_remote) {
+  Target t;
+  t.row = nullptr; t.version = nullptr; t.flag = nullptr;
+  const int me = c.rank;
+  int32_t s = __ldcg(slot_of(c, me) + key);
+  if (s >= 0) {
+    uint32_t st = meta_state(__ldcg(meta_of(c, me) + s));
+    if (st == S_OWNED || st == S_INCOMING_REPLICA) {
+      t.row = row_ptr<float>(c, me, cls, (uint32_t)s); t.version = version_of(c, me) + s; ++*n_local;
+      return t;
+    }
+    if (st == S_REPLICA) {
+      t.row = row_ptr<float>(c, me, cls, (uint32_t)s); t.flag = dirty_of(c, me) + s; ++*n_local;
+      return t;
+    }
+    if (st == S_INCOMING || st == S_FINALIZING) return t;  // needs the 3-way read: slow path
+    // REPLICA_PENDING / OUTGOING / DEAD / DROPPING: not usable locally -> go to the owner
+  }
+  if (c.L.world == 1) return t;
+  int o = (int)__ldcg(dir_of(c, me) + key);
+  if (o == me) return t;
+  int32_t ps = mem::ld_relaxed(slot_of(c, o) + key);  // NVLink load
+  if (ps < 0) return t;
+  uint32_t pst = meta_state(mem::ld_relaxed(meta_of(c, o) + ps));
+  if (pst != S_OWNED) return t;
+  t.row = row_ptr<float>(c, o, cls, (uint32_t)ps); t.version = version_of(c, o) + ps; ++*n_remote;
+  return t;
+}
+
+// lane 0 marks a completed fast-path push
+__device__ __forceinline__ void mark_pushed(const Target& t) {
+  if (t.version) mem::red_add(t.version, 1u);
+  if (t.flag) *t.flag = (uint8_t)1;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// generic out-of-line fallbacks (warp-cooperative)
+static __device__ __noinline__ bool slow_pull(const Ctx& c, Key key, float* stage) {
+  WarpGroup g;
+  bool ok = pull_key<float>(c, g, key, stage, false, nullptr);
+  __syncwarp();
+  return ok;
+}
+static __device__ __noinline__ bool slow_push(const Ctx& c, Key key, const float* stage) {
+  WarpGroup g;
+  __syncwarp();
+  bool ok = push_key<float>(c, g, key, stage, nullptr);
+  __syncwarp();
+  return ok;
+}
+
 }  // namespace dev
 }  // namespace adapm

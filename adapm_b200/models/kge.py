@@ -1,0 +1,342 @@
+"""Knowledge-graph embeddings (ComplEx, RESCAL) on the parameter manager.
+
+Behavioural parity with the reference application ``apps/knowledge_graph_embeddings.cc``:
+
+* keys: entities ``0..ne-1``, relations ``ne..ne+nr-1``, ``loss_key``, ``eval_key`` (len 20)
+  (kge.cc:121-127,1296-1306); per-key value lengths (RESCAL relations are ``2*d*d``) (kge.cc:1243-1254);
+* per training triple: one positive call and ``neg_ratio`` x {corrupted object, corrupted subject} negative
+  calls, each pulling/pushing (s, r, o): ``3 * (1 + 2*neg_ratio)`` updates per triple (kge.cc:1107-1119);
+* BCE gradient, L2 only on positives, AdaGrad with the pulled accumulator and init 1e-6
+  (kge.cc:437-531,415-435,309); negatives uniform over entities through PrepareSample/PullSample
+  (kge.cc:131-137,1063-1086);
+* intent: ``Intent({s,r,o}, futureClock)`` ``signal_intent_ahead`` clocks ahead; optional long-term relation
+  intent ``[0, CLOCK_MAX)`` (kge.cc:1022-1032); one clock per batch instead of per triple;
+* filtered ranking evaluation (MRR, Hits@k) (kge.cc:555-774) - on the GPU one 1-vs-all score GEMM per side
+  with the rank counted in the epilogue;
+* checkpoints: ``export.epoch.N.{entities,relations}.bin`` (row-major float32 embeddings) and
+  ``checkpoint.epoch.N.{entities,relations}[.adagrad].bin`` (raw float64) (kge.cc:327-401; the reference's
+  byte-offset bug for the adagrad half is not replicated).
+
+The ComplEx train calls run as ONE fused kernel (``ops.kge_complex_step``); RESCAL uses the public
+Pull/Push API with PyTorch math (its relation rows are d x d matrices).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .. import CLOCK_MAX
+
+
+@dataclass
+class KGEConfig:
+    num_entities: int = 14951
+    num_relations: int = 1345
+    embed_dim: int = 512            # ComplEx: real half + imaginary half
+    algorithm: str = "ComplEx"      # ComplEx | RESCAL
+    neg_ratio: int = 6
+    eta: float = 0.1
+    gamma_entity: float = 1e-3
+    gamma_relation: float = 1e-3
+    batch_triples: int = 4096
+    read_ahead: int = 4
+    sampling_scheme: str = "local"
+    signal_intent: bool = True
+    signal_initial_relations_intent: bool = False
+    init_std: float = 0.1
+    model_seed: int = 134827
+
+    @property
+    def entity_len(self) -> int:
+        return 2 * self.embed_dim
+
+    @property
+    def relation_len(self) -> int:
+        return 2 * self.embed_dim * (self.embed_dim if self.algorithm == "RESCAL" else 1)
+
+    @property
+    def loss_key(self) -> int:
+        return self.num_entities + self.num_relations
+
+    @property
+    def eval_key(self) -> int:
+        return self.num_entities + self.num_relations + 1
+
+    @property
+    def num_keys(self) -> int:
+        return self.num_entities + self.num_relations + 2
+
+    def value_lengths(self) -> torch.Tensor:
+        l = torch.empty(self.num_keys, dtype=torch.int64)
+        l[: self.num_entities] = self.entity_len
+        l[self.num_entities: self.num_entities + self.num_relations] = self.relation_len
+        l[self.loss_key] = 2
+        l[self.eval_key] = 20
+        return l
+
+    @property
+    def updates_per_triple(self) -> int:
+        return 3 * (1 + 2 * self.neg_ratio)
+
+
+def synthetic_triples(cfg: KGEConfig, n: int, seed: int = 0) -> torch.Tensor:
+    """FB15k-shaped synthetic triples: Zipf-skewed entities/relations, [n, 3] int64 (s, r, o)."""
+    rng = np.random.default_rng(seed)
+
+    def zipf(size, k):
+        p = 1.0 / np.arange(1, k + 1) ** 0.8
+        p /= p.sum()
+        return rng.choice(k, size=size, p=p)
+
+    perm_e = rng.permutation(cfg.num_entities)
+    s = perm_e[zipf(n, cfg.num_entities)]
+    r = zipf(n, cfg.num_relations)
+    # learnable structure: 80% of the objects are a fixed function of (s, r), the rest is noise
+    o_fn = perm_e[(s * 7 + r * 13 + 1) % cfg.num_entities]
+    o = np.where(rng.random(n) < 0.8, o_fn, perm_e[zipf(n, cfg.num_entities)])
+    return torch.from_numpy(np.stack([s, r, o], 1).astype(np.int64))
+
+
+def load_triples(path: str) -> torch.Tensor:
+    """TSV ``s r o`` per line (apps/data/kge/*.del)."""
+    return torch.from_numpy(np.loadtxt(path, dtype=np.int64).reshape(-1, 3))
+
+
+class KGE:
+    def __init__(self, server, worker, cfg: KGEConfig):
+        self.server, self.worker, self.cfg = server, worker, cfg
+        self.cuda = server.backend == "cuda"
+        self.step_no = 0
+        dev = server.device
+        self._gen = torch.Generator().manual_seed(cfg.model_seed + 31 * server.my_rank())
+        if self.cuda:
+            from ..ops import DeviceSampler
+
+            self.sampler = DeviceSampler(server, distribution="uniform", first_key=0, num_keys=cfg.num_entities)
+            self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+            self.stats = torch.zeros(4, dtype=torch.int64, device=dev)
+
+    # ------------------------------------------------------------------ keys
+    def entity_key(self, e):
+        return e
+
+    def relation_key(self, r):
+        return r + self.cfg.num_entities
+
+    # ------------------------------------------------------------------ init
+    def init_model(self, chunk: int = 8192) -> None:
+        """normal{0/init_std} embeddings, AdaGrad accumulators 1e-6 (reference init_parameters default)."""
+        cfg, world, rank = self.cfg, self.server.num_servers(), self.server.my_rank()
+        gen = torch.Generator().manual_seed(cfg.model_seed + rank)
+        self.worker.begin_setup()
+        for first, count, ln in ((0, cfg.num_entities, cfg.entity_len),
+                                 (cfg.num_entities, cfg.num_relations, cfg.relation_len)):
+            keys = torch.arange(first + ((rank - first) % world), first + count, world, dtype=torch.int64)
+            per = max(1, min(chunk, (64 << 20) // (4 * ln)))
+            for i in range(0, keys.numel(), per):
+                k = keys[i:i + per]
+                rows = torch.empty(k.numel(), ln)
+                rows[:, : ln // 2] = torch.randn(k.numel(), ln // 2, generator=gen) * cfg.init_std
+                rows[:, ln // 2:] = 1e-6
+                self.worker.set(k, rows.view(-1))
+        self.worker.waitall()
+        self.worker.end_setup()
+        if cfg.signal_initial_relations_intent and world > 1:
+            self.worker.intent(torch.arange(cfg.num_entities, cfg.num_entities + cfg.num_relations), 0, CLOCK_MAX)
+
+    # ------------------------------------------------------------------ intent
+    def signal_intent(self, triples: torch.Tensor, clock: int) -> None:
+        if not self.cfg.signal_intent or self.server.num_servers() == 1:
+            return
+        keys = torch.cat([triples[:, 0], triples[:, 2], triples[:, 1] + self.cfg.num_entities])
+        self.worker.intent(keys, clock, clock + 1)
+
+    # ------------------------------------------------------------------ training calls of one batch
+    def _expand(self, triples: torch.Tensor, neg_ent: torch.Tensor):
+        """triples [B,3], neg_ent [B, 2*neg_ratio] entity ids -> flat (s, r, o, label) call lists in the
+        reference's order: positive, then per j: (s, r, o'), (s', r, o)."""
+        B, nr = triples.shape[0], self.cfg.neg_ratio
+        s, r, o = triples[:, 0:1], triples[:, 1:2], triples[:, 2:3]
+        C = 1 + 2 * nr
+        S = s.expand(B, C).clone()
+        O = o.expand(B, C).clone()
+        S[:, 2::2] = neg_ent[:, nr:]          # corrupted subjects at odd positions 2,4,..
+        O[:, 1::2] = neg_ent[:, :nr]          # corrupted objects at positions 1,3,..
+        R = (r + self.cfg.num_entities).expand(B, C)
+        L = torch.zeros(B, C, dtype=torch.float32, device=triples.device)
+        L[:, 0] = 1
+        return S.reshape(-1), R.reshape(-1).contiguous(), O.reshape(-1), L.reshape(-1)
+
+    def step(self, triples_host: torch.Tensor) -> torch.Tensor:
+        """One batch of positive triples ([B,3] int64 CPU tensor, pinned for the e2e path)."""
+        cfg = self.cfg
+        B = triples_host.shape[0]
+        if self.cuda and cfg.algorithm == "ComplEx":
+            from ..ops import kge_complex_step
+
+            tr = triples_host.to(self.server.device, non_blocking=True)
+            local_only = cfg.sampling_scheme == "local" and self.server.num_servers() > 1
+            seed = (cfg.model_seed * 7 + self.server.my_rank() * 7919 + self.step_no) & 0xFFFFFFFFFFFF
+            neg = self.sampler.sample(B * 2 * cfg.neg_ratio, seed, local_only=local_only).view(B, 2 * cfg.neg_ratio)
+            S, R, O, L = self._expand(tr, neg)
+            kge_complex_step(self.server, S, R, O, L, cfg.embed_dim, cfg.eta, cfg.gamma_entity, cfg.gamma_relation,
+                             self.loss, self.stats)
+            self.step_no += 1
+            return self.loss
+        neg = torch.randint(0, cfg.num_entities, (B, 2 * cfg.neg_ratio), generator=self._gen)
+        S, R, O, L = self._expand(triples_host, neg)
+        loss = kge_reference_step(self.worker, S, R, O, L, cfg)
+        self.step_no += 1
+        return torch.tensor([loss], dtype=torch.float32)
+
+    # ------------------------------------------------------------------ full-model pull (eval / checkpoints)
+    def pull_embeddings(self, device=None):
+        """Returns (E [ne, d], Eg [ne, d], R [nr, rel_dim], Rg) by pulling the whole model through the API."""
+        cfg, kv = self.cfg, self.worker
+        ek = torch.arange(cfg.num_entities)
+        ev = torch.empty(cfg.num_entities * cfg.entity_len, dtype=torch.float32)
+        kv.wait(kv.pull(ek, ev))
+        rk = torch.arange(cfg.num_entities, cfg.num_entities + cfg.num_relations)
+        rv = torch.empty(cfg.num_relations * cfg.relation_len, dtype=torch.float32)
+        kv.wait(kv.pull(rk, rv))
+        ev = ev.view(cfg.num_entities, cfg.entity_len)
+        rv = rv.view(cfg.num_relations, cfg.relation_len)
+        d, rd = cfg.embed_dim, cfg.relation_len // 2
+        out = (ev[:, :d].contiguous(), ev[:, d:].contiguous(), rv[:, :rd].contiguous(), rv[:, rd:].contiguous())
+        return tuple(t.to(device) for t in out) if device is not None else out
+
+    def save(self, path_prefix: str, epoch: int, write_checkpoint: bool = False) -> None:
+        self.worker.wait_sync()
+        if self.server.my_rank() != 0:
+            return
+        E, Eg, R, Rg = self.pull_embeddings()
+        E.numpy().astype(np.float32).tofile(f"{path_prefix}export.epoch.{epoch}.entities.bin")
+        R.numpy().astype(np.float32).tofile(f"{path_prefix}export.epoch.{epoch}.relations.bin")
+        if write_checkpoint:
+            E.numpy().astype(np.float64).tofile(f"{path_prefix}checkpoint.epoch.{epoch}.entities.bin")
+            R.numpy().astype(np.float64).tofile(f"{path_prefix}checkpoint.epoch.{epoch}.relations.bin")
+            Eg.numpy().astype(np.float64).tofile(f"{path_prefix}checkpoint.epoch.{epoch}.entities.adagrad.bin")
+            Rg.numpy().astype(np.float64).tofile(f"{path_prefix}checkpoint.epoch.{epoch}.relations.adagrad.bin")
+
+    # ------------------------------------------------------------------ evaluation
+    def evaluate(self, triples: torch.Tensor, known: torch.Tensor, batch: int = 2048, use_tensor_cores: bool = True):
+        """Filtered ranking (reference kge.cc:716-774): rank of the true object among all entities for
+        (s, r, ?) and of the true subject for (?, r, o); other known-true answers are filtered out.
+        Returns dict(mrr, mrr_raw, hits@1/3/10). ``known``: all true triples (train+valid+test)."""
+        cfg = self.cfg
+        dev = self.server.device if self.cuda else torch.device("cpu")
+        E, _, R, _ = self.pull_embeddings(dev)
+        triples = triples.to(dev)
+        known = torch.unique(known.to(dev), dim=0)   # duplicates must not be filtered twice
+        ne = cfg.num_entities
+        # index of known answers: key = (a * nr + r) -> list of entities
+        sr_key = known[:, 0] * cfg.num_relations + known[:, 1]
+        or_key = known[:, 2] * cfg.num_relations + known[:, 1]
+        ranks_f, ranks_r = [], []
+        for i in range(0, triples.shape[0], batch):
+            t = triples[i:i + batch]
+            for side in (0, 1):  # 0: predict object, 1: predict subject
+                if cfg.algorithm == "ComplEx":
+                    q = complex_query(E[t[:, 0]] if side == 0 else E[t[:, 2]], R[t[:, 1]], conj=(side == 1))
+                    scores = score_all(q, E, self.server if (self.cuda and use_tensor_cores) else None)
+                else:
+                    Rm = R[t[:, 1]].view(-1, cfg.embed_dim, cfg.embed_dim)
+                    q = torch.einsum("bi,bij->bj", E[t[:, 0]], Rm) if side == 0 else torch.einsum("bij,bj->bi", Rm, E[t[:, 2]])
+                    scores = q @ E.t()
+                true_e = t[:, 2] if side == 0 else t[:, 0]
+                true_score = scores.gather(1, true_e.view(-1, 1))
+                raw = (scores > true_score).sum(1) + 1
+                # filtering: known answers of the same query do not count
+                qkey = (t[:, 0] if side == 0 else t[:, 2]) * cfg.num_relations + t[:, 1]
+                kk, kv_e = (sr_key, known[:, 2]) if side == 0 else (or_key, known[:, 0])
+                m = qkey.view(-1, 1) == kk.view(1, -1) if kk.numel() * qkey.numel() <= (1 << 26) else None
+                if m is not None:
+                    rows, cols = m.nonzero(as_tuple=True)
+                    better = scores[rows, kv_e[cols]] > true_score[rows, 0]
+                    filt = raw - torch.zeros_like(raw).index_add_(0, rows, better.to(raw.dtype))
+                else:
+                    filt = raw.clone()
+                    order = torch.argsort(kk)
+                    kks, kes = kk[order], kv_e[order]
+                    lo = torch.searchsorted(kks, qkey)
+                    hi = torch.searchsorted(kks, qkey, right=True)
+                    for b in range(t.shape[0]):
+                        ents = kes[lo[b]:hi[b]]
+                        filt[b] -= (scores[b, ents] > true_score[b, 0]).sum()
+                ranks_r.append(raw)
+                ranks_f.append(filt)
+        rf = torch.cat(ranks_f).double()
+        rr = torch.cat(ranks_r).double()
+        return {"mrr": float((1 / rf).mean()), "mrr_raw": float((1 / rr).mean()),
+                "hits@1": float((rf <= 1).double().mean()), "hits@3": float((rf <= 3).double().mean()),
+                "hits@10": float((rf <= 10).double().mean()), "n": int(rf.numel() // 2)}
+
+
+def complex_query(a: torch.Tensor, r: torch.Tensor, conj: bool) -> torch.Tensor:
+    """Query vector q such that score(s, r, e) = <q, E[e]> for all e (object side), or the subject-side
+    equivalent (conj=True): scores against all candidate subjects."""
+    h = a.shape[1] // 2
+    are, aim, rre, rim = a[:, :h], a[:, h:], r[:, :h], r[:, h:]
+    if not conj:   # object side: q = [r_re s_re - r_im s_im | r_re s_im + r_im s_re]
+        return torch.cat([rre * are - rim * aim, rre * aim + rim * are], 1)
+    # subject side: d score / d s = [r_re o_re + r_im o_im | r_re o_im - r_im o_re]
+    return torch.cat([rre * are + rim * aim, rre * aim - rim * are], 1)
+
+
+def score_all(q: torch.Tensor, E: torch.Tensor, server=None) -> torch.Tensor:
+    """1-vs-all scores [B, ne] = q @ E^T. With a CUDA server the hand-written tcgen05 GEMM is used
+    (bf16 operands, fp32 accumulation in TMEM); otherwise a plain fp32 matmul."""
+    if server is not None:
+        from ..ops import gemm_nt_bf16
+
+        if gemm_nt_bf16 is not None:
+            return gemm_nt_bf16(q, E)
+    return q @ E.t()
+
+
+def kge_reference_step(kv, S, R, O, L, cfg: KGEConfig) -> float:
+    """Plain PyTorch fp32 training calls through Pull/Push with the reference's update rule
+    (all calls of the batch read the state at the start of the step)."""
+    d = cfg.embed_dim
+    n = S.numel()
+
+    def pull(keys, ln):
+        v = torch.empty(n * ln, dtype=torch.float32)
+        kv.wait(kv.pull(keys.contiguous(), v))
+        return v.view(n, ln)
+
+    rs, ro = pull(S, cfg.entity_len), pull(O, cfg.entity_len)
+    rr = pull(R, cfg.relation_len)
+    Es, As, Eo, Ao = rs[:, :d], rs[:, d:], ro[:, :d], ro[:, d:]
+    rd = cfg.relation_len // 2
+    Er, Ar = rr[:, :rd], rr[:, rd:]
+    if cfg.algorithm == "ComplEx":
+        h = d // 2
+        sre, sim, rre, rim, ore, oim = Es[:, :h], Es[:, h:], Er[:, :h], Er[:, h:], Eo[:, :h], Eo[:, h:]
+        sc = (rre * sre * ore + rre * sim * oim + rim * sre * oim - rim * sim * ore).sum(1)
+        ds = torch.cat([rre * ore + rim * oim, rre * oim - rim * ore], 1)
+        dr = torch.cat([sre * ore + sim * oim, sre * oim - sim * ore], 1)
+        do = torch.cat([rre * sre - rim * sim, rre * sim + rim * sre], 1)
+    else:  # RESCAL: s^T R o
+        Rm = Er.view(n, d, d)
+        sc = torch.einsum("bi,bij,bj->b", Es, Rm, Eo)
+        ds = torch.einsum("bij,bj->bi", Rm, Eo)
+        do = torch.einsum("bi,bij->bj", Es, Rm)
+        dr = torch.einsum("bi,bj->bij", Es, Eo).reshape(n, d * d)
+    dl = (torch.sigmoid(sc) - L).view(-1, 1)
+    pos = (L > 0.5).view(-1, 1).float()
+    gs = dl * ds + pos * cfg.gamma_entity * Es
+    gr = dl * dr + pos * cfg.gamma_relation * Er
+    go = dl * do + pos * cfg.gamma_entity * Eo
+
+    def upd(g, a):
+        return torch.cat([-cfg.eta * g / torch.sqrt(a + g * g), g * g], 1).contiguous().view(-1)
+
+    kv.wait(kv.push(S.contiguous(), upd(gs, As)))
+    kv.wait(kv.push(R.contiguous(), upd(gr, Ar)))
+    kv.wait(kv.push(O.contiguous(), upd(go, Ao)))
+    y = torch.where(L > 0.5, sc, -sc).clamp(-30, 30)
+    return float(torch.log1p(torch.exp(-y)).sum())

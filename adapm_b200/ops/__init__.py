@@ -87,3 +87,41 @@ class DeviceSampler:
 def track_current_stream(server) -> None:
     """Tell the sync engine that kernels touching the store run on the current CUDA stream."""
     _C.track_stream(server._impl.backend_handle(), torch.cuda.current_stream().cuda_stream)
+
+
+def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+        raise TypeError(f"{name} must be a contiguous CUDA float32 tensor")
+    return t
+
+
+def kge_complex_step(server, subj: torch.Tensor, rel: torch.Tensor, obj: torch.Tensor, labels: torch.Tensor,
+                     embed_dim: int, eta: float, gamma_entity: float, gamma_relation: float, loss: torch.Tensor,
+                     stats: Optional[torch.Tensor] = None) -> None:
+    """Fused ComplEx training calls: for every i, one Model::train(s[i], r[i], o[i], label[i]) of the
+    reference (pull 3 rows, score, BCE gradient, L2 on positives, AdaGrad, push 3 rows)."""
+    _i64(subj, "subj"); _i64(rel, "rel"); _i64(obj, "obj"); _f32(labels, "labels"); _f32(loss, "loss")
+    n = subj.numel()
+    if not (rel.numel() == n and obj.numel() == n and labels.numel() == n):
+        raise ValueError("subj, rel, obj and labels must have the same length")
+    _C.kge_complex_step(server._impl.backend_handle(), _stream(subj), subj.data_ptr(), rel.data_ptr(), obj.data_ptr(),
+                        labels.data_ptr(), n, int(embed_dim), float(eta), float(gamma_entity), float(gamma_relation),
+                        loss.data_ptr(), stats.data_ptr() if stats is not None else 0)
+
+
+def mf_step(server, row_keys: torch.Tensor, col_keys: torch.Tensor, x: torch.Tensor, row_nnz: torch.Tensor,
+            col_nnz: torch.Tensor, rank: int, eps: float, lam: float, loss: torch.Tensor,
+            stats: Optional[torch.Tensor] = None) -> None:
+    """Fused matrix-factorisation SGD/AdaGrad step over a batch of non-zeros (reference apps/mf/update.h)."""
+    _i64(row_keys, "row_keys"); _i64(col_keys, "col_keys"); _f32(x, "x"); _f32(loss, "loss")
+    for t, nm in ((row_nnz, "row_nnz"), (col_nnz, "col_nnz")):
+        if not (t.is_cuda and t.dtype == torch.int32 and t.is_contiguous()):
+            raise TypeError(f"{nm} must be a contiguous CUDA int32 tensor")
+    n = row_keys.numel()
+    _C.mf_step(server._impl.backend_handle(), _stream(x), row_keys.data_ptr(), col_keys.data_ptr(), x.data_ptr(),
+               row_nnz.data_ptr(), col_nnz.data_ptr(), n, int(rank), float(eps), float(lam), loss.data_ptr(),
+               stats.data_ptr() if stats is not None else 0)
+
+
+# 1-vs-all score GEMM on the tcgen05 tensor cores (set by ops/gemm.py when the kernel is available)
+gemm_nt_bf16 = None

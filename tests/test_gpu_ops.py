@@ -166,3 +166,81 @@ def test_word2vec_training_reduces_loss(cluster1):
         model.step(data.batch(s % 3))
         losses.append(model.loss.item())
     assert losses[-1] < 0.9 * losses[0]
+
+
+@pytest.mark.parametrize("nh", [512, 128, 20])
+def test_kge_complex_step_matches_pytorch_reference(cluster1, nh):
+    """Distinct keys per call -> the fused kernel must equal the reference formula evaluated in PyTorch
+    (nh=20 exercises the generic scalar path: 20/8 is not integral)."""
+    from adapm_b200.models.kge import KGEConfig, kge_reference_step
+    from adapm_b200.ops import kge_complex_step
+    import adapm_b200 as ad
+
+    n = 48
+    cfg = KGEConfig(num_entities=2 * n + 5, num_relations=n + 3, embed_dim=nh, neg_ratio=1)
+    server, kv = cluster1(cfg.value_lengths(), cfg.num_keys)
+    dev = server.device
+    g = torch.Generator().manual_seed(nh)
+    ek = torch.arange(cfg.num_entities)
+    rk = torch.arange(cfg.num_entities, cfg.num_entities + cfg.num_relations)
+    erows = torch.cat([torch.randn(cfg.num_entities, nh, generator=g) * 0.3, torch.rand(cfg.num_entities, nh, generator=g) + 1e-3], 1)
+    rrows = torch.cat([torch.randn(cfg.num_relations, nh, generator=g) * 0.3, torch.rand(cfg.num_relations, nh, generator=g) + 1e-3], 1)
+    kv.set(ek, erows.clone().view(-1)); kv.set(rk, rrows.clone().view(-1))
+    perm = torch.randperm(cfg.num_entities, generator=g)
+    S, O = perm[:n], perm[n:2 * n]
+    R = torch.randperm(cfg.num_relations, generator=g)[:n] + cfg.num_entities
+    L = (torch.arange(n) % 3 == 0).float()
+    loss = torch.zeros(1, device=dev)
+    stats = torch.zeros(4, dtype=torch.int64, device=dev)
+    kge_complex_step(server, S.to(dev), R.to(dev), O.to(dev), L.to(dev), nh, cfg.eta, cfg.gamma_entity, cfg.gamma_relation, loss, stats)
+    torch.cuda.synchronize()
+    got_e = torch.empty(cfg.num_entities * 2 * nh); kv.pull(ek, got_e)
+    got_r = torch.empty(cfg.num_relations * 2 * nh); kv.pull(rk, got_r)
+
+    # reference: the same calls through a CPU store with the PyTorch formula
+    ref_server = ad.Server(cfg.value_lengths(), num_keys=cfg.num_keys, num_threads=1, rank=0, world=1, backend="cpu",
+                           fabric="inproc", job=f"kgeref{nh}")
+    ref_kv = ad.Worker(0, ref_server)
+    ref_kv.set(ek, erows.clone().view(-1)); ref_kv.set(rk, rrows.clone().view(-1))
+    ref_loss = kge_reference_step(ref_kv, S, R, O, L, cfg)
+    ref_e = torch.empty_like(got_e); ref_kv.pull(ek, ref_e)
+    ref_r = torch.empty_like(got_r); ref_kv.pull(rk, ref_r)
+    ref_kv.finalize(); ref_server.shutdown()
+    torch.testing.assert_close(got_e, ref_e, rtol=3e-4, atol=3e-5)
+    torch.testing.assert_close(got_r, ref_r, rtol=3e-4, atol=3e-5)
+    torch.testing.assert_close(loss.cpu()[0], torch.tensor(ref_loss), rtol=1e-3, atol=1e-3)
+    assert stats.tolist()[3] == 3 * n
+
+
+@pytest.mark.parametrize("rank", [128, 64, 10])
+def test_mf_step_matches_pytorch_reference(cluster1, rank):
+    from adapm_b200.models.mf import mf_reference_step
+    from adapm_b200.ops import mf_step
+    import adapm_b200 as ad
+
+    n, nk = 64, 300
+    server, kv = cluster1(2 * rank, nk)
+    dev = server.device
+    g = torch.Generator().manual_seed(rank)
+    keys = torch.arange(nk)
+    rows = torch.cat([torch.randn(nk, rank, generator=g) * 0.3, torch.rand(nk, rank, generator=g)], 1)
+    kv.set(keys, rows.clone().view(-1))
+    perm = torch.randperm(nk, generator=g)
+    rk, ck = perm[:n], perm[n:2 * n]
+    x = torch.randn(n, generator=g)
+    rn = torch.randint(1, 50, (n,), generator=g, dtype=torch.int32)
+    cn = torch.randint(1, 50, (n,), generator=g, dtype=torch.int32)
+    loss = torch.zeros(1, device=dev)
+    stats = torch.zeros(4, dtype=torch.int64, device=dev)
+    mf_step(server, rk.to(dev), ck.to(dev), x.to(dev), rn.to(dev), cn.to(dev), rank, 0.05, 0.02, loss, stats)
+    torch.cuda.synchronize()
+    got = torch.empty(nk * 2 * rank); kv.pull(keys, got)
+    ref_server = ad.Server(2 * rank, num_keys=nk, num_threads=1, rank=0, world=1, backend="cpu", fabric="inproc", job=f"mfref{rank}")
+    ref_kv = ad.Worker(0, ref_server)
+    ref_kv.set(keys, rows.clone().view(-1))
+    ref_loss = mf_reference_step(ref_kv, rk, ck, x, rn, cn, rank, 0.05, 0.02)
+    ref = torch.empty_like(got); ref_kv.pull(keys, ref)
+    ref_kv.finalize(); ref_server.shutdown()
+    torch.testing.assert_close(got, ref, rtol=3e-4, atol=3e-5)
+    torch.testing.assert_close(loss.cpu()[0], torch.tensor(ref_loss), rtol=1e-3, atol=1e-3)
+    assert stats.tolist()[3] == 2 * n

@@ -1,0 +1,133 @@
+"""Application models on the CPU backend (reference semantics through the public Pull/Push API):
+word2vec SGNS, KGE ComplEx/RESCAL (+ filtered ranking eval, checkpoints), MF (DSGD/columnwise/plain)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from harness import run_cluster
+
+
+def _w2v_worker(kv, server, wid):
+    from adapm_b200.models.word2vec import SyntheticPairs, Word2Vec, Word2VecConfig, zipf_counts
+
+    cfg = Word2VecConfig(vocab_size=300, embed_dim=16, negative=3, batch_pairs=256, read_ahead=2, sampling_scheme="naive")
+    counts = zipf_counts(cfg.vocab_size)
+    model = Word2Vec(server, kv, cfg, counts)
+    model.init_model()
+    data = SyntheticPairs(cfg, counts, server.my_rank())
+    losses = []
+    for s in range(12):
+        model.signal_intent(data.batch((s + cfg.read_ahead) % 3), kv.current_clock() + cfg.read_ahead)
+        losses.append(float(model.step(data.batch(s % 3))))
+        kv.advance_clock()
+    kv.barrier()
+    if wid == 0:
+        model.write_checkpoint(os.path.join(server._tmp, "vectors.bin"))
+    kv.finalize()
+    return losses
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_word2vec_cpu(tmp_path, world):
+    def setup(server):
+        server._tmp = str(tmp_path)
+
+    res = run_cluster(_w2v_worker, world=world, workers=1, mode="threads", setup_fn=setup, value_lengths=32, num_keys=600)
+    for r in res.values():
+        losses = r[0]
+        assert losses[-1] < losses[0]
+    hdr = open(tmp_path / "vectors.bin", "rb").readline()
+    assert hdr == b"300 16\n"
+    # header + per word: "w<i> " + 16 float32 + "\n"
+    assert os.path.getsize(tmp_path / "vectors.bin") > 300 * (16 * 4 + 3)
+
+
+def _kge_worker(kv, server, wid):
+    from adapm_b200.models.kge import KGE, KGEConfig, synthetic_triples
+
+    cfg = server._cfg
+    model = KGE(server, kv, cfg)
+    model.init_model()
+    tr = synthetic_triples(cfg, 600, seed=3)
+    mine = tr[server.my_rank()::server.num_servers()]
+    losses = []
+    for ep in range(25):
+        tot = 0.0
+        for s in range(0, mine.shape[0], cfg.batch_triples):
+            b = mine[s:s + cfg.batch_triples]
+            model.signal_intent(b, kv.current_clock())
+            tot += float(model.step(b))
+            kv.advance_clock()
+        losses.append(tot)
+    kv.barrier()
+    out = {"losses": losses}
+    if wid == 0:
+        out["eval"] = model.evaluate(tr[:100], tr)
+        model.save(os.path.join(server._tmp, "m."), 6, write_checkpoint=True)
+    kv.barrier()
+    kv.finalize()
+    return out
+
+
+@pytest.mark.parametrize("algo,world", [("ComplEx", 1), ("ComplEx", 2), ("RESCAL", 1)])
+def test_kge_cpu(tmp_path, algo, world):
+    from adapm_b200.models.kge import KGEConfig
+
+    cfg = KGEConfig(num_entities=60, num_relations=7, embed_dim=8, algorithm=algo, neg_ratio=2, batch_triples=100,
+                    sampling_scheme="naive", eta=0.2)
+
+    def setup(server):
+        server._cfg, server._tmp = cfg, str(tmp_path)
+
+    res = run_cluster(_kge_worker, world=world, workers=1, mode="threads", setup_fn=setup,
+                      value_lengths=cfg.value_lengths(), num_keys=cfg.num_keys)
+    for r in res.values():
+        assert r[0]["losses"][-1] < r[0]["losses"][0]
+    ev = res[0][0]["eval"]
+    assert 0 < ev["mrr"] <= 1 and ev["mrr"] >= ev["mrr_raw"] - 1e-9 and ev["n"] == 100
+    assert ev["mrr"] > 0.2, ev   # chance level is ~0.08 for 60 entities
+    e = np.fromfile(tmp_path / "m.export.epoch.6.entities.bin", dtype=np.float32)
+    assert e.size == cfg.num_entities * cfg.embed_dim
+    a = np.fromfile(tmp_path / "m.checkpoint.epoch.6.relations.adagrad.bin", dtype=np.float64)
+    assert a.size == cfg.num_relations * cfg.relation_len // 2 and (a > 0).all()
+
+
+def _mf_worker(kv, server, wid):
+    from adapm_b200.models.mf import MatrixFactorization, SparseMatrix
+
+    cfg = server._cfg
+    data = SparseMatrix.synthetic(cfg.num_rows, cfg.num_cols, 6000, 4, server.num_servers(), server.my_rank(), seed=5)
+    model = MatrixFactorization(server, kv, cfg, data)
+    model.init_model()
+    kv.barrier()
+    losses, prev = [], None
+    for ep in range(8):
+        l = model.run_epoch(ep)
+        model.bold_driver(l, prev)
+        prev = l
+        losses.append(l)
+        kv.barrier()
+    if wid == 0:
+        model.write_factors(os.path.join(server._tmp, ""))
+    kv.barrier()
+    kv.finalize()
+    return losses
+
+
+@pytest.mark.parametrize("algo,world", [("dsgd", 2), ("columnwise", 2), ("plain", 1)])
+def test_mf_cpu(tmp_path, algo, world):
+    from adapm_b200.models.mf import MFConfig
+
+    cfg = MFConfig(num_rows=80, num_cols=40, rank=8, algorithm=algo, eps=0.05, lam=0.01, batch_nnz=500, read_ahead=1)
+
+    def setup(server):
+        server._cfg, server._tmp = cfg, str(tmp_path)
+
+    res = run_cluster(_mf_worker, world=world, workers=1, mode="threads", setup_fn=setup, value_lengths=2 * cfg.rank,
+                      num_keys=cfg.num_keys(world))
+    for r in res.values():
+        assert r[0][-1] < 0.7 * r[0][0], r[0]
+    lines = open(tmp_path / "W.mma").read().splitlines()
+    assert lines[0].startswith("%%MatrixMarket matrix array") and lines[1] == "80 8" and len(lines) == 2 + 80 * 8
