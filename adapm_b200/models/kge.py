@@ -236,36 +236,47 @@ class KGE:
         sr_key = known[:, 0] * cfg.num_relations + known[:, 1]
         or_key = known[:, 2] * cfg.num_relations + known[:, 1]
         ranks_f, ranks_r = [], []
+        tc = self.cuda and use_tensor_cores and cfg.algorithm == "ComplEx"
+        if tc:
+            from ..ops import gemm_nt_rank_count
+
+            E_s = E.to(torch.bfloat16).float()   # score with the operands the tensor cores see
+        else:
+            E_s = E
+        order = torch.argsort(sr_key)
+        sr_sorted, sr_ent = sr_key[order], known[order, 2]
+        order = torch.argsort(or_key)
+        or_sorted, or_ent = or_key[order], known[order, 0]
         for i in range(0, triples.shape[0], batch):
             t = triples[i:i + batch]
             for side in (0, 1):  # 0: predict object, 1: predict subject
                 if cfg.algorithm == "ComplEx":
                     q = complex_query(E[t[:, 0]] if side == 0 else E[t[:, 2]], R[t[:, 1]], conj=(side == 1))
-                    scores = score_all(q, E, self.server if (self.cuda and use_tensor_cores) else None)
                 else:
                     Rm = R[t[:, 1]].view(-1, cfg.embed_dim, cfg.embed_dim)
                     q = torch.einsum("bi,bij->bj", E[t[:, 0]], Rm) if side == 0 else torch.einsum("bij,bj->bi", Rm, E[t[:, 2]])
-                    scores = q @ E.t()
+                if tc:
+                    q = q.to(torch.bfloat16).float()
                 true_e = t[:, 2] if side == 0 else t[:, 0]
-                true_score = scores.gather(1, true_e.view(-1, 1))
-                raw = (scores > true_score).sum(1) + 1
-                # filtering: known answers of the same query do not count
-                qkey = (t[:, 0] if side == 0 else t[:, 2]) * cfg.num_relations + t[:, 1]
-                kk, kv_e = (sr_key, known[:, 2]) if side == 0 else (or_key, known[:, 0])
-                m = qkey.view(-1, 1) == kk.view(1, -1) if kk.numel() * qkey.numel() <= (1 << 26) else None
-                if m is not None:
-                    rows, cols = m.nonzero(as_tuple=True)
-                    better = scores[rows, kv_e[cols]] > true_score[rows, 0]
-                    filt = raw - torch.zeros_like(raw).index_add_(0, rows, better.to(raw.dtype))
+                true_score = (q * E_s[true_e]).sum(1)
+                if tc:   # tcgen05 GEMM with the rank-count epilogue: the [B, ne] scores never reach HBM
+                    raw = gemm_nt_rank_count(q, E_s, true_score, true_e).long() + 1
                 else:
-                    filt = raw.clone()
-                    order = torch.argsort(kk)
-                    kks, kes = kk[order], kv_e[order]
-                    lo = torch.searchsorted(kks, qkey)
-                    hi = torch.searchsorted(kks, qkey, right=True)
-                    for b in range(t.shape[0]):
-                        ents = kes[lo[b]:hi[b]]
-                        filt[b] -= (scores[b, ents] > true_score[b, 0]).sum()
+                    scores = q @ E_s.t()
+                    scores.scatter_(1, true_e.view(-1, 1), float("-inf"))
+                    raw = (scores > true_score.view(-1, 1)).sum(1) + 1
+                # filtering: other known answers of the same query do not count
+                qkey = (t[:, 0] if side == 0 else t[:, 2]) * cfg.num_relations + t[:, 1]
+                kks, kes = (sr_sorted, sr_ent) if side == 0 else (or_sorted, or_ent)
+                lo = torch.searchsorted(kks, qkey)
+                hi = torch.searchsorted(kks, qkey, right=True)
+                cnt = hi - lo
+                rows = torch.repeat_interleave(torch.arange(t.shape[0], device=dev), cnt)
+                offs = torch.arange(rows.numel(), device=dev) - torch.repeat_interleave(torch.cumsum(cnt, 0) - cnt, cnt)
+                ents = kes[lo[rows] + offs]
+                ks = (q[rows] * E_s[ents]).sum(1)
+                better = (ks > true_score[rows]) & (ents != true_e[rows])
+                filt = raw - torch.zeros_like(raw).index_add_(0, rows, better.to(raw.dtype))
                 ranks_r.append(raw)
                 ranks_f.append(filt)
         rf = torch.cat(ranks_f).double()

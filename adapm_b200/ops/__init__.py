@@ -123,5 +123,35 @@ def mf_step(server, row_keys: torch.Tensor, col_keys: torch.Tensor, x: torch.Ten
                stats.data_ptr() if stats is not None else 0)
 
 
-# 1-vs-all score GEMM on the tcgen05 tensor cores (set by ops/gemm.py when the kernel is available)
-gemm_nt_bf16 = None
+def _bf16_k8(t: torch.Tensor) -> torch.Tensor:
+    """contiguous bf16 copy whose K (last dim) is padded to a multiple of 8 (16-byte TMA row pitch)."""
+    t = t.to(torch.bfloat16)
+    k = t.shape[1]
+    if k % 8:
+        t = torch.nn.functional.pad(t, (0, 8 - k % 8))
+    return t.contiguous()
+
+
+def gemm_nt_bf16(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """C[M,N] fp32 = a[M,K] x b[N,K]^T on the 5th-gen tensor cores (hand-written tcgen05/TMEM/TMA kernel,
+    bf16 operands, fp32 accumulation)."""
+    if not (a.is_cuda and b.is_cuda and a.dim() == 2 and b.dim() == 2 and a.shape[1] == b.shape[1]):
+        raise ValueError("gemm_nt_bf16 expects CUDA matrices a[M,K], b[N,K]")
+    a16, b16 = _bf16_k8(a), _bf16_k8(b)
+    M, N, K = a16.shape[0], b16.shape[0], a16.shape[1]
+    c = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    _C.gemm_nt_bf16(_stream(a16), a16.data_ptr(), b16.data_ptr(), M, N, K, c.data_ptr(), N)
+    return c
+
+
+def gemm_nt_rank_count(q: torch.Tensor, e: torch.Tensor, true_score: torch.Tensor, true_col: torch.Tensor) -> torch.Tensor:
+    """counts[i] = #{j != true_col[i] : <q[i], e[j]> > true_score[i]} without materialising the score matrix
+    (rank-count epilogue of the tcgen05 GEMM)."""
+    q16, e16 = _bf16_k8(q), _bf16_k8(e)
+    M, N, K = q16.shape[0], e16.shape[0], q16.shape[1]
+    ts = true_score.to(torch.float32).contiguous()
+    tc = true_col.to(torch.int32).contiguous()
+    out = torch.zeros(M, dtype=torch.int32, device=q.device)
+    _C.gemm_nt_bf16_rank_count(_stream(q16), q16.data_ptr(), e16.data_ptr(), M, N, K, ts.data_ptr(), tc.data_ptr(),
+                               out.data_ptr())
+    return out

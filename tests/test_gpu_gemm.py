@@ -1,0 +1,63 @@
+"""tcgen05/TMEM/TMA GEMM (ops_gemm_tcgen05.cu) against torch.matmul on the same bf16-rounded operands."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 128, 512), (256, 384, 512), (100, 1000, 72), (2048, 14951, 512),
+                                   (1, 7, 8), (333, 129, 200)])
+def test_gemm_nt_bf16_matches_torch(M, N, K):
+    from adapm_b200.ops import gemm_nt_bf16
+
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, device="cuda", generator=g)
+    b = torch.randn(N, K, device="cuda", generator=g)
+    c = gemm_nt_bf16(a, b)
+    torch.cuda.synchronize()
+    ref = a.to(torch.bfloat16).float() @ b.to(torch.bfloat16).float().t()
+    torch.testing.assert_close(c, ref, rtol=1e-3, atol=1e-2 * (K ** 0.5) / 8)
+
+
+def test_gemm_rank_count_epilogue():
+    from adapm_b200.ops import gemm_nt_rank_count
+
+    M, N, K = 500, 3000, 128
+    g = torch.Generator(device="cuda").manual_seed(1)
+    q = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16).float()
+    e = torch.randn(N, K, device="cuda", generator=g).to(torch.bfloat16).float()
+    tcol = torch.randint(0, N, (M,), device="cuda", generator=g)
+    ts = (q * e[tcol]).sum(1)
+    got = gemm_nt_rank_count(q, e, ts, tcol)
+    torch.cuda.synchronize()
+    scores = q @ e.t()
+    scores.scatter_(1, tcol.view(-1, 1), float("-inf"))
+    margin = (scores - ts.view(-1, 1)).abs()
+    ref = (scores > ts.view(-1, 1)).sum(1)
+    # fp32 summation order differs between the tensor cores and torch: only near-ties may flip
+    ambiguous = (margin < 1e-3).sum(1)
+    assert ((got.long() - ref).abs() <= ambiguous).all()
+    assert (got.long() == ref).float().mean() > 0.98
+
+
+def test_kge_eval_tensor_core_path_matches_fp32():
+    import adapm_b200 as ad
+    from adapm_b200.models.kge import KGE, KGEConfig, synthetic_triples
+
+    cfg = KGEConfig(num_entities=700, num_relations=11, embed_dim=64, neg_ratio=2, batch_triples=512)
+    server = ad.Server(cfg.value_lengths(), num_keys=cfg.num_keys, num_threads=1, rank=0, world=1, backend="cuda",
+                       fabric="inproc", job="kgeeval", device=0)
+    kv = ad.Worker(0, server)
+    model = KGE(server, kv, cfg)
+    model.init_model()
+    tr = synthetic_triples(cfg, 4000, seed=2)
+    for ep in range(3):
+        for s in range(0, tr.shape[0], cfg.batch_triples):
+            model.step(tr[s:s + cfg.batch_triples])
+    torch.cuda.synchronize()
+    a = model.evaluate(tr[:300], tr, use_tensor_cores=True)
+    b = model.evaluate(tr[:300], tr, use_tensor_cores=False)
+    assert abs(a["mrr"] - b["mrr"]) < 0.02 and abs(a["hits@10"] - b["hits@10"]) < 0.03, (a, b)
+    assert a["mrr"] > 0.05
+    kv.finalize()
+    server.shutdown()
