@@ -1,0 +1,59 @@
+"""CTR DeepFM application (BASELINE config #5) on the bindings-style API.
+
+    python -m adapm_b200.launch -s 8 --backend cuda -m adapm_b200.apps.ctr -- --num_features 100000000
+    python -m adapm_b200.apps.ctr --backend cpu --num_features 20000 --steps 30 --batch_size 512
+"""
+from __future__ import annotations
+
+import argparse
+import sys
+import time
+
+import adapm_b200 as ad
+from adapm_b200.apps._common import add_system_options, strip_dashes, system_options
+from adapm_b200.models.deepfm import DeepFM, DeepFMConfig, synthetic_ctr_batch
+
+
+def main(argv=None) -> int:
+    ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    ap.add_argument("--num_features", type=int, default=1_000_000)
+    ap.add_argument("--num_fields", type=int, default=26)
+    ap.add_argument("--embed_dim", type=int, default=16)
+    ap.add_argument("--batch_size", type=int, default=8192)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--read_ahead", type=int, default=4)
+    ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16", "fp8"])
+    add_system_options(ap)
+    args = ap.parse_args(strip_dashes(argv if argv is not None else sys.argv[1:]))
+    cfg = DeepFMConfig(num_features=args.num_features, num_fields=args.num_fields, embed_dim=args.embed_dim,
+                       batch_size=args.batch_size, read_ahead=args.read_ahead, precision=args.precision)
+    ad.setup(cfg.num_features, 1)
+    server = ad.Server(cfg.row_len, backend=args.backend, options=system_options(args))
+    kv = ad.Worker(0, server)
+    model = DeepFM(server, kv, cfg)
+    model.init_model()
+    rank = server.my_rank()
+    fut = [synthetic_ctr_batch(cfg, s, rank) for s in range(cfg.read_ahead)]
+    for s, (ids, _) in enumerate(fut):
+        model.signal_intent(ids, kv.current_clock() + s)
+    t0, losses = time.time(), []
+    for s in range(args.steps):
+        nxt = synthetic_ctr_batch(cfg, s + cfg.read_ahead, rank)
+        model.signal_intent(nxt[0], kv.current_clock() + cfg.read_ahead)
+        fut.append(nxt)
+        ids, y = fut.pop(0)
+        losses.append(model.step(ids, y))
+        kv.advance_clock()
+        if rank == 0 and (s + 1) % max(1, args.steps // 5) == 0:
+            print(f"[ctr] step {s + 1}: loss {sum(losses[-10:]) / len(losses[-10:]):.4f} "
+                  f"({(s + 1) * cfg.batch_size / (time.time() - t0):.0f} examples/s/rank)", flush=True)
+    kv.barrier()
+    kv.finalize()
+    if rank == 0:
+        print(server.stats(), flush=True)
+    server.shutdown()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

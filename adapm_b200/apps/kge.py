@@ -1,0 +1,112 @@
+"""Knowledge-graph-embedding application (reference apps/knowledge_graph_embeddings.cc), same flag names.
+
+    python -m adapm_b200.launch -s 2 -m adapm_b200.apps.kge -- --dataset apps/data/kge/ --num_entities 280 \\
+        --num_relations 112 --embed_dim 100 --num_epochs 12 --algorithm ComplEx --eval_freq 4
+    python -m adapm_b200.apps.kge --synthetic 100000 --embed_dim 128           (FB15k-shaped synthetic triples)
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+import time
+
+import torch
+
+import adapm_b200 as ad
+from adapm_b200.apps._common import add_system_options, strip_dashes, system_options
+from adapm_b200.models.kge import KGE, KGEConfig, load_triples, synthetic_triples
+from adapm_b200.utils.allreduce import ps_allreduce
+
+
+def main(argv=None) -> int:
+    ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    ap.add_argument("--dataset", default=None, help="directory with train.del / valid.del / test.del (s r o per line)")
+    ap.add_argument("--synthetic", type=int, default=0, help="number of synthetic training triples")
+    ap.add_argument("--algorithm", default="ComplEx", choices=["ComplEx", "RESCAL"])
+    ap.add_argument("--embed_dim", type=int, default=10)
+    ap.add_argument("--num_threads", "-t", type=int, default=1)
+    ap.add_argument("--num_epochs", type=int, default=10)
+    ap.add_argument("--eta", type=float, default=0.1)
+    ap.add_argument("--gamma_entity", type=float, default=1e-3)
+    ap.add_argument("--gamma_relation", type=float, default=1e-3)
+    ap.add_argument("--neg_ratio", type=int, default=6)
+    ap.add_argument("--eval_freq", type=int, default=-1)
+    ap.add_argument("--num_entities", type=int, default=14951)
+    ap.add_argument("--num_relations", type=int, default=1345)
+    ap.add_argument("--signal_intent_ahead", type=int, default=4, help="batches of look-ahead")
+    ap.add_argument("--signal_initial_relations_intent", type=int, default=0)
+    ap.add_argument("--batch_triples", type=int, default=4096)
+    ap.add_argument("--model_path", default="")
+    ap.add_argument("--write_end_checkpoint", type=int, default=0)
+    ap.add_argument("--write_every", type=int, default=1)
+    ap.add_argument("--eval_truncate_tr", type=int, default=2048)
+    ap.add_argument("--model_seed", type=int, default=134827)
+    ap.add_argument("--max_runtime", type=float, default=float("inf"))
+    add_system_options(ap)
+    args = ap.parse_args(strip_dashes(argv if argv is not None else sys.argv[1:]))
+
+    cfg = KGEConfig(num_entities=args.num_entities, num_relations=args.num_relations, embed_dim=args.embed_dim,
+                    algorithm=args.algorithm, neg_ratio=args.neg_ratio, eta=args.eta, gamma_entity=args.gamma_entity,
+                    gamma_relation=args.gamma_relation, batch_triples=args.batch_triples,
+                    read_ahead=args.signal_intent_ahead, sampling_scheme=getattr(args, "sampling.scheme") or "local",
+                    signal_initial_relations_intent=bool(args.signal_initial_relations_intent), model_seed=args.model_seed)
+    if args.dataset:
+        tr = load_triples(os.path.join(args.dataset, "train.del"))
+        va = load_triples(os.path.join(args.dataset, "valid.del"))
+        te = load_triples(os.path.join(args.dataset, "test.del"))
+    else:
+        n = args.synthetic or 100000
+        allt = synthetic_triples(cfg, n + 2000, seed=args.model_seed)
+        tr, va, te = allt[:n], allt[n:n + 1000], allt[n + 1000:]
+    ad.setup(cfg.num_keys, args.num_threads)
+    server = ad.Server(cfg.value_lengths(), backend=args.backend, options=system_options(args))
+    kv = ad.Worker(0, server)
+    model = KGE(server, kv, cfg)
+    model.init_model()
+    rank, world = server.my_rank(), server.num_servers()
+    mine = tr[rank::world]                      # data parallelism: each worker trains on its partition
+    known = torch.cat([tr, va, te])
+    t0 = time.time()
+    for epoch in range(1, args.num_epochs + 1):
+        perm = mine[torch.randperm(mine.shape[0], generator=torch.Generator().manual_seed(epoch * 977 + rank))]
+        starts = list(range(0, perm.shape[0], cfg.batch_triples))
+        if model.cuda:
+            model.loss.zero_()
+        bce = 0.0
+        for bi, s in enumerate(starts):
+            if bi + cfg.read_ahead < len(starts):
+                f = starts[bi + cfg.read_ahead]
+                model.signal_intent(perm[f:f + cfg.batch_triples], kv.current_clock() + cfg.read_ahead)
+            out = model.step(perm[s:s + cfg.batch_triples])
+            if not model.cuda:
+                bce += float(out)
+            kv.advance_clock()
+        if model.cuda:
+            bce = float(model.loss.item())
+        kv.barrier()
+        total = ps_allreduce(kv, cfg.loss_key, torch.tensor([bce, 0.0]))     # loss all-reduce through the PS
+        if rank == 0:
+            print(f"[kge] epoch {epoch}: bce loss {float(total[0]):.4f} ({time.time() - t0:.1f}s)", flush=True)
+        if args.eval_freq > 0 and epoch % args.eval_freq == 0:
+            if rank == 0:
+                ev = model.evaluate(va, known)
+                trn = model.evaluate(tr[: args.eval_truncate_tr], known) if args.eval_truncate_tr else None
+                print(f"[kge] epoch {epoch} valid: {ev}" + (f" train: {trn}" if trn else ""), flush=True)
+            kv.barrier()
+        if args.model_path and epoch % args.write_every == 0:
+            model.save(args.model_path, epoch, write_checkpoint=bool(args.write_end_checkpoint) and epoch == args.num_epochs)
+        if time.time() - t0 > args.max_runtime:
+            break
+    if rank == 0:
+        print(f"[kge] test: {model.evaluate(te, known)}", flush=True)
+    kv.barrier()
+    kv.finalize()
+    if rank == 0:
+        print(server.stats(), flush=True)
+    server.shutdown()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

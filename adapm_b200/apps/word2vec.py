@@ -1,0 +1,125 @@
+"""word2vec application (reference apps/word2vec.cc), flags keep the reference's names.
+
+    python -m adapm_b200.launch -s 2 -m adapm_b200.apps.word2vec -- --input_file corpus.txt --embed_dim 100 ...
+    python -m adapm_b200.apps.word2vec --synthetic_vocab 100000 --num_iterations 1     (synthetic Zipf corpus)
+"""
+from __future__ import annotations
+
+import argparse
+import sys
+import time
+
+import numpy as np
+import torch
+
+import adapm_b200 as ad
+from adapm_b200.apps._common import add_system_options, strip_dashes, system_options
+from adapm_b200.models.word2vec import SyntheticPairs, Word2Vec, Word2VecConfig, syn0_key, syn1_key, zipf_counts
+from adapm_b200.utils.text import Vocabulary, pairs_from_sentences, read_sentences
+
+
+def main(argv=None) -> int:
+    ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    ap.add_argument("--num_threads", "-t", type=int, default=1)
+    ap.add_argument("--num_iterations", "-i", type=int, default=15)
+    ap.add_argument("--input_file", "-f", default=None)
+    ap.add_argument("--output_file", "-o", default="vectors.bin")
+    ap.add_argument("--vocab_save", default=None)
+    ap.add_argument("--vocab_retrieve", default=None)
+    ap.add_argument("--window", "-w", type=int, default=5)
+    ap.add_argument("--embed_dim", "-v", type=int, default=200)
+    ap.add_argument("--negative", type=int, default=25)
+    ap.add_argument("--min_count", type=int, default=5)
+    ap.add_argument("--neg_power", type=float, default=0.75)
+    ap.add_argument("--starting_alpha", type=float, default=0.025)
+    ap.add_argument("--subsample", type=float, default=1e-4)
+    ap.add_argument("--read_sentences_ahead", type=int, default=4, help="batches of look-ahead for intent signalling")
+    ap.add_argument("--signal_intent", type=int, default=1)
+    ap.add_argument("--write_results", type=int, default=0)
+    ap.add_argument("--binary", type=int, default=1)
+    ap.add_argument("--model_seed", type=int, default=134827)
+    ap.add_argument("--max_runtime", type=float, default=float("inf"))
+    ap.add_argument("--batch_pairs", type=int, default=32768)
+    ap.add_argument("--synthetic_vocab", type=int, default=0, help="train on a synthetic Zipf corpus of this vocabulary size")
+    ap.add_argument("--synthetic_batches", type=int, default=50)
+    add_system_options(ap)
+    args = ap.parse_args(strip_dashes(argv if argv is not None else sys.argv[1:]))
+
+    rng = np.random.default_rng(args.model_seed)
+    words = None
+    if args.input_file:
+        vocab = Vocabulary.load(args.vocab_retrieve) if args.vocab_retrieve else Vocabulary.build(args.input_file, args.min_count)
+        if args.vocab_save:
+            vocab.save(args.vocab_save)
+        counts, words = vocab.counts.astype(np.float64), vocab.words
+        V = len(words)
+    else:
+        V = args.synthetic_vocab or 100000
+        counts = zipf_counts(V)
+    cfg = Word2VecConfig(vocab_size=V, embed_dim=args.embed_dim, negative=args.negative, window=args.window,
+                         starting_alpha=args.starting_alpha, neg_power=args.neg_power, batch_pairs=args.batch_pairs,
+                         read_ahead=args.read_sentences_ahead, signal_intent=bool(args.signal_intent),
+                         sampling_scheme=getattr(args, "sampling.scheme") or "local", model_seed=args.model_seed)
+    ad.setup(cfg.num_keys, args.num_threads)
+    server = ad.Server(cfg.row_len, backend=args.backend, options=system_options(args))
+    kv = ad.Worker(0, server)
+    model = Word2Vec(server, kv, cfg, counts)
+    model.init_model()
+    rank, world = server.my_rank(), server.num_servers()
+
+    def batches(epoch):
+        if args.input_file:
+            sents = read_sentences(args.input_file, vocab, rank, world, args.subsample, rng)
+            yield from pairs_from_sentences(sents, args.window, cfg.batch_pairs, rng)
+        else:
+            data = SyntheticPairs(cfg, counts, rank, seed=epoch + 1)
+            for s in range(args.synthetic_batches):
+                yield data.batch(s)
+
+    t0 = time.time()
+    total_pairs, est_total = 0, None
+    for epoch in range(args.num_iterations):
+        it = batches(epoch)
+        window = []
+        for b in it:
+            window.append(b)
+            if len(window) <= cfg.read_ahead:
+                model.signal_intent(b, kv.current_clock() + len(window) - 1)
+                continue
+            model.signal_intent(b, kv.current_clock() + cfg.read_ahead)
+            cur = window.pop(0)
+            if model.cuda:
+                model.loss.zero_()
+            loss = model.step(cur if cur.shape[1] == cfg.batch_pairs or not model.cuda else _pad(cur, cfg.batch_pairs))
+            kv.advance_clock()
+            total_pairs += cur.shape[1]
+            if time.time() - t0 > args.max_runtime:
+                break
+        for cur in window:
+            if model.cuda:
+                model.loss.zero_()
+            loss = model.step(cur if cur.shape[1] == cfg.batch_pairs or not model.cuda else _pad(cur, cfg.batch_pairs))
+            kv.advance_clock()
+            total_pairs += cur.shape[1]
+        model.set_alpha((epoch + 1) / args.num_iterations)
+        kv.barrier()
+        if rank == 0:
+            print(f"[w2v] epoch {epoch} done: {total_pairs} pairs on rank 0, {time.time() - t0:.1f}s, "
+                  f"last batch loss {float(loss) / max(1, cfg.batch_pairs * (cfg.negative + 1)):.4f}", flush=True)
+        if args.write_results:
+            model.write_checkpoint(f"{args.output_file}.epoch.{epoch}", words)
+    kv.finalize()
+    if rank == 0:
+        print(server.stats(), flush=True)
+    server.shutdown()
+    return 0
+
+
+def _pad(b: torch.Tensor, n: int) -> torch.Tensor:
+    """pad a short final batch by repeating pairs (the fused kernel works on fixed-size batches)."""
+    reps = (n + b.shape[1] - 1) // b.shape[1]
+    return b.repeat(1, reps)[:, :n].contiguous()
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -28,6 +28,7 @@ void mf_step(CudaBackend& be, cudaStream_t stream, const Key* row_keys, const Ke
 
 // tcgen05/TMEM/TMA GEMM: C[M,N] fp32 = A[M,K] bf16 x B[N,K]^T bf16 (ops_gemm_tcgen05.cu)
 void gemm_nt_bf16(cudaStream_t stream, const void* A, const void* B, int M, int N, int K, float* C, int ldc);
+void gemm_nt_e4m3(cudaStream_t stream, const void* A, const void* B, int M, int N, int K, float* C, int ldc, float alpha);
 // same GEMM with the ranking epilogue: rank_out[row] += #{col != true_col[row] : score > true_score[row]}
 void gemm_nt_bf16_rank_count(cudaStream_t stream, const void* A, const void* B, int M, int N, int K,
                              const float* true_score, const int* true_col, int* rank_out);

@@ -46,6 +46,9 @@ void bind(py::module_& m) {
   m.def("gemm_nt_bf16", [](uintptr_t stream, uintptr_t A, uintptr_t B, int M, int N, int K, uintptr_t C, int ldc) {
     gemm_nt_bf16((cudaStream_t)stream, ptr<const void>(A), ptr<const void>(B), M, N, K, ptr<float>(C), ldc);
   });
+  m.def("gemm_nt_e4m3", [](uintptr_t stream, uintptr_t A, uintptr_t B, int M, int N, int K, uintptr_t C, int ldc, float alpha) {
+    gemm_nt_e4m3((cudaStream_t)stream, ptr<const void>(A), ptr<const void>(B), M, N, K, ptr<float>(C), ldc, alpha);
+  });
   m.def("gemm_nt_bf16_rank_count", [](uintptr_t stream, uintptr_t A, uintptr_t B, int M, int N, int K, uintptr_t ts,
                                       uintptr_t tc, uintptr_t rank) {
     gemm_nt_bf16_rank_count((cudaStream_t)stream, ptr<const void>(A), ptr<const void>(B), M, N, K, ptr<const float>(ts),

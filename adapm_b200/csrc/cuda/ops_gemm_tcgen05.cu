@@ -28,11 +28,13 @@ namespace cudaops {
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64;   // BK * 2 B = 128 B = one swizzle-128B row
-constexpr int UMMA_K = 16;
+constexpr int BM = 128, BN = 128;
+constexpr int ROW_BYTES = 128;                // one K-block row = 128 B = one swizzle-128B row
+constexpr int MMA_K_BYTES = 32;               // one tcgen05.mma consumes 32 B of K per row (16 bf16 / 32 fp8)
 constexpr int STAGES = 6;
-constexpr int A_BYTES = BM * BK * 2;          // 16 KiB
-constexpr int B_BYTES = BN * BK * 2;          // 16 KiB
+constexpr int A_BYTES = BM * ROW_BYTES;       // 16 KiB
+constexpr int B_BYTES = BN * ROW_BYTES;       // 16 KiB
+enum Kind : int { KIND_BF16 = 0, KIND_E4M3 = 1 };
 constexpr int kGemmThreads = 256;
 constexpr int TMEM_COLS = 128;                // fp32 accumulator: one column per output column
 
@@ -79,16 +81,27 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                              // layout type: SWIZZLE_128B
   return d;
 }
-// instruction descriptor for kind::f16: D = fp32, A = B = bf16, both K-major, M x N tile
-__device__ __forceinline__ constexpr uint32_t umma_idesc(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// instruction descriptor: D = fp32, both operands K-major, M x N tile.
+//   kind::f16     a/b format 1 = bf16        kind::f8f6f4  a/b format 0 = e4m3
+__device__ __forceinline__ constexpr uint32_t umma_idesc(int kind, int m, int n) {
+  return (1u << 4) | ((kind == KIND_BF16 ? 1u : 0u) << 7) | ((kind == KIND_BF16 ? 1u : 0u) << 10) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+template <int KIND>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (KIND == KIND_BF16) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  }
 }
 __device__ __forceinline__ void umma_commit(unsigned long long* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -107,11 +120,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 
 enum Epilogue : int { EPI_STORE = 0, EPI_RANK_COUNT = 1 };
 
-template <int EPI>
+template <int EPI, int KIND>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_nt_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M,
-                       int N, int K, float* __restrict__ C, int ldc, const float* __restrict__ true_score,
+                       int N, int K, float* __restrict__ C, int ldc, float alpha, const float* __restrict__ true_score,
                        const int* __restrict__ true_col, int* __restrict__ rank_out) {
+  constexpr int BK = KIND == KIND_BF16 ? 64 : 128;   // elements per 128-byte K-block row
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   SmemLayout& sm = *reinterpret_cast<SmemLayout*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5;
@@ -153,7 +167,7 @@ gemm_nt_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   } else if (warp == 1) {
     // ===================== MMA issuer (single thread) =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(BM, BN);
+      constexpr uint32_t idesc = umma_idesc(KIND, BM, BN);
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
@@ -162,10 +176,10 @@ gemm_nt_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         const uint32_t a_addr = smem_u32(sm.a[s]);
         const uint32_t b_addr = smem_u32(sm.b[s]);
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          const uint64_t ad = umma_desc(a_addr + k * UMMA_K * 2);
-          const uint64_t bd = umma_desc(b_addr + k * UMMA_K * 2);
-          umma_f16(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+        for (int k = 0; k < ROW_BYTES / MMA_K_BYTES; ++k) {
+          const uint64_t ad = umma_desc(a_addr + k * MMA_K_BYTES);
+          const uint64_t bd = umma_desc(b_addr + k * MMA_K_BYTES);
+          umma<KIND>(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
         }
         umma_commit(&sm.empty_bar[s]);  // frees this smem stage once the MMAs above retire
       }
@@ -192,12 +206,13 @@ gemm_nt_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
           if (col0 + 32 <= N && (((uintptr_t)dst) & 15u) == 0) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                               __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+              *reinterpret_cast<float4*>(dst + j) =
+                  make_float4(alpha * __uint_as_float(r[j]), alpha * __uint_as_float(r[j + 1]),
+                              alpha * __uint_as_float(r[j + 2]), alpha * __uint_as_float(r[j + 3]));
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (col0 + j < N) dst[j] = __uint_as_float(r[j]);
+              if (col0 + j < N) dst[j] = alpha * __uint_as_float(r[j]);
           }
         }
       } else {
@@ -235,35 +250,39 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// row-major [rows, cols] bf16 matrix, box = [box_rows, 64 cols], 128-byte swizzle
-CUtensorMap make_map(const void* base, int64_t rows, int64_t cols, int box_rows) {
+// row-major [rows, cols] matrix of 2-byte (bf16) or 1-byte (e4m3) elements,
+// box = [box_rows, 128 bytes of K], 128-byte swizzle
+CUtensorMap make_map(const void* base, int64_t rows, int64_t cols, int box_rows, int kind) {
   CUtensorMap m;
+  const int esz = kind == KIND_BF16 ? 2 : 1;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * esz};
+  cuuint32_t box[2] = {(cuuint32_t)(ROW_BYTES / esz), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = encode_fn()(&m, kind == KIND_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2,
+                           const_cast<void*>(base), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   ADAPM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " << (int)r);
   return m;
 }
 
-template <int EPI>
-void launch(cudaStream_t stream, const void* A, const void* B, int M, int N, int K, float* C, int ldc,
+template <int EPI, int KIND>
+void launch(cudaStream_t stream, const void* A, const void* B, int M, int N, int K, float* C, int ldc, float alpha,
             const float* true_score, const int* true_col, int* rank_out) {
-  ADAPM_CHECK(K % 8 == 0, "gemm_nt_bf16: K must be a multiple of 8 (16-byte TMA row pitch)");
-  ADAPM_CHECK((((uintptr_t)A) & 15u) == 0 && (((uintptr_t)B) & 15u) == 0, "gemm_nt_bf16: operands must be 16-byte aligned");
-  CUtensorMap ma = make_map(A, M, K, BM);
-  CUtensorMap mb = make_map(B, N, K, BN);
+  ADAPM_CHECK((K * (KIND == KIND_BF16 ? 2 : 1)) % 16 == 0, "gemm_nt: the K extent must be a multiple of 16 bytes (TMA row pitch)");
+  ADAPM_CHECK((((uintptr_t)A) & 15u) == 0 && (((uintptr_t)B) & 15u) == 0, "gemm_nt: operands must be 16-byte aligned");
+  CUtensorMap ma = make_map(A, M, K, BM, KIND);
+  CUtensorMap mb = make_map(B, N, K, BN, KIND);
   const size_t smem = sizeof(SmemLayout) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    ADAPM_CUDA_CHECK(cudaFuncSetAttribute(gemm_nt_tcgen05_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ADAPM_CUDA_CHECK(cudaFuncSetAttribute(gemm_nt_tcgen05_kernel<EPI, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
-  gemm_nt_tcgen05_kernel<EPI><<<grid, kGemmThreads, smem, stream>>>(ma, mb, M, N, K, C, ldc, true_score, true_col, rank_out);
+  gemm_nt_tcgen05_kernel<EPI, KIND><<<grid, kGemmThreads, smem, stream>>>(ma, mb, M, N, K, C, ldc, alpha, true_score,
+                                                                          true_col, rank_out);
   ADAPM_COUNT_LAUNCH();
   ADAPM_CUDA_CHECK(cudaGetLastError());
 }
@@ -272,13 +291,19 @@ void launch(cudaStream_t stream, const void* A, const void* B, int M, int N, int
 
 void gemm_nt_bf16(cudaStream_t stream, const void* A, const void* B, int M, int N, int K, float* C, int ldc) {
   if (M == 0 || N == 0) return;
-  launch<EPI_STORE>(stream, A, B, M, N, K, C, ldc, nullptr, nullptr, nullptr);
+  launch<EPI_STORE, KIND_BF16>(stream, A, B, M, N, K, C, ldc, 1.f, nullptr, nullptr, nullptr);
+}
+
+// fp8 (e4m3) operands, fp32 accumulation, C = alpha * A B^T  (alpha = product of the per-tensor scales)
+void gemm_nt_e4m3(cudaStream_t stream, const void* A, const void* B, int M, int N, int K, float* C, int ldc, float alpha) {
+  if (M == 0 || N == 0) return;
+  launch<EPI_STORE, KIND_E4M3>(stream, A, B, M, N, K, C, ldc, alpha, nullptr, nullptr, nullptr);
 }
 
 void gemm_nt_bf16_rank_count(cudaStream_t stream, const void* A, const void* B, int M, int N, int K,
                              const float* true_score, const int* true_col, int* rank_out) {
   if (M == 0 || N == 0) return;
-  launch<EPI_RANK_COUNT>(stream, A, B, M, N, K, nullptr, 0, true_score, true_col, rank_out);
+  launch<EPI_RANK_COUNT, KIND_BF16>(stream, A, B, M, N, K, nullptr, 0, 1.f, true_score, true_col, rank_out);
 }
 
 }  // namespace cudaops

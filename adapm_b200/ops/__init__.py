@@ -144,6 +144,25 @@ def gemm_nt_bf16(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return c
 
 
+def gemm_nt_fp8(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """C = a @ b^T with e4m3 operands on the fp8 tensor-core path (tcgen05.mma kind::f8f6f4), per-tensor scales
+    chosen from the absolute maxima, fp32 accumulation; the scale product is applied in the epilogue."""
+    if not (a.is_cuda and b.is_cuda and a.shape[1] == b.shape[1]):
+        raise ValueError("gemm_nt_fp8 expects CUDA matrices a[M,K], b[N,K]")
+    k = a.shape[1]
+    if k % 16:
+        pad = 16 - k % 16
+        a = torch.nn.functional.pad(a, (0, pad)); b = torch.nn.functional.pad(b, (0, pad))
+    sa = a.detach().abs().amax().clamp(min=1e-12) / 448.0
+    sb = b.detach().abs().amax().clamp(min=1e-12) / 448.0
+    a8 = (a / sa).to(torch.float8_e4m3fn).contiguous()
+    b8 = (b / sb).to(torch.float8_e4m3fn).contiguous()
+    M, N, K = a8.shape[0], b8.shape[0], a8.shape[1]
+    c = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    _C.gemm_nt_e4m3(_stream(a8), a8.data_ptr(), b8.data_ptr(), M, N, K, c.data_ptr(), N, float(sa * sb))
+    return c
+
+
 def gemm_nt_rank_count(q: torch.Tensor, e: torch.Tensor, true_score: torch.Tensor, true_col: torch.Tensor) -> torch.Tensor:
     """counts[i] = #{j != true_col[i] : <q[i], e[j]> > true_score[i]} without materialising the score matrix
     (rank-count epilogue of the tcgen05 GEMM)."""

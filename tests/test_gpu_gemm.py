@@ -61,3 +61,43 @@ def test_kge_eval_tensor_core_path_matches_fp32():
     assert a["mrr"] > 0.05
     kv.finalize()
     server.shutdown()
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 128), (300, 500, 416), (64, 1000, 80)])
+def test_gemm_nt_fp8_matches_torch(M, N, K):
+    """e4m3 operands on the kind::f8f6f4 tensor-core path vs the same quantised operands multiplied in fp32."""
+    from adapm_b200.ops import gemm_nt_fp8
+
+    g = torch.Generator(device="cuda").manual_seed(K)
+    a = torch.randn(M, K, device="cuda", generator=g)
+    b = torch.randn(N, K, device="cuda", generator=g)
+    c = gemm_nt_fp8(a, b)
+    torch.cuda.synchronize()
+    sa, sb = a.abs().amax() / 448.0, b.abs().amax() / 448.0
+    aq = (a / sa).to(torch.float8_e4m3fn).float() * sa
+    bq = (b / sb).to(torch.float8_e4m3fn).float() * sb
+    torch.testing.assert_close(c, aq @ bq.t(), rtol=2e-3, atol=2e-3 * (K ** 0.5))
+    # and it is a sane approximation of the fp32 product
+    rel = (c - a @ b.t()).norm() / (a @ b.t()).norm()
+    assert rel < 0.08
+
+
+def test_deepfm_trains_on_gpu_with_tensor_core_mlp():
+    import adapm_b200 as ad
+    from adapm_b200.models.deepfm import DeepFM, DeepFMConfig, synthetic_ctr_batch
+
+    for precision in ("bf16", "fp8"):
+        cfg = DeepFMConfig(num_features=26 * 2000, num_fields=26, embed_dim=16, hidden=(128, 128), batch_size=1024,
+                           precision=precision)
+        server = ad.Server(cfg.row_len, num_keys=cfg.num_features, num_threads=1, rank=0, world=1, backend="cuda",
+                           fabric="inproc", job=f"dfm{precision}", device=0)
+        kv = ad.Worker(0, server)
+        model = DeepFM(server, kv, cfg)
+        model.init_model()
+        losses = []
+        for s in range(60):
+            ids, y = synthetic_ctr_batch(cfg, s % 8)
+            losses.append(model.step(ids, y))
+        kv.finalize()
+        server.shutdown()
+        assert sum(losses[-10:]) < sum(losses[:10]), (precision, losses[:3], losses[-3:])
