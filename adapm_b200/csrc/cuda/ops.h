@@ -8,8 +8,11 @@ namespace adapm {
 namespace cudaops {
 
 // word2vec SGNS: fused pull + score + AdaGrad + push   (ops_sgns.cu)
+// impl: 0 = auto, 1 = LDG variant (ops_sgns.cu), 2 = TMA-prefetch variant (ops_sgns_tma.cu)
 void sgns_step(CudaBackend& be, cudaStream_t stream, const Key* centers, const Key* contexts, const Key* negatives,
-               int n_pairs, int neg, int d, float alpha, float* loss_out, unsigned long long* stats);
+               int n_pairs, int neg, int d, float alpha, float* loss_out, unsigned long long* stats, int impl = 0);
+bool sgns_step_tma(CudaBackend& be, cudaStream_t stream, const Key* centers, const Key* contexts, const Key* negatives,
+                   int n_pairs, int neg, int d, float alpha, float* loss_out, unsigned long long* stats);
 
 // key sampling (ops_sampler.cu). kind: 0 alias table, 1 uniform, 2 log-uniform
 void sample_keys(CudaBackend& be, cudaStream_t stream, int kind, const float* prob, const int32_t* alias,

@@ -21,9 +21,9 @@ CudaBackend& backend_of(uintptr_t handle) {
 
 void bind(py::module_& m) {
   m.def("sgns_step", [](uintptr_t be, uintptr_t stream, uintptr_t centers, uintptr_t contexts, uintptr_t negatives,
-                        int n_pairs, int neg, int d, float alpha, uintptr_t loss, uintptr_t stats) {
+                        int n_pairs, int neg, int d, float alpha, uintptr_t loss, uintptr_t stats, int impl) {
     sgns_step(backend_of(be), (cudaStream_t)stream, ptr<const Key>(centers), ptr<const Key>(contexts),
-              ptr<const Key>(negatives), n_pairs, neg, d, alpha, ptr<float>(loss), ptr<unsigned long long>(stats));
+              ptr<const Key>(negatives), n_pairs, neg, d, alpha, ptr<float>(loss), ptr<unsigned long long>(stats), impl);
   });
   m.def("sample_keys", [](uintptr_t be, uintptr_t stream, int kind, uintptr_t prob, uintptr_t alias, int64_t n_table,
                           Key first, Key stride, uintptr_t out, int64_t n, uint64_t seed, bool local_only, int max_tries,

@@ -298,13 +298,16 @@ sgns_step_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ centers,
 // keys are int64 device pointers; negatives has n_pairs*neg entries. loss_out (1 float) and
 // stats (4 x u64: local rows, remote rows, slow-path rows, updates applied) are accumulated.
 void sgns_step(CudaBackend& be, cudaStream_t stream, const Key* centers, const Key* contexts, const Key* negatives,
-               int n_pairs, int neg, int d, float alpha, float* loss_out, unsigned long long* stats) {
+               int n_pairs, int neg, int d, float alpha, float* loss_out, unsigned long long* stats, int impl) {
   const Ctx& c = be.ctx();
   ADAPM_CHECK(c.L.num_classes == 1 && (int)c.L.cls[0].len == 2 * d, "sgns_step: store rows must be 2*embed_dim floats");
   ADAPM_CHECK(d % 4 == 0 && d <= 512, "sgns_step: embed_dim must be a multiple of 4 and <= 512");
   ADAPM_CHECK(neg >= 0, "sgns_step: negative must be >= 0");
   if (n_pairs == 0) return;
   be.track_stream(stream);
+  static const int env_impl = [] { const char* e = getenv("ADAPM_SGNS_IMPL"); return e ? (e[0] == 't' ? 2 : 1) : 0; }();
+  if (impl == 0) impl = env_impl ? env_impl : 2;
+  if (impl == 2 && sgns_step_tma(be, stream, centers, contexts, negatives, n_pairs, neg, d, alpha, loss_out, stats)) return;
   const int vpl = (d / 4 + 31) / 32;
   const int warps_per_block = kThreads / 32;
   int blocks = std::min((n_pairs + warps_per_block - 1) / warps_per_block, be.num_sms() * 8);

@@ -1,0 +1,373 @@
+// SGNS step, TMA-prefetch variant (sm_100a): same semantics as ops_sgns.cu, but the target rows of a
+// pair stream through a per-warp shared-memory ring that is filled by the TMA engine
+// (cp.async.bulk global -> shared, completion on an mbarrier) several targets ahead of the math.
+//
+// Why: the LDG variant keeps one target (2 x 1200 B per warp) in flight per warp and is register
+// limited to 16 warps/SM -> ~48 KB in flight per SM, latency bound (ncu: DRAM 42 %, L2 49 %).
+// Here rows never occupy registers while in flight: 16 warps/SM x RING (4) rows x 2400 B = 150 KB per SM.
+//   lane 0      : mbarrier.arrive.expect_tx + cp.async.bulk (UBLKCP) for target t + RING
+//   whole warp  : mbarrier.try_wait, LDS.128 the row from shared memory, dot / sigmoid / AdaGrad,
+//                 RED.128 the update to the row's home (local HBM or NVLink peer)
+// Rows that live on a peer GPU are staged with ordinary 16-byte loads into the same ring slot;
+// rows in a transitional protocol state take the generic out-of-line path.
+#include <cuda_runtime.h>
+
+#include <cstdlib>
+
+#include "ops.h"
+#include "pm_kernels.cuh"
+
+namespace adapm {
+namespace cudaops {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int RING = 4;
+constexpr float kMaxExp = 6.0f;
+
+using dev::Target;
+using dev::warp_sum;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  } while (!ok);
+}
+// 1-D bulk copy global -> shared through the TMA engine; completes `bytes` on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+struct WarpSmem {
+  unsigned long long bar[RING];
+};
+
+// out-of-line generic target (transitional protocol states), same as in ops_sgns.cu
+__device__ __noinline__ float slow_target_tma(const Ctx& c, Key tkey, float label, float alpha, int d, float* stage,
+                                              const float* e0s, float* g0s, bool* applied) {
+  WarpGroup g;
+  const int lane = threadIdx.x & 31;
+  *applied = false;
+  if (!pull_key<float>(c, g, tkey, stage, false, nullptr)) return 0.f;
+  __syncwarp();
+  float f = 0.f;
+  for (int j = lane; j < d; j += 32) f += e0s[j] * stage[j];
+  f = warp_sum(f);
+  float gs;
+  if (f > kMaxExp) gs = label - 1.f;
+  else if (f < -kMaxExp) gs = label;
+  else gs = label - 1.f / (1.f + __expf(-f));
+  for (int j = lane; j < d; j += 32) {
+    float e1 = stage[j], a1 = stage[d + j];
+    g0s[j] += gs * e1;
+    float gr = gs * e0s[j];
+    float ua = gr * gr;
+    stage[j] = alpha * gr * rsqrtf(a1 + ua);
+    stage[d + j] = ua;
+  }
+  __syncwarp();
+  *applied = push_key<float>(c, g, tkey, stage, nullptr);
+  __syncwarp();
+  float z = label > 0.5f ? f : -f;
+  z = fminf(fmaxf(z, -kMaxExp), kMaxExp);
+  return __logf(1.f + __expf(-z));
+}
+
+// VPL = float4 per lane over d floats
+template <int VPL>
+__global__ void __launch_bounds__(kThreads, 2)
+sgns_step_tma_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ centers, const Key* __restrict__ contexts,
+                     const Key* __restrict__ negatives, int n_pairs, int neg, int d, float alpha,
+                     float* __restrict__ loss_out, unsigned long long* __restrict__ stats) {
+  // per warp: RING row buffers of 2*d floats (16-byte aligned) | generic-path scratch is carved from the ring
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ WarpSmem wsm[kWarps];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int nvec = d >> 2;
+  const uint32_t row_bytes = (uint32_t)(2 * d * sizeof(float));
+  const size_t buf_floats = ((size_t)2 * d + 31) & ~(size_t)31;  // keep every ring slot 128-byte aligned
+  float* ring = reinterpret_cast<float*>(smem_raw) + (size_t)wib * (RING + 1) * buf_floats;
+  float* scratch = ring + (size_t)RING * buf_floats;             // e0s | g0s for the generic path (2*d floats)
+  unsigned long long* bars = wsm[wib].bar;
+  if (lane == 0) {
+    for (int r = 0; r < RING; ++r) mbar_init(&bars[r], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
+  uint32_t issued = 0, consumed = 0;   // ring counters (buffer = n % RING, phase parity = (n / RING) & 1)
+  float loss_acc = 0.f;
+  unsigned n_local = 0, n_remote = 0, n_slow = 0, n_upd = 0;
+  const int n_targets = neg + 1;
+
+  for (int p = warp; p < n_pairs; p += nwarps) {
+    const Key ckey = centers[p];
+    const Key pos_key = contexts[p];
+    // ---- resolve center (lane 0) + up to 31 targets (lanes 1..31) with one dependent-load chain
+    Key my_key = -1;
+    Target my_t;
+    my_t.row = nullptr; my_t.version = nullptr; my_t.flag = nullptr;
+    int my_remote = 0;
+    if (lane == 0) my_key = ckey;
+    else if (lane - 1 < n_targets) my_key = (lane == 1) ? pos_key : negatives[(size_t)p * neg + (lane - 2)];
+    if (my_key >= 0) {
+      unsigned r0 = n_remote;
+      my_t = dev::resolve_fast(c, my_key, 0, &n_local, &n_remote);
+      my_remote = (n_remote != r0) ? 1 : 0;
+    }
+    // target t (0-based) -> lane t+1 (only pairs with <= 31 targets use this kernel)
+    auto issue = [&](int t) {
+      const int b = issued % RING;
+      float* buf = ring + (size_t)b * buf_floats;
+      const Key tkey = (Key)__shfl_sync(0xffffffffu, (unsigned long long)my_key, t + 1);
+      float* row = (float*)__shfl_sync(0xffffffffu, (unsigned long long)my_t.row, t + 1);
+      const int remote = __shfl_sync(0xffffffffu, my_remote, t + 1);
+      const bool skip = (t > 0 && tkey == pos_key) || row == nullptr;
+      if (skip) {
+        if (lane == 0) mbar_arrive(&bars[b]);            // nothing to load: complete the phase
+      } else if (!remote) {
+        if (lane == 0) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // order earlier LDS of this slot before the TMA write
+          mbar_expect_tx(&bars[b], row_bytes);
+          bulk_g2s(buf, row, row_bytes, &bars[b]);
+        }
+      } else {
+        // NVLink peer row: stage with 16-byte loads (the copy engine path is kept for local HBM)
+        for (int j = lane; j < 2 * nvec; j += 32) reinterpret_cast<float4*>(buf)[j] = dev::ld_row4(row + 4 * j);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[b]);
+      }
+      ++issued;
+    };
+
+    // ---- center row (registers)
+    float* c_row = (float*)__shfl_sync(0xffffffffu, (unsigned long long)my_t.row, 0);
+    const bool c_slow = (c_row == nullptr);
+    float4 e0[VPL], g0[VPL];
+    // prefetch the first RING targets before touching the center row
+    const int pre = n_targets < RING ? n_targets : RING;
+    for (int t = 0; t < pre; ++t) issue(t);
+    if (c_slow) {
+      ++n_slow;
+      if (!dev::slow_pull(c, ckey, scratch)) {
+        // drain the ring so that the barrier phases stay in step, then skip the pair
+        for (int t = 0; t < pre; ++t) { mbar_wait(&bars[consumed % RING], (consumed / RING) & 1u); ++consumed; }
+        for (int t = pre; t < n_targets; ++t) { issue(t); mbar_wait(&bars[consumed % RING], (consumed / RING) & 1u); ++consumed; }
+        continue;
+      }
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        int j = lane + v * 32;
+        e0[v] = j < nvec ? reinterpret_cast<float4*>(scratch)[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      __syncwarp();
+    } else {
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        int j = lane + v * 32;
+        e0[v] = j < nvec ? dev::ld_row4(c_row + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) g0[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool have_slow = false;
+
+    // ---- targets
+    for (int t = 0; t < n_targets; ++t) {
+      const int b = consumed % RING;
+      float* buf = ring + (size_t)b * buf_floats;
+      const Key tkey = (Key)__shfl_sync(0xffffffffu, (unsigned long long)my_key, t + 1);
+      float* t_row = (float*)__shfl_sync(0xffffffffu, (unsigned long long)my_t.row, t + 1);
+      mbar_wait(&bars[b], (consumed / RING) & 1u);
+      ++consumed;
+      const float label = (t == 0) ? 1.f : 0.f;
+      const bool dup = (t > 0 && tkey == pos_key);  // reference: negative == positive target is skipped
+      if (!dup && t_row == nullptr) {
+        ++n_slow;
+        float* e0s = scratch; float* g0s = scratch + d;
+        if (!have_slow) {
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) {
+            int j = lane + v * 32;
+            if (j < nvec) {
+              reinterpret_cast<float4*>(e0s)[j] = e0[v];
+              reinterpret_cast<float4*>(g0s)[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+          __syncwarp();
+          have_slow = true;
+        }
+        bool applied;
+        loss_acc += slow_target_tma(c, tkey, label, alpha, d, buf, e0s, g0s, &applied);  // ring slot b is free: use it as stage
+        if (applied) ++n_upd;
+      } else if (!dup) {
+        float4 e1[VPL];
+        float f = 0.f;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+          int j = lane + v * 32;
+          e1[v] = j < nvec ? reinterpret_cast<const float4*>(buf)[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+          f += e0[v].x * e1[v].x + e0[v].y * e1[v].y + e0[v].z * e1[v].z + e0[v].w * e1[v].w;
+        }
+        f = warp_sum(f);
+        float gs;
+        if (f > kMaxExp) gs = label - 1.f;
+        else if (f < -kMaxExp) gs = label;
+        else gs = label - 1.f / (1.f + __expf(-f));
+        {
+          float z = label > 0.5f ? f : -f;
+          z = fminf(fmaxf(z, -kMaxExp), kMaxExp);
+          loss_acc += __logf(1.f + __expf(-z));
+        }
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+          int j = lane + v * 32;
+          if (j < nvec) {
+            float4 a1 = reinterpret_cast<const float4*>(buf + d)[j];
+            g0[v].x += gs * e1[v].x; g0[v].y += gs * e1[v].y; g0[v].z += gs * e1[v].z; g0[v].w += gs * e1[v].w;
+            float4 gr = make_float4(gs * e0[v].x, gs * e0[v].y, gs * e0[v].z, gs * e0[v].w);
+            float4 ua = make_float4(gr.x * gr.x, gr.y * gr.y, gr.z * gr.z, gr.w * gr.w);
+            float4 ue;
+            ue.x = alpha * gr.x * rsqrtf(a1.x + ua.x);
+            ue.y = alpha * gr.y * rsqrtf(a1.y + ua.y);
+            ue.z = alpha * gr.z * rsqrtf(a1.z + ua.z);
+            ue.w = alpha * gr.w * rsqrtf(a1.w + ua.w);
+            dev::red_row4(t_row + 4 * j, ue);
+            dev::red_row4(t_row + d + 4 * j, ua);
+          }
+        }
+        if (lane == t + 1) dev::mark_pushed(my_t);
+        ++n_upd;
+      }
+      __syncwarp();                       // all lanes are done reading ring slot b
+      if (t + RING < n_targets) issue(t + RING);
+    }
+
+    // ---- center update
+    if (have_slow) {
+      const float* g0s = scratch + d;
+      __syncwarp();
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        int j = lane + v * 32;
+        if (j < nvec) {
+          float4 q = reinterpret_cast<const float4*>(g0s)[j];
+          g0[v].x += q.x; g0[v].y += q.y; g0[v].z += q.z; g0[v].w += q.w;
+        }
+      }
+      __syncwarp();
+    }
+    if (c_slow) {
+      float* stage = ring;  // every ring slot is free here; 2*d floats needed
+      if (dev::slow_pull(c, ckey, stage)) {
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+          int j = lane + v * 32;
+          if (j < nvec) {
+            float4 a0 = reinterpret_cast<float4*>(stage + d)[j];
+            float4 ua = make_float4(g0[v].x * g0[v].x, g0[v].y * g0[v].y, g0[v].z * g0[v].z, g0[v].w * g0[v].w);
+            float4 ue;
+            ue.x = alpha * g0[v].x * rsqrtf(a0.x + ua.x);
+            ue.y = alpha * g0[v].y * rsqrtf(a0.y + ua.y);
+            ue.z = alpha * g0[v].z * rsqrtf(a0.z + ua.z);
+            ue.w = alpha * g0[v].w * rsqrtf(a0.w + ua.w);
+            reinterpret_cast<float4*>(stage)[j] = ue;
+            reinterpret_cast<float4*>(stage + d)[j] = ua;
+          }
+        }
+        if (dev::slow_push(c, ckey, stage)) ++n_upd;
+      }
+    } else {
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        int j = lane + v * 32;
+        if (j < nvec) {
+          float4 a0 = dev::ld_row4(c_row + d + 4 * j);
+          float4 ua = make_float4(g0[v].x * g0[v].x, g0[v].y * g0[v].y, g0[v].z * g0[v].z, g0[v].w * g0[v].w);
+          float4 ue;
+          ue.x = alpha * g0[v].x * rsqrtf(a0.x + ua.x);
+          ue.y = alpha * g0[v].y * rsqrtf(a0.y + ua.y);
+          ue.z = alpha * g0[v].z * rsqrtf(a0.z + ua.z);
+          ue.w = alpha * g0[v].w * rsqrtf(a0.w + ua.w);
+          dev::red_row4(c_row + 4 * j, ue);
+          dev::red_row4(c_row + d + 4 * j, ua);
+        }
+      }
+      if (lane == 0) dev::mark_pushed(my_t);
+      ++n_upd;
+    }
+    __syncwarp();
+  }
+
+  __syncwarp();
+  if (lane == 0 && loss_out) atomicAdd(loss_out, loss_acc);
+  unsigned sum_local = n_local, sum_remote = n_remote;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sum_local += __shfl_xor_sync(0xffffffffu, sum_local, o);
+    sum_remote += __shfl_xor_sync(0xffffffffu, sum_remote, o);
+  }
+  if (lane == 0 && stats) {
+    if (sum_local) atomicAdd(stats + 0, (unsigned long long)sum_local);
+    if (sum_remote) atomicAdd(stats + 1, (unsigned long long)sum_remote);
+    if (n_slow) atomicAdd(stats + 2, (unsigned long long)n_slow);
+    if (n_upd) atomicAdd(stats + 3, (unsigned long long)n_upd);
+  }
+}
+
+}  // namespace
+
+// Returns false if this variant does not support the shape (the caller falls back to the LDG kernel).
+bool sgns_step_tma(CudaBackend& be, cudaStream_t stream, const Key* centers, const Key* contexts, const Key* negatives,
+                   int n_pairs, int neg, int d, float alpha, float* loss_out, unsigned long long* stats) {
+  if (neg + 1 > 31 || d % 4 != 0 || d > 384) return false;
+  const Ctx& c = be.ctx();
+  const int vpl = (d / 4 + 31) / 32;
+  const size_t buf_floats = ((size_t)2 * d + 31) & ~(size_t)31;
+  const size_t smem = (size_t)kWarps * (RING + 1) * buf_floats * sizeof(float) + 128;
+  if (smem > 110 * 1024) return false;  // keep 2 blocks per SM
+  int blocks = std::min((n_pairs + kWarps - 1) / kWarps, be.num_sms() * 12);
+#define ADAPM_LAUNCH_TMA(V)                                                                                  \
+  do {                                                                                                       \
+    static bool attr_set = false;                                                                            \
+    if (!attr_set) {                                                                                         \
+      cudaFuncSetAttribute(sgns_step_tma_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024); \
+      attr_set = true;                                                                                       \
+    }                                                                                                        \
+    sgns_step_tma_kernel<V><<<blocks, kThreads, smem, stream>>>(c, centers, contexts, negatives, n_pairs, neg, d, \
+                                                               alpha, loss_out, stats);                     \
+  } while (0)
+  switch (vpl) {
+    case 1: ADAPM_LAUNCH_TMA(1); break;
+    case 2: ADAPM_LAUNCH_TMA(2); break;
+    default: ADAPM_LAUNCH_TMA(3); break;
+  }
+  ADAPM_COUNT_LAUNCH();
+  ADAPM_CUDA_CHECK(cudaGetLastError());
+  return true;
+}
+
+}  // namespace cudaops
+}  // namespace adapm

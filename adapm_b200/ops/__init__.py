@@ -25,12 +25,14 @@ def _i64(t: torch.Tensor, name: str) -> torch.Tensor:
 
 
 def sgns_step(server, centers: torch.Tensor, contexts: torch.Tensor, negatives: torch.Tensor, embed_dim: int,
-              alpha: float, loss: torch.Tensor, stats: Optional[torch.Tensor] = None) -> None:
+              alpha: float, loss: torch.Tensor, stats: Optional[torch.Tensor] = None, impl: str = "auto") -> None:
     """Fused word2vec SGNS step (pull + score + AdaGrad + push) on ``server``'s store.
 
     ``centers``/``contexts``: [B] syn0 / syn1 keys; ``negatives``: [B, neg] syn1 keys;
     ``loss``: float32[1] accumulated (+=) with the summed logistic loss;
     ``stats``: optional int64[4] accumulated with (local rows, remote rows, slow-path rows, updates).
+    ``impl``: ``tma`` (rows prefetched by the TMA engine into a shared-memory ring), ``ldg`` (register
+    variant) or ``auto`` (tma when the shape fits, else ldg; ``ADAPM_SGNS_IMPL`` overrides).
     """
     _i64(centers, "centers"); _i64(contexts, "contexts"); _i64(negatives, "negatives")
     B = centers.numel()
@@ -41,7 +43,7 @@ def sgns_step(server, centers: torch.Tensor, contexts: torch.Tensor, negatives: 
         raise TypeError("loss must be a CUDA float32 tensor")
     _C.sgns_step(server._impl.backend_handle(), _stream(centers), centers.data_ptr(), contexts.data_ptr(),
                  negatives.data_ptr(), B, neg, int(embed_dim), float(alpha), loss.data_ptr(),
-                 stats.data_ptr() if stats is not None else 0)
+                 stats.data_ptr() if stats is not None else 0, {"auto": 0, "ldg": 1, "tma": 2}[impl])
 
 
 class DeviceSampler:

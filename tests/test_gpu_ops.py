@@ -69,8 +69,9 @@ def test_mixed_value_lengths(cluster1):
     assert kv.get_key_size(10) == 20 and kv.get_key_size(40) == 4
 
 
-@pytest.mark.parametrize("d,neg", [(300, 25), (128, 5), (64, 40), (512, 3)])
-def test_sgns_step_matches_pytorch_reference(cluster1, d, neg):
+@pytest.mark.parametrize("d,neg,impl", [(300, 25, "tma"), (300, 25, "ldg"), (128, 5, "tma"), (128, 5, "ldg"),
+                                        (64, 40, "auto"), (512, 3, "auto"), (200, 30, "tma"), (16, 2, "tma")])
+def test_sgns_step_matches_pytorch_reference(cluster1, d, neg, impl):
     """Distinct keys per batch -> every row is touched by exactly one pair-target, so the batched kernel and the
     PyTorch fp32 formula must agree (AdaGrad with the pulled accumulator, |f|>6 saturation, negative==target skip)."""
     from adapm_b200.ops import sgns_step
@@ -94,7 +95,7 @@ def test_sgns_step_matches_pytorch_reference(cluster1, d, neg):
     alpha = 0.05
     loss = torch.zeros(1, device=dev)
     stats = torch.zeros(4, dtype=torch.int64, device=dev)
-    sgns_step(server, centers.to(dev), contexts.to(dev), negatives.contiguous().to(dev), d, alpha, loss, stats)
+    sgns_step(server, centers.to(dev), contexts.to(dev), negatives.contiguous().to(dev), d, alpha, loss, stats, impl=impl)
     torch.cuda.synchronize()
     got = torch.empty(n_keys * 2 * d)
     kv.pull(allk, got)
