@@ -36,6 +36,7 @@ struct Options {
   int channels = 4;                          // sys.channels             (no effect)
   std::string trace_keys;                    // sys.trace.keys
   std::string stats_out;                     // sys.stats.out
+  bool locality_stats = false;               // sys.stats.locality (reference: compile-time PS_LOCALITY_STATS)
   double sync_max_per_sec = 1000;            // sys.sync.max_per_sec
   int sync_pause_ms = 0;                     // sys.sync.pause
   double sync_threshold = 0;                 // sys.sync.threshold (-1 all, 0 non-zero, >0 L2, inf off)
@@ -90,6 +91,7 @@ struct Options {
     }
     else if (name == "sys.trace.keys") trace_keys = v;
     else if (name == "sys.stats.out") stats_out = v;
+    else if (name == "sys.stats.locality") locality_stats = b(v);
     else if (name == "sys.sync.max_per_sec") { sync_max_per_sec = std::stod(v); }
     else if (name == "sys.sync.pause") { sync_pause_ms = std::stoi(v); if (sync_pause_ms > 0) sync_max_per_sec = 0; }
     else if (name == "sys.sync.threshold") sync_threshold = (v == "inf") ? std::numeric_limits<double>::infinity() : std::stod(v);

@@ -44,8 +44,8 @@ struct Layout {
   uint64_t off_dirty;      // uint8[S]          replica got local pushes since the last delta ship (blind store 1)
   uint64_t off_free_top;   // int32[MAX_CLASSES]
   uint64_t off_counters;   // uint64[C_NUM_COUNTERS]
-  uint64_t off_retry;      // IntentRec[retry_cap] x2 + counts (deferred intents)
-  uint32_t retry_cap;
+  uint64_t off_access;     // uint32[2*num_keys] (accesses, local accesses) - only if locality stats are on, else 0
+  uint32_t locality_stats; // PS_LOCALITY_STATS equivalent (run-time switch sys.stats.locality)
   uint32_t pad2;
   ClassInfo cls[MAX_CLASSES];
   uint64_t heap_bytes;

@@ -51,6 +51,7 @@ void Server::shutdown() {
   fabric_->node_barrier("shutdown");
   if (verbosity() >= 1) ALOG(stats_string());
   if (tracing()) write_traces();
+  if (opt_.locality_stats) write_locality_stats();
   fabric_->node_barrier("shutdown done");
   backend_.reset();
   fabric_.reset();
@@ -159,6 +160,52 @@ void Server::write_traces() {
   std::lock_guard<std::mutex> lk(trace_mu_);
   for (auto& t : trace_log_) f << std::get<0>(t) << "\t" << std::get<1>(t) << "\t" << opt_.rank << "\t" << names[std::get<2>(t)] << "\n";
   ALOG("Wrote " << trace_log_.size() << " key trace events to " << fn);
+}
+
+void Server::write_locality_stats() {
+  const Layout& L = backend_->ctx().L;
+  if (!L.off_access) return;
+  std::vector<uint32_t> acc((size_t)L.num_keys * 2);
+  backend_->read_heap(L.off_access, acc.data(), acc.size() * 4);
+  std::string dir = opt_.stats_out.empty() ? std::string(".") : opt_.stats_out;
+  std::string fn = dir + "/locality_stats.rank." + std::to_string(opt_.rank) + ".tsv";
+  std::ofstream f(fn, std::ofstream::trunc);
+  f << "Param\tAccesses\tLocalAccesses\n";
+  uint64_t tot = 0, loc = 0;
+  for (int64_t k = 0; k < L.num_keys; ++k) {
+    if (acc[2 * k]) f << k << "\t" << acc[2 * k] << "\t" << acc[2 * k + 1] << "\n";
+    tot += acc[2 * k]; loc += acc[2 * k + 1];
+  }
+  ALOG("Wrote locality stats for rank " << opt_.rank << " to " << fn << ": " << loc << " of " << tot << " accesses were local");
+}
+
+// Key tracing by observation: after every sync round the states of the traced keys are compared with the
+// previous round and the transitions are logged as the reference's events
+// (ALLOC, DEALLOC, REPLICA_SETUP, REPLICA_DROP; INTENT_START is logged when the intent is acted upon).
+void Server::observe_traced_keys() {
+  if (traced_list_.empty()) {
+    if (trace_all_) {
+      int64_t n = std::min<int64_t>(spec_.num_keys, 1 << 20);
+      for (Key k = 0; k < n; ++k) traced_list_.push_back(k);
+    } else {
+      traced_list_.assign(traced_.begin(), traced_.end());
+    }
+    traced_prev_.assign(traced_list_.size(), 0xff);
+  }
+  std::vector<uint8_t> st(traced_list_.size()), ow(traced_list_.size());
+  backend_->peek_states(traced_list_.data(), traced_list_.size(), st.data(), ow.data());
+  auto resident = [](uint8_t s) { return s == S_OWNED || s == S_REPLICA || s == S_REPLICA_PENDING || state_is_incoming(s) || s == S_FINALIZING; };
+  for (size_t i = 0; i < st.size(); ++i) {
+    uint8_t p = traced_prev_[i], s = st[i];
+    traced_prev_[i] = s;
+    if (p == 0xff) { if (s == S_OWNED) trace(traced_list_[i], TraceEvent::ALLOC); continue; }
+    if (p == s) continue;
+    const Key k = traced_list_[i];
+    if (!resident(p) && resident(s)) trace(k, TraceEvent::ALLOC);
+    if (s == S_REPLICA && p != S_REPLICA) trace(k, TraceEvent::REPLICA_SETUP);
+    if ((p == S_REPLICA || p == S_REPLICA_PENDING) && !resident(s)) { trace(k, TraceEvent::INTENT_STOP); trace(k, TraceEvent::REPLICA_DROP); }
+    if (resident(p) && !resident(s)) trace(k, TraceEvent::DEALLOC);
+  }
 }
 
 // ======================================================================== Worker

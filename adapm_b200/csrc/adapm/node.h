@@ -169,6 +169,8 @@ class Server {
   void trace(Key k, TraceEvent e);
   bool tracing() const { return trace_all_ || !traced_.empty(); }
   void write_traces();
+  void write_locality_stats();   // locality_stats.rank.<r>.tsv (reference coloc_kv_server_handle.h:963-975)
+  void observe_traced_keys();    // called by the sync thread after every round
 
  private:
   friend class Worker;
@@ -189,6 +191,8 @@ class Server {
   std::unordered_set<Key> traced_;
   std::mutex trace_mu_;
   std::vector<std::tuple<int64_t, Key, int>> trace_log_;
+  std::vector<Key> traced_list_;
+  std::vector<uint8_t> traced_prev_;
 };
 
 // -------------------------------------------------------------------------------------

@@ -143,6 +143,11 @@ ADAPM_HD bool pull_key(const Ctx& c, const G& g, Key key, Val* out, bool local_o
     if (loc.kind == LOC_FAIL) return false;
     if (read_row(g, loc, out, len)) {
       if (was_local) *was_local = loc.local;
+      if (c.L.off_access && g.lane() == 0) {  // per-key locality statistics (PS_LOCALITY_STATS equivalent)
+        uint32_t* acc = at<uint32_t>(c, c.rank, c.L.off_access) + 2 * (size_t)key;
+        mem::red_add(acc, 1u);
+        if (loc.local) mem::red_add(acc + 1, 1u);
+      }
       return true;
     }
     mem::cpu_relax();

@@ -101,6 +101,8 @@ inline Layout build_layout(const ValueSpec& spec, const Options& opt, std::vecto
   L.off_dirty = take((uint64_t)L.total_slots);
   L.off_free_top = take(MAX_CLASSES * 4);
   L.off_counters = take(C_NUM_COUNTERS * 8);
+  L.locality_stats = opt.locality_stats ? 1u : 0u;
+  L.off_access = opt.locality_stats ? take((uint64_t)L.num_keys * 8) : 0;
   for (int c = 0; c < L.num_classes; ++c) {
     uint64_t row_bytes = (uint64_t)L.cls[c].len * L.val_bytes;
     L.cls[c].rows_off = take((uint64_t)L.cls[c].cap * row_bytes);
@@ -166,6 +168,8 @@ class Backend {
   virtual void grace() = 0;
   virtual void read_counters(uint64_t* out) = 0;
   virtual void reset_counters() = 0;
+  // copy `bytes` at heap offset `off` of THIS rank into host memory (statistics / debugging)
+  virtual void read_heap(uint64_t off, void* dst, size_t bytes) = 0;
 };
 
 std::unique_ptr<Backend> make_cpu_backend(const Options& opt, const Layout& L, std::shared_ptr<Fabric> fabric);

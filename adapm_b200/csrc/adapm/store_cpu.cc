@@ -169,6 +169,7 @@ class CpuBackend : public Backend {
     const uint64_t* c = counters_of(ctx_, ctx_.rank);
     for (int i = 0; i < C_NUM_COUNTERS; ++i) out[i] = mem::ld_relaxed(c + i);
   }
+  void read_heap(uint64_t off, void* dst, size_t bytes) override { memcpy(dst, ctx_.heap[ctx_.rank] + off, bytes); }
   void reset_counters() override {
     uint64_t* c = counters_of(ctx_, ctx_.rank);
     for (int i = 0; i < C_NUM_COUNTERS; ++i) mem::st_relaxed(c + i, (uint64_t)0);

@@ -171,6 +171,7 @@ void SyncEngine::round(bool sweep) {
   be.phase_c(rp);
   be.round_fence();
   sw_phase_c_.stop();
+  if (server_->tracing()) server_->observe_traced_keys();
 }
 
 void SyncEngine::loop() {

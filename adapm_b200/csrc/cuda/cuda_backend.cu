@@ -595,6 +595,10 @@ void CudaBackend::read_counters(uint64_t* out) {
   use_device();
   ADAPM_CUDA_CHECK(cudaMemcpy(out, ctx_.heap[ctx_.rank] + ctx_.L.off_counters, C_NUM_COUNTERS * 8, cudaMemcpyDeviceToHost));
 }
+void CudaBackend::read_heap(uint64_t off, void* dst, size_t bytes) {
+  use_device();
+  ADAPM_CUDA_CHECK(cudaMemcpy(dst, ctx_.heap[ctx_.rank] + off, bytes, cudaMemcpyDeviceToHost));
+}
 void CudaBackend::reset_counters() {
   use_device();
   ADAPM_CUDA_CHECK(cudaMemset(ctx_.heap[ctx_.rank] + ctx_.L.off_counters, 0, C_NUM_COUNTERS * 8));

@@ -45,6 +45,7 @@ class CudaBackend : public Backend {
   void grace() override;
   void read_counters(uint64_t* out) override;
   void reset_counters() override;
+  void read_heap(uint64_t off, void* dst, size_t bytes) override;
 
   // ---- used by the fused application kernels (cuda/ops_*.cu)
   int device() const { return device_; }
