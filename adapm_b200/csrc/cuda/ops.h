@@ -36,5 +36,12 @@ void gemm_nt_e4m3(cudaStream_t stream, const void* A, const void* B, int M, int 
 void gemm_nt_bf16_rank_count(cudaStream_t stream, const void* A, const void* B, int M, int N, int K,
                              const float* true_score, const int* true_col, int* rank_out);
 
+// fused gather (local HBM / NVLink peers, through the directory) + tcgen05 GEMM (ops_gather_gemm.cu):
+// C[M,N] = Q[M,K] (bf16, row pitch ldq) x rows(keys[0..N))[0..K)^T, rows read from the parameter store
+void gather_gemm(CudaBackend& be, cudaStream_t stream, const void* Q, const Key* keys, int M, int N, int K, int ldq, float* C,
+                 int ldc, unsigned long long* stats);
+void gather_gemm_rank_count(CudaBackend& be, cudaStream_t stream, const void* Q, const Key* keys, int M, int N, int K, int ldq,
+                            const float* true_score, const int* true_col, int* rank_out, unsigned long long* stats);
+
 }  // namespace cudaops
 }  // namespace adapm

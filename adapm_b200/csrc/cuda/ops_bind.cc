@@ -54,6 +54,16 @@ void bind(py::module_& m) {
     gemm_nt_bf16_rank_count((cudaStream_t)stream, ptr<const void>(A), ptr<const void>(B), M, N, K, ptr<const float>(ts),
                             ptr<const int>(tc), ptr<int>(rank));
   });
+  m.def("gather_gemm", [](uintptr_t be, uintptr_t stream, uintptr_t Q, uintptr_t keys, int M, int N, int K, int ldq,
+                          uintptr_t C, int ldc, uintptr_t stats) {
+    gather_gemm(backend_of(be), (cudaStream_t)stream, ptr<const void>(Q), ptr<const Key>(keys), M, N, K, ldq, ptr<float>(C),
+                ldc, ptr<unsigned long long>(stats));
+  });
+  m.def("gather_gemm_rank_count", [](uintptr_t be, uintptr_t stream, uintptr_t Q, uintptr_t keys, int M, int N, int K,
+                                     int ldq, uintptr_t ts, uintptr_t tc, uintptr_t rank, uintptr_t stats) {
+    gather_gemm_rank_count(backend_of(be), (cudaStream_t)stream, ptr<const void>(Q), ptr<const Key>(keys), M, N, K, ldq,
+                           ptr<const float>(ts), ptr<const int>(tc), ptr<int>(rank), ptr<unsigned long long>(stats));
+  });
   m.def("kernel_launches", [] { return kernel_launch_counter().load(); });
   m.def("track_stream", [](uintptr_t be, uintptr_t stream) { backend_of(be).track_stream((cudaStream_t)stream); });
 }

@@ -176,3 +176,32 @@ def gemm_nt_rank_count(q: torch.Tensor, e: torch.Tensor, true_score: torch.Tenso
     _C.gemm_nt_bf16_rank_count(_stream(q16), q16.data_ptr(), e16.data_ptr(), M, N, K, ts.data_ptr(), tc.data_ptr(),
                                out.data_ptr())
     return out
+
+
+def gather_gemm(server, q: torch.Tensor, keys: torch.Tensor, k: int, stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """scores[M, N] = q[M, k] @ E^T where row n of E is the first ``k`` values of store row ``keys[n]`` - the rows
+    are gathered inside the GEMM kernel from the local slab, local replicas or peer GPUs over NVLink (fused
+    gather + tcgen05 GEMM); the gathered matrix never exists in HBM."""
+    _i64(keys, "keys")
+    q16 = _bf16_k8(q)
+    M, N = q16.shape[0], keys.numel()
+    c = torch.empty(M, N, dtype=torch.float32, device=q.device)
+    _C.gather_gemm(server._impl.backend_handle(), _stream(q16), q16.data_ptr(), keys.data_ptr(), M, N, int(k), q16.shape[1],
+                   c.data_ptr(), N, stats.data_ptr() if stats is not None else 0)
+    return c
+
+
+def gather_gemm_rank_count(server, q: torch.Tensor, keys: torch.Tensor, k: int, true_score: torch.Tensor,
+                           true_col: torch.Tensor, stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """counts[i] = #{n != true_col[i] : <q[i], row(keys[n])[:k]> > true_score[i]}: fused gather + GEMM + ranking
+    epilogue - neither the gathered rows nor the [M, N] scores are materialised."""
+    _i64(keys, "keys")
+    q16 = _bf16_k8(q)
+    M, N = q16.shape[0], keys.numel()
+    out = torch.zeros(M, dtype=torch.int32, device=q.device)
+    ts = true_score.to(torch.float32).contiguous()
+    tc = true_col.to(torch.int32).contiguous()
+    _C.gather_gemm_rank_count(server._impl.backend_handle(), _stream(q16), q16.data_ptr(), keys.data_ptr(), M, N, int(k),
+                              q16.shape[1], ts.data_ptr(), tc.data_ptr(), out.data_ptr(),
+                              stats.data_ptr() if stats is not None else 0)
+    return out
