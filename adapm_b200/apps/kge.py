@@ -30,6 +30,8 @@ def main(argv=None) -> int:
     ap.add_argument("--eta", type=float, default=0.1)
     ap.add_argument("--gamma_entity", type=float, default=1e-3)
     ap.add_argument("--gamma_relation", type=float, default=1e-3)
+    ap.add_argument("--dropout_entity", type=float, default=0.0)
+    ap.add_argument("--dropout_relation", type=float, default=0.0)
     ap.add_argument("--neg_ratio", type=int, default=6)
     ap.add_argument("--eval_freq", type=int, default=-1)
     ap.add_argument("--num_entities", type=int, default=14951)
@@ -48,7 +50,8 @@ def main(argv=None) -> int:
 
     cfg = KGEConfig(num_entities=args.num_entities, num_relations=args.num_relations, embed_dim=args.embed_dim,
                     algorithm=args.algorithm, neg_ratio=args.neg_ratio, eta=args.eta, gamma_entity=args.gamma_entity,
-                    gamma_relation=args.gamma_relation, batch_triples=args.batch_triples,
+                    gamma_relation=args.gamma_relation, dropout_entity=args.dropout_entity,
+                    dropout_relation=args.dropout_relation, batch_triples=args.batch_triples,
                     read_ahead=args.signal_intent_ahead, sampling_scheme=getattr(args, "sampling.scheme") or "local",
                     signal_initial_relations_intent=bool(args.signal_initial_relations_intent), model_seed=args.model_seed)
     if args.dataset:

@@ -97,7 +97,7 @@ template <int VPL>
 __global__ void __launch_bounds__(kThreads, 2)
 sgns_step_tma_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ centers, const Key* __restrict__ contexts,
                      const Key* __restrict__ negatives, int n_pairs, int neg, int d, float alpha,
-                     float* __restrict__ loss_out, unsigned long long* __restrict__ stats) {
+                     float* __restrict__ loss_out, unsigned long long* __restrict__ stats, int tma_remote) {
   // per warp: RING row buffers of 2*d floats (16-byte aligned) | generic-path scratch is carved from the ring
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ WarpSmem wsm[kWarps];
@@ -147,14 +147,15 @@ sgns_step_tma_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ cent
       const bool skip = (t > 0 && tkey == pos_key) || row == nullptr;
       if (skip) {
         if (lane == 0) mbar_arrive(&bars[b]);            // nothing to load: complete the phase
-      } else if (!remote) {
+      } else if (!remote || tma_remote) {
+        // local HBM row - or a peer's row: the TMA engine reads NVLink-mapped addresses as well
         if (lane == 0) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // order earlier LDS of this slot before the TMA write
           mbar_expect_tx(&bars[b], row_bytes);
           bulk_g2s(buf, row, row_bytes, &bars[b]);
         }
       } else {
-        // NVLink peer row: stage with 16-byte loads (the copy engine path is kept for local HBM)
+        // NVLink peer row staged with 16-byte loads (ADAPM_TMA_REMOTE=0)
         for (int j = lane; j < 2 * nvec; j += 32) reinterpret_cast<float4*>(buf)[j] = dev::ld_row4(row + 4 * j);
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[b]);
@@ -349,6 +350,7 @@ bool sgns_step_tma(CudaBackend& be, cudaStream_t stream, const Key* centers, con
   const size_t smem = (size_t)kWarps * (RING + 1) * buf_floats * sizeof(float) + 128;
   if (smem > 110 * 1024) return false;  // keep 2 blocks per SM
   int blocks = std::min((n_pairs + kWarps - 1) / kWarps, be.num_sms() * 12);
+  static const int tma_remote = [] { const char* e = getenv("ADAPM_TMA_REMOTE"); return e ? atoi(e) : 1; }();
 #define ADAPM_LAUNCH_TMA(V)                                                                                  \
   do {                                                                                                       \
     static bool attr_set = false;                                                                            \
@@ -357,7 +359,7 @@ bool sgns_step_tma(CudaBackend& be, cudaStream_t stream, const Key* centers, con
       attr_set = true;                                                                                       \
     }                                                                                                        \
     sgns_step_tma_kernel<V><<<blocks, kThreads, smem, stream>>>(c, centers, contexts, negatives, n_pairs, neg, d, \
-                                                               alpha, loss_out, stats);                     \
+                                                               alpha, loss_out, stats, tma_remote);         \
   } while (0)
   switch (vpl) {
     case 1: ADAPM_LAUNCH_TMA(1); break;

@@ -37,8 +37,12 @@ class DeepFMConfig:
     model_seed: int = 1
 
     @property
-    def row_len(self) -> int:           # [w | v | acc_w | acc_v]
-        return 2 * (1 + self.embed_dim)
+    def emb_len(self) -> int:           # [w | v] padded to a multiple of 4 floats (16-byte vector row accesses)
+        return (1 + self.embed_dim + 3) // 4 * 4
+
+    @property
+    def row_len(self) -> int:           # [w | v | pad | acc_w | acc_v | pad]
+        return 2 * self.emb_len
 
 
 class TensorCoreLinear(torch.autograd.Function):
@@ -102,10 +106,9 @@ class DeepFM:
         keys = torch.arange(rank, cfg.num_features, world, dtype=torch.int64)
         for i in range(0, keys.numel(), chunk):
             kk = keys[i:i + chunk].to(self.dev)
-            rows = torch.empty(kk.numel(), cfg.row_len, device=self.dev)
-            rows[:, 0] = 0
+            rows = torch.zeros(kk.numel(), cfg.row_len, device=self.dev)
             rows[:, 1:1 + k] = torch.randn(kk.numel(), k, generator=gen, device=self.dev) * 0.01
-            rows[:, 1 + k:] = 1e-6
+            rows[:, cfg.emb_len:] = 1e-6
             self.worker.set(kk, rows.view(-1))
         self.worker.waitall()
         self.worker.end_setup()
@@ -124,10 +127,11 @@ class DeepFM:
         rows = torch.empty(uniq.numel() * cfg.row_len, dtype=torch.float32, device=self.dev)
         kv.wait(kv.pull(uniq, rows, True))
         rows = rows.view(-1, cfg.row_len)
-        emb = rows[:, :1 + k].detach().clone().requires_grad_(True)   # [U, 1+k]
-        acc = rows[:, 1 + k:]
-        e = emb[inv].view(B, F, 1 + k)
-        w1, v = e[:, :, 0], e[:, :, 1:]
+        el = cfg.emb_len
+        emb = rows[:, :el].detach().clone().requires_grad_(True)      # [U, el]  (w | v | pad)
+        acc = rows[:, el:]
+        e = emb[inv].view(B, F, el)
+        w1, v = e[:, :, 0], e[:, :, 1:1 + k]
         fm = w1.sum(1) + 0.5 * ((v.sum(1) ** 2) - (v ** 2).sum(1)).sum(1)
         logit = fm + self.net(v.reshape(B, F * k))
         loss = torch.nn.functional.binary_cross_entropy_with_logits(logit, y)

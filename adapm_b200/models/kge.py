@@ -41,6 +41,8 @@ class KGEConfig:
     eta: float = 0.1
     gamma_entity: float = 1e-3
     gamma_relation: float = 1e-3
+    dropout_entity: float = 0.0      # training-time dropout on embeddings (kge.cc:405-413,478-484)
+    dropout_relation: float = 0.0
     batch_triples: int = 4096
     read_ahead: int = 4
     sampling_scheme: str = "local"
@@ -174,7 +176,7 @@ class KGE:
         """One batch of positive triples ([B,3] int64 CPU tensor, pinned for the e2e path)."""
         cfg = self.cfg
         B = triples_host.shape[0]
-        if self.cuda and cfg.algorithm == "ComplEx":
+        if self.cuda and cfg.algorithm == "ComplEx" and cfg.dropout_entity == 0 and cfg.dropout_relation == 0:
             from ..ops import kge_complex_step
 
             tr = triples_host.to(self.server.device, non_blocking=True)
@@ -324,6 +326,13 @@ def kge_reference_step(kv, S, R, O, L, cfg: KGEConfig) -> float:
     Es, As, Eo, Ao = rs[:, :d], rs[:, d:], ro[:, :d], ro[:, d:]
     rd = cfg.relation_len // 2
     Er, Ar = rr[:, :rd], rr[:, rd:]
+    if cfg.dropout_entity > 0:      # Bernoulli mask + 1/(1-p) scaling, applied to the pulled copies only
+        p = cfg.dropout_entity
+        Es = Es * (torch.rand_like(Es) >= p) / (1 - p)
+        Eo = Eo * (torch.rand_like(Eo) >= p) / (1 - p)
+    if cfg.dropout_relation > 0:
+        p = cfg.dropout_relation
+        Er = Er * (torch.rand_like(Er) >= p) / (1 - p)
     if cfg.algorithm == "ComplEx":
         h = d // 2
         sre, sim, rre, rim, ore, oim = Es[:, :h], Es[:, h:], Er[:, :h], Er[:, h:], Eo[:, :h], Eo[:, h:]

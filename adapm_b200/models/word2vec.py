@@ -43,7 +43,7 @@ class Word2VecConfig:
     signal_intent: bool = True
     model_seed: int = 134827
     zipf_exponent: float = 1.0       # synthetic corpus skew
-    max_inflight: int = 2            # steps the host may run ahead of the GPU (bounds the sync grace period)
+    max_inflight: int = 3            # steps the host may run ahead of the GPU (bounds the sync grace period)
 
     @property
     def row_len(self) -> int:

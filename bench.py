@@ -41,7 +41,7 @@ def parse_args():
     ap.add_argument("--dim", type=int, default=300)
     ap.add_argument("--negative", type=int, default=25)
     ap.add_argument("--batch-pairs", type=int, default=32768)
-    ap.add_argument("--read-ahead", type=int, default=4)
+    ap.add_argument("--read-ahead", type=int, default=8)
     ap.add_argument("--sampling", default="local", choices=["local", "naive"])
     ap.add_argument("--techniques", default="all")
     ap.add_argument("--no-intent", action="store_true")
