@@ -132,6 +132,7 @@ class Server:
         opts = {str(k): (("1" if v else "0") if isinstance(v, bool) else str(v)) for k, v in opts.items()}
 
         self._lens_t = None
+        self._lens_dev = None
         if isinstance(value_lengths, (int, np.integer)):
             nk = num_keys if num_keys is not None else cfg["num_keys"]
             if nk is None:
@@ -242,11 +243,11 @@ class Worker:
                 raise IndexError(f"At least one of the provided keys ({kmax}) is outside the key range [0, {nk})")
         if not keys.is_cuda:
             need = self.server.total_len(keys)
+        elif self.server._uniform_len is None:
+            need = None   # mixed lengths on the device: checked through the offsets in _io
         else:
-            if self.server._uniform_len is None:
-                raise ValueError("CUDA key tensors need a uniform value length")
             need = keys.numel() * self.server._uniform_len
-        if vals.numel() != need:
+        if need is not None and vals.numel() != need:
             raise ValueError("The provided value array does not match the size specified in the parameter server: "
                              f"{vals.numel()} != {need}")
 
@@ -256,32 +257,43 @@ class Worker:
         if keys.is_cuda:
             if self.server.backend != "cuda":
                 raise ValueError("CUDA tensors need backend='cuda'")
-            return True, torch.cuda.current_stream(keys.device).cuda_stream
-        return False, 0
+            offs = 0
+            if self.server._uniform_len is None:
+                # mixed-length store: per-key value offsets are computed on the device
+                if self.server._lens_dev is None:
+                    self.server._lens_dev = self.server._lens_t.to(keys.device)
+                lens = self.server._lens_dev[keys]
+                o = torch.cumsum(lens, 0) - lens
+                if int((o[-1] + lens[-1]).item()) != vals.numel():
+                    raise ValueError("The provided value array does not match the size specified in the parameter server")
+                self._offs_keep = o
+                offs = o.data_ptr()
+            return True, torch.cuda.current_stream(keys.device).cuda_stream, offs
+        return False, 0, 0
 
     # -- data ops -----------------------------------------------------------------
     def pull(self, keys, vals, asynchronous: bool = False) -> int:
         k = _as_keys(keys)
         v = self._vals(vals, k, True)
         self._check(k, v)
-        dev, stream = self._io(k, v)
-        ts = self._impl.pull(k.data_ptr(), k.numel(), v.data_ptr(), dev, stream)
+        dev, stream, offs = self._io(k, v)
+        ts = self._impl.pull(k.data_ptr(), k.numel(), v.data_ptr(), dev, stream, offs)
         return self._finish(ts, asynchronous, (k, v))
 
     def push(self, keys, vals, asynchronous: bool = False) -> int:
         k = _as_keys(keys)
         v = self._vals(vals, k, False)
         self._check(k, v)
-        dev, stream = self._io(k, v)
-        ts = self._impl.push(k.data_ptr(), k.numel(), v.data_ptr(), False, dev, stream)
+        dev, stream, offs = self._io(k, v)
+        ts = self._impl.push(k.data_ptr(), k.numel(), v.data_ptr(), False, dev, stream, offs)
         return self._finish(ts, asynchronous, (k, v))
 
     def set(self, keys, vals, asynchronous: bool = False) -> int:
         k = _as_keys(keys)
         v = self._vals(vals, k, False)
         self._check(k, v)
-        dev, stream = self._io(k, v)
-        ts = self._impl.push(k.data_ptr(), k.numel(), v.data_ptr(), True, dev, stream)
+        dev, stream, offs = self._io(k, v)
+        ts = self._impl.push(k.data_ptr(), k.numel(), v.data_ptr(), True, dev, stream, offs)
         return self._finish(ts, asynchronous, (k, v))
 
     def _finish(self, ts: int, asynchronous: bool, keep) -> int:

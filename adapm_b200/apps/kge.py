@@ -15,7 +15,7 @@ import torch
 
 import adapm_b200 as ad
 from adapm_b200.apps._common import add_system_options, strip_dashes, system_options
-from adapm_b200.models.kge import KGE, KGEConfig, load_triples, synthetic_triples
+from adapm_b200.models.kge import KGE, KGEConfig, evaluate_fused, load_triples, synthetic_triples
 from adapm_b200.utils.allreduce import ps_allreduce
 
 
@@ -102,6 +102,9 @@ def main(argv=None) -> int:
         if time.time() - t0 > args.max_runtime:
             break
     if rank == 0:
+        if model.cuda and cfg.algorithm == "ComplEx" and cfg.embed_dim % 4 == 0:
+            # fused gather + tcgen05 GEMM + rank count: entity rows are read from every GPU's HBM in-kernel
+            print(f"[kge] test (fused gather-GEMM eval): {evaluate_fused(model, te, known)}", flush=True)
         print(f"[kge] test: {model.evaluate(te, known)}", flush=True)
     kv.barrier()
     kv.finalize()

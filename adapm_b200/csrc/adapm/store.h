@@ -129,6 +129,7 @@ struct IoDesc {
   bool on_device = false;
   bool has_stream = false;   // false: use the worker's own stream
   void* stream = nullptr;    // cudaStream_t (0 is the legacy default stream, hence has_stream)
+  const int64_t* offsets = nullptr;  // device path on mixed-length stores: value offset of every key (device ptr)
 };
 
 // One backend instance per rank. Thread-safety: worker ops may be called concurrently from

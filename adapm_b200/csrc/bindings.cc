@@ -23,11 +23,12 @@ Options make_options(const std::map<std::string, std::string>& kv) {
   return o;
 }
 
-IoDesc make_io(bool on_device, uintptr_t stream) {
+IoDesc make_io(bool on_device, uintptr_t stream, uintptr_t offsets = 0) {
   IoDesc io;
   io.on_device = on_device;
   io.has_stream = on_device;
   io.stream = reinterpret_cast<void*>(stream);
+  io.offsets = reinterpret_cast<const int64_t*>(offsets);
   return io;
 }
 
@@ -121,12 +122,14 @@ PYBIND11_MODULE(_C, m) {
              return std::make_shared<Worker>(customer_id, *server);
            }),
            py::keep_alive<1, 3>())
-      .def("pull", [](Worker& w, uintptr_t keys, size_t n, uintptr_t vals, bool on_device, uintptr_t stream) {
-             return w.Pull(ptr<const Key>(keys), n, ptr<void>(vals), make_io(on_device, stream));
-           }, py::call_guard<py::gil_scoped_release>())
-      .def("push", [](Worker& w, uintptr_t keys, size_t n, uintptr_t vals, bool set, bool on_device, uintptr_t stream) {
-             return w.Push(ptr<const Key>(keys), n, ptr<const void>(vals), set, make_io(on_device, stream));
-           }, py::call_guard<py::gil_scoped_release>())
+      .def("pull", [](Worker& w, uintptr_t keys, size_t n, uintptr_t vals, bool on_device, uintptr_t stream, uintptr_t offsets) {
+             return w.Pull(ptr<const Key>(keys), n, ptr<void>(vals), make_io(on_device, stream, offsets));
+           }, py::arg("keys"), py::arg("n"), py::arg("vals"), py::arg("on_device"), py::arg("stream"), py::arg("offsets") = 0,
+           py::call_guard<py::gil_scoped_release>())
+      .def("push", [](Worker& w, uintptr_t keys, size_t n, uintptr_t vals, bool set, bool on_device, uintptr_t stream, uintptr_t offsets) {
+             return w.Push(ptr<const Key>(keys), n, ptr<const void>(vals), set, make_io(on_device, stream, offsets));
+           }, py::arg("keys"), py::arg("n"), py::arg("vals"), py::arg("set"), py::arg("on_device"), py::arg("stream"),
+           py::arg("offsets") = 0, py::call_guard<py::gil_scoped_release>())
       .def("pull_if_local", [](Worker& w, Key key, uintptr_t vals) { return w.PullIfLocal(key, ptr<void>(vals)); },
            py::call_guard<py::gil_scoped_release>())
       .def("intent", [](Worker& w, uintptr_t keys, size_t n, Clock start, Clock end) {

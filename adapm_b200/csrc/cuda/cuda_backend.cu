@@ -395,9 +395,9 @@ uint64_t CudaBackend::pull(int worker, const Key* keys, size_t n, void* vals, bo
   const Layout& L = ctx_.L;
   const bool uniform = L.num_classes == 1;
   if (io.on_device) {
-    ADAPM_CHECK(uniform, "device-pointer pull needs a uniform value length (use host tensors for mixed lengths)");
+    ADAPM_CHECK(uniform || io.offsets, "device-pointer pull on a mixed-length store needs per-key value offsets");
     cudaStream_t s = resolve_stream(worker, io);
-    pull_kernel<<<grid_for_warps(n, num_sms_), kThreads, 0, s>>>(ctx_, keys, n, (float*)vals, nullptr, L.cls[0].len,
+    pull_kernel<<<grid_for_warps(n, num_sms_), kThreads, 0, s>>>(ctx_, keys, n, (float*)vals, uniform ? nullptr : io.offsets, L.cls[0].len,
                                                                  local_only ? 1 : 0, ok, nullptr);
     ADAPM_COUNT_LAUNCH();
   ADAPM_CUDA_CHECK(cudaGetLastError());
@@ -454,9 +454,9 @@ uint64_t CudaBackend::push(int worker, const Key* keys, size_t n, const void* va
   const Layout& L = ctx_.L;
   const bool uniform = L.num_classes == 1;
   if (io.on_device) {
-    ADAPM_CHECK(uniform, "device-pointer push needs a uniform value length (use host tensors for mixed lengths)");
+    ADAPM_CHECK(uniform || io.offsets, "device-pointer push on a mixed-length store needs per-key value offsets");
     cudaStream_t s = resolve_stream(worker, io);
-    push_kernel<<<grid_for_warps(n, num_sms_), kThreads, 0, s>>>(ctx_, keys, n, (const float*)vals, nullptr, L.cls[0].len,
+    push_kernel<<<grid_for_warps(n, num_sms_), kThreads, 0, s>>>(ctx_, keys, n, (const float*)vals, uniform ? nullptr : io.offsets, L.cls[0].len,
                                                                  set ? 1 : 0, nullptr);
     ADAPM_COUNT_LAUNCH();
   ADAPM_CUDA_CHECK(cudaGetLastError());

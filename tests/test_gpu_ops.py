@@ -67,6 +67,14 @@ def test_mixed_value_lengths(cluster1):
     kv.pull(keys, out)
     torch.testing.assert_close(out, vals)
     assert kv.get_key_size(10) == 20 and kv.get_key_size(40) == 4
+    # device path on a mixed-length store (per-key offsets computed on the device)
+    dev = server.device
+    dout = torch.zeros(vals.numel(), device=dev)
+    kv.wait(kv.pull(keys.to(dev), dout, True))
+    torch.testing.assert_close(dout.cpu(), vals)
+    kv.wait(kv.push(keys.to(dev), torch.ones(vals.numel(), device=dev), True))
+    kv.pull(keys, out)
+    torch.testing.assert_close(out, vals + 1)
 
 
 @pytest.mark.parametrize("d,neg,impl", [(300, 25, "tma"), (300, 25, "ldg"), (128, 5, "tma"), (128, 5, "ldg"),
