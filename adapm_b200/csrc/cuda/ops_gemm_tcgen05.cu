@@ -20,6 +20,9 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <cstdlib>
+
 #include "ops.h"
 #include "tcgen05_utils.cuh"
 
@@ -146,12 +149,180 @@ gemm_nt_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Persistent variant for large problems: one CTA per SM walks over 128 x 256 output tiles; the fp32
+// accumulator is double-buffered in TMEM (2 x 256 columns = all 512) so that the epilogue of tile i
+// (tcgen05.ld -> registers -> HBM) overlaps the MMAs of tile i+1; UMMA shape 128 x 256 x 16 halves the
+// number of MMA instructions and of A-tile re-reads per output element.
+constexpr int PBN = 256;
+constexpr int PSTAGES = 4;
+constexpr int PB_BYTES = PBN * ROW_BYTES;     // 32 KiB
+struct PSmemLayout {
+  alignas(1024) unsigned char a[PSTAGES][A_BYTES];
+  alignas(1024) unsigned char b[PSTAGES][PB_BYTES];
+  alignas(8) unsigned long long full_bar[PSTAGES];
+  alignas(8) unsigned long long empty_bar[PSTAGES];
+  alignas(8) unsigned long long tmem_full_bar[2];
+  alignas(8) unsigned long long tmem_empty_bar[2];
+  unsigned int tmem_base;
+};
+
+template <int EPI, int KIND>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_nt_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                                  int M, int N, int K, float* __restrict__ C, int ldc, float alpha,
+                                  const float* __restrict__ true_score, const int* __restrict__ true_col,
+                                  int* __restrict__ rank_out) {
+  constexpr int BK = KIND == KIND_BF16 ? 64 : 128;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  PSmemLayout& sm = *reinterpret_cast<PSmemLayout*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_kb = (K + BK - 1) / BK;
+  const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + PBN - 1) / PBN;
+  const int num_tiles = tiles_m * tiles_n;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < PSTAGES; ++s) { mbar_init(&sm.full_bar[s], 1); mbar_init(&sm.empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&sm.tmem_full_bar[a], 1); mbar_init(&sm.tmem_empty_bar[a], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = sm.tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;  // running k-block counter across tiles (stage = it % PSTAGES)
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tile_m = tile % tiles_m, tile_n = tile / tiles_m;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % PSTAGES;
+          mbar_wait(&sm.empty_bar[s], ((it / PSTAGES) & 1u) ^ 1u);
+          mbar_expect_tx(&sm.full_bar[s], A_BYTES + PB_BYTES);
+          tma_load_2d(sm.a[s], &tmap_a, &sm.full_bar[s], kb * BK, tile_m * BM);
+          tma_load_2d(sm.b[s], &tmap_b, &sm.full_bar[s], kb * BK, tile_n * PBN);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(KIND, BM, PBN);
+      uint32_t it = 0, t_local = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t_local) {
+        const uint32_t acc = t_local & 1u;
+        mbar_wait(&sm.tmem_empty_bar[acc], ((t_local >> 1) & 1u) ^ 1u);   // epilogue drained this accumulator
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_base + acc * PBN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % PSTAGES;
+          mbar_wait(&sm.full_bar[s], (it / PSTAGES) & 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_addr = smem_u32(sm.a[s]);
+          const uint32_t b_addr = smem_u32(sm.b[s]);
+#pragma unroll
+          for (int k = 0; k < ROW_BYTES / MMA_K_BYTES; ++k)
+            umma<KIND>(d_tmem, umma_desc(a_addr + k * MMA_K_BYTES), umma_desc(b_addr + k * MMA_K_BYTES), idesc,
+                       (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&sm.empty_bar[s]);
+        }
+        umma_commit(&sm.tmem_full_bar[acc]);
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    uint32_t t_local = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t_local) {
+      const int tile_m = tile % tiles_m, tile_n = tile / tiles_m;
+      const uint32_t acc = t_local & 1u;
+      mbar_wait(&sm.tmem_full_bar[acc], (t_local >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int row = tile_m * BM + q * 32 + lane;
+      float ts = 0.f;
+      int tc = -1, cnt = 0;
+      if (EPI == EPI_RANK_COUNT && row < M) { ts = true_score[row]; tc = true_col[row]; }
+#pragma unroll 1
+      for (int c0 = 0; c0 < PBN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * PBN + (uint32_t)c0, r);
+        const int col0 = tile_n * PBN + c0;
+        if (EPI == EPI_STORE) {
+          if (row < M && col0 < N) {
+            float* dst = C + (size_t)row * ldc + col0;
+            if (col0 + 32 <= N && (((uintptr_t)dst) & 15u) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(dst + j) =
+                    make_float4(alpha * __uint_as_float(r[j]), alpha * __uint_as_float(r[j + 1]),
+                                alpha * __uint_as_float(r[j + 2]), alpha * __uint_as_float(r[j + 3]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < N) dst[j] = alpha * __uint_as_float(r[j]);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = col0 + j;
+            cnt += (col < N && col != tc && __uint_as_float(r[j]) > ts) ? 1 : 0;
+          }
+        }
+      }
+      if (EPI == EPI_RANK_COUNT && row < M && cnt) atomicAdd(rank_out + row, cnt);
+      // hand the accumulator back to the MMA warp
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&sm.tmem_empty_bar[acc])) : "memory");
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}
+
 template <int EPI, int KIND>
 void launch(cudaStream_t stream, const void* A, const void* B, int M, int N, int K, float* C, int ldc, float alpha,
             const float* true_score, const int* true_col, int* rank_out) {
   ADAPM_CHECK((K * (KIND == KIND_BF16 ? 2 : 1)) % 16 == 0, "gemm_nt: the K extent must be a multiple of 16 bytes (TMA row pitch)");
   ADAPM_CHECK((((uintptr_t)A) & 15u) == 0 && (((uintptr_t)B) & 15u) == 0, "gemm_nt: operands must be 16-byte aligned");
   CUtensorMap ma = make_map(A, M, K, BM, KIND);
+  // large problems: persistent kernel with 128x256 tiles and a double-buffered TMEM accumulator
+  static const int impl = [] { const char* e = getenv("ADAPM_GEMM_IMPL"); return e ? (e[0] == 'p' ? 2 : 1) : 0; }();
+  const long tiles_p = (long)((M + BM - 1) / BM) * ((N + PBN - 1) / PBN);
+  if (impl == 2 || (impl == 0 && tiles_p >= 128)) {
+    CUtensorMap mbp = make_map(B, N, K, PBN, KIND);
+    const size_t psmem = sizeof(PSmemLayout) + 1024;
+    static bool pattr_set = false;
+    static int num_sms = 0;
+    if (!pattr_set) {
+      ADAPM_CUDA_CHECK(cudaFuncSetAttribute(gemm_nt_tcgen05_persistent_kernel<EPI, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+      int dev = 0;
+      ADAPM_CUDA_CHECK(cudaGetDevice(&dev));
+      ADAPM_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+      pattr_set = true;
+    }
+    const int grid = (int)std::min<long>(tiles_p, num_sms);
+    gemm_nt_tcgen05_persistent_kernel<EPI, KIND><<<grid, kGemmThreads, psmem, stream>>>(ma, mbp, M, N, K, C, ldc, alpha,
+                                                                                      true_score, true_col, rank_out);
+    ADAPM_COUNT_LAUNCH();
+    ADAPM_CUDA_CHECK(cudaGetLastError());
+    return;
+  }
   CUtensorMap mb = make_map(B, N, K, BN, KIND);
   const size_t smem = sizeof(SmemLayout) + 1024;
   static bool attr_set = false;

@@ -6,7 +6,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 128, 512), (256, 384, 512), (100, 1000, 72), (2048, 14951, 512),
-                                   (1, 7, 8), (333, 129, 200)])
+                                   (1, 7, 8), (333, 129, 200), (1000, 5000, 200), (4096, 4096, 1024)])
 def test_gemm_nt_bf16_matches_torch(M, N, K):
     from adapm_b200.ops import gemm_nt_bf16
 
@@ -63,7 +63,7 @@ def test_kge_eval_tensor_core_path_matches_fp32():
     server.shutdown()
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 128, 128), (300, 500, 416), (64, 1000, 80)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 128), (300, 500, 416), (64, 1000, 80), (2048, 4096, 256)])
 def test_gemm_nt_fp8_matches_torch(M, N, K):
     """e4m3 operands on the kind::f8f6f4 tensor-core path vs the same quantised operands multiplied in fp32."""
     from adapm_b200.ops import gemm_nt_fp8
