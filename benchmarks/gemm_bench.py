@@ -42,6 +42,11 @@ def main():
         out = {"shape": [M, N, K], "name": name, "tcgen05_ms": mine, "cublas_bf16_out_ms": ref,
                "tcgen05_tflops": fl / mine / 1e9, "cublas_tflops": fl / ref / 1e9,
                "frac_of_measured_cublas_peak": fl / mine / 1e9 / peaks["bf16_tflops"]}
+        if M >= 4096 and N >= 4096:
+            a8 = a.float().to(torch.float8_e4m3fn); b8 = b.float().to(torch.float8_e4m3fn)
+            f8 = timeit(lambda: _C.gemm_nt_e4m3(st, a8.data_ptr(), b8.data_ptr(), M, N, K, c.data_ptr(), N, 1.0))
+            out["tcgen05_fp8_ms"] = f8
+            out["tcgen05_fp8_tflops"] = fl / f8 / 1e9
         if "KGE" in name:
             ts = torch.zeros(M, device="cuda"); tc = torch.zeros(M, dtype=torch.int64, device="cuda")
             af, bf = a.float(), b.float()
