@@ -80,7 +80,14 @@ def _ninja_file() -> str:
         lines.append(f"build {o}: nvcc {CSRC / s}")
         objs.append(str(o))
     lines.append(f"build {ext_path()}: link {' '.join(objs)}")
-    lines.append(f"default {ext_path()}")
+    # native (Python-free) application on the core API
+    core = [o for o in objs if not (o.endswith("bindings.cc.o") or o.endswith("ops_bind.cc.o"))]
+    app_o = BUILD / "apps_simple.cc.o"
+    lines.append(f"build {app_o}: cxx {CSRC / 'apps/simple.cc'}")
+    lines.append("rule linkexe")
+    lines.append(f"  command = g++ -o $out $in -L{CUDA_HOME}/lib64 -lcudart_static -ldl -lrt -lpthread")
+    lines.append(f"build {BUILD / 'adapm_simple'}: linkexe {app_o} {' '.join(core)}")
+    lines.append(f"default {ext_path()} {BUILD / 'adapm_simple'}")
     return "\n".join(lines) + "\n"
 
 
