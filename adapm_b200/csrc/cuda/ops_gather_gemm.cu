@@ -158,12 +158,7 @@ gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
       const int col0 = tile_n * BN + c0;
       if (EPI == G_STORE) {
-        if (row < M) {
-          float* dst = C + (size_t)row * ldc + col0;
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < N) dst[j] = __uint_as_float(r[j]);
-        }
+        store_chunk_coalesced(r, sm.epi[q], 1.f, C, ldc, tile_m * BM + q * 32, col0, M, N, lane);
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {

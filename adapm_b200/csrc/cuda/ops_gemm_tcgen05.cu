@@ -116,20 +116,7 @@ gemm_nt_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
       const int col0 = tile_n * BN + c0;
       if (EPI == EPI_STORE) {
-        if (row < M) {
-          float* dst = C + (size_t)row * ldc + col0;
-          if (col0 + 32 <= N && (((uintptr_t)dst) & 15u) == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(dst + j) =
-                  make_float4(alpha * __uint_as_float(r[j]), alpha * __uint_as_float(r[j + 1]),
-                              alpha * __uint_as_float(r[j + 2]), alpha * __uint_as_float(r[j + 3]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < N) dst[j] = alpha * __uint_as_float(r[j]);
-          }
-        }
+        store_chunk_coalesced(r, sm.epi[q], alpha, C, ldc, tile_m * BM + q * 32, col0, M, N, lane);
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -165,6 +152,7 @@ struct PSmemLayout {
   alignas(8) unsigned long long tmem_full_bar[2];
   alignas(8) unsigned long long tmem_empty_bar[2];
   unsigned int tmem_base;
+  float epi[4][32 * 33];
 };
 
 template <int EPI, int KIND>
@@ -257,20 +245,7 @@ gemm_nt_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, co
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * PBN + (uint32_t)c0, r);
         const int col0 = tile_n * PBN + c0;
         if (EPI == EPI_STORE) {
-          if (row < M && col0 < N) {
-            float* dst = C + (size_t)row * ldc + col0;
-            if (col0 + 32 <= N && (((uintptr_t)dst) & 15u) == 0) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(dst + j) =
-                    make_float4(alpha * __uint_as_float(r[j]), alpha * __uint_as_float(r[j + 1]),
-                                alpha * __uint_as_float(r[j + 2]), alpha * __uint_as_float(r[j + 3]));
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < N) dst[j] = alpha * __uint_as_float(r[j]);
-            }
-          }
+          if (col0 < N) store_chunk_coalesced(r, sm.epi[q], alpha, C, ldc, tile_m * BM + q * 32, col0, M, N, lane);
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {

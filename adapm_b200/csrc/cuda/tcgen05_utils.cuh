@@ -29,7 +29,24 @@ struct SmemLayout {
   alignas(8) unsigned long long empty_bar[STAGES];
   alignas(8) unsigned long long tmem_full_bar;
   unsigned int tmem_base;
+  float epi[4][32 * 33];   // per epilogue warp: 32x32 transpose tile (padded) for coalesced C stores
 };
+
+// Epilogue helper: lane i holds 32 consecutive columns of tile row i (what tcgen05.ld 32x32b gives); write them
+// through a padded shared-memory tile so that every global store instruction covers one 128-byte row segment.
+__device__ __forceinline__ void store_chunk_coalesced(const uint32_t (&r)[32], float* tile, float alpha, float* C, int ldc,
+                                                      int row0, int col0, int M, int N, int lane) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = alpha * __uint_as_float(r[j]);
+  __syncwarp();
+  const int col = col0 + lane;
+#pragma unroll 4
+  for (int rr = 0; rr < 32; ++rr) {
+    const int row = row0 + rr;
+    if (row < M && col < N) C[(size_t)row * ldc + col] = tile[rr * 33 + lane];
+  }
+  __syncwarp();
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
