@@ -1,0 +1,91 @@
+"""Auxiliary subsystems: key tracing, locality statistics, PS all-reduce, options, ActionTimer, launcher."""
+import glob
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from harness import run_cluster
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _trace_worker(kv, server, wid):
+    kv.barrier()
+    if wid == 0:
+        kv.intent(torch.tensor([3, 4]), 1)      # key 3 is home at rank 1, key 4 at rank 0
+    v = torch.zeros(4)
+    kv.pull(torch.tensor([3, 5]), v)
+    kv.advance_clock(); kv.wait_sync(); kv.barrier()
+    kv.advance_clock(); kv.advance_clock(); kv.wait_sync(); kv.barrier()
+    kv.pull(torch.tensor([3, 5]), v)
+    kv.finalize()
+    return None
+
+
+def test_key_tracing_and_locality_stats(tmp_path):
+    run_cluster(_trace_worker, world=2, workers=1, mode="threads", value_lengths=2, num_keys=12,
+                options={"sys.trace.keys": "3,4", "sys.stats.out": str(tmp_path), "sys.stats.locality": 1})
+    t0 = open(tmp_path / "traces.0.tsv").read().splitlines()
+    t1 = open(tmp_path / "traces.1.tsv").read().splitlines()
+    ev0 = [(l.split("\t")[1], l.split("\t")[3]) for l in t0]
+    ev1 = [(l.split("\t")[1], l.split("\t")[3]) for l in t1]
+    assert ("3", "INTENT_START") in ev0 and ("3", "ALLOC") in ev0     # key 3 relocated to rank 0 ...
+    assert ("3", "DEALLOC") in ev1                                     # ... and left rank 1
+    loc = open(tmp_path / "locality_stats.rank.0.tsv").read().splitlines()
+    assert loc[0] == "Param\tAccesses\tLocalAccesses" and any(l.startswith("3\t2\t") for l in loc[1:])
+
+
+def _allreduce_worker(kv, server, wid):
+    from adapm_b200.utils.allreduce import ps_allreduce
+
+    out = ps_allreduce(kv, 7, torch.tensor([float(wid + 1), 10.0 * (wid + 1)]))
+    kv.barrier()
+    kv.finalize()
+    return out.tolist()
+
+
+def test_ps_allreduce():
+    res = run_cluster(_allreduce_worker, world=3, workers=1, mode="threads", value_lengths=4, num_keys=10)
+    for r in res.values():
+        assert r[0] == [6.0, 60.0]
+
+
+def test_options_and_action_timer():
+    from adapm_b200 import _C
+    import adapm_b200 as ad
+
+    # Poisson quantile used by the ActionTimer (values from scipy.stats.poisson.ppf): the reference's start-up
+    # window is quantile_0.9999(Poisson(2 * 10)) = 39 clocks
+    assert _C.poisson_quantile(20.0, 0.9999) == 39
+    assert _C.poisson_quantile(399.0, 0.9999) == 475
+    assert abs(_C.poisson_quantile(2e6, 0.9999) - 2005262) <= 2
+    with pytest.raises(RuntimeError):
+        ad.Server(2, num_keys=10, rank=0, world=1, backend="cpu", options={"sys.unknown_flag": 1})
+    with pytest.raises(RuntimeError):
+        ad.Server(2, num_keys=10, rank=0, world=1, backend="cpu", options={"sys.channels": 3})
+    s = ad.Server(2, num_keys=10, rank=0, world=1, backend="cpu", job="opts",
+                  options={"sys.techniques": "replication_only", "sys.sync.threshold": "inf", "sys.sync.max_per_sec": 50,
+                           "sys.zmq_threads": 5, "sys.location_caches": 0, "sampling.scheme": "naive"})
+    w = ad.Worker(0, s)
+    with pytest.raises(IndexError):
+        w.pull(torch.tensor([10]), torch.zeros(2))
+    with pytest.raises(ValueError):
+        w.pull(torch.tensor([1]), torch.zeros(3))
+    w.finalize(); s.shutdown()
+
+
+def test_launcher_runs_simple_app():
+    out = subprocess.run([sys.executable, "-m", "adapm_b200.launch", "-s", "2", "--backend", "cpu", "-m",
+                          "adapm_b200.apps.simple", "--", "-k", "10", "-t", "2", "-i", "2", "-v", "2"],
+                         capture_output=True, text=True, timeout=120, cwd=ROOT)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert out.stdout.count("iteration") == 2 * 2 * 2
+
+
+def test_bindings_example_runs():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "examples", "bindings_example.py")], capture_output=True,
+                         text=True, timeout=180, cwd=ROOT, env={**os.environ, "ADAPM_BACKEND": "cpu"})
+    assert out.returncode == 0 and out.stdout.count("done") == 4, out.stdout[-2000:] + out.stderr[-2000:]
