@@ -108,7 +108,7 @@ def main():
         kv.intent(torch.arange(rank * rpb, min(cfg.num_rows, (rank + 1) * rpb)), 0, ad.CLOCK_MAX)
     loss = torch.zeros(1, device=dev); stats = torch.zeros(4, dtype=torch.int64, device=dev)
     n = cfg.batch_nnz
-    steps_per_block = 6
+    steps_per_block = 32
     packs = {}
     for b in range(world):
         packs[b] = []
