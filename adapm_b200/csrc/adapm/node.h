@@ -65,6 +65,9 @@ class SyncEngine {
   std::deque<FutureIntent> incoming_;
   std::vector<std::priority_queue<FutureIntent, std::vector<FutureIntent>, IntentLater>> heaps_;  // per worker
   std::vector<IntentRec> recs_, deferred_;
+  std::vector<uint32_t> seen_epoch_;   // intent dedupe table (one stamp per key)
+  uint32_t epoch_ = 0;
+  std::atomic<uint64_t> deferred_pending_{0};  // intent records that could not be registered in the last round
   std::vector<uint8_t> status_;
   uint64_t round_no_ = 0;
   std::chrono::steady_clock::time_point last_run_;

@@ -320,7 +320,12 @@ ADAPM_HD int register_intent(const Ctx& c, const IntentRec& rec, const Clock* cl
     }
     const int cls = class_of_key(c, key);
     int32_t ns = alloc_slot(c, cls);
-    if (ns < 0) { mem::st_relaxed(slot_of(c, me) + key, (int32_t)-1); count(c, C_ALLOC_FAIL); return 2; }
+    if (ns < 0) {
+      // pool exhausted: give the claim back and retry in a later round (slots free up as replicas expire)
+      mem::st_relaxed(slot_of(c, me) + key, (int32_t)-1);
+      count(c, C_ALLOC_FAIL);
+      return 1;
+    }
     const uint32_t len = c.L.cls[cls].len;
     Val* row = row_ptr<Val>(c, me, cls, ns);
     Val* base = base_ptr<Val>(c, me, cls, ns);

@@ -70,14 +70,17 @@ inline Layout build_layout(const ValueSpec& spec, const Options& opt, std::vecto
   for (int c = 0; c < L.num_classes; ++c) {
     int64_t n_c = 0, home_max = 0;
     for (int r = 0; r < opt.world; ++r) { n_c += home_count[c][r]; home_max = std::max(home_max, home_count[c][r]); }
+    // A key can transiently occupy two slots on a rank (relocation source kept readable for one round while
+    // the key is already requested back; worst case: every key), so "every key everywhere" needs slack above n_c.
+    const int64_t full = n_c <= (1 << 16) ? 2 * n_c + 64 : n_c + n_c / 4;
     int64_t cap;
     if (opt.world == 1) cap = n_c;
-    else if (n_c <= (1 << 16) && opt.pool_factor <= 0) cap = n_c;
+    else if (n_c <= (1 << 16) && opt.pool_factor <= 0) cap = full;
     else {
       double f = opt.pool_factor > 0 ? opt.pool_factor : 2.0;
-      cap = std::min<int64_t>(n_c, (int64_t)std::ceil(home_max * f) + 1024);
+      cap = std::min<int64_t>(full, (int64_t)std::ceil(home_max * f) + 1024);
     }
-    cap = std::max<int64_t>(cap, std::min<int64_t>(n_c, opt.min_pool));
+    cap = std::max<int64_t>(cap, std::min<int64_t>(full, opt.min_pool));
     cap = std::max<int64_t>(cap, home_max);
     L.cls[c].len = class_len[c];
     L.cls[c].cap = (uint32_t)cap;

@@ -65,13 +65,24 @@ uint64_t SyncEngine::rounds_done() const {
 void SyncEngine::wait_sync() {
   if (server_->num_servers() == 1) return;
   RankControl& rc = server_->my_control();
-  const uint64_t target = rc.rounds_done.load(std::memory_order_acquire) + 2;
+  uint64_t target = rc.rounds_done.load(std::memory_order_acquire) + 2;
   // ask for (at least) two guaranteed-propagation rounds
   int32_t cur = rc.sweep_requested.load();
   while (cur < 2 && !rc.sweep_requested.compare_exchange_weak(cur, 2)) {}
   auto t0 = std::chrono::steady_clock::now();
   int spins = 0;
-  while (rc.rounds_done.load(std::memory_order_acquire) < target) {
+  // ... and keep waiting (bounded) while intents of this rank are still deferred, e.g. because a key's old
+  // slot has to be recycled first or the pool is momentarily full
+  int extensions = 0;
+  for (;;) {
+    const uint64_t done = rc.rounds_done.load(std::memory_order_acquire);
+    if (done >= target) {
+      if (deferred_pending_.load(std::memory_order_acquire) == 0 || extensions >= 4) break;
+      target = done + 2;   // the deferred records register in the next round; wait until that round is complete
+      ++extensions;
+      int32_t c2 = rc.sweep_requested.load();
+      while (c2 < 2 && !rc.sweep_requested.compare_exchange_weak(c2, 2)) {}
+    }
     if (++spins < 50) std::this_thread::yield();
     else std::this_thread::sleep_for(std::chrono::microseconds(50));
     if ((spins & 4095) == 0) {
@@ -106,8 +117,21 @@ void SyncEngine::collect_intents(const std::vector<Clock>& clocks, const std::ve
         // worker thread, once per batch
         std::vector<Key>& ks = *fi.keys;
         if (ks.size() > 1) {
-          std::sort(ks.begin(), ks.end());
-          ks.erase(std::unique(ks.begin(), ks.end()), ks.end());
+          const int64_t nk = server_->num_keys();
+          if (nk <= (int64_t)1 << 25) {
+            // O(n) dedupe with an epoch-stamped table (4 B per key) instead of a sort
+            if (seen_epoch_.empty()) seen_epoch_.assign((size_t)nk, 0u);
+            if (++epoch_ == 0) { std::fill(seen_epoch_.begin(), seen_epoch_.end(), 0u); epoch_ = 1; }
+            size_t m = 0;
+            for (size_t i = 0; i < ks.size(); ++i) {
+              const Key k = ks[i];
+              if (seen_epoch_[(size_t)k] != epoch_) { seen_epoch_[(size_t)k] = epoch_; ks[m++] = k; }
+            }
+            ks.resize(m);
+          } else {
+            std::sort(ks.begin(), ks.end());
+            ks.erase(std::unique(ks.begin(), ks.end()), ks.end());
+          }
         }
         for (Key k : ks) {
           IntentRec r;
@@ -148,6 +172,7 @@ void SyncEngine::round(bool sweep) {
       else if (status_[i] == 0) ++recs_registered_;
     }
   }
+  deferred_pending_.store(deferred_.size(), std::memory_order_release);
   sw_register_.stop();
 
   sw_phase_a_.resume();

@@ -115,6 +115,18 @@ PYBIND11_MODULE(_C, m) {
         if (s.sampling()) { m["checks"] = s.sampling()->local_checks(); m["pulls"] = s.sampling()->local_pulls(); }
         return m;
       })
+      .def("slot_histogram", [](Server& s) {
+        // debugging / tests: number of slots per state on this rank + free-stack fill per class
+        const Layout& L = s.backend().ctx().L;
+        std::vector<uint32_t> meta(L.total_slots);
+        s.backend().read_heap(L.off_meta, meta.data(), meta.size() * 4);
+        std::map<int, int64_t> h;
+        for (uint32_t m : meta) h[(int)meta_state(m)]++;
+        int32_t tops[MAX_CLASSES];
+        s.backend().read_heap(L.off_free_top, tops, sizeof(tops));
+        for (int c = 0; c < L.num_classes; ++c) h[100 + c] = tops[c];
+        return h;
+      })
       .def("backend_handle", [](Server& s) { return (uintptr_t)&s.backend(); });
 
   py::class_<Worker, std::shared_ptr<Worker>>(m, "Worker")
