@@ -92,11 +92,6 @@ ADAPM_D uint64_t fetch_or(uint64_t* p, uint64_t v) {
 ADAPM_D uint64_t exchange(uint64_t* p, uint64_t v) {
   return (uint64_t)atomicExch_system((unsigned long long*)p, (unsigned long long)v);
 }
-ADAPM_D uint8_t exchange_u8_nonatomic(uint8_t* p, uint8_t v) {
-  uint8_t o = ld_relaxed(p);
-  st_relaxed(p, v);
-  return o;
-}
 // fire-and-forget reductions (REDG; over NVLink for peer pointers)
 ADAPM_D void red_add(float* p, float v) {
   asm volatile("red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
@@ -141,7 +136,6 @@ inline void st_relaxed(double* p, double v) {
 template <class T> inline T fetch_add(T* p, T v) { return __atomic_fetch_add(p, v, __ATOMIC_ACQ_REL); }
 inline uint64_t fetch_or(uint64_t* p, uint64_t v) { return __atomic_fetch_or(p, v, __ATOMIC_ACQ_REL); }
 inline uint64_t exchange(uint64_t* p, uint64_t v) { return __atomic_exchange_n(p, v, __ATOMIC_ACQ_REL); }
-inline uint8_t exchange_u8_nonatomic(uint8_t* p, uint8_t v) { return __atomic_exchange_n(p, v, __ATOMIC_ACQ_REL); }
 inline void red_add(int64_t* p, int64_t v) { __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline void red_add(uint64_t* p, uint64_t v) { __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline void red_add(uint32_t* p, uint32_t v) { __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }

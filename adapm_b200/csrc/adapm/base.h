@@ -66,15 +66,14 @@ ADAPM_HD uint32_t meta_next(uint32_t m, uint32_t state, uint32_t peer) {
 }
 
 // slot flag bits (one byte per slot)
-constexpr uint8_t F_DIRTY = 1;      // hint: replica received local pushes since last delta ship
 constexpr uint8_t F_REQUESTED = 2;  // this rank asked the owner for a refresh in this round
 
 // Counters written by the PM kernels / loops (one block per rank, in the heap).
 enum Counter : int {
-  C_PULL_LOCAL = 0, C_PULL_REMOTE, C_PUSH_LOCAL, C_PUSH_REMOTE, C_PUSH_REPLICA,
+  C_PULL_LOCAL = 0, C_PULL_REMOTE, C_PUSH_LOCAL, C_PUSH_REMOTE,
   C_RELOCATIONS, C_REPLICA_SETUPS, C_REPLICA_DROPS, C_REFRESHES, C_DELTAS_SHIPPED,
-  C_INTENTS_REGISTERED, C_INTENTS_DEFERRED, C_ALLOC_FAIL, C_RETRIES, C_PROTOCOL_ERRORS,
-  C_SAMPLE_CHECKS, C_SAMPLES, C_REMOTE_BYTES, C_NUM_COUNTERS = 32
+  C_INTENTS_REGISTERED, C_INTENTS_DEFERRED, C_ALLOC_FAIL, C_PROTOCOL_ERRORS,
+  C_NUM_COUNTERS = 32
 };
 
 }  // namespace adapm

@@ -86,15 +86,6 @@ ADAPM_HD int class_of_key(const Ctx& c, Key k) {
   if (c.L.num_classes == 1) return 0;
   return at<uint8_t>(c, c.rank, c.L.off_key_class)[k];
 }
-ADAPM_HD int class_of_slot(const Ctx& c, uint32_t slot) {
-  int k = 0;
-#if defined(__CUDACC__)
-#pragma unroll
-#endif
-  for (int i = 1; i < MAX_CLASSES; ++i)
-    if (i < c.L.num_classes && slot >= c.L.cls[i].slot_begin) k = i;
-  return k;
-}
 template <class Val> ADAPM_HD Val* row_ptr(const Ctx& c, int r, int cls, uint32_t slot) {
   const ClassInfo& ci = c.L.cls[cls];
   return reinterpret_cast<Val*>(c.heap[r] + ci.rows_off) + (size_t)(slot - ci.slot_begin) * ci.len;

@@ -96,8 +96,7 @@ std::map<std::string, uint64_t> Server::counters() {
   m["replica_drops"] = c[C_REPLICA_DROPS]; m["refreshes"] = c[C_REFRESHES];
   m["deltas_shipped"] = c[C_DELTAS_SHIPPED]; m["intents_registered"] = c[C_INTENTS_REGISTERED];
   m["intents_deferred"] = c[C_INTENTS_DEFERRED]; m["alloc_fail"] = c[C_ALLOC_FAIL];
-  m["protocol_errors"] = c[C_PROTOCOL_ERRORS]; m["samples"] = c[C_SAMPLES];
-  m["sample_checks"] = c[C_SAMPLE_CHECKS];
+  m["protocol_errors"] = c[C_PROTOCOL_ERRORS];
   m["sync_rounds"] = sync_ ? sync_->rounds_done() : 0;
   return m;
 }

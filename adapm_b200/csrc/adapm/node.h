@@ -73,7 +73,6 @@ class SyncEngine {
   std::chrono::steady_clock::time_point last_run_;
   Stopwatch sw_total_, sw_pausing_, sw_register_, sw_phase_a_, sw_phase_b_, sw_grace_, sw_phase_c_, sw_barriers_;
   uint64_t intents_seen_ = 0, recs_registered_ = 0;
-  bool started_ = false;
 };
 
 // -------------------------------------------------------------------------------------

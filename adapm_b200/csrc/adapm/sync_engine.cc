@@ -32,7 +32,6 @@ SyncEngine::~SyncEngine() {
 }
 
 void SyncEngine::start() {
-  started_ = true;
   if (server_->num_servers() == 1) return;  // nothing to synchronise
   last_run_ = std::chrono::steady_clock::now();
   thread_ = std::thread([this] {
