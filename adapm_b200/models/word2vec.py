@@ -119,6 +119,12 @@ class Word2Vec:
             self._keys_dev = [torch.empty(2, cfg.batch_pairs, dtype=torch.int64, device=dev)
                               for _ in range(max(1, cfg.max_inflight) + 1)]
             self._events = [None] * len(self._keys_dev)
+            # data-loader side: the NEXT batch is copied host->device on a copy stream while the current step runs
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._pf_bufs = [torch.empty(2, cfg.batch_pairs, dtype=torch.int64, device=dev)
+                             for _ in range(max(1, cfg.max_inflight) + 2)]
+            self._pf_no = 0
+            self._pf = None
         else:
             w = torch.from_numpy(weights)
             self._neg_cdf = torch.cumsum(w / w.sum(), 0)
@@ -162,8 +168,13 @@ class Word2Vec:
             slot = self.step_no % len(self._keys_dev)
             if self._events[slot] is not None:
                 self._events[slot].synchronize()   # bounded run-ahead: at most max_inflight steps queued
-            kd = self._keys_dev[slot]
-            kd.copy_(keys_host, non_blocking=True)  # H2D of this step's inputs
+            if self._pf is not None and self._pf[0] is keys_host:
+                kd = self._pf_bufs[self._pf[1]]                      # H2D of this step's inputs was prefetched
+                torch.cuda.current_stream().wait_event(self._pf[2])
+                self._pf = None
+            else:
+                kd = self._keys_dev[slot]
+                kd.copy_(keys_host, non_blocking=True)               # H2D of this step's inputs
             self.sample_negatives()
             sgns_step(self.server, kd[0], kd[1], self._neg, cfg.embed_dim, self.alpha, self.loss, self.stats)
             ev = self._events[slot] or torch.cuda.Event()
@@ -172,6 +183,19 @@ class Word2Vec:
             self.step_no += 1
             return self.loss
         return self._step_cpu(keys_host)
+
+    def prefetch(self, keys_host: torch.Tensor) -> None:
+        """Start the host->device copy of a future step's key batch (pinned memory) on the copy stream; the
+        next ``step(keys_host)`` with the same tensor uses the prefetched copy."""
+        if not self.cuda:
+            return
+        b = self._pf_no % len(self._pf_bufs)
+        self._pf_no += 1
+        with torch.cuda.stream(self._copy_stream):
+            self._pf_bufs[b].copy_(keys_host, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        self._pf = (keys_host, b, ev)
 
     def sample_negatives(self) -> torch.Tensor:
         """PrepareSample/PullSample on the device: draws batch_pairs*negative syn1 keys; the ``local``

@@ -183,8 +183,9 @@ def main():
         if resident:
             model.step_resident(dev_ring[s % len(dev_ring)])
         else:
-            model.step(batches[s])                                       # H2D copy + sampler + fused step
+            model.step(batches[s])                                       # (prefetched) H2D copy + sampler + fused step
             loss_host[s:s + 1].copy_(model.loss, non_blocking=True)      # D2H read of the step result
+            model.prefetch(batches[s + 1])                               # H2D of the next step's keys (copy stream)
         worker.advance_clock()
 
     # ---------------- warm-up (also lets the sync engine localise the first batches)
