@@ -23,6 +23,7 @@ CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
 CXX_SOURCES = [
     "adapm/fabric.cc",
     "adapm/node.cc",
+    "adapm/rpc.cc",
     "adapm/sampling.cc",
     "adapm/store_cpu.cc",
     "adapm/sync_engine.cc",

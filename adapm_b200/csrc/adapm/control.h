@@ -66,6 +66,25 @@ struct alignas(64) RankControl {
   int32_t pid;
 };
 
+// Host RPC mailboxes (rpc.h): one multi-producer / single-consumer ring of fragments per rank.
+constexpr int MAIL_SLOTS = 64;
+constexpr int MAIL_BODY = 976;
+
+struct MailSlot {
+  std::atomic<uint32_t> state;   // 0 = free, 1 = published
+  int32_t sender, app_id, customer_id, head, timestamp;
+  int32_t flags;                 // bit 0: request (else response)
+  uint32_t msg_id, frag_off, total_len, frag_len;
+  char body[MAIL_BODY];
+};
+static_assert(sizeof(MailSlot) == 1024 - 4, "MailSlot layout");
+
+struct Mailbox {
+  std::atomic<uint64_t> tail;    // next ticket (producers)
+  std::atomic<uint64_t> head;    // next ticket to consume (owner)
+  MailSlot slots[MAIL_SLOTS];
+};
+
 struct ControlBlock {
   uint32_t magic;
   int32_t world;
@@ -78,6 +97,7 @@ struct ControlBlock {
   std::atomic<int32_t> round_stop;
   std::atomic<int64_t> allreduce_buf[64];
   RankControl ranks[MAX_RANKS];
+  Mailbox mail[MAX_RANKS];
 };
 
 constexpr uint32_t kControlMagic = 0xADA9B200u;

@@ -40,6 +40,13 @@ void Server::enable_sampling_support(std::shared_ptr<KeyDistribution> dist, cons
 
 void Server::barrier() { fabric_->node_barrier("Server::barrier"); }
 
+MailRouter& Server::router() {
+  std::lock_guard<std::mutex> lk(mu_);
+  ADAPM_CHECK(!shut_down_, "rpc: the server is shut down");
+  if (!router_) router_.reset(new MailRouter(this));
+  return *router_;
+}
+
 void Server::worker_barrier() {
   control()->worker_barrier.wait(opt_.world * opt_.workers, opt_.wait_timeout_s, "Worker::Barrier");
 }
@@ -53,6 +60,7 @@ void Server::shutdown() {
   if (tracing()) write_traces();
   if (opt_.locality_stats) write_locality_stats();
   fabric_->node_barrier("shutdown done");
+  if (router_) router_->stop();   // after the barrier: every peer's requests have been answered
   backend_.reset();
   fabric_.reset();
 }
@@ -266,9 +274,20 @@ int Worker::Intent(const Key* keys, size_t n, Clock start, Clock end) {
   if (end == 0) end = start + 1;
   if (server_.num_servers() == 1 || n == 0) return LOCAL;  // single node: nothing to manage
   // Copy only: duplicates are removed by the sync thread (off the worker's critical path).
-  auto uniq = std::make_shared<std::vector<Key>>(keys, keys + n);
-  for (Key k : *uniq)
-    ADAPM_CHECK(k >= 0 && k < server_.num_keys(), "[ERROR] Intent key " << k << " is outside the configured key range");
+  auto uniq = server_.sync_->acquire_key_buffer();
+  uniq->resize(n);
+  Key* dst = uniq->data();
+  const Key nk = server_.num_keys();
+  Key bad = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const Key k = keys[i];
+    dst[i] = k;
+    bad |= (Key)((uint64_t)k >= (uint64_t)nk);
+  }
+  if (bad) {
+    for (size_t i = 0; i < n; ++i)
+      ADAPM_CHECK(keys[i] >= 0 && keys[i] < nk, "[ERROR] Intent key " << keys[i] << " is outside the configured key range");
+  }
   FutureIntent fi;
   fi.start = start; fi.end = end; fi.worker = id_; fi.keys = uniq;
   server_.sync_->enqueue(std::move(fi));

@@ -18,6 +18,7 @@
 #include <unordered_map>
 #include <unordered_set>
 #include "action_timer.h"
+#include "rpc.h"
 #include "store.h"
 
 namespace adapm {
@@ -46,6 +47,8 @@ class SyncEngine {
   void request_stop_and_join();   // collective: returns once all ranks agreed to stop
 
   void enqueue(FutureIntent&& fi);
+  // key buffers of processed intents are recycled (a fresh 512 KB vector per batch would page-fault every step)
+  std::shared_ptr<std::vector<Key>> acquire_key_buffer();
   uint64_t rounds_done() const;
   // Block until one complete round that started after this call has finished on this rank
   // (reference WaitSync, coloc_kv_worker.h:517-550). Requests guaranteed propagation.
@@ -63,6 +66,8 @@ class SyncEngine {
   ActionTimer timer_;
   std::mutex in_mu_;
   std::deque<FutureIntent> incoming_;
+  std::mutex pool_mu_;
+  std::vector<std::shared_ptr<std::vector<Key>>> key_pool_;
   std::vector<std::priority_queue<FutureIntent, std::vector<FutureIntent>, IntentLater>> heaps_;  // per worker
   std::vector<IntentRec> recs_, deferred_;
   std::vector<uint32_t> seen_epoch_;   // intent dedupe table (one stamp per key)
@@ -151,6 +156,8 @@ class Server {
   Sampling* sampling() { return sampling_.get(); }
   ControlBlock* control() { return fabric_->control(); }
   RankControl& my_control() { return fabric_->control()->ranks[opt_.rank]; }
+  MailRouter& router();                        // host RPC (rpc.h); created on first use
+  MailRouter* router_if_any() { return router_.get(); }
 
   // Addressbook-style queries (addressbook.h:50-112)
   int owner_of(Key k);                 // this rank's view of the current owner
@@ -186,6 +193,7 @@ class Server {
   std::unique_ptr<Backend> backend_;
   std::unique_ptr<SyncEngine> sync_;
   std::unique_ptr<Sampling> sampling_;
+  std::unique_ptr<MailRouter> router_;
   std::mutex mu_;
   std::vector<Worker*> workers_;
   bool shut_down_ = false;

@@ -57,6 +57,18 @@ void SyncEngine::enqueue(FutureIntent&& fi) {
   incoming_.push_back(std::move(fi));
 }
 
+std::shared_ptr<std::vector<Key>> SyncEngine::acquire_key_buffer() {
+  {
+    std::lock_guard<std::mutex> lk(pool_mu_);
+    if (!key_pool_.empty()) {
+      auto b = std::move(key_pool_.back());
+      key_pool_.pop_back();
+      return b;
+    }
+  }
+  return std::make_shared<std::vector<Key>>();
+}
+
 uint64_t SyncEngine::rounds_done() const {
   return server_->my_control().rounds_done.load(std::memory_order_acquire);
 }
@@ -139,7 +151,12 @@ void SyncEngine::collect_intents(const std::vector<Clock>& clocks, const std::ve
           if (server_->tracing() && (server_->trace_all_ || server_->traced_.count(k))) server_->trace(k, TraceEvent::INTENT_START);
         }
       }
+      std::shared_ptr<std::vector<Key>> done = fi.keys;
       h.pop();
+      if (done.use_count() == 1) {
+        std::lock_guard<std::mutex> lk(pool_mu_);
+        if (key_pool_.size() < 64) key_pool_.push_back(std::move(done));
+      }
     }
   }
 }

@@ -177,5 +177,49 @@ PYBIND11_MODULE(_C, m) {
         return m;
       });
 
+  // host RPC (legacy SimpleApp capability, rpc.h)
+  m.attr("kServerGroup") = (int)kServerGroup;
+  m.attr("kWorkerGroup") = (int)kWorkerGroup;
+  m.attr("kAllNodes") = (int)kAllNodes;
+  py::class_<SimpleData>(m, "SimpleData")
+      .def(py::init<>())
+      .def_readwrite("head", &SimpleData::head)
+      .def_property("body", [](const SimpleData& d) { return py::bytes(d.body); },
+                    [](SimpleData& d, const std::string& b) { d.body = b; })
+      .def_readwrite("sender", &SimpleData::sender)
+      .def_readwrite("timestamp", &SimpleData::timestamp)
+      .def_readwrite("customer_id", &SimpleData::customer_id);
+  auto wrap_handle = [](py::function fn) {
+    // the handle runs on the router thread: take the GIL there; the Python callable gets (SimpleData, app)
+    auto f = std::shared_ptr<py::function>(new py::function(std::move(fn)), [](py::function* p) {
+      py::gil_scoped_acquire g;
+      delete p;
+    });
+    return SimpleApp::Handle([f](const SimpleData& d, SimpleApp* app) {
+      py::gil_scoped_acquire g;
+      try {
+        (*f)(d, py::cast(app, py::return_value_policy::reference));
+      } catch (py::error_already_set& e) {
+        ALOG("[adapm] rpc handle raised: " << e.what());
+      }
+    });
+  };
+  py::class_<SimpleApp, std::shared_ptr<SimpleApp>>(m, "SimpleApp")
+      .def(py::init([](int app_id, int customer_id, std::shared_ptr<Server> server, bool serves_requests) {
+             return std::make_shared<SimpleApp>(app_id, customer_id, *server, serves_requests);
+           }),
+           py::keep_alive<1, 4>())
+      .def("request", [](SimpleApp& a, int head, const std::string& body, int recv_id) {
+             return a.Request(head, body, recv_id);
+           }, py::call_guard<py::gil_scoped_release>())
+      .def("response", [](SimpleApp& a, const SimpleData& req, const std::string& body) { a.Response(req, body); },
+           py::arg("req"), py::arg("body") = std::string(), py::call_guard<py::gil_scoped_release>())
+      .def("wait", &SimpleApp::Wait, py::call_guard<py::gil_scoped_release>())
+      .def("num_response", &SimpleApp::NumResponse)
+      .def("set_request_handle", [wrap_handle](SimpleApp& a, py::function fn) { a.set_request_handle(wrap_handle(std::move(fn))); })
+      .def("set_response_handle", [wrap_handle](SimpleApp& a, py::function fn) { a.set_response_handle(wrap_handle(std::move(fn))); })
+      .def_property_readonly("app_id", &SimpleApp::app_id)
+      .def_property_readonly("customer_id", &SimpleApp::customer_id);
+
   adapm::cudaops::bind(m);
 }

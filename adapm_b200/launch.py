@@ -22,9 +22,9 @@ import uuid
 
 
 def _free_port() -> int:
-    with socket.socket() as s:
-        s.bind(("127.0.0.1", 0))
-        return s.getsockname()[1]
+    from .utils.net import get_available_port
+
+    return get_available_port("127.0.0.1")
 
 
 def main(argv=None) -> int:

@@ -89,3 +89,35 @@ def test_bindings_example_runs():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "examples", "bindings_example.py")], capture_output=True,
                          text=True, timeout=180, cwd=ROOT, env={**os.environ, "ADAPM_BACKEND": "cpu"})
     assert out.returncode == 0 and out.stdout.count("done") == 4, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_kv_match_and_sort():
+    from adapm_b200.utils import kvmatch as km
+
+    g = torch.Generator().manual_seed(3)
+    keys = torch.randperm(1000, generator=g)[:300]
+    srt = km.parallel_sort(keys.clone())
+    assert torch.equal(srt, torch.sort(keys).values)
+    sk, sv = km.sort_by_key(keys, torch.arange(600.), k=2)
+    assert torch.equal(sk, srt) and sv.view(-1, 2)[0].tolist() == [2.0 * int(torch.argmin(keys)), 2.0 * int(torch.argmin(keys)) + 1]
+    src_k = torch.tensor([1, 3, 5, 9]); src_v = torch.arange(8.)
+    dst_k = torch.tensor([0, 1, 2, 5, 9, 11]); dst_v = torch.ones(12)
+    n = km.parallel_ordered_match(src_k, src_v, dst_k, dst_v, k=2, op=km.PLUS)
+    assert n == 6 and dst_v.tolist() == [1, 1, 1, 2, 1, 1, 5, 6, 7, 8, 1, 1]
+    n = km.parallel_ordered_match(src_k, src_v, dst_k, dst_v, k=2, op=km.ASSIGN)
+    assert n == 6 and dst_v.view(-1, 2)[1].tolist() == [0, 1] and dst_v.view(-1, 2)[4].tolist() == [6, 7]
+    assert km.parallel_ordered_match(torch.tensor([100]), torch.zeros(2), dst_k, dst_v, k=2) == 0
+
+
+def test_network_utils():
+    import socket
+
+    from adapm_b200.utils import net
+
+    ifs = net.list_interfaces()
+    assert ifs and all(len(p) == 2 for p in ifs)
+    name, ip = net.get_available_interface_and_ip()
+    assert net.get_ip(name) == ip and net.get_ip("no-such-if0") is None
+    port = net.get_available_port()
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", port))          # the port really is free
