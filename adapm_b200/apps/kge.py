@@ -38,7 +38,9 @@ def main(argv=None) -> int:
     ap.add_argument("--num_relations", type=int, default=1345)
     ap.add_argument("--signal_intent_ahead", type=int, default=4, help="batches of look-ahead")
     ap.add_argument("--signal_initial_relations_intent", type=int, default=0)
-    ap.add_argument("--batch_triples", type=int, default=4096)
+    ap.add_argument("--batch_triples", type=int, default=0,
+                    help="triples per step; 0 = auto: min(4096, max(32, num_entities / 4)) (all triples of a step read the "
+                         "state at the start of the step, so a step must stay small relative to the number of entities)")
     ap.add_argument("--model_path", default="")
     ap.add_argument("--write_end_checkpoint", type=int, default=0)
     ap.add_argument("--write_every", type=int, default=1)
@@ -48,6 +50,8 @@ def main(argv=None) -> int:
     add_system_options(ap)
     args = ap.parse_args(strip_dashes(argv if argv is not None else sys.argv[1:]))
 
+    if args.batch_triples <= 0:
+        args.batch_triples = min(4096, max(32, args.num_entities // 4))
     cfg = KGEConfig(num_entities=args.num_entities, num_relations=args.num_relations, embed_dim=args.embed_dim,
                     algorithm=args.algorithm, neg_ratio=args.neg_ratio, eta=args.eta, gamma_entity=args.gamma_entity,
                     gamma_relation=args.gamma_relation, dropout_entity=args.dropout_entity,
@@ -77,6 +81,8 @@ def main(argv=None) -> int:
         if model.cuda:
             model.loss.zero_()
         bce = 0.0
+        for j, f in enumerate(starts[:cfg.read_ahead]):       # prime the look-ahead window of this epoch
+            model.signal_intent(perm[f:f + cfg.batch_triples], kv.current_clock() + j)
         for bi, s in enumerate(starts):
             if bi + cfg.read_ahead < len(starts):
                 f = starts[bi + cfg.read_ahead]

@@ -152,7 +152,7 @@ def main():
     data = SyntheticPairs(cfg, counts, rank, seed=1)
 
     K, W, RA = args.steps, args.warmup, cfg.read_ahead
-    total_steps = W + 2 * K + 256   # e2e loop + device-resident loop (+ profiling)
+    total_steps = W + 2 * K + 640   # e2e loop + device-resident loop (+ profiling)
     # data loader: pre-read all batches into pinned host memory (the reference reads sentences ahead too)
     RING = 64  # distinct pinned batches, cycled (64 x 32768 pairs x 27 rows touch far more than L2 holds)
     ring = [data.batch(s).pin_memory() for s in range(min(RING, total_steps + RA + 1))]
@@ -293,6 +293,30 @@ def main():
         prof["host_ms"] = {k_: round(v_, 4) for k_, v_ in sec.items()}
         prof["cpus"] = len(os.sched_getaffinity(0))
         prof["resident_ms_without_clock_sampler"] = second_pass_ms
+        # per-step device time distribution (steady contention or periodic stalls?) and the same loop with
+        # intent signalling switched off (how much of the step time is relocation/replication churn?)
+        def per_step(first, n, intent):
+            st0 = model.stats.tolist()
+            marks = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+            barrier()
+            marks[0].record(stream)
+            for i, s in enumerate(range(first, first + n)):
+                if intent and s + RA < len(batches):
+                    model.signal_intent(batches[s + RA], worker.current_clock() + RA)
+                model.loss.zero_()
+                model.step_resident(dev_ring[s % len(dev_ring)])
+                worker.advance_clock()
+                marks[i + 1].record(stream)
+            barrier()
+            ts = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(n))
+            st1 = model.stats.tolist()
+            rows = [b_ - a_ for a_, b_ in zip(st0, st1)][:3]
+            return {"mean": round(sum(ts) / n, 4), "p10": round(ts[n // 10], 4), "p50": round(ts[n // 2], 4),
+                    "p90": round(ts[9 * n // 10], 4), "max": round(ts[-1], 4),
+                    "rows_local_remote_slow": rows}
+        first = W + 2 * K + 243
+        prof["steps_with_intent"] = per_step(first, 192, True)
+        prof["steps_without_intent"] = per_step(first + 192, 192, False)
 
     # max over ranks
     t = torch.tensor([e2e_ms, dev_ms], dtype=torch.float64, device=dev)

@@ -78,7 +78,9 @@ def main():
         upd = world * cfg.batch_triples * cfg.updates_per_triple
         print(json.dumps({"bench": "kge_complex", "n_gpus": world, "config": "FB15k scale, d=512, neg_ratio=6, 8192 triples/GPU/step",
                           "ms_per_step": ms, "updates_per_s": upd / ms * 1e3,
-                          "rows_local_remote_slow": st[:3], "pm": {k: v for k, v in server.counters().items() if k in ("relocations", "replica_setups", "refreshes", "protocol_errors")}}), flush=True)
+                          "rows_local_remote_slow": st[:3],
+                          "pm": {k: v for k, v in server.counters().items()
+                                 if k in ("relocations", "replica_setups", "refreshes", "protocol_errors")}}), flush=True)
     kv.finalize(); server.shutdown()
     barrier()
 
@@ -141,7 +143,8 @@ def main():
     st = stats.tolist()
     if rank == 0:
         upd = world * n_se * steps_per_block * 2 * n
-        print(json.dumps({"bench": "mf_dsgd", "n_gpus": world, "config": "10M x 1M, rank 128, DSGD sub-epochs (intent + WaitSync + barrier per sub-epoch included)",
+        print(json.dumps({"bench": "mf_dsgd", "n_gpus": world,
+                          "config": "10M x 1M, rank 128, DSGD sub-epochs (intent + WaitSync + barrier per sub-epoch included)",
                           "ms_total": ms, "updates_per_s": upd / ms * 1e3, "rows_local_remote_slow": st[:3]}), flush=True)
     kv.finalize(); server.shutdown()
     if world > 1:

@@ -121,3 +121,24 @@ def test_network_utils():
     port = net.get_available_port()
     with socket.socket() as s:
         s.bind(("127.0.0.1", port))          # the port really is free
+
+
+def test_lint_clean():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "lint.py")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]
+
+
+def test_launcher_dry_run_mpi_and_ssh(tmp_path):
+    base = [sys.executable, "-m", "adapm_b200.launch", "-s", "2", "--dry-run"]
+    r = subprocess.run(base + ["--launcher", "mpi", "-m", "adapm_b200.apps.simple", "--", "-k", "10"], cwd=ROOT,
+                       capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("mpirun -n 2") and "-x ADAPM_JOB=" in r.stdout
+    hf = tmp_path / "hosts"
+    hf.write_text("localhost\n")
+    r = subprocess.run(base + ["--launcher", "ssh", "-H", str(hf), "-m", "adapm_b200.apps.simple"], cwd=ROOT,
+                       capture_output=True, text=True)
+    lines = r.stdout.strip().splitlines()
+    assert r.returncode == 0 and len(lines) == 2 and "RANK=1" in lines[1] and lines[0].startswith("ssh ")
+    hf.write_text("hostA\nhostB\n")     # the fabric is single-node: two hosts are refused
+    r = subprocess.run(base + ["--launcher", "ssh", "-H", str(hf), "-m", "x"], cwd=ROOT, capture_output=True, text=True)
+    assert r.returncode == 2 and "single-node" in r.stderr
