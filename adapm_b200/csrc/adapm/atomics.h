@@ -89,6 +89,9 @@ ADAPM_D int32_t fetch_add(int32_t* p, int32_t v) { return atomicAdd_system(p, v)
 ADAPM_D uint64_t fetch_or(uint64_t* p, uint64_t v) {
   return (uint64_t)atomicOr_system((unsigned long long*)p, (unsigned long long)v);
 }
+ADAPM_D uint64_t fetch_and(uint64_t* p, uint64_t v) {
+  return (uint64_t)atomicAnd_system((unsigned long long*)p, (unsigned long long)v);
+}
 ADAPM_D uint64_t exchange(uint64_t* p, uint64_t v) {
   return (uint64_t)atomicExch_system((unsigned long long*)p, (unsigned long long)v);
 }
@@ -135,6 +138,7 @@ inline void st_relaxed(double* p, double v) {
 }
 template <class T> inline T fetch_add(T* p, T v) { return __atomic_fetch_add(p, v, __ATOMIC_ACQ_REL); }
 inline uint64_t fetch_or(uint64_t* p, uint64_t v) { return __atomic_fetch_or(p, v, __ATOMIC_ACQ_REL); }
+inline uint64_t fetch_and(uint64_t* p, uint64_t v) { return __atomic_fetch_and(p, v, __ATOMIC_ACQ_REL); }
 inline uint64_t exchange(uint64_t* p, uint64_t v) { return __atomic_exchange_n(p, v, __ATOMIC_ACQ_REL); }
 inline void red_add(int64_t* p, int64_t v) { __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline void red_add(uint64_t* p, uint64_t v) { __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }

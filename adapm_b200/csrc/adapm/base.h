@@ -66,7 +66,8 @@ ADAPM_HD uint32_t meta_next(uint32_t m, uint32_t state, uint32_t peer) {
 }
 
 // slot flag bits (one byte per slot)
-constexpr uint8_t F_REQUESTED = 2;  // this rank asked the owner for a refresh in this round
+constexpr uint8_t F_REQUESTED = 2;  // phase A visited this replica in the current round (refresh it in phase C)
+constexpr uint8_t F_WANT_SET = 4;   // this rank's bit is set in the want-mask of the owner named by want_owner[slot]
 
 // Counters written by the PM kernels / loops (one block per rank, in the heap).
 enum Counter : int {

@@ -40,7 +40,8 @@ struct Options {
   double sync_max_per_sec = 1000;            // sys.sync.max_per_sec
   int sync_pause_ms = 0;                     // sys.sync.pause
   double sync_threshold = 0;                 // sys.sync.threshold (-1 all, 0 non-zero, >0 L2, inf off)
-  int sweep_period = 8;                      // every n-th round ignores dirty hints/versions (new)
+  int sweep_period = 64;                     // rolling sweep: every slot ignores dirty hints/versions once per n rounds (new)
+  int idle_period = 4;                       // idle replicas check the owner's version every n-th round (new; 1 = every round)
   float timing_initial_estimate = 10;        // sys.timing.initial_estimate
   bool timing_autotune = true;               // sys.timing.autotune
   float timing_smoothing_factor = 0.1f;      // sys.timing.smoothing_factor
@@ -96,6 +97,7 @@ struct Options {
     else if (name == "sys.sync.pause") { sync_pause_ms = std::stoi(v); if (sync_pause_ms > 0) sync_max_per_sec = 0; }
     else if (name == "sys.sync.threshold") sync_threshold = (v == "inf") ? std::numeric_limits<double>::infinity() : std::stod(v);
     else if (name == "sys.sync.sweep_period") sweep_period = std::stoi(v);
+    else if (name == "sys.sync.idle_period") idle_period = std::stoi(v);
     else if (name == "sys.timing.initial_estimate") timing_initial_estimate = std::stof(v);
     else if (name == "sys.timing.autotune") timing_autotune = b(v);
     else if (name == "sys.timing.smoothing_factor") timing_smoothing_factor = std::stof(v);

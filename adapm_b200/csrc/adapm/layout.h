@@ -37,7 +37,8 @@ struct Layout {
   uint64_t off_meta;       // uint32[S]         state | peer | seq
   uint64_t off_version;    // uint32[S]         owner: #pushes applied
   uint64_t off_ver_seen;   // uint32[S]         replica: owner version at last refresh
-  uint64_t off_want;       // uint64[S]         owner: ranks that requested the key this round
+  uint64_t off_want;       // uint64[S]         owner: ranks that hold a replica / placeholder of the key (sticky bits)
+  uint64_t off_want_owner; // uint8[S]          holder: the owner whose want-mask carries this rank's bit (0xff none)
   uint64_t off_slot_key;   // int64[S]
   uint64_t off_intent_end; // int64[S*workers]  end clock of the local intents
   uint64_t off_flags;      // uint8[S]          F_REQUESTED (sync thread only)
@@ -79,6 +80,7 @@ ADAPM_HD int64_t* slot_key_of(const Ctx& c, int r) { return at<int64_t>(c, r, c.
 ADAPM_HD int64_t* intent_end_of(const Ctx& c, int r) { return at<int64_t>(c, r, c.L.off_intent_end); }
 ADAPM_HD uint8_t* flags_of(const Ctx& c, int r) { return at<uint8_t>(c, r, c.L.off_flags); }
 ADAPM_HD uint8_t* dirty_of(const Ctx& c, int r) { return at<uint8_t>(c, r, c.L.off_dirty); }
+ADAPM_HD uint8_t* want_owner_of(const Ctx& c, int r) { return at<uint8_t>(c, r, c.L.off_want_owner); }
 ADAPM_HD int32_t* free_top_of(const Ctx& c, int r) { return at<int32_t>(c, r, c.L.off_free_top); }
 ADAPM_HD uint64_t* counters_of(const Ctx& c, int r) { return at<uint64_t>(c, r, c.L.off_counters); }
 

@@ -339,6 +339,7 @@ ADAPM_HD int register_intent(const Ctx& c, const IntentRec& rec, const Clock* cl
     mem::st_relaxed(want_of(c, me) + ns, (uint64_t)0);
     mem::st_relaxed(flags_of(c, me) + ns, (uint8_t)0);
     mem::st_relaxed(dirty_of(c, me) + ns, (uint8_t)0);
+    mem::st_relaxed(want_owner_of(c, me) + ns, (uint8_t)0xff);
     uint32_t m = mem::ld_relaxed(meta_of(c, me) + ns);
     mem::fence();
     mem::st_release(meta_of(c, me) + ns, meta_next(m, S_REPLICA_PENDING, 0));
@@ -356,10 +357,45 @@ ADAPM_HD int register_intent(const Ctx& c, const IntentRec& rec, const Clock* cl
 
 struct RoundParams {
   Clock clocks[MAX_LOCAL_WORKERS];
-  double threshold;   // sys.sync.threshold: -1 all, 0 non-zero, >0 L2 norm, inf = never
-  int32_t sweep;      // ignore dirty hints / versions (guaranteed propagation)
-  int32_t pad;
+  double threshold;     // sys.sync.threshold: -1 all, 0 non-zero, >0 L2 norm, inf = never
+  int32_t sweep;        // full sweep: ignore dirty hints / versions for every slot (WaitSync: guaranteed propagation)
+  uint32_t round_no;    // same on every rank (rounds run in lock-step)
+  int32_t sweep_period; // rolling sweep: slot s is swept in the rounds with (s + round_no) % sweep_period == 0
+  int32_t idle_period;  // idle replicas (no local push, intent active) check the owner's version every n-th round
 };
+
+ADAPM_HD bool round_due(uint32_t s, uint32_t round_no, int32_t period) {
+  return period <= 1 || ((s + round_no) % (uint32_t)period) == 0u;
+}
+ADAPM_HD bool slot_swept(uint32_t s, const RoundParams& rp) {
+  return rp.sweep != 0 || (rp.sweep_period > 0 && round_due(s, rp.round_no, rp.sweep_period));
+}
+
+// Which slots does phase A have to visit? ONE lane, local reads only (the compaction scan of the CUDA backend and
+// the slot loop of the CPU backend use it). An idle replica - intent active, no local push since the last
+// round, want-bit already standing at the current owner - needs nothing in phase A.
+ADAPM_HD bool phase_a_wants(const Ctx& c, uint32_t s, const RoundParams& rp) {
+  const int me = c.rank;
+  const uint32_t st = meta_state(mem::ld_relaxed(meta_of(c, me) + s));
+  if (st == S_REPLICA_PENDING) return true;
+  if (st != S_REPLICA) return false;
+  if (mem::ld_relaxed(dirty_of(c, me) + s) != 0) return true;
+  if (slot_swept(s, rp)) return true;
+  if (!intent_active(c, s, rp.clocks)) return true;
+  if (!(mem::ld_relaxed(flags_of(c, me) + s) & F_WANT_SET)) return true;
+  const Key key = mem::ld_relaxed(slot_key_of(c, me) + s);
+  return mem::ld_relaxed(dir_of(c, me) + key) != mem::ld_relaxed(want_owner_of(c, me) + s);  // owner changed
+}
+// ... and phase C: everything in a transitional state, replicas that phase A visited, and a rolling share
+// of the idle replicas (owner version check).
+ADAPM_HD bool phase_c_wants(const Ctx& c, uint32_t s, const RoundParams& rp) {
+  const int me = c.rank;
+  const uint32_t st = meta_state(mem::ld_relaxed(meta_of(c, me) + s));
+  if (st == S_FREE || st == S_OWNED) return false;
+  if (st != S_REPLICA) return true;
+  if (mem::ld_relaxed(flags_of(c, me) + s) & F_REQUESTED) return true;
+  return slot_swept(s, rp) || round_due(s, rp.round_no, rp.idle_period);
+}
 
 // Phase A, step 2: visit one non-owned slot: ship the replica delta to the owner, decide
 // whether the replica is still needed, request a refresh.
@@ -382,13 +418,14 @@ ADAPM_HD void phase_a_slot(const Ctx& c, const G& g, uint32_t s, const RoundPara
   if (st == S_REPLICA) {
     uint8_t* dp = dirty_of(c, me) + s;
     uint8_t f = (uint8_t)g.bcast((uint32_t)(g.lane() == 0 ? mem::ld_relaxed(dp) : 0));
-    bool consider = (f != 0) || rp.sweep || !active;
+    const bool swept = slot_swept(s, rp);
+    bool consider = (f != 0) || swept || !active;
     bool never = rp.threshold > 1e300;  // inf: replicas never synchronise (except on drop)
     if (consider && (!never || !active)) {
       Val* row = row_ptr<Val>(c, me, cls, s);
       Val* base = base_ptr<Val>(c, me, cls, s);
       bool ship = true;
-      if (rp.threshold > 0 && active && !rp.sweep) {
+      if (rp.threshold > 0 && active && !swept) {
         double acc = 0;
         for (uint32_t i = g.lane(); i < len; i += g.size()) {
           double d = (double)(mem::ld_relaxed(row + i) - mem::ld_relaxed(base + i));
@@ -421,16 +458,27 @@ ADAPM_HD void phase_a_slot(const Ctx& c, const G& g, uint32_t s, const RoundPara
       }
     }
   }
+  uint8_t* wo = want_owner_of(c, me) + s;
   if (!active) {
     if (g.lane() == 0) {
-      mem::st_relaxed(fl, (uint8_t)(mem::ld_relaxed(fl) & ~F_REQUESTED));
+      // withdraw the standing request (the bit lives in the mask of the owner it was sent to; a relocation resets it)
+      const uint8_t f = mem::ld_relaxed(fl);
+      if ((f & F_WANT_SET) && (int)mem::ld_relaxed(wo) == o) mem::fetch_and(want_of(c, o) + ps, ~((uint64_t)1 << me));
+      mem::st_relaxed(wo, (uint8_t)0xff);
+      mem::st_relaxed(fl, (uint8_t)(f & ~(F_REQUESTED | F_WANT_SET)));
       mem::st_release(mp, meta_next(m, S_DROPPING, 0));
     }
     return;
   }
   if (g.lane() == 0) {
-    mem::fetch_or(want_of(c, o) + ps, (uint64_t)1 << me);
-    mem::st_relaxed(fl, (uint8_t)(mem::ld_relaxed(fl) | F_REQUESTED));
+    // the request is sticky: it stands in the owner's want-mask until this rank drops the replica
+    uint8_t f = mem::ld_relaxed(fl);
+    if (!(f & F_WANT_SET) || (int)mem::ld_relaxed(wo) != o) {
+      mem::fetch_or(want_of(c, o) + ps, (uint64_t)1 << me);
+      mem::st_relaxed(wo, (uint8_t)o);
+      f |= F_WANT_SET;
+    }
+    mem::st_relaxed(fl, (uint8_t)(f | F_REQUESTED));
   }
 }
 
@@ -443,7 +491,7 @@ ADAPM_HD void phase_b_slot(const Ctx& c, uint32_t s, const RoundParams& rp) {
   if (mem::ld_relaxed(wp) == 0) return;
   uint32_t* mp = meta_of(c, me) + s;
   uint32_t m = mem::ld_acquire(mp);
-  uint64_t mask = mem::exchange(wp, (uint64_t)0);
+  uint64_t mask = mem::ld_relaxed(wp);   // sticky: holders clear their own bit when they drop the replica
   if (meta_state(m) != S_OWNED || mask == 0) return;
   mask &= ~((uint64_t)1 << me);
   if (mask == 0) return;
@@ -467,6 +515,7 @@ ADAPM_HD void phase_b_slot(const Ctx& c, uint32_t s, const RoundParams& rp) {
   mem::fence();
   mem::st_release(dmp, meta_next(dm, dst_state == S_REPLICA ? S_INCOMING_REPLICA : S_INCOMING, (uint32_t)me));
   mem::st_release(mp, meta_next(m, S_OUTGOING, (uint32_t)dst));
+  mem::st_relaxed(wp, (uint64_t)0);   // the only requester becomes the owner: nothing stands against this slot any more
   mem::fence();
   for (int r = 0; r < c.L.world; ++r) mem::st_relaxed(dir_of(c, r) + key, (uint8_t)dst);
   count(c, C_RELOCATIONS);
@@ -506,14 +555,16 @@ ADAPM_HD void phase_c_slot(const Ctx& c, const G& g, uint32_t s, const RoundPara
       mem::red_add(version_of(c, me) + s, sv + 1u);
       mem::st_relaxed(ver_seen_of(c, me) + s, 0xffffffffu);
       mem::st_relaxed(fl, (uint8_t)0);
+      mem::st_relaxed(want_owner_of(c, me) + s, (uint8_t)0xff);
       mem::st_release(mp, meta_next(m1, S_OWNED, 0));
     }
     return;
   }
   if (st == S_REPLICA || st == S_REPLICA_PENDING) {
     uint8_t f = (uint8_t)g.bcast((uint32_t)(g.lane() == 0 ? mem::ld_relaxed(fl) : 0));
-    if (!(f & F_REQUESTED)) return;
-    if (g.lane() == 0) mem::st_relaxed(fl, (uint8_t)(f & ~F_REQUESTED));
+    const bool requested = (f & F_REQUESTED) != 0;
+    if (requested && g.lane() == 0) mem::st_relaxed(fl, (uint8_t)(f & ~F_REQUESTED));
+    if (st == S_REPLICA_PENDING && !requested) return;  // the owner has not seen the request yet
     if (c.technique == (int)MgmtTechniques::RELOCATION_ONLY) return;
     const int o = (int)g.bcast((uint32_t)(g.lane() == 0 ? mem::ld_relaxed(dir_of(c, me) + key) : 0));
     if (o == me) return;
@@ -523,7 +574,7 @@ ADAPM_HD void phase_c_slot(const Ctx& c, const G& g, uint32_t s, const RoundPara
     if (meta_state(pm) != S_OWNED) return;  // owner is mid-relocation: ask again next round
     uint32_t v = g.bcast(g.lane() == 0 ? mem::ld_acquire(version_of(c, o) + ps) : 0u);
     uint32_t seen = g.bcast(g.lane() == 0 ? mem::ld_relaxed(ver_seen_of(c, me) + s) : 0u);
-    if (st == S_REPLICA && v == seen && !rp.sweep) return;
+    if (st == S_REPLICA && v == seen && !slot_swept(s, rp)) return;
     Val* row = row_ptr<Val>(c, me, cls, s);
     Val* base = base_ptr<Val>(c, me, cls, s);
     const Val* orow = row_ptr<Val>(c, o, cls, ps);

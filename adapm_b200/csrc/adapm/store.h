@@ -102,6 +102,7 @@ inline Layout build_layout(const ValueSpec& spec, const Options& opt, std::vecto
   L.off_intent_end = take((uint64_t)L.total_slots * 8 * L.workers);
   L.off_flags = take((uint64_t)L.total_slots);
   L.off_dirty = take((uint64_t)L.total_slots);
+  L.off_want_owner = take((uint64_t)L.total_slots);
   L.off_free_top = take(MAX_CLASSES * 4);
   L.off_counters = take(C_NUM_COUNTERS * 8);
   L.locality_stats = opt.locality_stats ? 1u : 0u;

@@ -128,11 +128,8 @@ class CpuBackend : public Backend {
   void phase_a(const RoundParams& rp) override {
     HostGroup g;
     const uint32_t S = ctx_.L.total_slots;
-    const uint32_t* meta = meta_of(ctx_, ctx_.rank);
-    for (uint32_t s = 0; s < S; ++s) {
-      uint32_t st = meta_state(meta[s]);
-      if (st == S_REPLICA || st == S_REPLICA_PENDING) phase_a_slot<Val>(ctx_, g, s, rp);
-    }
+    for (uint32_t s = 0; s < S; ++s)
+      if (phase_a_wants(ctx_, s, rp)) phase_a_slot<Val>(ctx_, g, s, rp);
     mem::fence();
   }
   void phase_b(const RoundParams& rp) override {
@@ -145,11 +142,8 @@ class CpuBackend : public Backend {
   void phase_c(const RoundParams& rp) override {
     HostGroup g;
     const uint32_t S = ctx_.L.total_slots;
-    const uint32_t* meta = meta_of(ctx_, ctx_.rank);
-    for (uint32_t s = 0; s < S; ++s) {
-      uint32_t st = meta_state(mem::ld_relaxed(meta + s));
-      if (st != S_FREE && st != S_OWNED) phase_c_slot<Val>(ctx_, g, s, rp);
-    }
+    for (uint32_t s = 0; s < S; ++s)
+      if (phase_c_wants(ctx_, s, rp)) phase_c_slot<Val>(ctx_, g, s, rp);
     mem::fence();
   }
   void round_fence() override { mem::fence(); }

@@ -177,6 +177,9 @@ void SyncEngine::round(bool sweep) {
   for (size_t w = 0; w < clocks.size(); ++w) rp.clocks[w] = clocks[w];
   rp.threshold = opt.sync_threshold;
   rp.sweep = sweep ? 1 : 0;
+  rp.round_no = (uint32_t)round_no_;
+  rp.sweep_period = opt.sweep_period;
+  rp.idle_period = opt.idle_period;
 
   sw_register_.resume();
   collect_intents(clocks, windows);
@@ -248,7 +251,6 @@ void SyncEngine::loop() {
       any_sweep = any_sweep || ctl->ranks[r].snap_sweep.load() != 0;
     }
     if (all_stop) break;
-    if (opt.sweep_period > 0 && round_no_ % (uint64_t)opt.sweep_period == 0) any_sweep = true;
 
     round(any_sweep);
 

@@ -172,7 +172,8 @@ __global__ void register_kernel(const __grid_constant__ Ctx c, const IntentRec* 
 // would leave most warps idle), (2) one warp per worklist item, grid-strided, so that the long
 // dependent-load chains of many slots overlap.
 template <int PHASE>
-__global__ void __launch_bounds__(kThreads) phase_scan_kernel(const __grid_constant__ Ctx c, uint32_t* __restrict__ worklist,
+__global__ void __launch_bounds__(kThreads) phase_scan_kernel(const __grid_constant__ Ctx c, RoundParams rp,
+                                                              uint32_t* __restrict__ worklist,
                                                               unsigned int* __restrict__ count) {
   const uint32_t S = c.L.total_slots;
   const uint32_t* meta = meta_of(c, c.rank);
@@ -181,8 +182,7 @@ __global__ void __launch_bounds__(kThreads) phase_scan_kernel(const __grid_const
     bool hit = false;
     if (s < S) {
       uint32_t st = meta_state(__ldcg(meta + s));
-      if (PHASE == 0) hit = (st == S_REPLICA || st == S_REPLICA_PENDING);
-      else hit = (st != S_FREE && st != S_OWNED);
+      if (st != S_FREE && st != S_OWNED) hit = (PHASE == 0) ? phase_a_wants(c, s, rp) : phase_c_wants(c, s, rp);
     }
     unsigned mask = __ballot_sync(0xffffffffu, hit);
     if (mask) {
@@ -239,6 +239,8 @@ CudaBackend::CudaBackend(const Options& opt, const Layout& L, std::shared_ptr<Fa
   cudaDeviceProp prop;
   ADAPM_CUDA_CHECK(cudaGetDeviceProperties(&prop, device_));
   num_sms_ = prop.multiProcessorCount;
+  if (const char* e = getenv("ADAPM_SYNC_SCAN_BLOCKS")) scan_blocks_per_sm_ = std::max(1, atoi(e));
+  if (const char* e = getenv("ADAPM_SYNC_WORK_BLOCKS")) work_blocks_per_sm_ = std::max(1, atoi(e));
   int lo = 0, hi = 0;
   ADAPM_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
   ADAPM_CUDA_CHECK(cudaStreamCreateWithPriority(&sync_stream_, cudaStreamNonBlocking, hi));
@@ -545,24 +547,24 @@ void CudaBackend::register_intents(const IntentRec* recs, size_t n, const RoundP
 void CudaBackend::phase_a(const RoundParams& rp) {
   use_device();
   ADAPM_CUDA_CHECK(cudaMemsetAsync(work_count_, 0, sizeof(unsigned int), sync_stream_));
-  phase_scan_kernel<0><<<num_sms_ * 2, kThreads, 0, sync_stream_>>>(ctx_, worklist_, work_count_);
+  phase_scan_kernel<0><<<num_sms_ * scan_blocks_per_sm_, kThreads, 0, sync_stream_>>>(ctx_, rp, worklist_, work_count_);
   ADAPM_COUNT_LAUNCH();
-  phase_work_kernel<0><<<num_sms_ * 4, kThreads, 0, sync_stream_>>>(ctx_, rp, worklist_, work_count_);
+  phase_work_kernel<0><<<num_sms_ * work_blocks_per_sm_, kThreads, 0, sync_stream_>>>(ctx_, rp, worklist_, work_count_);
   ADAPM_COUNT_LAUNCH();
   ADAPM_CUDA_CHECK(cudaGetLastError());
 }
 void CudaBackend::phase_b(const RoundParams& rp) {
   use_device();
-  phase_b_kernel<<<num_sms_ * 2, kThreads, 0, sync_stream_>>>(ctx_, rp);
+  phase_b_kernel<<<num_sms_ * scan_blocks_per_sm_, kThreads, 0, sync_stream_>>>(ctx_, rp);
   ADAPM_COUNT_LAUNCH();
   ADAPM_CUDA_CHECK(cudaGetLastError());
 }
 void CudaBackend::phase_c(const RoundParams& rp) {
   use_device();
   ADAPM_CUDA_CHECK(cudaMemsetAsync(work_count_, 0, sizeof(unsigned int), sync_stream_));
-  phase_scan_kernel<1><<<num_sms_ * 2, kThreads, 0, sync_stream_>>>(ctx_, worklist_, work_count_);
+  phase_scan_kernel<1><<<num_sms_ * scan_blocks_per_sm_, kThreads, 0, sync_stream_>>>(ctx_, rp, worklist_, work_count_);
   ADAPM_COUNT_LAUNCH();
-  phase_work_kernel<1><<<num_sms_ * 4, kThreads, 0, sync_stream_>>>(ctx_, rp, worklist_, work_count_);
+  phase_work_kernel<1><<<num_sms_ * work_blocks_per_sm_, kThreads, 0, sync_stream_>>>(ctx_, rp, worklist_, work_count_);
   ADAPM_COUNT_LAUNCH();
   ADAPM_CUDA_CHECK(cudaGetLastError());
 }

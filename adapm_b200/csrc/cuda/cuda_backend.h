@@ -74,6 +74,10 @@ class CudaBackend : public Backend {
   Ctx ctx_;
   int device_ = 0;
   int num_sms_ = 148;
+  // grid sizes of the sync-round kernels, in blocks per SM. The round runs on a high-priority stream next to the
+  // training kernels: a small footprint lets it share the SMs with them instead of displacing them.
+  int scan_blocks_per_sm_ = 1;   // ADAPM_SYNC_SCAN_BLOCKS
+  int work_blocks_per_sm_ = 1;   // ADAPM_SYNC_WORK_BLOCKS
   cudaStream_t sync_stream_ = nullptr;
   std::vector<cudaStream_t> worker_streams_;
   std::vector<std::unique_ptr<Staging>> staging_;  // per worker

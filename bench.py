@@ -41,7 +41,8 @@ def parse_args():
     ap.add_argument("--dim", type=int, default=300)
     ap.add_argument("--negative", type=int, default=25)
     ap.add_argument("--batch-pairs", type=int, default=32768)
-    ap.add_argument("--read-ahead", type=int, default=8)
+    ap.add_argument("--read-ahead", type=int, default=16, help="intent look-ahead in steps")
+    ap.add_argument("--max-inflight", type=int, default=3, help="steps the host may run ahead of the GPU")
     ap.add_argument("--sampling", default="local", choices=["local", "naive"])
     ap.add_argument("--techniques", default="all")
     ap.add_argument("--no-intent", action="store_true")
@@ -141,7 +142,7 @@ def main():
 
     cfg = Word2VecConfig(vocab_size=args.vocab, embed_dim=args.dim, negative=args.negative,
                          batch_pairs=args.batch_pairs, read_ahead=args.read_ahead, sampling_scheme=args.sampling,
-                         signal_intent=not args.no_intent)
+                         signal_intent=not args.no_intent, max_inflight=args.max_inflight)
     server = ad.Server(cfg.row_len, num_keys=cfg.num_keys, num_threads=1, rank=rank, world=world, backend="cuda",
                        fabric="shm" if world > 1 else "inproc", device=local_rank,
                        options={"sys.techniques": args.techniques, "sys.sync.max_per_sec": args.sync_per_sec})
