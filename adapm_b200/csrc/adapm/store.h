@@ -175,6 +175,9 @@ class Backend {
   virtual void reset_counters() = 0;
   // copy `bytes` at heap offset `off` of THIS rank into host memory (statistics / debugging)
   virtual void read_heap(uint64_t off, void* dst, size_t bytes) = 0;
+  // Kernel timeline (ADAPM_SYNC_TRACE=1, cuda backend): mark a point on a stream / write all records as TSV.
+  virtual void trace_mark(const char* /*name*/, void* /*stream*/) {}
+  virtual void dump_trace(const std::string& /*path*/) {}
 };
 
 std::unique_ptr<Backend> make_cpu_backend(const Options& opt, const Layout& L, std::shared_ptr<Fabric> fabric);

@@ -127,7 +127,16 @@ PYBIND11_MODULE(_C, m) {
         for (int c = 0; c < L.num_classes; ++c) h[100 + c] = tops[c];
         return h;
       })
-      .def("backend_handle", [](Server& s) { return (uintptr_t)&s.backend(); });
+      .def("backend_handle", [](Server& s) { return (uintptr_t)&s.backend(); })
+      .def("trace_mark", [](Server& s, const std::string& name, uintptr_t stream) {
+        // names are interned: the tracer keeps the pointer
+        static std::mutex mu;
+        static std::unordered_set<std::string> names;
+        const char* p;
+        { std::lock_guard<std::mutex> lk(mu); p = names.insert(name).first->c_str(); }
+        s.backend().trace_mark(p, reinterpret_cast<void*>(stream));
+      })
+      .def("dump_trace", [](Server& s, const std::string& path) { s.backend().dump_trace(path); });
 
   py::class_<Worker, std::shared_ptr<Worker>>(m, "Worker")
       .def(py::init([](int customer_id, std::shared_ptr<Server> server) {

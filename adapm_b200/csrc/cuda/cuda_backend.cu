@@ -239,6 +239,7 @@ CudaBackend::CudaBackend(const Options& opt, const Layout& L, std::shared_ptr<Fa
   cudaDeviceProp prop;
   ADAPM_CUDA_CHECK(cudaGetDeviceProperties(&prop, device_));
   num_sms_ = prop.multiProcessorCount;
+  if (const char* e = getenv("ADAPM_SYNC_TRACE")) trace_on_ = atoi(e) != 0;
   if (const char* e = getenv("ADAPM_SYNC_SCAN_BLOCKS")) scan_blocks_per_sm_ = std::max(1, atoi(e));
   if (const char* e = getenv("ADAPM_SYNC_WORK_BLOCKS")) work_blocks_per_sm_ = std::max(1, atoi(e));
   int lo = 0, hi = 0;
@@ -535,6 +536,7 @@ void CudaBackend::register_intents(const IntentRec* recs, size_t n, const RoundP
   ensure_staging(sync_staging_, o_st + n + 256);
   Staging& st = sync_staging_;
   memcpy(st.host, recs, n * sizeof(IntentRec));
+  TraceScope ts_(this, "register", sync_stream_);
   ADAPM_CUDA_CHECK(cudaMemcpyAsync(st.dev, st.host, n * sizeof(IntentRec), cudaMemcpyHostToDevice, sync_stream_));
   register_kernel<<<(int)((n + 255) / 256), 256, 0, sync_stream_>>>(ctx_, (const IntentRec*)st.dev, n, rp, (uint8_t*)(st.dev + o_st));
   ADAPM_COUNT_LAUNCH();
@@ -546,6 +548,7 @@ void CudaBackend::register_intents(const IntentRec* recs, size_t n, const RoundP
 
 void CudaBackend::phase_a(const RoundParams& rp) {
   use_device();
+  TraceScope ts_(this, "phaseA", sync_stream_);
   ADAPM_CUDA_CHECK(cudaMemsetAsync(work_count_, 0, sizeof(unsigned int), sync_stream_));
   phase_scan_kernel<0><<<num_sms_ * scan_blocks_per_sm_, kThreads, 0, sync_stream_>>>(ctx_, rp, worklist_, work_count_);
   ADAPM_COUNT_LAUNCH();
@@ -555,12 +558,14 @@ void CudaBackend::phase_a(const RoundParams& rp) {
 }
 void CudaBackend::phase_b(const RoundParams& rp) {
   use_device();
+  TraceScope ts_(this, "phaseB", sync_stream_);
   phase_b_kernel<<<num_sms_ * scan_blocks_per_sm_, kThreads, 0, sync_stream_>>>(ctx_, rp);
   ADAPM_COUNT_LAUNCH();
   ADAPM_CUDA_CHECK(cudaGetLastError());
 }
 void CudaBackend::phase_c(const RoundParams& rp) {
   use_device();
+  TraceScope ts_(this, "phaseC", sync_stream_);
   ADAPM_CUDA_CHECK(cudaMemsetAsync(work_count_, 0, sizeof(unsigned int), sync_stream_));
   phase_scan_kernel<1><<<num_sms_ * scan_blocks_per_sm_, kThreads, 0, sync_stream_>>>(ctx_, rp, worklist_, work_count_);
   ADAPM_COUNT_LAUNCH();
@@ -568,6 +573,53 @@ void CudaBackend::phase_c(const RoundParams& rp) {
   ADAPM_COUNT_LAUNCH();
   ADAPM_CUDA_CHECK(cudaGetLastError());
 }
+// ---------------------------------------------------------------------------------------- kernel timeline
+CudaBackend::TraceScope::TraceScope(CudaBackend* be, const char* name, cudaStream_t st) : b(be), idx(-1), s(st) {
+  if (!b->trace_on_) return;
+  std::lock_guard<std::mutex> lk(b->trace_mu_);
+  if (b->trace_.size() >= (size_t)1 << 20) return;
+  if (!b->trace_base_) {
+    cudaEventCreate(&b->trace_base_);
+    cudaEventRecord(b->trace_base_, s);
+  }
+  TraceRec r;
+  r.name = name;
+  cudaEventCreate(&r.a);
+  cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, s);
+  idx = (int)b->trace_.size();
+  b->trace_.push_back(r);
+}
+CudaBackend::TraceScope::~TraceScope() {
+  if (idx < 0) return;
+  std::lock_guard<std::mutex> lk(b->trace_mu_);
+  cudaEventRecord(b->trace_[idx].b, s);
+}
+void CudaBackend::trace_mark(const char* name, void* stream) {
+  if (!trace_on_) return;
+  use_device();
+  TraceScope t(this, name, (cudaStream_t)stream);
+}
+void CudaBackend::dump_trace(const std::string& path) {
+  if (!trace_on_) return;
+  use_device();
+  cudaDeviceSynchronize();
+  std::lock_guard<std::mutex> lk(trace_mu_);
+  FILE* f = fopen(path.c_str(), "w");
+  if (!f) return;
+  fprintf(f, "name\tstart_ms\tend_ms\n");
+  for (auto& r : trace_) {
+    float a = 0, b = 0;
+    if (cudaEventElapsedTime(&a, trace_base_, r.a) != cudaSuccess) { cudaGetLastError(); continue; }
+    if (cudaEventElapsedTime(&b, trace_base_, r.b) != cudaSuccess) { cudaGetLastError(); b = a; }
+    fprintf(f, "%s\t%.4f\t%.4f\n", r.name, a, b);
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  fclose(f);
+  trace_.clear();
+}
+
 void CudaBackend::round_fence() {
   use_device();
   ADAPM_CUDA_CHECK(cudaStreamSynchronize(sync_stream_));

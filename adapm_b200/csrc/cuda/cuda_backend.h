@@ -60,6 +60,16 @@ class CudaBackend : public Backend {
   }
   int num_sms() const { return num_sms_; }
 
+  // ---- kernel timeline: CUDA events around every sync-round kernel plus user marks, all relative to one base
+  // event, so that the round's kernels and the training kernels of other streams land on one time axis
+  void trace_mark(const char* name, void* stream) override;
+  void dump_trace(const std::string& path) override;
+  struct TraceScope {
+    TraceScope(CudaBackend* b, const char* name, cudaStream_t s);
+    ~TraceScope();
+    CudaBackend* b; int idx; cudaStream_t s;
+  };
+
  private:
   struct Staging {
     char* host = nullptr;
@@ -76,6 +86,11 @@ class CudaBackend : public Backend {
   int num_sms_ = 148;
   // grid sizes of the sync-round kernels, in blocks per SM. The round runs on a high-priority stream next to the
   // training kernels: a small footprint lets it share the SMs with them instead of displacing them.
+  struct TraceRec { const char* name; cudaEvent_t a, b; };
+  bool trace_on_ = false;        // ADAPM_SYNC_TRACE
+  cudaEvent_t trace_base_ = nullptr;
+  std::vector<TraceRec> trace_;
+  std::mutex trace_mu_;
   int scan_blocks_per_sm_ = 1;   // ADAPM_SYNC_SCAN_BLOCKS
   int work_blocks_per_sm_ = 1;   // ADAPM_SYNC_WORK_BLOCKS
   cudaStream_t sync_stream_ = nullptr;

@@ -41,7 +41,7 @@ def parse_args():
     ap.add_argument("--dim", type=int, default=300)
     ap.add_argument("--negative", type=int, default=25)
     ap.add_argument("--batch-pairs", type=int, default=32768)
-    ap.add_argument("--read-ahead", type=int, default=16, help="intent look-ahead in steps")
+    ap.add_argument("--read-ahead", type=int, default=32, help="intent look-ahead in steps (the reference reads 1000 sentences ahead)")
     ap.add_argument("--max-inflight", type=int, default=3, help="steps the host may run ahead of the GPU")
     ap.add_argument("--sampling", default="local", choices=["local", "naive"])
     ap.add_argument("--techniques", default="all")
@@ -296,6 +296,8 @@ def main():
         prof["resident_ms_without_clock_sampler"] = second_pass_ms
         # per-step device time distribution (steady contention or periodic stalls?) and the same loop with
         # intent signalling switched off (how much of the step time is relocation/replication churn?)
+        tracing = bool(os.environ.get("ADAPM_SYNC_TRACE"))
+
         def per_step(first, n, intent):
             st0 = model.stats.tolist()
             marks = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
@@ -305,7 +307,11 @@ def main():
                 if intent and s + RA < len(batches):
                     model.signal_intent(batches[s + RA], worker.current_clock() + RA)
                 model.loss.zero_()
+                if tracing:
+                    server._impl.trace_mark("step_begin", stream.cuda_stream)
                 model.step_resident(dev_ring[s % len(dev_ring)])
+                if tracing:
+                    server._impl.trace_mark("step_end", stream.cuda_stream)
                 worker.advance_clock()
                 marks[i + 1].record(stream)
             barrier()
@@ -317,6 +323,9 @@ def main():
                     "rows_local_remote_slow": rows}
         first = W + 2 * K + 243
         prof["steps_with_intent"] = per_step(first, 192, True)
+        if tracing:   # kernel timeline of the round kernels and the steps, one file per rank
+            os.makedirs("gpurun_out", exist_ok=True)
+            server._impl.dump_trace(f"gpurun_out/kernel_trace.rank{rank}.tsv")
         prof["steps_without_intent"] = per_step(first + 192, 192, False)
 
     # max over ranks

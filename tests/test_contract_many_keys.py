@@ -147,3 +147,17 @@ def test_many_key_operations(mode, technique):
         errs = [e for e in errs if "were not local" not in e]
     assert not errs, "\n".join(errs)
     assert all(r["counters"]["protocol_errors"] == 0 for r in res.values())
+
+
+@pytest.mark.parametrize("opts", [{"sys.sync.idle_period": 1, "sys.sync.sweep_period": 0},
+                                  {"sys.sync.idle_period": 7, "sys.sync.sweep_period": 3}])
+def test_many_key_operations_sync_pacing_options(opts):
+    """The replica-maintenance pacing knobs (rolling sweep, idle-replica check period) change when work is done,
+    never what the store returns."""
+    o = {"sys.techniques": "all"}
+    o.update(opts)
+    res = run_cluster(_worker, world=4, workers=2, mode="threads", value_lengths=VPK, num_keys=NUM_KEYS, dtype="int64",
+                      options=o)
+    errs = [e for r in res.values() for k, v in r.items() if k != "counters" for e in v]
+    assert not errs, "\n".join(errs)
+    assert all(r["counters"]["protocol_errors"] == 0 for r in res.values())
