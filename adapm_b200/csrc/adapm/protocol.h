@@ -120,16 +120,39 @@ ADAPM_HD PullLoc<Val> locate_pull(const Ctx& c, const G& g, Key key, bool local_
   return r;
 }
 
+// Row loops run in batches: all loads of a batch are issued before their first use, so that a warp keeps kRowBatch
+// independent (possibly NVLink) loads in flight. Written element-by-element they serialise on one dependent round
+// trip per element (system-scope loads are not reordered): 19 round trips for a 600-float row.
+constexpr int kRowBatch = 8;
+#if defined(__CUDA_ARCH__)
+#define ADAPM_UNROLL _Pragma("unroll")
+#else
+#define ADAPM_UNROLL
+#endif
+#define ADAPM_ROW_BATCHES(g, len) for (uint32_t i0_ = (g).lane(); i0_ < (len); i0_ += (g).size() * kRowBatch)
+#define ADAPM_ROW_ELEMS(g, len, u, i) \
+  ADAPM_UNROLL for (int u = 0; u < kRowBatch; ++u) \
+    for (uint32_t i = i0_ + (uint32_t)u * (g).size(); i < (len); i = 0xffffffffu)
+
 // Copy the located row into `out` (len values). Returns false if a SUM3 read raced with the
 // finalize step and must be retried by the caller.
 template <class Val, class G>
 ADAPM_HD bool read_row(const G& g, const PullLoc<Val>& loc, Val* out, uint32_t len) {
   if (loc.kind == LOC_DIRECT) {
-    for (uint32_t i = g.lane(); i < len; i += g.size()) out[i] = mem::ld_relaxed(loc.row + i);
+    ADAPM_ROW_BATCHES(g, len) {
+      Val v[kRowBatch];
+      ADAPM_ROW_ELEMS(g, len, u, i) v[u] = mem::ld_relaxed(loc.row + i);
+      ADAPM_ROW_ELEMS(g, len, u, i) out[i] = v[u];
+    }
     return true;
   }
-  for (uint32_t i = g.lane(); i < len; i += g.size())
-    out[i] = mem::ld_relaxed(loc.row + i) - mem::ld_relaxed(loc.base + i) + mem::ld_relaxed(loc.row2 + i);
+  ADAPM_ROW_BATCHES(g, len) {
+    Val v[kRowBatch];
+    ADAPM_ROW_ELEMS(g, len, u, i) v[u] = mem::ld_relaxed(loc.row2 + i);   // the remote one first
+    ADAPM_ROW_ELEMS(g, len, u, i) v[u] += mem::ld_relaxed(loc.row + i);
+    ADAPM_ROW_ELEMS(g, len, u, i) v[u] -= mem::ld_relaxed(loc.base + i);
+    ADAPM_ROW_ELEMS(g, len, u, i) out[i] = v[u];
+  }
   mem::fence();
   uint32_t m2 = g.bcast(g.lane() == 0 ? mem::ld_acquire(loc.meta_ptr) : 0u);
   return m2 == loc.meta_val;
@@ -200,7 +223,11 @@ ADAPM_HD bool push_key(const Ctx& c, const G& g, Key key, const Val* vals, bool*
   const uint32_t len = c.L.cls[class_of_key(c, key)].len;
   PushLoc<Val> loc = locate_push<Val>(c, g, key);
   if (!loc.row) return false;
-  for (uint32_t i = g.lane(); i < len; i += g.size()) mem::red_add(loc.row + i, vals[i]);
+  ADAPM_ROW_BATCHES(g, len) {
+    Val v[kRowBatch];
+    ADAPM_ROW_ELEMS(g, len, u, i) v[u] = vals[i];
+    ADAPM_ROW_ELEMS(g, len, u, i) mem::red_add(loc.row + i, v[u]);
+  }
   if (g.lane() == 0) {
     if (loc.version) mem::red_add(loc.version, 1u);
     if (loc.flag) mem::st_relaxed(loc.flag, (uint8_t)1);
@@ -427,9 +454,11 @@ ADAPM_HD void phase_a_slot(const Ctx& c, const G& g, uint32_t s, const RoundPara
       bool ship = true;
       if (rp.threshold > 0 && active && !swept) {
         double acc = 0;
-        for (uint32_t i = g.lane(); i < len; i += g.size()) {
-          double d = (double)(mem::ld_relaxed(row + i) - mem::ld_relaxed(base + i));
-          acc += d * d;
+        ADAPM_ROW_BATCHES(g, len) {
+          Val v[kRowBatch];
+          ADAPM_ROW_ELEMS(g, len, u, i) v[u] = mem::ld_relaxed(row + i);
+          ADAPM_ROW_ELEMS(g, len, u, i) v[u] -= mem::ld_relaxed(base + i);
+          ADAPM_ROW_ELEMS(g, len, u, i) acc += (double)v[u] * (double)v[u];
         }
         acc = g.sum(acc);
         ship = acc >= rp.threshold * rp.threshold;
@@ -439,13 +468,17 @@ ADAPM_HD void phase_a_slot(const Ctx& c, const G& g, uint32_t s, const RoundPara
         mem::fence();
         Val* orow = row_ptr<Val>(c, o, cls, ps);
         bool nz = false;
-        for (uint32_t i = g.lane(); i < len; i += g.size()) {
-          Val v = mem::ld_relaxed(row + i);
-          Val d = v - mem::ld_relaxed(base + i);
-          if (d != (Val)0 || rp.threshold < 0) {
-            if (d != (Val)0) mem::red_add(orow + i, d);
-            mem::st_relaxed(base + i, v);
-            nz = nz || (d != (Val)0);
+        ADAPM_ROW_BATCHES(g, len) {
+          Val v[kRowBatch], b[kRowBatch];
+          ADAPM_ROW_ELEMS(g, len, u, i) v[u] = mem::ld_relaxed(row + i);
+          ADAPM_ROW_ELEMS(g, len, u, i) b[u] = mem::ld_relaxed(base + i);
+          ADAPM_ROW_ELEMS(g, len, u, i) {
+            const Val d = v[u] - b[u];
+            if (d != (Val)0 || rp.threshold < 0) {
+              if (d != (Val)0) mem::red_add(orow + i, d);
+              mem::st_relaxed(base + i, v[u]);
+              nz = nz || (d != (Val)0);
+            }
           }
         }
         nz = g.any(nz);
@@ -543,11 +576,14 @@ ADAPM_HD void phase_c_slot(const Ctx& c, const G& g, uint32_t s, const RoundPara
     Val* row = row_ptr<Val>(c, me, cls, s);
     Val* base = base_ptr<Val>(c, me, cls, s);
     const Val* srow = row_ptr<Val>(c, src, cls, ss);
-    for (uint32_t i = g.lane(); i < len; i += g.size()) {
-      Val S = mem::ld_relaxed(srow + i);
-      Val b = mem::ld_relaxed(base + i);
-      if (S != b) mem::red_add(row + i, (Val)(S - b));
-      mem::st_relaxed(base + i, (Val)0);
+    ADAPM_ROW_BATCHES(g, len) {
+      Val S[kRowBatch], b[kRowBatch];
+      ADAPM_ROW_ELEMS(g, len, u, i) S[u] = mem::ld_relaxed(srow + i);
+      ADAPM_ROW_ELEMS(g, len, u, i) b[u] = mem::ld_relaxed(base + i);
+      ADAPM_ROW_ELEMS(g, len, u, i) {
+        if (S[u] != b[u]) mem::red_add(row + i, (Val)(S[u] - b[u]));
+        mem::st_relaxed(base + i, (Val)0);
+      }
     }
     mem::fence(); g.sync();
     if (g.lane() == 0) {
@@ -578,10 +614,13 @@ ADAPM_HD void phase_c_slot(const Ctx& c, const G& g, uint32_t s, const RoundPara
     Val* row = row_ptr<Val>(c, me, cls, s);
     Val* base = base_ptr<Val>(c, me, cls, s);
     const Val* orow = row_ptr<Val>(c, o, cls, ps);
-    for (uint32_t i = g.lane(); i < len; i += g.size()) {
-      Val S = mem::ld_relaxed(orow + i);
-      Val b = mem::ld_relaxed(base + i);
-      if (S != b) { mem::red_add(row + i, (Val)(S - b)); mem::st_relaxed(base + i, S); }
+    ADAPM_ROW_BATCHES(g, len) {
+      Val S[kRowBatch], b[kRowBatch];
+      ADAPM_ROW_ELEMS(g, len, u, i) S[u] = mem::ld_relaxed(orow + i);
+      ADAPM_ROW_ELEMS(g, len, u, i) b[u] = mem::ld_relaxed(base + i);
+      ADAPM_ROW_ELEMS(g, len, u, i) {
+        if (S[u] != b[u]) { mem::red_add(row + i, (Val)(S[u] - b[u])); mem::st_relaxed(base + i, S[u]); }
+      }
     }
     mem::fence(); g.sync();
     if (g.lane() == 0) {
@@ -603,9 +642,11 @@ ADAPM_HD void phase_c_slot(const Ctx& c, const G& g, uint32_t s, const RoundPara
       Val* base = base_ptr<Val>(c, me, cls, s);
       Val* orow = row_ptr<Val>(c, o, cls, ps);
       bool nz = false;
-      for (uint32_t i = g.lane(); i < len; i += g.size()) {
-        Val d = mem::ld_relaxed(row + i) - mem::ld_relaxed(base + i);
-        if (d != (Val)0) { mem::red_add(orow + i, d); nz = true; }
+      ADAPM_ROW_BATCHES(g, len) {
+        Val v[kRowBatch];
+        ADAPM_ROW_ELEMS(g, len, u, i) v[u] = mem::ld_relaxed(row + i);
+        ADAPM_ROW_ELEMS(g, len, u, i) v[u] -= mem::ld_relaxed(base + i);
+        ADAPM_ROW_ELEMS(g, len, u, i) if (v[u] != (Val)0) { mem::red_add(orow + i, v[u]); nz = true; }
       }
       nz = g.any(nz);
       if (nz && g.lane() == 0) mem::red_add(version_of(c, o) + ps, 1u);

@@ -194,8 +194,11 @@ __global__ void __launch_bounds__(kThreads) phase_scan_kernel(const __grid_const
   }
 }
 
+// 128-thread blocks: at ~80 registers one block fits into the 12 K registers per SM that the lean training kernels
+// (ops_sgns_tma.cu, 104 registers x 512 threads) leave free, so the round's row work runs next to them
+constexpr int kWorkThreads = 128;
 template <int PHASE>
-__global__ void __launch_bounds__(kThreads) phase_work_kernel(const __grid_constant__ Ctx c, RoundParams rp,
+__global__ void __launch_bounds__(kWorkThreads) phase_work_kernel(const __grid_constant__ Ctx c, RoundParams rp,
                                                               const uint32_t* __restrict__ worklist,
                                                               const unsigned int* __restrict__ count) {
   WarpGroup g;
@@ -552,7 +555,7 @@ void CudaBackend::phase_a(const RoundParams& rp) {
   ADAPM_CUDA_CHECK(cudaMemsetAsync(work_count_, 0, sizeof(unsigned int), sync_stream_));
   phase_scan_kernel<0><<<num_sms_ * scan_blocks_per_sm_, kThreads, 0, sync_stream_>>>(ctx_, rp, worklist_, work_count_);
   ADAPM_COUNT_LAUNCH();
-  phase_work_kernel<0><<<num_sms_ * work_blocks_per_sm_, kThreads, 0, sync_stream_>>>(ctx_, rp, worklist_, work_count_);
+  phase_work_kernel<0><<<num_sms_ * work_blocks_per_sm_, kWorkThreads, 0, sync_stream_>>>(ctx_, rp, worklist_, work_count_);
   ADAPM_COUNT_LAUNCH();
   ADAPM_CUDA_CHECK(cudaGetLastError());
 }
@@ -569,7 +572,7 @@ void CudaBackend::phase_c(const RoundParams& rp) {
   ADAPM_CUDA_CHECK(cudaMemsetAsync(work_count_, 0, sizeof(unsigned int), sync_stream_));
   phase_scan_kernel<1><<<num_sms_ * scan_blocks_per_sm_, kThreads, 0, sync_stream_>>>(ctx_, rp, worklist_, work_count_);
   ADAPM_COUNT_LAUNCH();
-  phase_work_kernel<1><<<num_sms_ * work_blocks_per_sm_, kThreads, 0, sync_stream_>>>(ctx_, rp, worklist_, work_count_);
+  phase_work_kernel<1><<<num_sms_ * work_blocks_per_sm_, kWorkThreads, 0, sync_stream_>>>(ctx_, rp, worklist_, work_count_);
   ADAPM_COUNT_LAUNCH();
   ADAPM_CUDA_CHECK(cudaGetLastError());
 }

@@ -92,7 +92,7 @@ class CudaBackend : public Backend {
   std::vector<TraceRec> trace_;
   std::mutex trace_mu_;
   int scan_blocks_per_sm_ = 1;   // ADAPM_SYNC_SCAN_BLOCKS
-  int work_blocks_per_sm_ = 1;   // ADAPM_SYNC_WORK_BLOCKS
+  int work_blocks_per_sm_ = 2;   // ADAPM_SYNC_WORK_BLOCKS (blocks of 128 threads)
   cudaStream_t sync_stream_ = nullptr;
   std::vector<cudaStream_t> worker_streams_;
   std::vector<std::unique_ptr<Staging>> staging_;  // per worker

@@ -92,9 +92,11 @@ __device__ __noinline__ float slow_target_tma(const Ctx& c, Key tkey, float labe
   return __logf(1.f + __expf(-z));
 }
 
-// VPL = float4 per lane over d floats
-template <int VPL>
-__global__ void __launch_bounds__(kThreads, 2)
+// VPL = float4 per lane over d floats. MAXREG is the register budget: the kernel runs 2 blocks of 256 threads per SM;
+// 128 registers use the whole register file, 104 leave 12 K registers per SM free so that one block of the
+// sync-round kernels (40 registers x 256 threads) can be co-resident instead of waiting for a step block to retire.
+template <int VPL, int MAXREG>
+__global__ void __maxnreg__(MAXREG)
 sgns_step_tma_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ centers, const Key* __restrict__ contexts,
                      const Key* __restrict__ negatives, int n_pairs, int neg, int d, float alpha,
                      float* __restrict__ loss_out, unsigned long long* __restrict__ stats, int tma_remote) {
@@ -351,15 +353,23 @@ bool sgns_step_tma(CudaBackend& be, cudaStream_t stream, const Key* centers, con
   if (smem > 110 * 1024) return false;  // keep 2 blocks per SM
   int blocks = std::min((n_pairs + kWarps - 1) / kWarps, be.num_sms() * 12);
   static const int tma_remote = [] { const char* e = getenv("ADAPM_TMA_REMOTE"); return e ? atoi(e) : 1; }();
-#define ADAPM_LAUNCH_TMA(V)                                                                                  \
-  do {                                                                                                       \
-    static bool attr_set = false;                                                                            \
-    if (!attr_set) {                                                                                         \
-      cudaFuncSetAttribute(sgns_step_tma_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024); \
-      attr_set = true;                                                                                       \
-    }                                                                                                        \
-    sgns_step_tma_kernel<V><<<blocks, kThreads, smem, stream>>>(c, centers, contexts, negatives, n_pairs, neg, d, \
-                                                               alpha, loss_out, stats, tma_remote);         \
+  // register budget: 128 (single GPU: nothing to share the SMs with) or 104 (multi GPU); ADAPM_SGNS_REGS overrides
+  static const int regs_env = [] { const char* e = getenv("ADAPM_SGNS_REGS"); return e ? atoi(e) : 0; }();
+  const bool lean = regs_env ? (regs_env < 128) : (c.L.world > 1);
+#define ADAPM_LAUNCH_TMA2(V, T)                                                                                 \
+  do {                                                                                                          \
+    static bool attr_set = false;                                                                               \
+    if (!attr_set) {                                                                                            \
+      cudaFuncSetAttribute(sgns_step_tma_kernel<V, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024); \
+      attr_set = true;                                                                                          \
+    }                                                                                                           \
+    sgns_step_tma_kernel<V, T><<<blocks, kThreads, smem, stream>>>(c, centers, contexts, negatives, n_pairs, neg, \
+                                                                  d, alpha, loss_out, stats, tma_remote);      \
+  } while (0)
+#define ADAPM_LAUNCH_TMA(V)              \
+  do {                                   \
+    if (lean) ADAPM_LAUNCH_TMA2(V, 104); \
+    else ADAPM_LAUNCH_TMA2(V, 128);      \
   } while (0)
   switch (vpl) {
     case 1: ADAPM_LAUNCH_TMA(1); break;
