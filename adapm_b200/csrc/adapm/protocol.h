@@ -139,20 +139,13 @@ constexpr int kRowBatch = 8;
 template <class Val, class G>
 ADAPM_HD bool read_row(const G& g, const PullLoc<Val>& loc, Val* out, uint32_t len) {
   if (loc.kind == LOC_DIRECT) {
-    ADAPM_ROW_BATCHES(g, len) {
-      Val v[kRowBatch];
-      ADAPM_ROW_ELEMS(g, len, u, i) v[u] = mem::ld_relaxed(loc.row + i);
-      ADAPM_ROW_ELEMS(g, len, u, i) out[i] = v[u];
-    }
+    // (element-wise on purpose: read_row / push_key are inlined into the out-of-line paths of the fused training
+    // kernels, whose register budget must not grow; the batched form is for the round kernels)
+    for (uint32_t i = g.lane(); i < len; i += g.size()) out[i] = mem::ld_relaxed(loc.row + i);
     return true;
   }
-  ADAPM_ROW_BATCHES(g, len) {
-    Val v[kRowBatch];
-    ADAPM_ROW_ELEMS(g, len, u, i) v[u] = mem::ld_relaxed(loc.row2 + i);   // the remote one first
-    ADAPM_ROW_ELEMS(g, len, u, i) v[u] += mem::ld_relaxed(loc.row + i);
-    ADAPM_ROW_ELEMS(g, len, u, i) v[u] -= mem::ld_relaxed(loc.base + i);
-    ADAPM_ROW_ELEMS(g, len, u, i) out[i] = v[u];
-  }
+  for (uint32_t i = g.lane(); i < len; i += g.size())
+    out[i] = mem::ld_relaxed(loc.row + i) - mem::ld_relaxed(loc.base + i) + mem::ld_relaxed(loc.row2 + i);
   mem::fence();
   uint32_t m2 = g.bcast(g.lane() == 0 ? mem::ld_acquire(loc.meta_ptr) : 0u);
   return m2 == loc.meta_val;
@@ -223,11 +216,7 @@ ADAPM_HD bool push_key(const Ctx& c, const G& g, Key key, const Val* vals, bool*
   const uint32_t len = c.L.cls[class_of_key(c, key)].len;
   PushLoc<Val> loc = locate_push<Val>(c, g, key);
   if (!loc.row) return false;
-  ADAPM_ROW_BATCHES(g, len) {
-    Val v[kRowBatch];
-    ADAPM_ROW_ELEMS(g, len, u, i) v[u] = vals[i];
-    ADAPM_ROW_ELEMS(g, len, u, i) mem::red_add(loc.row + i, v[u]);
-  }
+  for (uint32_t i = g.lane(); i < len; i += g.size()) mem::red_add(loc.row + i, vals[i]);
   if (g.lane() == 0) {
     if (loc.version) mem::red_add(loc.version, 1u);
     if (loc.flag) mem::st_relaxed(loc.flag, (uint8_t)1);
@@ -353,10 +342,9 @@ ADAPM_HD int register_intent(const Ctx& c, const IntentRec& rec, const Clock* cl
       count(c, C_ALLOC_FAIL);
       return 1;
     }
-    const uint32_t len = c.L.cls[cls].len;
-    Val* row = row_ptr<Val>(c, me, cls, ns);
-    Val* base = base_ptr<Val>(c, me, cls, ns);
-    for (uint32_t i = 0; i < len; ++i) { mem::st_relaxed(row + i, (Val)0); mem::st_relaxed(base + i, (Val)0); }
+    // row and base of a free slot are all-zero: the heap starts zeroed and phase C clears a slot before it returns
+    // it to the pool (warp-cooperative, coalesced) - a single lane zeroing 2 x len values here was the most
+    // expensive part of the round
     int64_t* ie = intent_end_of(c, me) + (size_t)ns * c.L.workers;
     for (int w = 0; w < c.L.workers; ++w) mem::st_relaxed(ie + w, (int64_t)0);
     mem::st_relaxed(ie + rec.worker, rec.end);
@@ -554,6 +542,17 @@ ADAPM_HD void phase_b_slot(const Ctx& c, uint32_t s, const RoundParams& rp) {
   count(c, C_RELOCATIONS);
 }
 
+// A slot goes back to the pool with all-zero row and base (register_intent relies on it).
+template <class Val, class G>
+ADAPM_HD void clear_slot_rows(const Ctx& c, const G& g, int cls, uint32_t s, uint32_t len) {
+  Val* row = row_ptr<Val>(c, c.rank, cls, s);
+  Val* base = base_ptr<Val>(c, c.rank, cls, s);
+  for (uint32_t i = g.lane(); i < len; i += g.size()) {
+    mem::st_relaxed(row + i, (Val)0);
+    mem::st_relaxed(base + i, (Val)0);
+  }
+}
+
 // Phase C: transfers, refreshes, drops.  (after the grace period)
 template <class Val, class G>
 ADAPM_HD void phase_c_slot(const Ctx& c, const G& g, uint32_t s, const RoundParams& rp) {
@@ -653,6 +652,7 @@ ADAPM_HD void phase_c_slot(const Ctx& c, const G& g, uint32_t s, const RoundPara
     } else if (g.lane() == 0) {
       count(c, C_PROTOCOL_ERRORS);
     }
+    clear_slot_rows<Val>(c, g, cls, s, len);
     mem::fence(); g.sync();
     if (g.lane() == 0) {
       mem::st_release(slot_of(c, me) + key, (int32_t)-1);
@@ -667,6 +667,8 @@ ADAPM_HD void phase_c_slot(const Ctx& c, const G& g, uint32_t s, const RoundPara
     return;
   }
   if (st == S_DEAD) {
+    clear_slot_rows<Val>(c, g, cls, s, len);
+    mem::fence(); g.sync();
     if (g.lane() == 0) {
       // the key may already have a fresh slot on this rank (it was requested back)
       cas_i32(slot_of(c, me) + key, (int32_t)s, (int32_t)-1);
