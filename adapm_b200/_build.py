@@ -21,7 +21,9 @@ BUILD = ROOT.parent / "build" / "adapm_b200"
 CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
 
 CXX_SOURCES = [
+    "adapm/corpus.cc",
     "adapm/fabric.cc",
+    "adapm/io.cc",
     "adapm/node.cc",
     "adapm/rpc.cc",
     "adapm/sampling.cc",

@@ -15,7 +15,7 @@ import torch
 import adapm_b200 as ad
 from adapm_b200.apps._common import add_system_options, strip_dashes, system_options
 from adapm_b200.models.word2vec import SyntheticPairs, Word2Vec, Word2VecConfig, syn0_key, syn1_key, zipf_counts
-from adapm_b200.utils.text import Vocabulary, pairs_from_sentences, read_sentences
+from adapm_b200.utils.text import NativeCorpus, Vocabulary, pairs_from_sentences, read_sentences
 
 
 def main(argv=None) -> int:
@@ -42,13 +42,25 @@ def main(argv=None) -> int:
     ap.add_argument("--batch_pairs", type=int, default=32768)
     ap.add_argument("--synthetic_vocab", type=int, default=0, help="train on a synthetic Zipf corpus of this vocabulary size")
     ap.add_argument("--synthetic_batches", type=int, default=50)
+    ap.add_argument("--loader", default="native", choices=["native", "python"],
+                    help="native: C++ vocabulary / encoder / background pair generator (csrc/adapm/corpus.cc); "
+                         "python: the numpy reference implementation (utils/text.py)")
     add_system_options(ap)
     args = ap.parse_args(strip_dashes(argv if argv is not None else sys.argv[1:]))
 
     rng = np.random.default_rng(args.model_seed)
     words = None
+    native = None
     if args.input_file:
-        vocab = Vocabulary.load(args.vocab_retrieve) if args.vocab_retrieve else Vocabulary.build(args.input_file, args.min_count)
+        if args.vocab_retrieve:
+            vocab = Vocabulary.load(args.vocab_retrieve)
+            if args.loader == "native":
+                native = NativeCorpus.from_vocabulary(vocab)
+        elif args.loader == "native":
+            native = NativeCorpus.build(args.input_file, args.min_count)
+            vocab = native.vocabulary()
+        else:
+            vocab = Vocabulary.build(args.input_file, args.min_count)
         if args.vocab_save:
             vocab.save(args.vocab_save)
         counts, words = vocab.counts.astype(np.float64), vocab.words
@@ -67,8 +79,14 @@ def main(argv=None) -> int:
     model.init_model()
     rank, world = server.my_rank(), server.num_servers()
 
+    if args.input_file and native is not None:
+        native.encode(args.input_file, rank, world)      # this rank's share of the lines, as word ids
+
     def batches(epoch):
-        if args.input_file:
+        if args.input_file and native is not None:
+            yield from native.pair_batches(args.window, args.subsample, cfg.batch_pairs, args.model_seed + rank, epoch,
+                                           pin=model.cuda)
+        elif args.input_file:
             sents = read_sentences(args.input_file, vocab, rank, world, args.subsample, rng)
             yield from pairs_from_sentences(sents, args.window, cfg.batch_pairs, rng)
         else:
@@ -92,7 +110,7 @@ def main(argv=None) -> int:
                 model.loss.zero_()
             loss = model.step(cur if cur.shape[1] == cfg.batch_pairs or not model.cuda else _pad(cur, cfg.batch_pairs))
             kv.advance_clock()
-            total_pairs += cur.shape[1]
+            total_pairs += getattr(cur, "valid_pairs", cur.shape[1])
             if time.time() - t0 > args.max_runtime:
                 break
         for cur in window:
@@ -100,7 +118,7 @@ def main(argv=None) -> int:
                 model.loss.zero_()
             loss = model.step(cur if cur.shape[1] == cfg.batch_pairs or not model.cuda else _pad(cur, cfg.batch_pairs))
             kv.advance_clock()
-            total_pairs += cur.shape[1]
+            total_pairs += getattr(cur, "valid_pairs", cur.shape[1])
         model.set_alpha((epoch + 1) / args.num_iterations)
         kv.barrier()
         if rank == 0:

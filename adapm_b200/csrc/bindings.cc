@@ -6,6 +6,10 @@
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
+#include <pybind11/numpy.h>
+
+#include "adapm/corpus.h"
+#include "adapm/io.h"
 #include "adapm/node.h"
 
 namespace py = pybind11;
@@ -185,6 +189,52 @@ PYBIND11_MODULE(_C, m) {
         m["push_params"] = w.num_push_params; m["push_params_local"] = w.num_push_params_local;
         return m;
       });
+
+  // fast text parsers (io.h)
+  m.def("read_triples", [](const std::string& path) {
+    std::vector<int64_t> v;
+    { py::gil_scoped_release r; v = read_triples_file(path); }
+    py::array_t<int64_t> a({(py::ssize_t)(v.size() / 3), (py::ssize_t)3});
+    if (!v.empty()) memcpy(a.mutable_data(), v.data(), v.size() * sizeof(int64_t));
+    return a;
+  });
+  m.def("read_matrix_market_coo", [](const std::string& path) {
+    CooMatrix c;
+    { py::gil_scoped_release r; c = read_matrix_market_coo_file(path); }
+    const py::ssize_t n = (py::ssize_t)c.x.size();
+    py::array_t<int64_t> i(n), j(n);
+    py::array_t<float> x(n);
+    if (n) {
+      memcpy(i.mutable_data(), c.i.data(), (size_t)n * 8);
+      memcpy(j.mutable_data(), c.j.data(), (size_t)n * 8);
+      memcpy(x.mutable_data(), c.x.data(), (size_t)n * 4);
+    }
+    return py::make_tuple(i, j, x, c.rows, c.cols);
+  });
+
+  // native data loader (corpus.h)
+  py::class_<Corpus, std::shared_ptr<Corpus>>(m, "Corpus")
+      .def_static("build", &Corpus::build, py::arg("path"), py::arg("min_count") = 5,
+                  py::call_guard<py::gil_scoped_release>())
+      .def_static("from_vocab", &Corpus::from_vocab)
+      .def("encode", &Corpus::encode, py::arg("path"), py::arg("rank") = 0, py::arg("world") = 1,
+           py::call_guard<py::gil_scoped_release>())
+      .def("words", &Corpus::words)
+      .def("counts", &Corpus::counts)
+      .def("vocab_size", &Corpus::vocab_size)
+      .def("num_tokens", &Corpus::num_tokens)
+      .def("num_sentences", &Corpus::num_sentences)
+      .def("lookup", &Corpus::lookup)
+      .def("tokens_ptr", [](Corpus& c) { return (uintptr_t)c.tokens(); })
+      .def("sentence_offsets_ptr", [](Corpus& c) { return (uintptr_t)c.sentence_offsets(); });
+  py::class_<PairStream, std::shared_ptr<PairStream>>(m, "PairStream")
+      .def(py::init<std::shared_ptr<Corpus>, int, double, int64_t, uint64_t, int>(), py::arg("corpus"), py::arg("window"),
+           py::arg("subsample"), py::arg("batch_pairs"), py::arg("seed"), py::arg("queue_depth") = 8)
+      .def("start_epoch", &PairStream::start_epoch, py::call_guard<py::gil_scoped_release>())
+      .def("next", [](PairStream& p, uintptr_t out) { return p.next(ptr<Key>(out)); },
+           py::call_guard<py::gil_scoped_release>())
+      .def("batch_pairs", &PairStream::batch_pairs)
+      .def("pairs_produced", &PairStream::pairs_produced);
 
   // host RPC (legacy SimpleApp capability, rpc.h)
   m.attr("kServerGroup") = (int)kServerGroup;

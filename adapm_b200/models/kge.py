@@ -104,7 +104,9 @@ def synthetic_triples(cfg: KGEConfig, n: int, seed: int = 0) -> torch.Tensor:
 
 def load_triples(path: str) -> torch.Tensor:
     """TSV ``s r o`` per line (apps/data/kge/*.del)."""
-    return torch.from_numpy(np.loadtxt(path, dtype=np.int64).reshape(-1, 3))
+    from .. import _C
+
+    return torch.from_numpy(_C.read_triples(path))   # native parser (csrc/adapm/io.cc)
 
 
 class KGE:

@@ -6,6 +6,14 @@ import numpy as np
 
 
 def read_matrix_market_coo(path: str):
+    """(i, j, x, rows, cols) with 0-based int64 indices and float32 values; parsed by the native reader
+    (csrc/adapm/io.cc), ``read_matrix_market_coo_py`` is the numpy reference."""
+    from .. import _C
+
+    return tuple(_C.read_matrix_market_coo(path))
+
+
+def read_matrix_market_coo_py(path: str):
     with open(path) as f:
         header = f.readline()
         assert header.startswith("%%MatrixMarket matrix coordinate"), f"{path}: not a MatrixMarket coordinate file"

@@ -80,3 +80,64 @@ def pairs_from_sentences(sentences: Iterator[np.ndarray], window: int, batch_pai
                 n = buf_c[0].size
     if n:
         yield torch.from_numpy(np.stack([np.concatenate(buf_c), np.concatenate(buf_t)]))
+
+
+# ------------------------------------------------------------------------------------------ native loader
+class NativeCorpus:
+    """C++ corpus (csrc/adapm/corpus.{h,cc}): same vocabulary rules as :class:`Vocabulary` (count-descending, ties by
+    first occurrence, ``</s>`` = word 0), plus the encoded sentences of this rank and a background pair generator."""
+
+    def __init__(self, impl):
+        self._impl = impl
+
+    @staticmethod
+    def build(path: str, min_count: int = 5) -> "NativeCorpus":
+        from .. import _C
+
+        return NativeCorpus(_C.Corpus.build(path, int(min_count)))
+
+    @staticmethod
+    def from_vocabulary(vocab: Vocabulary) -> "NativeCorpus":
+        from .. import _C
+
+        return NativeCorpus(_C.Corpus.from_vocab(list(vocab.words), [int(c) for c in vocab.counts]))
+
+    def vocabulary(self) -> Vocabulary:
+        return Vocabulary(list(self._impl.words()), np.array(self._impl.counts(), dtype=np.int64))
+
+    def encode(self, path: str, rank: int = 0, world: int = 1) -> "NativeCorpus":
+        self._impl.encode(path, int(rank), int(world))
+        return self
+
+    def num_tokens(self) -> int:
+        return self._impl.num_tokens()
+
+    def num_sentences(self) -> int:
+        return self._impl.num_sentences()
+
+    def sentences(self) -> List[np.ndarray]:
+        """The encoded sentences (copies; for tests and small corpora)."""
+        import ctypes
+
+        n, ns = self.num_tokens(), self.num_sentences()
+        tok = np.ctypeslib.as_array((ctypes.c_int32 * max(n, 1)).from_address(self._impl.tokens_ptr()))[:n].copy()
+        off = np.ctypeslib.as_array((ctypes.c_int64 * (ns + 1)).from_address(self._impl.sentence_offsets_ptr())).copy()
+        return [tok[off[i]:off[i + 1]] for i in range(ns)]
+
+    def pair_batches(self, window: int, subsample: float, batch_pairs: int, seed: int, epoch: int = 0,
+                     pin: bool = False, queue_depth: int = 8) -> Iterator[torch.Tensor]:
+        """[2, batch_pairs] key batches of one epoch, generated by a background C++ thread. A short final batch is
+        padded by repeating its pairs; ``valid_pairs`` of the yielded tensor tells how many are real."""
+        from .. import _C
+
+        ps = _C.PairStream(self._impl, int(window), float(subsample), int(batch_pairs), int(seed), int(queue_depth))
+        ps.start_epoch(int(epoch))
+        while True:
+            t = torch.empty(2, batch_pairs, dtype=torch.int64)
+            if pin:
+                t = t.pin_memory()
+            valid = ps.next(t.data_ptr())
+            if valid == 0:
+                return
+            t.valid_pairs = int(valid)
+            yield t
