@@ -26,6 +26,7 @@ struct Options {
   int workers = 1;                  // logical workers per rank (reference: num_threads)
   double pool_factor = 0;           // slots per class per rank = max(min_pool, factor * keys/world); 0 = auto
   int64_t min_pool = 0;
+  int64_t pool_bytes = (int64_t)16 << 30;  // auto pool sizing: memory budget per rank for rows + replica bases
   double wait_timeout_s = 300;      // watchdog on every blocking wait (failure detection)
 
   // ---- reference "sys.*" options
@@ -81,6 +82,7 @@ struct Options {
     else if (name == "workers") workers = std::stoi(v);
     else if (name == "pool_factor") pool_factor = std::stod(v);
     else if (name == "min_pool") min_pool = std::stoll(v);
+    else if (name == "pool_bytes") pool_bytes = std::stoll(v);
     else if (name == "wait_timeout_s") wait_timeout_s = std::stod(v);
     else if (name == "sys.zmq_threads") zmq_threads = std::stoi(v);
     else if (name == "sys.techniques") techniques = parse_techniques(v);

@@ -76,9 +76,14 @@ inline Layout build_layout(const ValueSpec& spec, const Options& opt, std::vecto
     int64_t cap;
     if (opt.world == 1) cap = n_c;
     else if (n_c <= (1 << 16) && opt.pool_factor <= 0) cap = full;
-    else {
-      double f = opt.pool_factor > 0 ? opt.pool_factor : 2.0;
-      cap = std::min<int64_t>(full, (int64_t)std::ceil(home_max * f) + 1024);
+    else if (opt.pool_factor > 0) {
+      cap = std::min<int64_t>(full, (int64_t)std::ceil(home_max * opt.pool_factor) + 1024);
+    } else {
+      // auto: twice the home share, or as many slots as the pool memory budget buys (a long intent look-ahead keeps
+      // many replicas / relocated rows alive per rank: with 8 ranks, home is only 1/8 of the keys)
+      const int64_t slot_bytes = 2 * (int64_t)class_len[c] * L.val_bytes + 64;
+      const int64_t by_budget = (int64_t)(opt.pool_bytes / L.num_classes) / slot_bytes;
+      cap = std::min<int64_t>(full, std::max<int64_t>(2 * home_max + 1024, by_budget));
     }
     cap = std::max<int64_t>(cap, std::min<int64_t>(full, opt.min_pool));
     cap = std::max<int64_t>(cap, home_max);

@@ -142,3 +142,24 @@ def test_launcher_dry_run_mpi_and_ssh(tmp_path):
     hf.write_text("hostA\nhostB\n")     # the fabric is single-node: two hosts are refused
     r = subprocess.run(base + ["--launcher", "ssh", "-H", str(hf), "-m", "x"], cwd=ROOT, capture_output=True, text=True)
     assert r.returncode == 2 and "single-node" in r.stderr
+
+
+def _pool_worker(kv, server, wid):
+    h = server._impl.slot_histogram()
+    kv.barrier()
+    kv.finalize()
+    return h[100]          # free slots of length class 0 on this rank
+
+
+def test_pool_sizing_auto_and_explicit():
+    # auto: as many slots as the memory budget buys, capped at "every key + slack" (100k keys -> 125k slots)
+    res = run_cluster(_pool_worker, world=2, workers=1, mode="threads", value_lengths=2, num_keys=100000)
+    assert [r[0] for r in res.values()] == [125000 - 50000] * 2
+    # a tight memory budget falls back to twice the home share (+1024)
+    res = run_cluster(_pool_worker, world=2, workers=1, mode="threads", value_lengths=2, num_keys=100000,
+                      options={"pool_bytes": 1 << 20})
+    assert [r[0] for r in res.values()] == [2 * 50000 + 1024 - 50000] * 2
+    # explicit factor
+    res = run_cluster(_pool_worker, world=2, workers=1, mode="threads", value_lengths=2, num_keys=100000,
+                      options={"pool_factor": 1.5})
+    assert [r[0] for r in res.values()] == [75000 + 1024 - 50000] * 2
