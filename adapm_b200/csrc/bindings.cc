@@ -114,6 +114,9 @@ PYBIND11_MODULE(_C, m) {
         for (size_t i = 0; i < keys.size(); ++i) out.emplace_back((int)st[i], (int)ow[i]);
         return out;
       })
+      .def("peek_into", [](Server& s, uintptr_t keys, size_t n, uintptr_t states_u8, uintptr_t owners_u8) {
+        s.backend().peek_states(ptr<const Key>(keys), n, ptr<uint8_t>(states_u8), ptr<uint8_t>(owners_u8));
+      }, py::call_guard<py::gil_scoped_release>())
       .def("sampling_stats", [](Server& s) {
         std::map<std::string, uint64_t> m;
         if (s.sampling()) { m["checks"] = s.sampling()->local_checks(); m["pulls"] = s.sampling()->local_pulls(); }

@@ -163,3 +163,47 @@ def test_pool_sizing_auto_and_explicit():
     res = run_cluster(_pool_worker, world=2, workers=1, mode="threads", value_lengths=2, num_keys=100000,
                       options={"pool_factor": 1.5})
     assert [r[0] for r in res.values()] == [75000 + 1024 - 50000] * 2
+
+
+def _ckpt_save_worker(kv, server, wid, prefix=None):
+    from adapm_b200.utils.checkpoint import save_store
+
+    nk = server.num_keys()
+    keys = torch.arange(wid, nk, server.num_servers())
+    kv.wait(kv.set(keys, (keys.float().repeat_interleave(3) + 0.5)))
+    kv.barrier()
+    kv.intent(torch.tensor([1, 2, 3, 4, 5]), kv.current_clock() + 1)      # move / replicate a few keys first
+    kv.advance_clock(); kv.wait_sync(); kv.barrier()
+    kv.wait(kv.push(torch.tensor([1, 2, 3]), torch.ones(9)))
+    n = save_store(kv, prefix)
+    kv.finalize()
+    return n
+
+
+def _ckpt_load_worker(kv, server, wid, prefix=None):
+    from adapm_b200.utils.checkpoint import load_store
+
+    n = load_store(kv, prefix)
+    kv.barrier()
+    nk = server.num_keys()
+    out = torch.zeros(nk * 3)
+    kv.wait(kv.pull(torch.arange(nk), out))
+    kv.barrier()
+    kv.finalize()
+    return n, out.view(nk, 3)[:, 0].tolist()
+
+
+def test_store_checkpoint_roundtrip_across_world_sizes(tmp_path):
+    import functools
+
+    prefix = str(tmp_path / "ck")
+    nk = 50
+    res = run_cluster(functools.partial(_ckpt_save_worker, prefix=prefix), world=3, workers=1, mode="threads",
+                      value_lengths=3, num_keys=nk)
+    assert sum(r[0] for r in res.values()) == nk                      # every key written exactly once
+    res = run_cluster(functools.partial(_ckpt_load_worker, prefix=prefix), world=2, workers=1, mode="threads",
+                      value_lengths=3, num_keys=nk)
+    assert sum(r[0][0] for r in res.values()) == nk
+    want = [k + 0.5 + (3.0 if k in (1, 2, 3) else 0.0) for k in range(nk)]   # 3 ranks pushed +1 each
+    for r in res.values():
+        assert r[0][1] == want
