@@ -1,6 +1,7 @@
 #include "fabric.h"
 
 #include <fcntl.h>
+#include <signal.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -165,6 +166,7 @@ class ShmFabric : public Fabric {
       ADAPM_CHECK(ctl_->world == world_, "world size mismatch with rank 0");
     }
     ctl_sz_ = sz;
+    peers_are_processes_ = true;
     ctl_->ranks[rank_].pid = (int)getpid();
     ctl_->ranks[rank_].attached.store(1);
     if (cuda_) {
@@ -177,6 +179,7 @@ class ShmFabric : public Fabric {
   }
 
   ~ShmFabric() override {
+    stop_failure_detector();
     for (int r = 0; r < world_; ++r) {
       if (!heaps_[r]) continue;
       if (cuda_) {
@@ -251,5 +254,52 @@ std::shared_ptr<Fabric> Fabric::create(const Options& opt) {
   if (opt.fabric == "shm") return std::make_shared<ShmFabric>(opt);
   throw Error("unknown fabric '" + opt.fabric + "' (inproc|shm)");
 }
+
+// ------------------------------------------------------------------ failure detector
+namespace {
+bool process_dead(int pid) {
+  if (pid <= 0) return false;
+  if (kill(pid, 0) != 0 && errno == ESRCH) return true;
+  // a process that exited but was not reaped yet (zombie) still answers kill(pid, 0)
+  char path[64];
+  snprintf(path, sizeof(path), "/proc/%d/stat", pid);
+  FILE* f = fopen(path, "r");
+  if (!f) return false;
+  char buf[512];
+  size_t n = fread(buf, 1, sizeof(buf) - 1, f);
+  fclose(f);
+  buf[n] = 0;
+  const char* p = strrchr(buf, ')');   // the command name may contain spaces / parentheses
+  return p && p[1] == ' ' && (p[2] == 'Z' || p[2] == 'X');
+}
+}  // namespace
+
+void Fabric::start_failure_detector(int period_ms) {
+  if (!peers_are_processes_ || world_ <= 1 || fd_thread_.joinable()) return;
+  fd_stop_.store(false);
+  fd_thread_ = std::thread([this, period_ms] {
+    while (!fd_stop_.load(std::memory_order_acquire)) {
+      for (int r = 0; r < world_ && dead_peer_.load() < 0; ++r) {
+        if (r == rank_ || !ctl_->ranks[r].attached.load()) continue;
+        if (process_dead(ctl_->ranks[r].pid)) {
+          dead_peer_.store(r);
+          ALOG("[adapm] rank " << rank_ << ": peer rank " << r << " (pid " << ctl_->ranks[r].pid
+                               << ") died - aborting all collective waits");
+          ctl_->sync_barrier.broken.store(1);
+          ctl_->node_barrier.broken.store(1);
+          ctl_->worker_barrier.broken.store(1);
+        }
+      }
+      for (int i = 0; i < period_ms / 10 && !fd_stop_.load(std::memory_order_acquire); ++i)
+        std::this_thread::sleep_for(std::chrono::milliseconds(10));
+    }
+  });
+}
+
+void Fabric::stop_failure_detector() {
+  fd_stop_.store(true, std::memory_order_release);
+  if (fd_thread_.joinable()) fd_thread_.join();
+}
+
 
 }  // namespace adapm

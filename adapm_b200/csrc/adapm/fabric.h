@@ -11,7 +11,9 @@
 // (include/zmq_van.h:30-250, src/van.cc:267-357): there are no sockets and no message
 // (de)serialisation anywhere.
 #pragma once
+#include <atomic>
 #include <memory>
+#include <thread>
 #include <string>
 #include <vector>
 #include "config.h"
@@ -38,12 +40,24 @@ class Fabric {
     ctl_->node_barrier.wait(world_, timeout_s_, what);
   }
 
+  // Failure detector (the reference's heartbeat skeleton, van.cc:529-548, made effective): a thread that checks
+  // every `period_ms` whether the processes of the other ranks are still alive; a dead peer breaks all barriers so
+  // that every blocked call on this rank raises instead of waiting for the watchdog timeout. No-op for in-process
+  // ranks. stop_failure_detector() is called before the last shutdown barrier (peers exit at different times).
+  void start_failure_detector(int period_ms = 200);
+  void stop_failure_detector();
+  int dead_peer() const { return dead_peer_.load(); }   // -1: none detected
+
  protected:
   ControlBlock* ctl_ = nullptr;
   int rank_ = 0, world_ = 1, device_ = -1;
   bool cuda_ = false;
   double timeout_s_ = 300;
   std::vector<char*> heaps_;
+  bool peers_are_processes_ = false;
+  std::thread fd_thread_;
+  std::atomic<bool> fd_stop_{false};
+  std::atomic<int> dead_peer_{-1};
 };
 
 // device helpers implemented in cuda/device_mem.cu (only linked in the cuda build)

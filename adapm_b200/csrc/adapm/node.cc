@@ -22,6 +22,7 @@ Server::Server(const Options& opt, const ValueSpec& spec) : opt_(opt), spec_(spe
   sync_.reset(new SyncEngine(this));
   sync_->start();
   fabric_->node_barrier("server start");
+  fabric_->start_failure_detector();
 }
 
 Server::~Server() {
@@ -59,6 +60,7 @@ void Server::shutdown() {
   if (verbosity() >= 1) ALOG(stats_string());
   if (tracing()) write_traces();
   if (opt_.locality_stats) write_locality_stats();
+  fabric_->stop_failure_detector();   // from here on peers may exit at any time
   fabric_->node_barrier("shutdown done");
   if (router_) router_->stop();   // after the barrier: every peer's requests have been answered
   backend_.reset();
