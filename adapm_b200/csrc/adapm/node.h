@@ -72,6 +72,8 @@ class SyncEngine {
   std::vector<IntentRec> recs_, deferred_;
   std::vector<uint32_t> seen_epoch_;   // intent dedupe table (one stamp per key)
   uint32_t epoch_ = 0;
+  std::vector<uint32_t> rec_round_, rec_index_;   // per-round merge of records per key (single worker per rank)
+  uint32_t rec_epoch_ = 0;
   std::atomic<uint64_t> deferred_pending_{0};  // intent records that could not be registered in the last round
   std::vector<uint8_t> status_;
   uint64_t round_no_ = 0;
