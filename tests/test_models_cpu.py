@@ -120,7 +120,7 @@ def _mf_worker(kv, server, wid):
 def test_mf_cpu(tmp_path, algo, world):
     from adapm_b200.models.mf import MFConfig
 
-    cfg = MFConfig(num_rows=80, num_cols=40, rank=8, algorithm=algo, eps=0.05, lam=0.01, batch_nnz=500, read_ahead=1)
+    cfg = MFConfig(num_rows=80, num_cols=40, rank=8, algorithm=algo, eps=0.02, lam=0.01, batch_nnz=250, read_ahead=1)
 
     def setup(server):
         server._cfg, server._tmp = cfg, str(tmp_path)
