@@ -1,0 +1,79 @@
+"""Property-based test of the relocation / replication protocol (hypothesis): random programs of Intent / Push / Pull /
+advanceClock on every rank, executed concurrently on the CPU backend, must never lose or duplicate an update, must
+give each worker read-your-writes, and must converge to the exact sum after the WaitSync idiom - for every
+management technique and for random replica-maintenance pacing."""
+import os
+
+import torch
+from hypothesis import HealthCheck, given, settings
+from hypothesis import strategies as st
+
+from harness import run_cluster
+
+NUM_KEYS, VPK = 24, 2
+
+key_sets = st.lists(st.integers(0, NUM_KEYS - 1), min_size=1, max_size=6, unique=True)
+op = st.one_of(
+    st.tuples(st.just("intent"), key_sets, st.integers(0, 3), st.integers(1, 4)),   # keys, start offset, duration
+    st.tuples(st.just("push"), key_sets),
+    st.tuples(st.just("pull"), key_sets),
+    st.tuples(st.just("clock")),
+    st.tuples(st.just("sync")),
+)
+program = st.lists(st.lists(op, min_size=1, max_size=6), min_size=1, max_size=5)    # rounds of ops
+
+
+def _run(kv, server, wid, programs=None):
+    prog = programs[wid]
+    rounds = max(len(p) for p in programs)
+    mine = torch.zeros(NUM_KEYS, dtype=torch.int64)          # what this worker pushed so far, per key
+    errs = []
+    for r in range(rounds):
+        for o in (prog[r] if r < len(prog) else []):
+            if o[0] == "intent":
+                kv.intent(torch.tensor(o[1]), kv.current_clock() + o[2], kv.current_clock() + o[2] + o[3])
+            elif o[0] == "push":
+                k = torch.tensor(o[1])
+                kv.wait(kv.push(k, torch.ones(len(o[1]) * VPK, dtype=torch.int64)))
+                mine[k] += 1
+            elif o[0] == "pull":
+                k = torch.tensor(o[1])
+                v = torch.zeros(len(o[1]) * VPK, dtype=torch.int64)
+                kv.wait(kv.pull(k, v))
+                v = v.view(-1, VPK)
+                if not bool((v[:, 0] == v[:, 1]).all()):
+                    errs.append(f"w{wid} round {r}: torn row {v.tolist()}")
+                if bool((v[:, 0] < mine[k]).any()):
+                    errs.append(f"w{wid} round {r}: read-your-writes violated: {v[:, 0].tolist()} < {mine[k].tolist()}")
+            elif o[0] == "clock":
+                kv.advance_clock()
+            elif o[0] == "sync":
+                kv.wait_sync()
+        kv.barrier()
+    kv.waitall(); kv.wait_sync(); kv.barrier(); kv.wait_sync(); kv.barrier()
+    out = torch.zeros(NUM_KEYS * VPK, dtype=torch.int64)
+    kv.wait(kv.pull(torch.arange(NUM_KEYS), out))
+    kv.barrier()
+    kv.finalize()
+    return errs, out.view(-1, VPK)[:, 0].tolist(), mine.tolist()
+
+
+@settings(max_examples=int(os.environ.get("ADAPM_HYP_EXAMPLES", "20")), deadline=None, suppress_health_check=list(HealthCheck))
+@given(programs=st.lists(program, min_size=3, max_size=3),
+       technique=st.sampled_from(["all", "replication_only", "relocation_only"]),
+       idle_period=st.integers(1, 5), sweep_period=st.integers(0, 4))
+def test_random_programs_are_exact(programs, technique, idle_period, sweep_period):
+    import functools
+
+    res = run_cluster(functools.partial(_run, programs=programs), world=3, workers=1, mode="threads", value_lengths=VPK,
+                      num_keys=NUM_KEYS, dtype="int64",
+                      options={"sys.techniques": technique, "sys.sync.idle_period": idle_period,
+                               "sys.sync.sweep_period": sweep_period})
+    total = [0] * NUM_KEYS
+    for r in res.values():
+        errs, final, mine = r[0]
+        assert not errs, errs
+        total = [a + b for a, b in zip(total, mine)]
+    for r in res.values():
+        assert r[0][1] == total, (r[0][1], total)           # every rank sees the exact sum of all pushes
+        assert r["counters"]["protocol_errors"] == 0
