@@ -77,3 +77,24 @@ def test_random_programs_are_exact(programs, technique, idle_period, sweep_perio
     for r in res.values():
         assert r[0][1] == total, (r[0][1], total)           # every rank sees the exact sum of all pushes
         assert r["counters"]["protocol_errors"] == 0
+
+
+@settings(max_examples=int(os.environ.get("ADAPM_HYP_EXAMPLES", "10")), deadline=None, suppress_health_check=list(HealthCheck))
+@given(programs=st.lists(program, min_size=4, max_size=4), technique=st.sampled_from(["all", "replication_only"]))
+def test_random_programs_two_workers_per_rank(programs, technique):
+    """Two ranks x two worker threads: intents of co-located workers share slots (per-worker intent ends), pushes of
+    co-located workers hit the same replica."""
+    import functools
+
+    res = run_cluster(functools.partial(_run, programs=programs), world=2, workers=2, mode="threads", value_lengths=VPK,
+                      num_keys=NUM_KEYS, dtype="int64", options={"sys.techniques": technique})
+    total = [0] * NUM_KEYS
+    for r in res.values():
+        for cid in (0, 1):
+            errs, final, mine = r[cid]
+            assert not errs, errs
+            total = [a + b for a, b in zip(total, mine)]
+    for r in res.values():
+        for cid in (0, 1):
+            assert r[cid][1] == total, (r[cid][1], total)
+        assert r["counters"]["protocol_errors"] == 0
