@@ -12,6 +12,8 @@
 // One warp per training call; the three directory lookups are issued by three lanes at once.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "ops.h"
 #include "pm_kernels.cuh"
 
@@ -83,8 +85,10 @@ __device__ __noinline__ float kge_call_generic(const Ctx& c, Key ks, Key kr, Key
 }
 
 // VPLH = float4 vectors per lane per half-embedding (nh/8 float4 per half); VPLH = 0 -> generic only
-template <int VPLH>
-__global__ void __launch_bounds__(kThreads, 2)
+// MAXREG = register budget (2 blocks of 256 threads per SM): 128 uses the whole register file; 104 leaves room for one
+// block of the sync-round kernels per SM (see ops_sgns_tma.cu). ADAPM_KGE_REGS=104 selects the lean variant.
+template <int VPLH, int MAXREG>
+__global__ void __maxnreg__(MAXREG)
 kge_step_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ subj, const Key* __restrict__ rel,
                 const Key* __restrict__ obj, const float* __restrict__ labels, int n_calls, int nh, float eta,
                 float gamma_e, float gamma_r, float* __restrict__ loss_out, unsigned long long* __restrict__ stats) {
@@ -200,15 +204,22 @@ void kge_complex_step(CudaBackend& be, cudaStream_t stream, const Key* subj, con
   const int nvh = nh / 8;
   int vplh = (nh % 8 == 0) ? (nvh + 31) / 32 : 0;
   if (vplh > 2) vplh = 0;
-#define ADAPM_LAUNCH_KGE(V)                                                                                    \
+  static const int regs_env = [] { const char* e = getenv("ADAPM_KGE_REGS"); return e ? atoi(e) : 0; }();
+  const bool lean = regs_env > 0 && regs_env < 128;
+#define ADAPM_LAUNCH_KGE2(V, R)                                                                                 \
   do {                                                                                                         \
     static bool attr_set = false;                                                                              \
     if (!attr_set) {                                                                                           \
-      cudaFuncSetAttribute(kge_step_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);       \
+      cudaFuncSetAttribute(kge_step_kernel<V, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);    \
       attr_set = true;                                                                                         \
     }                                                                                                          \
-    kge_step_kernel<V><<<blocks, kThreads, smem, stream>>>(c, subj, rel, obj, labels, n_calls, nh, eta, gamma_e, \
-                                                           gamma_r, loss_out, stats);                          \
+    kge_step_kernel<V, R><<<blocks, kThreads, smem, stream>>>(c, subj, rel, obj, labels, n_calls, nh, eta,     \
+                                                              gamma_e, gamma_r, loss_out, stats);              \
+  } while (0)
+#define ADAPM_LAUNCH_KGE(V)              \
+  do {                                   \
+    if (lean) ADAPM_LAUNCH_KGE2(V, 104); \
+    else ADAPM_LAUNCH_KGE2(V, 128);      \
   } while (0)
   switch (vplh) {
     case 1: ADAPM_LAUNCH_KGE(1); break;

@@ -38,7 +38,7 @@ def test_hot_kernels_stay_within_their_register_budget():
         pytest.skip("no ptxas logs (extension was not built in-tree)")
     # full-register variants of the fused steps: 2 blocks x 256 threads x 128 registers = the register file, no spills
     for name in ("sgns_step_tma_kernel<3, 128>", "sgns_step_tma_kernel<2, 128>", "sgns_step_tma_kernel<1, 128>",
-                 "sgns_step_kernel<3, 2>", "kge_step_kernel<2>", "mf_step_kernel<1>"):
+                 "sgns_step_kernel<3, 2>", "kge_step_kernel<2, 128>", "kge_step_kernel<2, 104>", "mf_step_kernel<1>"):
         assert name in k, sorted(k)
         assert k[name]["regs"] <= 128 and k[name]["spill"] == 0, (name, k[name])
     # lean multi-GPU variant: 104 registers leave 12 K registers per SM for one block of the round kernels
