@@ -37,12 +37,12 @@ def test_hot_kernels_stay_within_their_register_budget():
     if not k:
         pytest.skip("no ptxas logs (extension was not built in-tree)")
     # full-register variants of the fused steps: 2 blocks x 256 threads x 128 registers = the register file, no spills
-    for name in ("sgns_step_tma_kernel<3, 128>", "sgns_step_tma_kernel<2, 128>", "sgns_step_tma_kernel<1, 128>",
+    for name in ("sgns_step_tma_kernel<3, 128, false>", "sgns_step_tma_kernel<2, 128, false>", "sgns_step_tma_kernel<1, 128, false>",
                  "sgns_step_kernel<3, 2>", "kge_step_kernel<2, 128>", "kge_step_kernel<2, 104>", "mf_step_kernel<1>"):
         assert name in k, sorted(k)
         assert k[name]["regs"] <= 128 and k[name]["spill"] == 0, (name, k[name])
     # lean multi-GPU variant: 104 registers leave 12 K registers per SM for one block of the round kernels
-    lean = k["sgns_step_tma_kernel<3, 104>"]
+    lean = k["sgns_step_tma_kernel<3, 104, false>"]
     assert lean["regs"] <= 104 and lean["spill"] <= 256, lean
     for name in ("phase_work_kernel<0>", "phase_work_kernel<1>"):
         assert k[name]["regs"] * 128 <= 65536 - 2 * 256 * 104, (name, k[name])   # 128-thread blocks
