@@ -207,3 +207,18 @@ def test_store_checkpoint_roundtrip_across_world_sizes(tmp_path):
     want = [k + 0.5 + (3.0 if k in (1, 2, 3) else 0.0) for k in range(nk)]   # 3 ranks pushed +1 each
     for r in res.values():
         assert r[0][1] == want
+
+
+def test_examples_run(tmp_path):
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    launch = [sys.executable, "-m", "adapm_b200.launch", "--backend", "cpu"]
+    r = subprocess.run(launch + ["-s", "2", os.path.join(ROOT, "examples", "legacy_kv_example.py")], cwd=ROOT, env=env,
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "pulled [2.0" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+    ck = str(tmp_path / "ck")
+    r = subprocess.run(launch + ["-s", "3", os.path.join(ROOT, "examples", "checkpoint_example.py"), "save", ck], cwd=ROOT,
+                       env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    r = subprocess.run(launch + ["-s", "2", os.path.join(ROOT, "examples", "checkpoint_example.py"), "load", ck], cwd=ROOT,
+                       env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "all 1000 rows verified" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
