@@ -177,6 +177,10 @@ class Server:
     def barrier(self) -> None:
         self._impl.barrier()
 
+    def allreduce_sum(self, values) -> list:
+        """Sum of up to 64 floats over all ranks (collective, one call per rank, host side)."""
+        return list(self._impl.allreduce_sum([float(v) for v in values]))
+
     def shutdown(self) -> None:
         self._impl.shutdown()
 

@@ -14,7 +14,8 @@ import time
 import torch
 
 import adapm_b200 as ad
-from adapm_b200.apps._common import add_system_options, strip_dashes, system_options
+from adapm_b200.apps._common import (add_ablation_options, add_system_options, enforce_full_replication, id_permutation,
+                                      strip_dashes, system_options, wants_sync_push)
 from adapm_b200.models.kge import KGE, KGEConfig, evaluate_fused, load_triples, synthetic_triples
 from adapm_b200.utils.allreduce import ps_allreduce
 
@@ -47,6 +48,15 @@ def main(argv=None) -> int:
     ap.add_argument("--eval_truncate_tr", type=int, default=2048)
     ap.add_argument("--model_seed", type=int, default=134827)
     ap.add_argument("--max_runtime", type=float, default=float("inf"))
+    ap.add_argument("--write_embeddings", default="", help="directory to checkpoint the model to after each epoch "
+                                                           "(the reference's spelling of --model_path)")
+    ap.add_argument("--init_parameters", default="", help="'none', 'uniform{a/b}' or 'normal{mean/std}' (default normal{0/0.1})")
+    ap.add_argument("--eval_initial", type=int, default=0, help="run an evaluation before the first epoch")
+    ap.add_argument("--eval_truncate_va", type=int, default=0, help="truncate the validation set in evaluations (0: all)")
+    ap.add_argument("--max_N", type=int, default=-1, help="artificial maximum of training triples per worker (fast tests)")
+    ap.add_argument("--read_partitioned_dataset", type=int, default=0,
+                    help="read train.partitioned.<servers>x<threads>.del: block b of the file is trained by worker b")
+    add_ablation_options(ap)
     add_system_options(ap)
     args = ap.parse_args(strip_dashes(argv if argv is not None else sys.argv[1:]))
 
@@ -58,23 +68,51 @@ def main(argv=None) -> int:
                     dropout_relation=args.dropout_relation, batch_triples=args.batch_triples,
                     read_ahead=args.signal_intent_ahead, sampling_scheme=getattr(args, "sampling.scheme") or "local",
                     signal_initial_relations_intent=bool(args.signal_initial_relations_intent), model_seed=args.model_seed)
+    if args.write_embeddings and not args.model_path:
+        os.makedirs(args.write_embeddings, exist_ok=True)
+        args.model_path = os.path.join(args.write_embeddings, "")
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
     if args.dataset:
-        tr = load_triples(os.path.join(args.dataset, "train.del"))
+        tr_name = "train.del"
+        if args.read_partitioned_dataset:
+            tr_name = f"train.partitioned.{world_env}x{args.num_threads}.del"
+        tr = load_triples(os.path.join(args.dataset, tr_name))
         va = load_triples(os.path.join(args.dataset, "valid.del"))
         te = load_triples(os.path.join(args.dataset, "test.del"))
     else:
         n = args.synthetic or 100000
         allt = synthetic_triples(cfg, n + 2000, seed=args.model_seed)
         tr, va, te = allt[:n], allt[n:n + 1000], allt[n + 1000:]
-    ad.setup(cfg.num_keys, args.num_threads)
+    if args.enforce_random_keys:
+        # entity / relation ids are labels: relabel them with a random permutation (keys = ids), the same on every rank
+        fe = torch.from_numpy(id_permutation(cfg.num_entities, args.model_seed, True))
+        fr = torch.from_numpy(id_permutation(cfg.num_relations, args.model_seed + 1, True))
+        tr, va, te = (torch.stack([fe[t[:, 0]], fr[t[:, 1]], fe[t[:, 2]]], 1) for t in (tr, va, te))
+    if args.eval_truncate_va:
+        va = va[: args.eval_truncate_va]
+    ad.setup(cfg.num_keys, 1)   # one worker per rank: the per-thread loops of the reference are batched kernels here
     server = ad.Server(cfg.value_lengths(), backend=args.backend, options=system_options(args))
     kv = ad.Worker(0, server)
     model = KGE(server, kv, cfg)
-    model.init_model()
+    model.init_model(init=args.init_parameters)
     rank, world = server.my_rank(), server.num_servers()
-    mine = tr[rank::world]                      # data parallelism: each worker trains on its partition
+    if args.read_partitioned_dataset:
+        n_blk = world * args.num_threads        # the file holds the blocks one after the other, equal sizes
+        per = (tr.shape[0] + n_blk - 1) // n_blk
+        mine = tr[rank * args.num_threads * per:(rank + 1) * args.num_threads * per]
+    else:
+        mine = tr[rank::world]                  # data parallelism: each worker trains on its partition
+    if args.max_N >= 0:
+        mine = mine[: args.max_N]
+    if args.enforce_full_replication:
+        enforce_full_replication(kv, cfg.num_keys)
+    sync_push = wants_sync_push(args)
     known = torch.cat([tr, va, te])
     t0 = time.time()
+    if args.eval_initial:
+        if rank == 0:
+            print(f"[kge] initial valid: {model.evaluate(va, known)}", flush=True)
+        kv.barrier()
     for epoch in range(1, args.num_epochs + 1):
         perm = mine[torch.randperm(mine.shape[0], generator=torch.Generator().manual_seed(epoch * 977 + rank))]
         starts = list(range(0, perm.shape[0], cfg.batch_triples))
@@ -90,6 +128,8 @@ def main(argv=None) -> int:
             out = model.step(perm[s:s + cfg.batch_triples])
             if not model.cuda:
                 bce += float(out)
+            elif sync_push:
+                torch.cuda.current_stream().synchronize()
             kv.advance_clock()
         if model.cuda:
             bce = float(model.loss.item())

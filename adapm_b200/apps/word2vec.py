@@ -13,8 +13,10 @@ import numpy as np
 import torch
 
 import adapm_b200 as ad
-from adapm_b200.apps._common import add_system_options, strip_dashes, system_options
-from adapm_b200.models.word2vec import SyntheticPairs, Word2Vec, Word2VecConfig, syn0_key, syn1_key, zipf_counts
+from adapm_b200.apps._common import (add_ablation_options, add_system_options, enforce_full_replication, id_permutation,
+                                      strip_dashes, system_options, wants_sync_push)
+from adapm_b200.models.word2vec import (SyntheticPairs, Word2Vec, Word2VecConfig, load_checkpoint, syn0_key, syn1_key,
+                                        zipf_counts)
 from adapm_b200.utils.text import NativeCorpus, Vocabulary, pairs_from_sentences, read_sentences
 
 
@@ -42,6 +44,15 @@ def main(argv=None) -> int:
     ap.add_argument("--batch_pairs", type=int, default=32768)
     ap.add_argument("--synthetic_vocab", type=int, default=0, help="train on a synthetic Zipf corpus of this vocabulary size")
     ap.add_argument("--synthetic_batches", type=int, default=50)
+    ap.add_argument("--init_model", default="random",
+                    help="'random' (syn0 ~ U(-.5,.5)/d, syn1 = 0), 'none', or the path of a checkpoint written with "
+                         "--write_results (its .syn1 companion is used when present)")
+    ap.add_argument("--data_words", type=int, default=0, help="stop an epoch after this many training pairs per rank (0: all)")
+    ap.add_argument("--clustered_input", type=int, default=0,
+                    help="accepted for parity: the loader always gives rank r the lines r, r + world, ...")
+    ap.add_argument("--debug_mode", "-d", type=int, default=0)
+    ap.add_argument("--num_keys", "-k", type=int, default=0, help="accepted for parity (derived from the vocabulary: 2 * |V|)")
+    add_ablation_options(ap)
     ap.add_argument("--loader", default="native", choices=["native", "python"],
                     help="native: C++ vocabulary / encoder / background pair generator (csrc/adapm/corpus.cc); "
                          "python: the numpy reference implementation (utils/text.py)")
@@ -63,6 +74,15 @@ def main(argv=None) -> int:
             vocab = Vocabulary.build(args.input_file, args.min_count)
         if args.vocab_save:
             vocab.save(args.vocab_save)
+        if args.enforce_random_keys:
+            # word ids are labels: shuffling the vocabulary order assigns the keys 2*id / 2*id+1 randomly
+            fw = id_permutation(len(vocab.words), args.model_seed, True)
+            sw, sc = [None] * len(fw), np.empty_like(vocab.counts)
+            for i, j in enumerate(fw):
+                sw[j], sc[j] = vocab.words[i], vocab.counts[i]
+            vocab = Vocabulary(sw, sc)
+            if native is not None:
+                native = NativeCorpus.from_vocabulary(vocab)
         counts, words = vocab.counts.astype(np.float64), vocab.words
         V = len(words)
     else:
@@ -72,11 +92,20 @@ def main(argv=None) -> int:
                          starting_alpha=args.starting_alpha, neg_power=args.neg_power, batch_pairs=args.batch_pairs,
                          read_ahead=args.read_sentences_ahead, signal_intent=bool(args.signal_intent),
                          sampling_scheme=getattr(args, "sampling.scheme") or "local", model_seed=args.model_seed)
-    ad.setup(cfg.num_keys, args.num_threads)
+    ad.setup(cfg.num_keys, 1)   # one worker per rank: the per-thread loops of the reference are batched kernels here
     server = ad.Server(cfg.row_len, backend=args.backend, options=system_options(args))
     kv = ad.Worker(0, server)
     model = Word2Vec(server, kv, cfg, counts)
-    model.init_model()
+    if args.init_model == "random":
+        model.init_model()
+    elif args.init_model != "none":
+        model.init_model()                                  # words that are not in the checkpoint start randomly
+        n = load_checkpoint(model, args.init_model, words)
+        if server.my_rank() == 0:
+            print(f"[w2v] initialised {n} of {V} words from {args.init_model}", flush=True)
+    if args.enforce_full_replication:
+        enforce_full_replication(kv, cfg.num_keys)
+    sync_push = wants_sync_push(args)
     rank, world = server.my_rank(), server.num_servers()
 
     if args.input_file and native is not None:
@@ -99,6 +128,7 @@ def main(argv=None) -> int:
     for epoch in range(args.num_iterations):
         it = batches(epoch)
         window = []
+        epoch_pairs = 0
         for b in it:
             window.append(b)
             if len(window) <= cfg.read_ahead:
@@ -109,9 +139,12 @@ def main(argv=None) -> int:
             if model.cuda:
                 model.loss.zero_()
             loss = model.step(cur if cur.shape[1] == cfg.batch_pairs or not model.cuda else _pad(cur, cfg.batch_pairs))
+            if sync_push and model.cuda:
+                torch.cuda.current_stream().synchronize()
             kv.advance_clock()
             total_pairs += getattr(cur, "valid_pairs", cur.shape[1])
-            if time.time() - t0 > args.max_runtime:
+            epoch_pairs += getattr(cur, "valid_pairs", cur.shape[1])
+            if time.time() - t0 > args.max_runtime or (args.data_words and epoch_pairs >= args.data_words):
                 break
         for cur in window:
             if model.cuda:

@@ -41,6 +41,33 @@ void Server::enable_sampling_support(std::shared_ptr<KeyDistribution> dist, cons
 
 void Server::barrier() { fabric_->node_barrier("Server::barrier"); }
 
+void Server::allreduce_sum(double* vals, int n) {
+  ADAPM_CHECK(n >= 0 && n <= 64, "allreduce_sum: at most 64 values");
+  if (opt_.world == 1 || n == 0) return;
+  ControlBlock* ctl = control();
+  fabric_->node_barrier("allreduce: enter");
+  if (opt_.rank == 0)
+    for (int i = 0; i < n; ++i) ctl->allreduce_buf[i].store(0, std::memory_order_relaxed);   // bit pattern of +0.0
+  fabric_->node_barrier("allreduce: cleared");
+  for (int i = 0; i < n; ++i) {
+    int64_t old = ctl->allreduce_buf[i].load(std::memory_order_relaxed);
+    for (;;) {   // atomic add on the bit pattern of a double
+      double cur;
+      memcpy(&cur, &old, 8);
+      cur += vals[i];
+      int64_t nw;
+      memcpy(&nw, &cur, 8);
+      if (ctl->allreduce_buf[i].compare_exchange_weak(old, nw, std::memory_order_acq_rel)) break;
+    }
+  }
+  fabric_->node_barrier("allreduce: added");
+  for (int i = 0; i < n; ++i) {
+    const int64_t bits = ctl->allreduce_buf[i].load(std::memory_order_acquire);
+    memcpy(&vals[i], &bits, 8);
+  }
+  fabric_->node_barrier("allreduce: read");
+}
+
 MailRouter& Server::router() {
   std::lock_guard<std::mutex> lk(mu_);
   ADAPM_CHECK(!shut_down_, "rpc: the server is shut down");

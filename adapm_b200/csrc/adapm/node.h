@@ -145,6 +145,9 @@ class Server {
   void enable_sampling_support(std::shared_ptr<KeyDistribution> dist, const std::string& scheme = "",
                                int with_replacement = -1);
   void barrier();    // among servers (one call per rank)
+  // Sum-all-reduce of up to 64 doubles over the ranks through the control block (collective, one call per rank):
+  // the host-side counterpart of ps_allreduce for values that must not live in a model key (losses, counters).
+  void allreduce_sum(double* vals, int n);
   void shutdown();   // collective
   int my_rank() const { return opt_.rank; }
   int num_servers() const { return opt_.world; }

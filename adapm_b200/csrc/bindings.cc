@@ -86,6 +86,10 @@ PYBIND11_MODULE(_C, m) {
       .def("enable_sampling_support", &Server::enable_sampling_support, py::arg("distribution"), py::arg("scheme") = "",
            py::arg("with_replacement") = -1)
       .def("barrier", &Server::barrier, py::call_guard<py::gil_scoped_release>())
+      .def("allreduce_sum", [](Server& s, std::vector<double> v) {
+        { py::gil_scoped_release r; s.allreduce_sum(v.data(), (int)v.size()); }
+        return v;
+      })
       .def("shutdown", &Server::shutdown, py::call_guard<py::gil_scoped_release>())
       .def("my_rank", &Server::my_rank)
       .def("num_servers", &Server::num_servers)

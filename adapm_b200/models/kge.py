@@ -131,9 +131,26 @@ class KGE:
         return r + self.cfg.num_entities
 
     # ------------------------------------------------------------------ init
-    def init_model(self, chunk: int = 8192) -> None:
-        """normal{0/init_std} embeddings, AdaGrad accumulators 1e-6 (reference init_parameters default)."""
+    def init_model(self, chunk: int = 8192, init: str = "") -> None:
+        """``init``: the reference's ``init_parameters`` syntax - ``normal{mean/std}`` (default ``normal{0/init_std}``),
+        ``uniform{a/b}`` or ``none``; AdaGrad accumulators start at 1e-6."""
         cfg, world, rank = self.cfg, self.server.num_servers(), self.server.my_rank()
+        kind, p1, p2 = "normal", 0.0, cfg.init_std
+        if init:
+            import re
+
+            mt = re.fullmatch(r"(none|normal|uniform)(?:\{([-+.\deE]+)/([-+.\deE]+)\})?", init.strip())
+            if not mt:
+                raise ValueError(f"init_parameters: cannot parse '{init}' (none | uniform{{a/b}} | normal{{mean/std}})")
+            kind = mt.group(1)
+            if mt.group(2) is not None:
+                p1, p2 = float(mt.group(2)), float(mt.group(3))
+            elif kind == "uniform":
+                p1, p2 = -cfg.init_std, cfg.init_std
+        if kind == "none":
+            if cfg.signal_initial_relations_intent and world > 1:
+                self.worker.intent(torch.arange(cfg.num_entities, cfg.num_entities + cfg.num_relations), 0, CLOCK_MAX)
+            return
         gen = torch.Generator().manual_seed(cfg.model_seed + rank)
         self.worker.begin_setup()
         for first, count, ln in ((0, cfg.num_entities, cfg.entity_len),
@@ -143,7 +160,10 @@ class KGE:
             for i in range(0, keys.numel(), per):
                 k = keys[i:i + per]
                 rows = torch.empty(k.numel(), ln)
-                rows[:, : ln // 2] = torch.randn(k.numel(), ln // 2, generator=gen) * cfg.init_std
+                if kind == "normal":
+                    rows[:, : ln // 2] = torch.randn(k.numel(), ln // 2, generator=gen) * p2 + p1
+                else:
+                    rows[:, : ln // 2] = torch.rand(k.numel(), ln // 2, generator=gen) * (p2 - p1) + p1
                 rows[:, ln // 2:] = 1e-6
                 self.worker.set(k, rows.view(-1))
         self.worker.waitall()

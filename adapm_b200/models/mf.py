@@ -41,6 +41,10 @@ class MFConfig:
     eps_inc: float = 1.05
     eps_dec: float = 0.5
     model_seed: int = 134827
+    signal_intent_rows: bool = True  # localise this rank's row block for the whole run (mf.cc:640)
+    wor_blocks: bool = True          # WOR schedule for the DSGD blocks (else the fixed rotation (rank + sub-epoch) % W)
+    wor_points: bool = True          # WOR schedule for the data points within a block / epoch (else file order)
+    early_stop: int = 0              # stop an epoch after N data points (debugging)
 
     def first_col_key(self, num_workers: int) -> int:
         return ((self.num_rows + num_workers - 1) // num_workers) * num_workers
@@ -129,7 +133,7 @@ class MatrixFactorization:
                 self.worker.set(k, rows.view(-1))
         self.worker.waitall()
         self.worker.end_setup()
-        if world > 1:  # row intents for the whole run (mf.cc:369-372)
+        if world > 1 and cfg.signal_intent_rows:  # row intents for the whole run (mf.cc:369-372)
             lo = rank * self.data.rows_per_block
             hi = min(cfg.num_rows, lo + self.data.rows_per_block)
             self.worker.intent(torch.arange(lo, hi), 0, CLOCK_MAX)
@@ -163,7 +167,8 @@ class MatrixFactorization:
         if self.cuda:
             self.loss.zero_()
         if cfg.algorithm == "dsgd":
-            sched = wor_block_schedule(W, epoch, cfg.model_seed)
+            sched = (wor_block_schedule(W, epoch, cfg.model_seed) if cfg.wor_blocks
+                     else np.array([[(r + se) % W for r in range(W)] for se in range(W)]))
             for se in range(W):
                 b = int(sched[se, self.server.my_rank()])
                 if cfg.signal_intent_cols != 0 and W > 1:
@@ -172,7 +177,10 @@ class MatrixFactorization:
                     kv.intent(torch.arange(lo, hi) + self.fck, kv.current_clock())
                     kv.wait_sync()
                 i, j, x = data.block(b)
-                perm = np.random.default_rng(epoch * 131 + se).permutation(i.shape[0])  # WOR point schedule
+                perm = (np.random.default_rng(epoch * 131 + se).permutation(i.shape[0]) if cfg.wor_points
+                        else np.arange(i.shape[0]))                                      # WOR point schedule
+                if cfg.early_stop:
+                    perm = perm[: cfg.early_stop]
                 for s in range(0, perm.shape[0], cfg.batch_nnz):
                     p = perm[s:s + cfg.batch_nnz]
                     out = self.step(i[p], j[p], x[p])
@@ -185,7 +193,10 @@ class MatrixFactorization:
             if cfg.algorithm == "columnwise":
                 order = np.argsort(data.j, kind="stable")
             else:
-                order = np.random.default_rng(epoch).permutation(n)
+                order = np.random.default_rng(epoch).permutation(n) if cfg.wor_points else np.arange(n)
+            if cfg.early_stop:
+                order = order[: cfg.early_stop]
+                n = order.shape[0]
             starts = list(range(0, n, cfg.batch_nnz))
             for bi, s in enumerate(starts):
                 fut = bi + cfg.read_ahead
@@ -199,6 +210,42 @@ class MatrixFactorization:
                 kv.advance_clock()
         if self.cuda:
             total = float(self.loss.item())
+        return total
+
+    def load_factors(self, w_path: str, h_path: str, chunk: int = 1 << 16) -> None:
+        """``init_parameters=1``: initial factors from MatrixMarket array files W (rows x rank) and H (rank x cols);
+        AdaGrad accumulators start at zero. Collective: every rank sets the keys it is home for."""
+        from ..utils.mmio import read_matrix_market_array
+
+        cfg, world, rank = self.cfg, self.world, self.server.my_rank()
+        Wm = torch.from_numpy(read_matrix_market_array(w_path)).float()
+        Hm = torch.from_numpy(read_matrix_market_array(h_path)).float().t().contiguous()
+        assert Wm.shape == (cfg.num_rows, cfg.rank) and Hm.shape == (cfg.num_cols, cfg.rank), (Wm.shape, Hm.shape)
+        self.worker.begin_setup()
+        for first, M in ((0, Wm), (self.fck, Hm)):
+            keys = torch.arange(M.shape[0], dtype=torch.int64) + first
+            sel = (keys % world) == rank
+            keys, vals = keys[sel], M[sel]
+            for s in range(0, keys.numel(), chunk):
+                rows = torch.zeros(min(chunk, keys.numel() - s), 2 * cfg.rank)
+                rows[:, :cfg.rank] = vals[s:s + chunk]
+                self.worker.wait(self.worker.set(keys[s:s + chunk], rows.view(-1)))
+        self.worker.waitall()
+        self.worker.end_setup()
+
+    def evaluate(self, i: np.ndarray, j: np.ndarray, x: np.ndarray) -> float:
+        """Summed squared error of the current factors on arbitrary entries (test set), through Pull."""
+        cfg, kv = self.cfg, self.worker
+        total = 0.0
+        for s in range(0, len(x), 1 << 16):
+            ri = torch.from_numpy(np.ascontiguousarray(i[s:s + (1 << 16)])).long()
+            cj = torch.from_numpy(np.ascontiguousarray(j[s:s + (1 << 16)])).long()
+            wv = torch.empty(ri.numel() * 2 * cfg.rank)
+            kv.wait(kv.pull(self.row_key(ri), wv))
+            hv = torch.empty(cj.numel() * 2 * cfg.rank)
+            kv.wait(kv.pull(self.col_key(cj), hv))
+            pred = (wv.view(-1, 2 * cfg.rank)[:, :cfg.rank] * hv.view(-1, 2 * cfg.rank)[:, :cfg.rank]).sum(1)
+            total += float(((torch.from_numpy(np.ascontiguousarray(x[s:s + (1 << 16)])).float() - pred) ** 2).sum())
         return total
 
     def bold_driver(self, loss: float, prev_loss: Optional[float]) -> None:

@@ -264,6 +264,59 @@ class Word2Vec:
             dump(path + ".syn1", syn1_key)
 
 
+def read_word2vec_binary(path: str):
+    """Parses the binary word2vec format written by write_checkpoint: returns (words, float32 [V, d])."""
+    with open(path, "rb") as f:
+        buf = f.read()
+    nl = buf.index(b"\n")
+    V, d = (int(t) for t in buf[:nl].split())
+    pos = nl + 1
+    words, vecs = [], np.empty((V, d), dtype=np.float32)
+    for i in range(V):
+        sp = buf.index(b" ", pos)
+        words.append(buf[pos:sp].decode(errors="replace"))
+        vecs[i] = np.frombuffer(buf, dtype=np.float32, count=d, offset=sp + 1)
+        pos = sp + 1 + 4 * d + 1      # vector + trailing newline
+    return words, vecs
+
+
+def load_checkpoint(model: "Word2Vec", path: str, words=None, chunk: int = 1 << 15) -> int:
+    """``init_model=<path>`` of the reference (word2vec.cc:832-900): syn0 from ``path``, syn1 from ``path.syn1`` when it
+    exists; AdaGrad accumulators restart at 1e-6. Words are matched by name when ``words`` (this job's vocabulary) is
+    given, by position otherwise. Collective (every rank sets the keys it is home for). Returns #words loaded."""
+    cfg, d = model.cfg, model.cfg.embed_dim
+    world, rank = model.server.num_servers(), model.server.my_rank()
+    loaded = 0
+    model.worker.begin_setup()
+    for fn, key_fn in ((path, syn0_key), (path + ".syn1", syn1_key)):
+        try:
+            fw, vecs = read_word2vec_binary(fn)
+        except FileNotFoundError:
+            if fn == path:
+                raise
+            continue
+        assert vecs.shape[1] == d, f"{fn}: dimension {vecs.shape[1]} != embed_dim {d}"
+        if words is not None:
+            index = {w: i for i, w in enumerate(words)}
+            ids = np.array([index.get(w, -1) for w in fw], dtype=np.int64)
+        else:
+            ids = np.arange(len(fw), dtype=np.int64)
+        ok = (ids >= 0) & (ids < cfg.vocab_size)
+        ids, vecs = ids[ok], vecs[ok]
+        keys = key_fn(torch.from_numpy(ids))
+        mine = (keys % world) == rank
+        keys, rows_e = keys[mine], torch.from_numpy(vecs)[mine]
+        for a in range(0, keys.numel(), chunk):
+            rows = torch.full((min(chunk, keys.numel() - a), 2 * d), 1e-6, dtype=torch.float32)
+            rows[:, :d] = rows_e[a:a + chunk]
+            model.worker.wait(model.worker.set(keys[a:a + chunk], rows.view(-1)))
+        if fn == path:
+            loaded = int(ok.sum())
+    model.worker.waitall()
+    model.worker.end_setup()
+    return loaded
+
+
 def sgns_reference_step(kv, centers: torch.Tensor, contexts: torch.Tensor, negatives: torch.Tensor, d: int,
                         alpha: float) -> float:
     """Plain PyTorch fp32 SGNS step through Pull/Push with the reference's exact update rule.

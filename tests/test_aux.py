@@ -222,3 +222,18 @@ def test_examples_run(tmp_path):
     r = subprocess.run(launch + ["-s", "2", os.path.join(ROOT, "examples", "checkpoint_example.py"), "load", ck], cwd=ROOT,
                        env=env, capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "all 1000 rows verified" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+def _allreduce_sum_worker(kv, server, wid):
+    out = server.allreduce_sum([float(wid + 1), 0.5, -2.0 * wid])
+    out2 = server.allreduce_sum([1.0])           # reusable
+    kv.barrier()
+    kv.finalize()
+    return out, out2
+
+
+@pytest.mark.parametrize("mode", ["threads", "procs"])
+def test_control_block_allreduce(mode):
+    res = run_cluster(_allreduce_sum_worker, world=3, workers=1, mode=mode, value_lengths=1, num_keys=8)
+    for r in res.values():
+        assert r[0][0] == [6.0, 1.5, -6.0] and r[0][1] == [3.0]
