@@ -11,17 +11,17 @@ import torch
 
 from harness import run_cluster
 
-RUNS = 6000
+RUNS = 6000            # the reference's scale; the single-technique variants run a third of it
 
 
-def _dyn_worker(kv, server, wid):
+def _dyn_worker(kv, server, wid, runs=RUNS):
     kv.barrier()
     rng = random.Random(wid * 31 + 7)
     keys = torch.tensor([9])
     vals1 = torch.tensor([1, 2], dtype=server.dtype)
     vals2 = torch.zeros(2, dtype=server.dtype)
     ts = []
-    for _ in range(RUNS):
+    for _ in range(runs):
         if rng.randrange(50) == 0:
             c = kv.current_clock()
             kv.intent(keys, c + 10, c + 40)
@@ -46,11 +46,14 @@ def _dyn_worker(kv, server, wid):
 @pytest.mark.parametrize("mode,technique", [("threads", "all"), ("procs", "all"), ("threads", "replication_only"),
                                             ("threads", "relocation_only")])
 def test_dynamic_allocation(mode, technique):
+    import functools
+
     world, workers = 3, 2
-    res = run_cluster(_dyn_worker, world=world, workers=workers, mode=mode, value_lengths=2, num_keys=20, dtype="int64",
-                      options={"sys.techniques": technique})
+    runs = RUNS if technique == "all" else RUNS // 3
+    res = run_cluster(functools.partial(_dyn_worker, runs=runs), world=world, workers=workers, mode=mode, value_lengths=2,
+                      num_keys=20, dtype="int64", options={"sys.techniques": technique})
     got = res[0][0]
-    total = world * workers * RUNS
+    total = world * workers * runs
     assert got == [total, 2 * total], f"lost or duplicated updates: {got} != {[total, 2 * total]}"
     moved = sum(r["counters"]["relocations"] + r["counters"]["replica_setups"] for r in res.values())
     assert moved > 0, "the hot key never relocated or replicated - the test did not exercise the adaptive path"
