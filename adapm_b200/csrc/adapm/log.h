@@ -1,6 +1,7 @@
 // Logging, checks and stopwatch (parity: include/dmlc/logging.h ALOG/CHECK,
 // include/utils.h:85-125 Stopwatch). Written fresh; no dmlc shim.
 #pragma once
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -49,19 +50,30 @@ struct Error : public std::runtime_error { using std::runtime_error::runtime_err
     }                                                                                  \
   } while (0)
 
+// Accumulating stopwatch. One thread drives it (start / resume / stop); any thread may read elapsed_*() concurrently
+// (statistics are printed while the sync thread is running), hence the atomics.
 class Stopwatch {
  public:
-  void start() { total_ = 0; resume(); }
-  void resume() { t0_ = clock::now(); running_ = true; }
-  void stop() { if (running_) { total_ += since(); running_ = false; } }
-  double elapsed_s() const { return (total_ + (running_ ? since() : 0)) * 1e-9; }
+  void start() { total_ns_.store(0, std::memory_order_relaxed); resume(); }
+  void resume() { t0_ns_.store(now_ns(), std::memory_order_relaxed); running_.store(true, std::memory_order_release); }
+  void stop() {
+    if (running_.load(std::memory_order_relaxed)) {
+      total_ns_.fetch_add(now_ns() - t0_ns_.load(std::memory_order_relaxed), std::memory_order_relaxed);
+      running_.store(false, std::memory_order_release);
+    }
+  }
+  double elapsed_s() const {
+    int64_t t = total_ns_.load(std::memory_order_relaxed);
+    if (running_.load(std::memory_order_acquire)) t += now_ns() - t0_ns_.load(std::memory_order_relaxed);
+    return (double)t * 1e-9;
+  }
   double elapsed_ms() const { return elapsed_s() * 1e3; }
  private:
-  using clock = std::chrono::steady_clock;
-  double since() const { return (double)std::chrono::duration_cast<std::chrono::nanoseconds>(clock::now() - t0_).count(); }
-  clock::time_point t0_{};
-  double total_ = 0;
-  bool running_ = false;
+  static int64_t now_ns() {
+    return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  }
+  std::atomic<int64_t> t0_ns_{0}, total_ns_{0};
+  std::atomic<bool> running_{false};
 };
 inline std::ostream& operator<<(std::ostream& os, const Stopwatch& sw) { return os << sw.elapsed_s() << "s"; }
 
