@@ -76,10 +76,10 @@ class SyncEngine {
   uint32_t rec_epoch_ = 0;
   std::atomic<uint64_t> deferred_pending_{0};  // intent records that could not be registered in the last round
   std::vector<uint8_t> status_;
-  uint64_t round_no_ = 0;
+  std::atomic<uint64_t> round_no_{0};   // written by the sync thread, read by report()
   std::chrono::steady_clock::time_point last_run_;
   Stopwatch sw_total_, sw_pausing_, sw_register_, sw_phase_a_, sw_phase_b_, sw_grace_, sw_phase_c_, sw_barriers_;
-  uint64_t intents_seen_ = 0, recs_registered_ = 0;
+  std::atomic<uint64_t> intents_seen_{0}, recs_registered_{0};
 };
 
 // -------------------------------------------------------------------------------------

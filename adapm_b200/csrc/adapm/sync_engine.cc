@@ -188,14 +188,14 @@ void SyncEngine::round(bool sweep) {
 
   std::vector<Clock> clocks = server_->worker_clocks();
   std::vector<Clock> windows(clocks.size(), WINDOW_MAX);
-  if (opt.time_intent_actions) windows = timer_.estimate_windows_and_tune(clocks, round_no_);
+  if (opt.time_intent_actions) windows = timer_.estimate_windows_and_tune(clocks, round_no_.load(std::memory_order_relaxed));
 
   RoundParams rp;
   memset(&rp, 0, sizeof(rp));
   for (size_t w = 0; w < clocks.size(); ++w) rp.clocks[w] = clocks[w];
   rp.threshold = opt.sync_threshold;
   rp.sweep = sweep ? 1 : 0;
-  rp.round_no = (uint32_t)round_no_;
+  rp.round_no = (uint32_t)round_no_.load(std::memory_order_relaxed);
   rp.sweep_period = opt.sweep_period;
   rp.idle_period = opt.idle_period;
 
@@ -285,8 +285,9 @@ void SyncEngine::loop() {
 std::string SyncEngine::report() const {
   std::ostringstream os;
   double tot = sw_total_.elapsed_s();
-  os << "[rank " << server_->my_rank() << "] sync: " << round_no_ << " rounds in " << tot << "s ("
-     << (tot > 0 ? round_no_ / tot : 0) << "/s), intents " << intents_seen_ << " (" << recs_registered_
+  const uint64_t rounds = round_no_.load(std::memory_order_relaxed);
+  os << "[rank " << server_->my_rank() << "] sync: " << rounds << " rounds in " << tot << "s ("
+     << (tot > 0 ? rounds / tot : 0) << "/s), intents " << intents_seen_.load() << " (" << recs_registered_.load()
      << " key registrations), clocks/round estimate " << timer_.avg_estimate() << "; time: pausing "
      << sw_pausing_.elapsed_s() << "s, register " << sw_register_.elapsed_s() << "s, phaseA "
      << sw_phase_a_.elapsed_s() << "s, phaseB " << sw_phase_b_.elapsed_s() << "s, grace " << sw_grace_.elapsed_s()

@@ -14,7 +14,7 @@ rc=0
 for kind in thread address,undefined; do
   exe=$OUT/simple_${kind%%,*}
   g++ -std=c++17 -O1 -g -fsanitize=$kind -fno-omit-frame-pointer -Wno-tsan -I"$SRC" -o "$exe" $FILES -lpthread -lrt
-  for args in "--stress" "-k 10 -t 2 -i 3 -v 2"; do
+  for args in "--stress 3000 -s 3 -t 2" "--fuzz 3000 -s 3 -t 2 --seed 3" "--fuzz 3000 -s 2 -t 2 --seed 4 --techniques relocation_only" "-k 10 -t 2 -i 3 -v 2"; do
     log=$OUT/$(basename "$exe")_$(echo "$args" | tr -c 'a-z0-9' _).log
     if ! TSAN_OPTIONS="halt_on_error=0" "$exe" $args > "$log" 2>&1; then rc=1; fi
     n=$(grep -c "WARNING: ThreadSanitizer\|ERROR: AddressSanitizer\|runtime error" "$log" || true)

@@ -28,3 +28,14 @@ def test_simple_app_native(exe):
 def test_dynamic_allocation_full_scale_native(exe, rep):
     out = subprocess.run([exe, "-s", "3", "-t", "2", "--stress", "100000"], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "Dynamic Allocation: PASSED" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("technique", ["all", "replication_only", "relocation_only"])
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_programs_native(exe, technique, seed):
+    """C++ fuzz: 6 workers x 5 000 random Intent / Push / Pull / clock / WaitSync operations over 24 keys with asynchronous
+    pushes: read-your-writes at every pull, exact sums on every rank at the end (scripts/sanitize.sh runs the same
+    binary under ThreadSanitizer / AddressSanitizer)."""
+    out = subprocess.run([exe, "--fuzz", "5000", "-s", "3", "-t", "2", "--seed", str(seed), "--techniques", technique],
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "errors: PASSED" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
