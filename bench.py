@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--no-intent", action="store_true")
     ap.add_argument("--sync-per-sec", type=float, default=1000)
     ap.add_argument("--profile", action="store_true", help="also report per-kernel device times")
+    ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
+                    help="extra server option (e.g. --opt sys.sync.idle_period=1); repeatable")
     return ap.parse_args()
 
 
@@ -146,7 +148,8 @@ def main():
                          signal_intent=not args.no_intent, max_inflight=args.max_inflight)
     server = ad.Server(cfg.row_len, num_keys=cfg.num_keys, num_threads=1, rank=rank, world=world, backend="cuda",
                        fabric="shm" if world > 1 else "inproc", device=local_rank,
-                       options={"sys.techniques": args.techniques, "sys.sync.max_per_sec": args.sync_per_sec})
+                       options=dict({"sys.techniques": args.techniques, "sys.sync.max_per_sec": args.sync_per_sec},
+                                    **dict(kv.split("=", 1) for kv in args.opt)))
     worker = ad.Worker(0, server)
     counts = zipf_counts(cfg.vocab_size, cfg.zipf_exponent)
     model = Word2Vec(server, worker, cfg, counts)

@@ -35,5 +35,7 @@ ADAPM_SYNC_WORK_BLOCKS=4 run work4
 run ra16 --read-ahead 16
 run ra64 --read-ahead 48
 run inflight1 --max-inflight 1
+run idle1 --opt sys.sync.idle_period=1
+run idle8 --opt sys.sync.idle_period=8
 ADAPM_SYNC_TRACE=1 run trace
 [ -f gpurun_out/kernel_trace.rank0.tsv ] && python scripts/analyze_kernel_trace.py gpurun_out/kernel_trace.rank0.tsv | head -14
