@@ -1,5 +1,6 @@
 #include "fabric.h"
 
+#include <dirent.h>
 #include <fcntl.h>
 #include <signal.h>
 #include <sys/mman.h>
@@ -10,6 +11,8 @@
 #include <mutex>
 
 namespace adapm {
+
+namespace { bool process_dead(int pid); }
 
 namespace {
 
@@ -118,6 +121,45 @@ class InProcFabric : public Fabric {
 };
 
 // ------------------------------------------------------------------ POSIX shm world
+// Crashed jobs cannot unlink their POSIX-shm segments. Rank 0 of every new job removes the segments of jobs whose
+// processes are all gone (and that are older than two minutes, so that a job that is just starting is never touched).
+void gc_stale_shm_segments() {
+  DIR* d = opendir("/dev/shm");
+  if (!d) return;
+  std::vector<std::string> ctl;
+  while (dirent* e = readdir(d)) {
+    const std::string n = e->d_name;
+    if (n.size() > 10 && n.compare(0, 6, "adapm_") == 0 && n.compare(n.size() - 4, 4, "_ctl") == 0) ctl.push_back(n);
+  }
+  closedir(d);
+  const time_t now = time(nullptr);
+  long min_age = 120;
+  if (const char* e = getenv("ADAPM_SHM_GC_AGE_S")) min_age = atol(e);
+  for (const std::string& n : ctl) {
+    const std::string path = "/dev/shm/" + n;
+    struct stat st;
+    if (stat(path.c_str(), &st) != 0 || now - st.st_ctime < min_age || (size_t)st.st_size < sizeof(ControlBlock)) continue;
+    int fd = open(path.c_str(), O_RDONLY);
+    if (fd < 0) continue;
+    void* p = mmap(nullptr, sizeof(ControlBlock), PROT_READ, MAP_SHARED, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) continue;
+    const ControlBlock* c = (const ControlBlock*)p;
+    bool stale = c->magic == kControlMagic && c->world >= 1 && c->world <= MAX_RANKS;
+    int world = stale ? c->world : 0;
+    for (int r = 0; r < world && stale; ++r) {
+      const int pid = c->ranks[r].pid;
+      if (pid > 0 && !process_dead(pid)) stale = false;
+    }
+    munmap(p, sizeof(ControlBlock));
+    if (!stale) continue;
+    const std::string prefix = "/" + n.substr(0, n.size() - 4);
+    for (int r = 0; r < world; ++r) shm_unlink((prefix + "_h" + std::to_string(r)).c_str());
+    shm_unlink((prefix + "_ctl").c_str());
+    VLOG(1, "removed the shared-memory segments of the dead job " << prefix.substr(7));
+  }
+}
+
 class ShmFabric : public Fabric {
  public:
   ShmFabric(const Options& opt) {
@@ -130,6 +172,7 @@ class ShmFabric : public Fabric {
     const std::string name = prefix_ + "_ctl";
     const size_t sz = (sizeof(ControlBlock) + 4095) / 4096 * 4096;
     if (rank_ == 0) {
+      gc_stale_shm_segments();
       shm_unlink(name.c_str());
       int fd = shm_open(name.c_str(), O_CREAT | O_EXCL | O_RDWR, 0600);
       ADAPM_CHECK(fd >= 0, "shm_open(" << name << ") failed: " << strerror(errno));

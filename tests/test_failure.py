@@ -57,3 +57,31 @@ def test_dead_peer_breaks_barriers(detector, monkeypatch):
             assert "timed out" in msg or "watchdog" in msg or "broken" in msg, (rank, msg)
     if not detector:                           # the first one to give up is the watchdog; it breaks the barrier for the rest
         assert any("watchdog" in m or "timed out" in m for _, m, _ in got), got
+
+
+def test_stale_shared_memory_segments_are_collected():
+    """A crashed job leaves its POSIX-shm segments behind; rank 0 of a later job removes segments whose processes are
+    all dead (and that are older than two minutes - simulated here by back-dating the control block)."""
+    import glob
+    import subprocess
+    import sys
+
+    ctx = mp.get_context("fork")
+    q = ctx.Queue()
+    job = f"stale{os.getpid()}_{uuid.uuid4().hex[:6]}"
+    ps = [ctx.Process(target=_rank, args=(r, 2, job, q, 1, 60)) for r in range(2)]   # rank 1 crashes, rank 0 hard-exits
+    [p.start() for p in ps]
+    q.get(timeout=60)
+    [p.join(30) for p in ps]
+    left = glob.glob(f"/dev/shm/adapm_{job}_*")
+    assert left, "the crashed job should have left its segments behind"
+    old = time.time() - 600
+    for f in left:
+        os.utime(f, (old, old))                 # ctime cannot be set: the collector is told to use a zero age threshold
+    env = dict(os.environ, ADAPM_SHM_GC_AGE_S="0")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "adapm_b200.launch", "-s", "2", "--backend", "cpu", "-m", "adapm_b200.apps.simple",
+                        "--", "-k", "10", "-t", "1", "-i", "1", "-v", "1"], cwd=root, env=env, capture_output=True, text=True,
+                       timeout=120)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    assert not glob.glob(f"/dev/shm/adapm_{job}_*"), "stale segments were not collected"
