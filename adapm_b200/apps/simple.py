@@ -14,16 +14,17 @@ import threading
 import torch
 
 import adapm_b200 as ad
+from adapm_b200.apps._common import add_system_options, system_options
 
 
 def run_worker(cid: int, server, args, out) -> None:
     kv = ad.Worker(cid, server)
     wid = server.my_rank() * args.num_threads + cid
-    vals = torch.zeros(args.vpk, dtype=torch.float64)
+    vals = torch.zeros(args.vpk, dtype=server.dtype)
     for x in range(args.num_iterations):
         key = torch.tensor([x % args.num_keys])
         kv.intent(key, kv.current_clock())
-        push = torch.arange(1, args.vpk + 1, dtype=torch.float64)
+        push = torch.arange(1, args.vpk + 1, dtype=server.dtype)
         kv.wait(kv.push(key, push))
         kv.wait(kv.pull(key, vals))
         print(f"Worker {wid} iteration {x}: key {int(key)} = {vals.tolist()}", flush=True)
@@ -39,10 +40,13 @@ def main(argv=None) -> int:
     ap.add_argument("-t", "--num_threads", type=int, default=2)
     ap.add_argument("-i", "--num_iterations", type=int, default=4)
     ap.add_argument("-v", "--vpk", type=int, default=2, help="values per key")
-    ap.add_argument("--sys.techniques", dest="techniques", default="all")
+    add_system_options(ap)      # sys.* / sampling.* flags by their reference names (+ --backend)
     args = ap.parse_args([a for a in (argv if argv is not None else sys.argv[1:]) if a != "--"])
-    ad.setup(args.num_keys, args.num_threads, use_techniques=args.techniques)
-    server = ad.Server(args.vpk, dtype="float64", backend="cpu" if not ad._C.cuda_available() else None)
+    ad.setup(args.num_keys, args.num_threads)
+    # ValT = double like the reference app: float64 rows live on the CPU backend (the CUDA backend stores float32)
+    backend = args.backend or "cpu"
+    server = ad.Server(args.vpk, dtype="float64" if backend == "cpu" else "float32", backend=backend,
+                       options=system_options(args))
     out = {}
     ths = [threading.Thread(target=run_worker, args=(c, server, args, out)) for c in range(args.num_threads)]
     [t.start() for t in ths]
