@@ -100,8 +100,9 @@ def reference_arm(args):
     # The reference (alexrenz/AdaPM) is a CPU-only C++14 project that needs libzmq, protobuf-lite,
     # Boost and Eigen headers; none is present in this offline image and pip cannot install it
     # (no setup.py at the root; bindings/setup.py fails compiling against missing zmq.h). See DESIGN.md.
-    print(json.dumps({"impl": "reference", "unavailable":
-                      "alexrenz/AdaPM needs libzmq+protobuf+Boost+Eigen (absent offline); it has no GPU path at all"}))
+    if int(os.environ.get("RANK", "0")) == 0:      # one line per job, also when launched with torchrun
+        print(json.dumps({"impl": "reference", "unavailable":
+                          "alexrenz/AdaPM needs libzmq+protoc/protobuf+Boost+Eigen (absent offline); it has no GPU path at all"}))
     return 0
 
 
