@@ -70,15 +70,16 @@ class SyncEngine {
   std::vector<std::shared_ptr<std::vector<Key>>> key_pool_;
   std::vector<std::priority_queue<FutureIntent, std::vector<FutureIntent>, IntentLater>> heaps_;  // per worker
   std::vector<IntentRec> recs_, deferred_;
+  std::vector<FutureIntent> due_;
   std::vector<uint32_t> seen_epoch_;   // intent dedupe table (one stamp per key)
   uint32_t epoch_ = 0;
-  std::vector<uint32_t> rec_round_, rec_index_;   // per-round merge of records per key (single worker per rank)
+  std::vector<uint64_t> rec_tab_;   // per-round merge of records per key (single worker per rank): stamp << 32 | index
   uint32_t rec_epoch_ = 0;
   std::atomic<uint64_t> deferred_pending_{0};  // intent records that could not be registered in the last round
   std::vector<uint8_t> status_;
   std::atomic<uint64_t> round_no_{0};   // written by the sync thread, read by report()
   std::chrono::steady_clock::time_point last_run_;
-  Stopwatch sw_total_, sw_pausing_, sw_register_, sw_phase_a_, sw_phase_b_, sw_grace_, sw_phase_c_, sw_barriers_;
+  Stopwatch sw_total_, sw_pausing_, sw_register_, sw_collect_, sw_phase_a_, sw_phase_b_, sw_grace_, sw_phase_c_, sw_barriers_;
   std::atomic<uint64_t> intents_seen_{0}, recs_registered_{0};
 };
 

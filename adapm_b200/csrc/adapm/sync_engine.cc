@@ -121,61 +121,86 @@ void SyncEngine::collect_intents(const std::vector<Clock>& clocks, const std::ve
   // latest end clock. O(1) per record with a round-stamped table (8 B per key; skipped for very large key spaces).
   const bool merge = server_->num_keys() <= ((int64_t)1 << 25) && heaps_.size() == 1;
   if (merge) {
-    if (rec_round_.empty()) { rec_round_.assign((size_t)server_->num_keys(), 0u); rec_index_.assign((size_t)server_->num_keys(), 0u); }
-    if (++rec_epoch_ == 0) { std::fill(rec_round_.begin(), rec_round_.end(), 0u); rec_epoch_ = 1; }
-    for (size_t i = 0; i < recs_.size(); ++i) { rec_round_[(size_t)recs_[i].key] = rec_epoch_; rec_index_[(size_t)recs_[i].key] = (uint32_t)i; }
+    // one 8-byte entry per key: round stamp << 32 | index of the key's record in recs_
+    if (rec_tab_.empty()) rec_tab_.assign((size_t)server_->num_keys(), 0ull);
+    if (++rec_epoch_ == 0) { std::fill(rec_tab_.begin(), rec_tab_.end(), 0ull); rec_epoch_ = 1; }
+    for (size_t i = 0; i < recs_.size(); ++i) rec_tab_[(size_t)recs_[i].key] = ((uint64_t)rec_epoch_ << 32) | (uint32_t)i;
   }
+  const bool tracing = server_->tracing();
   for (size_t w = 0; w < heaps_.size(); ++w) {
     auto& h = heaps_[w];
     const Clock clk = clocks[w];
     if (clk == WORKER_FINISHED) { while (!h.empty()) h.pop(); continue; }
     const Clock horizon = (windows[w] >= WINDOW_MAX || clk > CLOCK_MAX - windows[w]) ? CLOCK_MAX : clk + windows[w];
+    // the intents that become relevant now, latest first: with the usual "one intent per future step" pattern the
+    // first occurrence of a key then already carries the latest end clock and duplicates are a pure table hit
+    due_.clear();
     while (!h.empty() && h.top().start <= horizon) {
-      const FutureIntent& fi = h.top();
+      due_.push_back(h.top());
+      h.pop();
+    }
+    for (size_t di = due_.size(); di-- > 0;) {
+      const FutureIntent& fi = due_[di];
       if (fi.end > clk) {
-        // the reference dedupes in Intent() (coloc_kv_worker.h:394-401); here it happens off the
-        // worker thread, once per batch
         std::vector<Key>& ks = *fi.keys;
-        if (ks.size() > 1) {
-          const int64_t nk = server_->num_keys();
-          if (nk <= (int64_t)1 << 25) {
-            // O(n) dedupe with an epoch-stamped table (4 B per key) instead of a sort
-            if (seen_epoch_.empty()) seen_epoch_.assign((size_t)nk, 0u);
-            if (++epoch_ == 0) { std::fill(seen_epoch_.begin(), seen_epoch_.end(), 0u); epoch_ = 1; }
-            size_t m = 0;
-            for (size_t i = 0; i < ks.size(); ++i) {
-              const Key k = ks[i];
-              if (seen_epoch_[(size_t)k] != epoch_) { seen_epoch_[(size_t)k] = epoch_; ks[m++] = k; }
-            }
-            ks.resize(m);
-          } else {
-            std::sort(ks.begin(), ks.end());
-            ks.erase(std::unique(ks.begin(), ks.end()), ks.end());
-          }
-        }
-        for (Key k : ks) {
-          if (merge) {
-            if (rec_round_[(size_t)k] == rec_epoch_) {
-              IntentRec& prev = recs_[rec_index_[(size_t)k]];
+        if (merge) {
+          // duplicates inside one intent merge like duplicates across intents: one table access per key, prefetched
+          // (the table is far larger than the caches and the keys are random)
+          const size_t n = ks.size();
+          const Key* kp = ks.data();
+          const uint64_t stamp = (uint64_t)rec_epoch_ << 32;
+          for (size_t i = 0; i < n; ++i) {
+            if (i + 12 < n) __builtin_prefetch(&rec_tab_[(size_t)kp[i + 12]], 1, 0);
+            const Key k = kp[i];
+            uint64_t& e = rec_tab_[(size_t)k];
+            if ((e >> 32) == rec_epoch_) {
+              IntentRec& prev = recs_[(size_t)(uint32_t)e];
               if (fi.end > prev.end) prev.end = fi.end;
               continue;
             }
-            rec_round_[(size_t)k] = rec_epoch_;
-            rec_index_[(size_t)k] = (uint32_t)recs_.size();
+            e = stamp | (uint32_t)recs_.size();
+            IntentRec r;
+            r.key = k; r.end = fi.end; r.worker = (int32_t)w; r.pad = 0;
+            recs_.push_back(r);
+            if (tracing && (server_->trace_all_ || server_->traced_.count(k))) server_->trace(k, TraceEvent::INTENT_START);
           }
-          IntentRec r;
-          r.key = k; r.end = fi.end; r.worker = (int32_t)w; r.pad = 0;
-          recs_.push_back(r);
-          if (server_->tracing() && (server_->trace_all_ || server_->traced_.count(k))) server_->trace(k, TraceEvent::INTENT_START);
+        } else {
+          // the reference dedupes in Intent() (coloc_kv_worker.h:394-401); here it happens off the
+          // worker thread, once per batch
+          if (ks.size() > 1) {
+            const int64_t nk = server_->num_keys();
+            if (nk <= (int64_t)1 << 25) {
+              // O(n) dedupe with an epoch-stamped table (4 B per key) instead of a sort
+              if (seen_epoch_.empty()) seen_epoch_.assign((size_t)nk, 0u);
+              if (++epoch_ == 0) { std::fill(seen_epoch_.begin(), seen_epoch_.end(), 0u); epoch_ = 1; }
+              size_t m = 0;
+              for (size_t i = 0; i < ks.size(); ++i) {
+                const Key k = ks[i];
+                if (seen_epoch_[(size_t)k] != epoch_) { seen_epoch_[(size_t)k] = epoch_; ks[m++] = k; }
+              }
+              ks.resize(m);
+            } else {
+              std::sort(ks.begin(), ks.end());
+              ks.erase(std::unique(ks.begin(), ks.end()), ks.end());
+            }
+          }
+          for (Key k : ks) {
+            IntentRec r;
+            r.key = k; r.end = fi.end; r.worker = (int32_t)w; r.pad = 0;
+            recs_.push_back(r);
+            if (tracing && (server_->trace_all_ || server_->traced_.count(k))) server_->trace(k, TraceEvent::INTENT_START);
+          }
         }
       }
-      std::shared_ptr<std::vector<Key>> done = fi.keys;
-      h.pop();
-      if (done.use_count() == 1) {
+    }
+    for (FutureIntent& fi : due_) {   // recycle the key buffers
+      std::shared_ptr<std::vector<Key>> done = std::move(fi.keys);
+      if (done && done.use_count() == 1) {
         std::lock_guard<std::mutex> lk(pool_mu_);
         if (key_pool_.size() < 64) key_pool_.push_back(std::move(done));
       }
     }
+    due_.clear();
   }
 }
 
@@ -200,7 +225,9 @@ void SyncEngine::round(bool sweep) {
   rp.idle_period = opt.idle_period;
 
   sw_register_.resume();
+  sw_collect_.resume();
   collect_intents(clocks, windows);
+  sw_collect_.stop();
   if (!recs_.empty()) {
     status_.assign(recs_.size(), 0);
     be.register_intents(recs_.data(), recs_.size(), rp, status_.data());
@@ -289,7 +316,8 @@ std::string SyncEngine::report() const {
   os << "[rank " << server_->my_rank() << "] sync: " << rounds << " rounds in " << tot << "s ("
      << (tot > 0 ? rounds / tot : 0) << "/s), intents " << intents_seen_.load() << " (" << recs_registered_.load()
      << " key registrations), clocks/round estimate " << timer_.avg_estimate() << "; time: pausing "
-     << sw_pausing_.elapsed_s() << "s, register " << sw_register_.elapsed_s() << "s, phaseA "
+     << sw_pausing_.elapsed_s() << "s, register " << sw_register_.elapsed_s() << "s (of which host-side intent collection "
+     << sw_collect_.elapsed_s() << "s), phaseA "
      << sw_phase_a_.elapsed_s() << "s, phaseB " << sw_phase_b_.elapsed_s() << "s, grace " << sw_grace_.elapsed_s()
      << "s, phaseC " << sw_phase_c_.elapsed_s() << "s, barriers " << sw_barriers_.elapsed_s() << "s";
   return os.str();
