@@ -193,7 +193,8 @@ void PairStream::run(uint64_t epoch) {
       keep[i] = (float)((std::sqrt(fr / subsample_) + 1.0) * subsample_ / fr);
     }
   }
-  std::vector<Key> cur((size_t)(2 * batch_));
+  std::vector<Key> cur((size_t)(2 * batch_)), uniq;
+  uniq.reserve((size_t)(2 * batch_));
   int64_t n = 0;
   std::vector<int32_t> s;
 
@@ -204,11 +205,20 @@ void PairStream::run(uint64_t epoch) {
         cur[(size_t)(batch_ + i)] = cur[(size_t)(batch_ + i % valid)];
       }
     }
+    // distinct keys of the batch (before taking the lock: this is the expensive part)
+    if (seen_.empty()) seen_.assign((size_t)(2 * corpus_->vocab_size()), 0u);
+    if (++seen_epoch_ == 0) { std::fill(seen_.begin(), seen_.end(), 0u); seen_epoch_ = 1; }
+    uniq.clear();
+    for (int64_t i = 0; i < 2 * batch_; ++i) {
+      const Key k = cur[(size_t)i];
+      if (seen_[(size_t)k] != seen_epoch_) { seen_[(size_t)k] = seen_epoch_; uniq.push_back(k); }
+    }
     std::unique_lock<std::mutex> lk(mu_);
     cv_put_.wait(lk, [&] { return count_ < ring_.size() || abort_; });
     if (abort_) return false;
     Slot& sl = ring_[tail_];
     sl.keys.swap(cur);
+    sl.uniq.swap(uniq);
     sl.valid = valid;
     tail_ = (tail_ + 1) % ring_.size();
     ++count_;
@@ -253,7 +263,9 @@ void PairStream::run(uint64_t epoch) {
   cv_get_.notify_all();
 }
 
-int64_t PairStream::next(Key* out) {
+int64_t PairStream::next(Key* out) { return next_with_unique(out, nullptr, nullptr); }
+
+int64_t PairStream::next_with_unique(Key* out, Key* uniq, int64_t* n_uniq) {
   std::unique_lock<std::mutex> lk(mu_);
   cv_get_.wait(lk, [&] { return count_ > 0 || done_ || abort_; });
   if (count_ == 0) return 0;
@@ -261,6 +273,10 @@ int64_t PairStream::next(Key* out) {
   const int64_t valid = sl.valid;
   lk.unlock();
   memcpy(out, sl.keys.data(), (size_t)(2 * batch_) * sizeof(Key));   // the slot stays reserved while we copy
+  if (uniq) {
+    memcpy(uniq, sl.uniq.data(), sl.uniq.size() * sizeof(Key));
+    *n_uniq = (int64_t)sl.uniq.size();
+  }
   lk.lock();
   head_ = (head_ + 1) % ring_.size();
   --count_;

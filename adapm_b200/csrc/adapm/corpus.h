@@ -59,13 +59,18 @@ class PairStream {
   // Copies the next batch into out[2 * batch_pairs]; returns the number of valid pairs (a short last batch is padded
   // by repeating its pairs), 0 at the end of the epoch.
   int64_t next(Key* out);
+  // Same, and also writes the distinct keys of the batch (what Intent() should be called with: the deduplication
+  // happens here, on the loader thread, instead of on the sync thread) into uniq[0 .. *n_uniq); uniq holds 2*batch.
+  int64_t next_with_unique(Key* out, Key* uniq, int64_t* n_uniq);
   int64_t batch_pairs() const { return batch_; }
   uint64_t pairs_produced() const { return produced_.load(); }
 
  private:
   void run(uint64_t epoch);
   void stop();
-  struct Slot { std::vector<Key> keys; int64_t valid = 0; };
+  struct Slot { std::vector<Key> keys, uniq; int64_t valid = 0; };
+  std::vector<uint32_t> seen_;   // producer thread: round-stamped table for the per-batch deduplication
+  uint32_t seen_epoch_ = 0;
 
   std::shared_ptr<Corpus> corpus_;
   int window_;

@@ -240,6 +240,12 @@ PYBIND11_MODULE(_C, m) {
       .def("start_epoch", &PairStream::start_epoch, py::call_guard<py::gil_scoped_release>())
       .def("next", [](PairStream& p, uintptr_t out) { return p.next(ptr<Key>(out)); },
            py::call_guard<py::gil_scoped_release>())
+      .def("next_with_unique", [](PairStream& p, uintptr_t out, uintptr_t uniq) {
+             int64_t n = 0;
+             int64_t valid;
+             { py::gil_scoped_release r; valid = p.next_with_unique(ptr<Key>(out), ptr<Key>(uniq), &n); }
+             return py::make_tuple(valid, n);
+           })
       .def("batch_pairs", &PairStream::batch_pairs)
       .def("pairs_produced", &PairStream::pairs_produced);
 

@@ -155,7 +155,9 @@ class Word2Vec:
         """keys_host: [2, B] (syn0 keys, syn1 keys) of a future batch (CPU tensor)."""
         if not self.cfg.signal_intent or self.server.num_servers() == 1:
             return
-        self.worker.intent(keys_host.view(-1), clock, clock + 1)
+        # batches of the native loader carry their distinct keys (deduplicated on the loader thread)
+        keys = getattr(keys_host, "unique_keys", None)
+        self.worker.intent(keys if keys is not None else keys_host.view(-1), clock, clock + 1)
 
     # ------------------------------------------------------------------ one training step
     def step(self, keys_host: torch.Tensor) -> torch.Tensor:

@@ -136,8 +136,10 @@ class NativeCorpus:
             t = torch.empty(2, batch_pairs, dtype=torch.int64)
             if pin:
                 t = t.pin_memory()
-            valid = ps.next(t.data_ptr())
+            u = torch.empty(2 * batch_pairs, dtype=torch.int64)
+            valid, n_u = ps.next_with_unique(t.data_ptr(), u.data_ptr())
             if valid == 0:
                 return
             t.valid_pairs = int(valid)
+            t.unique_keys = u[:n_u]          # what to call Intent() with (deduplicated on the loader thread)
             yield t
