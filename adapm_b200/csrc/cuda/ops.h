@@ -19,6 +19,11 @@ void sample_keys(CudaBackend& be, cudaStream_t stream, int kind, const float* pr
                  int64_t n_table, Key first, Key stride, Key* out, int64_t n, uint64_t seed, bool local_only,
                  int max_tries, unsigned long long* stats);
 
+// Intent pre-pass (ops_intent.cu): extends the intent end clock of keys that already have a usable local slot on the
+// device and writes the other keys to out_keys[0 .. *out_count) (out_count must be zero on entry).
+void intent_prepass(CudaBackend& be, cudaStream_t stream, const Key* keys, int64_t n, Clock end, int worker, Key* out_keys,
+                    unsigned int* out_count);
+
 // knowledge-graph embeddings, ComplEx: fused pull + score + BCE/L2 gradient + AdaGrad + push (ops_kge.cu)
 void kge_complex_step(CudaBackend& be, cudaStream_t stream, const Key* subj, const Key* rel, const Key* obj,
                       const float* labels, int n_calls, int nh, float eta, float gamma_e, float gamma_r, float* loss_out,

@@ -31,6 +31,11 @@ void bind(py::module_& m) {
     sample_keys(backend_of(be), (cudaStream_t)stream, kind, ptr<const float>(prob), ptr<const int32_t>(alias), n_table,
                 first, stride, ptr<Key>(out), n, seed, local_only, max_tries, ptr<unsigned long long>(stats));
   });
+  m.def("intent_prepass", [](uintptr_t be, uintptr_t stream, uintptr_t keys, int64_t n, int64_t end, int worker, uintptr_t out_keys,
+                             uintptr_t out_count) {
+    intent_prepass(backend_of(be), (cudaStream_t)stream, ptr<const Key>(keys), n, (Clock)end, worker, ptr<Key>(out_keys),
+                   ptr<unsigned int>(out_count));
+  });
   m.def("kge_complex_step", [](uintptr_t be, uintptr_t stream, uintptr_t s, uintptr_t r, uintptr_t o, uintptr_t labels,
                                int n, int nh, float eta, float gamma_e, float gamma_r, uintptr_t loss, uintptr_t stats) {
     kge_complex_step(backend_of(be), (cudaStream_t)stream, ptr<const Key>(s), ptr<const Key>(r), ptr<const Key>(o),

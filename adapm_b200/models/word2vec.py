@@ -44,6 +44,7 @@ class Word2VecConfig:
     model_seed: int = 134827
     zipf_exponent: float = 1.0       # synthetic corpus skew
     max_inflight: int = 3            # steps the host may run ahead of the GPU (bounds the sync grace period)
+    intent_prepass: bool = False     # experimental: device-side Intent for keys that are already local (ops.IntentPrepass)
 
     @property
     def row_len(self) -> int:
@@ -125,6 +126,13 @@ class Word2Vec:
                              for _ in range(max(1, cfg.max_inflight) + 2)]
             self._pf_no = 0
             self._pf = None
+            self._prepass = None
+            import os as _os
+
+            if (cfg.intent_prepass or _os.environ.get("ADAPM_INTENT_PREPASS")) and server.num_servers() > 1:
+                from ..ops import IntentPrepass
+
+                self._prepass = IntentPrepass(server, worker, max_keys=2 * cfg.batch_pairs)
         else:
             w = torch.from_numpy(weights)
             self._neg_cdf = torch.cumsum(w / w.sum(), 0)
@@ -157,7 +165,12 @@ class Word2Vec:
             return
         # batches of the native loader carry their distinct keys (deduplicated on the loader thread)
         keys = getattr(keys_host, "unique_keys", None)
-        self.worker.intent(keys if keys is not None else keys_host.view(-1), clock, clock + 1)
+        keys = keys if keys is not None else keys_host.view(-1)
+        if self.cuda and self._prepass is not None:
+            self._prepass.harvest()                    # left-overs of earlier batches -> host path
+            self._prepass.submit(keys, clock, clock + 1)
+            return
+        self.worker.intent(keys, clock, clock + 1)
 
     # ------------------------------------------------------------------ one training step
     def step(self, keys_host: torch.Tensor) -> torch.Tensor:

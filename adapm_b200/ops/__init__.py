@@ -205,3 +205,70 @@ def gather_gemm_rank_count(server, q: torch.Tensor, keys: torch.Tensor, k: int, 
                               q16.shape[1], ts.data_ptr(), tc.data_ptr(), out.data_ptr(),
                               stats.data_ptr() if stats is not None else 0)
     return out
+
+
+class IntentPrepass:
+    """Device-side pre-pass for ``Worker.intent`` (experimental; ``csrc/cuda/ops_intent.cu``).
+
+    ``submit(keys, start, end)`` extends the intent end clock of every key that already has a usable local slot with an
+    ``atomicMax`` on the device and collects the remaining keys; ``harvest()`` hands the collected keys of finished
+    submissions to ``worker.intent`` (the host path: placeholder allocation + request to the owner). In steady state a
+    few per cent of the keys take the host path, which takes the per-key work off the sync thread.
+    """
+
+    def __init__(self, server, worker, max_keys: int, depth: int = 4):
+        self.server, self.worker = server, worker
+        dev = server.device
+        self.max_keys = int(max_keys)
+        self._slots = []
+        for _ in range(depth):
+            self._slots.append({
+                "keys": torch.empty(self.max_keys, dtype=torch.int64, device=dev),
+                "out": torch.empty(self.max_keys, dtype=torch.int64, device=dev),
+                "cnt": torch.zeros(1, dtype=torch.int32, device=dev),
+                "h_out": torch.empty(self.max_keys, dtype=torch.int64).pin_memory(),
+                "h_cnt": torch.zeros(1, dtype=torch.int32).pin_memory(),
+                "ev": torch.cuda.Event(), "busy": False, "start": 0, "end": 0,
+            })
+        self._next = 0
+        self.keys_total = 0
+        self.keys_to_host = 0
+
+    def submit(self, keys: torch.Tensor, start: int, end: int = 0) -> None:
+        """keys: 1-D int64 (CPU or CUDA). One submission per call; blocks only if ``depth`` submissions are in flight."""
+        end = int(end) if end else int(start) + 1
+        s = self._slots[self._next % len(self._slots)]
+        self._next += 1
+        if s["busy"]:
+            self._finish(s, block=True)
+        n = keys.numel()
+        if n > self.max_keys:
+            raise ValueError(f"IntentPrepass: {n} keys > max_keys {self.max_keys}")
+        kd = s["keys"][:n]
+        kd.copy_(keys.view(-1), non_blocking=True)
+        s["cnt"].zero_()
+        _C.intent_prepass(self.server._impl.backend_handle(), _stream(kd), kd.data_ptr(), n, end, self.worker._impl.id(),
+                          s["out"].data_ptr(), s["cnt"].data_ptr())
+        s["h_cnt"].copy_(s["cnt"], non_blocking=True)
+        s["h_out"][:n].copy_(s["out"][:n], non_blocking=True)
+        s["ev"].record()
+        s.update(busy=True, start=int(start), end=end, n=n)
+        self.keys_total += n
+
+    def _finish(self, s, block: bool) -> bool:
+        if not s["busy"]:
+            return True
+        if not block and not s["ev"].query():
+            return False
+        s["ev"].synchronize()
+        cnt = int(s["h_cnt"][0])
+        if cnt:
+            self.worker.intent(s["h_out"][:cnt].clone(), s["start"], s["end"])
+        self.keys_to_host += cnt
+        s["busy"] = False
+        return True
+
+    def harvest(self, block: bool = False) -> None:
+        """Hands the left-over keys of completed submissions to the host path (all submissions when ``block``)."""
+        for s in self._slots:
+            self._finish(s, block)

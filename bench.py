@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--no-intent", action="store_true")
     ap.add_argument("--sync-per-sec", type=float, default=1000)
     ap.add_argument("--profile", action="store_true", help="also report per-kernel device times")
+    ap.add_argument("--intent-prepass", action="store_true",
+                    help="experimental: device-side Intent for keys that are already local (ops.IntentPrepass)")
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
                     help="extra server option (e.g. --opt sys.sync.idle_period=1); repeatable")
     return ap.parse_args()
@@ -146,7 +148,8 @@ def main():
 
     cfg = Word2VecConfig(vocab_size=args.vocab, embed_dim=args.dim, negative=args.negative,
                          batch_pairs=args.batch_pairs, read_ahead=args.read_ahead, sampling_scheme=args.sampling,
-                         signal_intent=not args.no_intent, max_inflight=args.max_inflight)
+                         signal_intent=not args.no_intent, max_inflight=args.max_inflight,
+                         intent_prepass=args.intent_prepass)
     server = ad.Server(cfg.row_len, num_keys=cfg.num_keys, num_threads=1, rank=rank, world=world, backend="cuda",
                        fabric="shm" if world > 1 else "inproc", device=local_rank,
                        options=dict({"sys.techniques": args.techniques, "sys.sync.max_per_sec": args.sync_per_sec},
