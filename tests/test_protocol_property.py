@@ -61,14 +61,15 @@ def _run(kv, server, wid, programs=None):
 @settings(max_examples=int(os.environ.get("ADAPM_HYP_EXAMPLES", "20")), deadline=None, suppress_health_check=list(HealthCheck))
 @given(programs=st.lists(program, min_size=3, max_size=3),
        technique=st.sampled_from(["all", "replication_only", "relocation_only"]),
-       idle_period=st.integers(1, 5), sweep_period=st.integers(0, 4))
-def test_random_programs_are_exact(programs, technique, idle_period, sweep_period):
+       idle_period=st.integers(1, 5), sweep_period=st.integers(0, 4),
+       threshold=st.sampled_from(["-1", "0", "0.5", "3"]))
+def test_random_programs_are_exact(programs, technique, idle_period, sweep_period, threshold):
     import functools
 
     res = run_cluster(functools.partial(_run, programs=programs), world=3, workers=1, mode="threads", value_lengths=VPK,
                       num_keys=NUM_KEYS, dtype="int64",
                       options={"sys.techniques": technique, "sys.sync.idle_period": idle_period,
-                               "sys.sync.sweep_period": sweep_period})
+                               "sys.sync.sweep_period": sweep_period, "sys.sync.threshold": threshold})
     total = [0] * NUM_KEYS
     for r in res.values():
         errs, final, mine = r[0]
