@@ -326,6 +326,14 @@ class Worker:
             k = k.cpu()
         return self._impl.intent(k.data_ptr(), k.numel(), int(start), int(end))
 
+    def intent_fast(self, keys, start: int, end: int = 0) -> int:
+        """Intent with the pre-pass on the calling thread (CPU backend): keys that already have a usable local slot
+        only get their end clock extended, the others take the normal path. Returns #keys on the fast path."""
+        k = _as_keys(keys)
+        if k.is_cuda:
+            k = k.cpu()
+        return self._impl.intent_fast(k.data_ptr(), k.numel(), int(start), int(end))
+
     def advance_clock(self) -> int:
         return self._impl.advance_clock()
 

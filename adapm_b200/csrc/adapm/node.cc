@@ -323,6 +323,21 @@ int Worker::Intent(const Key* keys, size_t n, Clock start, Clock end) {
   return LOCAL;
 }
 
+size_t Worker::IntentFast(const Key* keys, size_t n, Clock start, Clock end) {
+  if (end == 0) end = start + 1;
+  if (server_.num_servers() == 1 || n == 0) return n;
+  ADAPM_CHECK(!server_.backend_->is_cuda(), "IntentFast is the host pre-pass; on the cuda backend use ops.IntentPrepass");
+  const Ctx& c = server_.backend_->ctx();
+  std::vector<Key> rest;
+  for (size_t i = 0; i < n; ++i) {
+    const Key k = keys[i];
+    ADAPM_CHECK(k >= 0 && k < server_.num_keys(), "[ERROR] Intent key " << k << " is outside the configured key range");
+    if (!extend_intent_if_local(c, k, id_, end)) rest.push_back(k);
+  }
+  if (!rest.empty()) Intent(rest.data(), rest.size(), start, end);
+  return n - rest.size();
+}
+
 Clock Worker::advanceClock() {
   return server_.my_control().worker_clock[id_].fetch_add(1, std::memory_order_acq_rel) + 1;
 }

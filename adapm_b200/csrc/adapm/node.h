@@ -228,6 +228,10 @@ class Worker {
   int Intent(const Key* keys, size_t n, Clock start, Clock end = 0);
   int Intent(const std::vector<Key>& keys, Clock start, Clock end = 0) { return Intent(keys.data(), keys.size(), start, end); }
   int Intent(Key key, Clock start, Clock end = 0) { return Intent(&key, 1, start, end); }
+  // Intent with the pre-pass done on the calling thread (CPU backend; the CUDA twin is cuda/ops_intent.cu): keys that
+  // already have a usable local slot only get their end clock extended, the rest goes through Intent(). Returns the
+  // number of keys that took the fast path.
+  size_t IntentFast(const Key* keys, size_t n, Clock start, Clock end = 0);
 
   Clock advanceClock();
   Clock currentClock() const;

@@ -679,6 +679,20 @@ ADAPM_HD void phase_c_slot(const Ctx& c, const G& g, uint32_t s, const RoundPara
   }
 }
 
+// Intent pre-pass for one key (ONE lane, any thread, any time): if the key already has a usable local slot, extending
+// the intent is just an atomic max on the slot's end clock - the sync round only reads the end clocks. Returns false
+// when the key needs the sync thread (no slot yet, or the slot is on its way out).
+ADAPM_HD bool extend_intent_if_local(const Ctx& c, Key key, int worker, Clock end) {
+  const int32_t s = mem::ld_relaxed(slot_of(c, c.rank) + key);
+  if (s < 0) return false;
+  const uint32_t st = meta_state(mem::ld_acquire(meta_of(c, c.rank) + s));
+  if (st == S_OWNED || st == S_REPLICA || st == S_REPLICA_PENDING || state_is_incoming(st)) {
+    atomic_max_i64(intent_end_of(c, c.rank) + (size_t)s * c.L.workers + worker, end);
+    return true;
+  }
+  return false;
+}
+
 // Is `key` usable from local memory right now (owned or usable replica)?  (PullIfLocal / local sampling)
 ADAPM_HD bool is_local(const Ctx& c, Key key) {
   int32_t s = mem::ld_relaxed(slot_of(c, c.rank) + key);

@@ -55,7 +55,8 @@ static void run_fuzz(Server& server, Worker& kv, int wid, const Args& a) {
     random_keys();
     if (what < 3) {
       const Clock c = kv.currentClock() + (Clock)(rng() % 4);
-      kv.Intent(ks.data(), ks.size(), c, c + 1 + (Clock)(rng() % 4));
+      if (rng() % 2) kv.Intent(ks.data(), ks.size(), c, c + 1 + (Clock)(rng() % 4));
+      else kv.IntentFast(ks.data(), ks.size(), c, c + 1 + (Clock)(rng() % 4));   // pre-pass on this thread
     } else if (what < 9) {
       vals.assign(ks.size() * (size_t)a.vpk, 1.0);
       const int ts = kv.Push(ks.data(), ks.size(), vals.data());

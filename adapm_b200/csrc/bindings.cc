@@ -167,6 +167,9 @@ PYBIND11_MODULE(_C, m) {
       .def("intent", [](Worker& w, uintptr_t keys, size_t n, Clock start, Clock end) {
              return w.Intent(ptr<const Key>(keys), n, start, end);
            }, py::call_guard<py::gil_scoped_release>())
+      .def("intent_fast", [](Worker& w, uintptr_t keys, size_t n, Clock start, Clock end) {
+             return w.IntentFast(ptr<const Key>(keys), n, start, end);
+           }, py::call_guard<py::gil_scoped_release>())
       .def("advance_clock", &Worker::advanceClock)
       .def("current_clock", &Worker::currentClock)
       .def("prepare_sample", &Worker::PrepareSample, py::call_guard<py::gil_scoped_release>())

@@ -24,7 +24,6 @@ namespace {
 __global__ void __launch_bounds__(256)
 intent_prepass_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ keys, int64_t n, Clock end, int worker,
                       Key* __restrict__ out_keys, unsigned int* __restrict__ out_count) {
-  const int me = c.rank;
   const int lane = threadIdx.x & 31;
   for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x; i0 < n; i0 += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i = i0 + threadIdx.x;
@@ -32,17 +31,7 @@ intent_prepass_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ key
     Key k = -1;
     if (i < n) {
       k = keys[i];
-      if (k >= 0 && k < c.L.num_keys) {
-        need = true;
-        const int32_t s = __ldcg(slot_of(c, me) + k);
-        if (s >= 0) {
-          const uint32_t st = meta_state(__ldcg(meta_of(c, me) + s));
-          if (st == S_OWNED || st == S_REPLICA || st == S_REPLICA_PENDING || state_is_incoming(st)) {
-            atomicMax(reinterpret_cast<long long*>(intent_end_of(c, me) + (size_t)s * c.L.workers + worker), (long long)end);
-            need = false;
-          }
-        }
-      }
+      if (k >= 0 && k < c.L.num_keys) need = !extend_intent_if_local(c, k, worker, end);   // protocol.h, shared with the host
     }
     // warp-aggregated append of the keys that still need the sync thread
     const unsigned mask = __ballot_sync(0xffffffffu, need);

@@ -15,6 +15,7 @@ NUM_KEYS, VPK = 24, 2
 key_sets = st.lists(st.integers(0, NUM_KEYS - 1), min_size=1, max_size=6, unique=True)
 op = st.one_of(
     st.tuples(st.just("intent"), key_sets, st.integers(0, 3), st.integers(1, 4)),   # keys, start offset, duration
+    st.tuples(st.just("intent_fast"), key_sets, st.integers(0, 3), st.integers(1, 4)),   # same, pre-pass on this thread
     st.tuples(st.just("push"), key_sets),
     st.tuples(st.just("pull"), key_sets),
     st.tuples(st.just("clock")),
@@ -32,6 +33,8 @@ def _run(kv, server, wid, programs=None):
         for o in (prog[r] if r < len(prog) else []):
             if o[0] == "intent":
                 kv.intent(torch.tensor(o[1]), kv.current_clock() + o[2], kv.current_clock() + o[2] + o[3])
+            elif o[0] == "intent_fast":
+                kv.intent_fast(torch.tensor(o[1]), kv.current_clock() + o[2], kv.current_clock() + o[2] + o[3])
             elif o[0] == "push":
                 k = torch.tensor(o[1])
                 kv.wait(kv.push(k, torch.ones(len(o[1]) * VPK, dtype=torch.int64)))
