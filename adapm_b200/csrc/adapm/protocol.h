@@ -575,15 +575,20 @@ ADAPM_HD void phase_c_slot(const Ctx& c, const G& g, uint32_t s, const RoundPara
     Val* row = row_ptr<Val>(c, me, cls, s);
     Val* base = base_ptr<Val>(c, me, cls, s);
     const Val* srow = row_ptr<Val>(c, src, cls, ss);
+    bool base_nonzero = false;
     ADAPM_ROW_BATCHES(g, len) {
       Val S[kRowBatch], b[kRowBatch];
       ADAPM_ROW_ELEMS(g, len, u, i) S[u] = mem::ld_relaxed(srow + i);
       ADAPM_ROW_ELEMS(g, len, u, i) b[u] = mem::ld_relaxed(base + i);
       ADAPM_ROW_ELEMS(g, len, u, i) {
+        base_nonzero = base_nonzero || b[u] != (Val)0;
         if (S[u] != b[u]) mem::red_add(row + i, (Val)(S[u] - b[u]));
         mem::st_relaxed(base + i, (Val)0);
       }
     }
+    // invariant used by the in-kernel read of in-flight rows (pm_kernels.cuh: value = local row + source row): a
+    // placeholder that became the relocation target (INCOMING, not INCOMING_REPLICA) has an all-zero base
+    if (st == S_INCOMING && g.any(base_nonzero) && g.lane() == 0) count(c, C_PROTOCOL_ERRORS);
     mem::fence(); g.sync();
     if (g.lane() == 0) {
       uint32_t sv = mem::ld_relaxed(version_of(c, src) + ss);

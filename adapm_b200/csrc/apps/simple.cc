@@ -186,6 +186,10 @@ int main(int argc, char** argv) {
       for (int c = 0; c < a.threads; ++c) ws.emplace_back(run_worker, std::ref(server), c, std::cref(a), result);
       for (auto& t : ws) t.join();
       if (r == 0) ALOG(server.stats_string());
+      if (a.fuzz) {   // the protocol's own consistency checks count as fuzz errors too
+        const uint64_t pe = server.counters()["protocol_errors"];
+        if (pe) { ALOG("fuzz: rank " << r << " counted " << pe << " protocol errors"); g_fuzz_errors.fetch_add((int)pe); }
+      }
       server.shutdown();
     });
   }
