@@ -111,6 +111,30 @@ ADAPM_D void red_add(uint64_t* p, uint64_t v) {
 ADAPM_D void red_add(uint32_t* p, uint32_t v) {
   asm volatile("red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// no-return bit operations (RED.OR / RED.AND over NVLink: nothing to wait for)
+ADAPM_D void red_or(uint64_t* p, uint64_t v) {
+  asm volatile("red.relaxed.sys.global.or.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+ADAPM_D void red_and(uint64_t* p, uint64_t v) {
+  asm volatile("red.relaxed.sys.global.and.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// 16-byte row accesses (local HBM or an NVLink peer: same instructions)
+struct alignas(16) F4 { float x, y, z, w; };
+ADAPM_D F4 ld_relaxed4(const float* p) {
+  F4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+ADAPM_D void st_relaxed4(float* p, F4 v) {
+  asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+ADAPM_D void red_add4(float* p, F4 v) {
+  asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
 ADAPM_D void fence() { __threadfence_system(); }
 ADAPM_D void cpu_relax() { __nanosleep(64); }
 
@@ -140,6 +164,8 @@ template <class T> inline T fetch_add(T* p, T v) { return __atomic_fetch_add(p, 
 inline uint64_t fetch_or(uint64_t* p, uint64_t v) { return __atomic_fetch_or(p, v, __ATOMIC_ACQ_REL); }
 inline uint64_t fetch_and(uint64_t* p, uint64_t v) { return __atomic_fetch_and(p, v, __ATOMIC_ACQ_REL); }
 inline uint64_t exchange(uint64_t* p, uint64_t v) { return __atomic_exchange_n(p, v, __ATOMIC_ACQ_REL); }
+inline void red_or(uint64_t* p, uint64_t v) { __atomic_fetch_or(p, v, __ATOMIC_ACQ_REL); }
+inline void red_and(uint64_t* p, uint64_t v) { __atomic_fetch_and(p, v, __ATOMIC_ACQ_REL); }
 inline void red_add(int64_t* p, int64_t v) { __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline void red_add(uint64_t* p, uint64_t v) { __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline void red_add(uint32_t* p, uint32_t v) { __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }

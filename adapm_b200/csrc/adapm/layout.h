@@ -39,6 +39,7 @@ struct Layout {
   uint64_t off_ver_seen;   // uint32[S]         replica: owner version at last refresh
   uint64_t off_want;       // uint64[S]         owner: ranks that hold a replica / placeholder of the key (sticky bits)
   uint64_t off_want_owner; // uint8[S]          holder: the owner whose want-mask carries this rank's bit (0xff none)
+  uint64_t off_peer_slot;  // int32[S]          holder: the key's slot id at want_owner (valid while dir[key] == want_owner)
   uint64_t off_slot_key;   // int64[S]
   uint64_t off_intent_end; // int64[S*workers]  end clock of the local intents
   uint64_t off_flags;      // uint8[S]          F_REQUESTED (sync thread only)
@@ -46,10 +47,27 @@ struct Layout {
   uint64_t off_free_top;   // int32[MAX_CLASSES]
   uint64_t off_counters;   // uint64[C_NUM_COUNTERS]
   uint64_t off_access;     // uint32[2*num_keys] (accesses, local accesses) - only if locality stats are on, else 0
+  uint64_t off_sync;       // SyncArea: device-side round state (grace epochs, cross-rank barrier flags)
   uint32_t locality_stats; // PS_LOCALITY_STATS equivalent (run-time switch sys.stats.locality)
   uint32_t pad2;
   ClassInfo cls[MAX_CLASSES];
   uint64_t heap_bytes;
+};
+
+// Device-side state of the sync round (one per rank, in the heap, written by peers):
+//  * grace epochs: every CTA of a kernel that touches the store registers in active[epoch & 1] for its lifetime;
+//    the round flips the epoch after phase B and waits until the old side has drained (an RCU grace period:
+//    everything that may have read the old directory is done) - no host involvement, no stream events;
+//  * cross-rank barrier: rank r's barrier kernel stores the barrier sequence number into bar_arrive[r] of EVERY
+//    rank's area (st.release.sys over NVLink) and then waits until all entries of its own area reached it;
+//  * flag exchange: the first barrier of a round also carries one word per rank (stop / sweep requests), so the
+//    ranks agree on them without a host barrier.
+struct SyncArea {
+  uint32_t epoch;
+  uint32_t active[2];
+  uint32_t pad0[29];
+  uint32_t bar_arrive[MAX_RANKS];
+  uint32_t flag_word[2][MAX_RANKS];   // [round parity][rank]
 };
 
 struct IntentRec {
@@ -81,8 +99,10 @@ ADAPM_HD int64_t* intent_end_of(const Ctx& c, int r) { return at<int64_t>(c, r, 
 ADAPM_HD uint8_t* flags_of(const Ctx& c, int r) { return at<uint8_t>(c, r, c.L.off_flags); }
 ADAPM_HD uint8_t* dirty_of(const Ctx& c, int r) { return at<uint8_t>(c, r, c.L.off_dirty); }
 ADAPM_HD uint8_t* want_owner_of(const Ctx& c, int r) { return at<uint8_t>(c, r, c.L.off_want_owner); }
+ADAPM_HD int32_t* peer_slot_of(const Ctx& c, int r) { return at<int32_t>(c, r, c.L.off_peer_slot); }
 ADAPM_HD int32_t* free_top_of(const Ctx& c, int r) { return at<int32_t>(c, r, c.L.off_free_top); }
 ADAPM_HD uint64_t* counters_of(const Ctx& c, int r) { return at<uint64_t>(c, r, c.L.off_counters); }
+ADAPM_HD SyncArea* sync_area_of(const Ctx& c, int r) { return at<SyncArea>(c, r, c.L.off_sync); }
 
 ADAPM_HD int class_of_key(const Ctx& c, Key k) {
   if (c.L.num_classes == 1) return 0;

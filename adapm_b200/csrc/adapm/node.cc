@@ -269,7 +269,28 @@ int Worker::Push(const Key* keys, size_t n, const void* vals, bool set, const Io
   ++num_push_ops;
   num_push_params += n;
   OpResult res;
-  uint64_t ticket = server_.backend_->push(id_, keys, n, vals, set, &res, io);
+  uint64_t ticket = 0;
+  if (set && server_.num_servers() > 1) {
+    // Set cannot complete for a key whose relocation is in flight; such keys are repeated after the next sync round
+    // (never wait for the round inside the op: the round's grace period waits for the op)
+    std::vector<uint8_t> todo(n, 1);
+    OpResult acc;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (;;) {
+      const uint64_t round0 = server_.sync_->rounds_done();
+      server_.backend_->push(id_, keys, n, vals, true, &res, io, todo.data());
+      acc.n_local += res.n_local; acc.n_remote += res.n_remote; acc.n_failed += res.n_failed;
+      if (res.n_retry == 0) break;
+      while (server_.sync_->rounds_done() == round0) {
+        std::this_thread::sleep_for(std::chrono::microseconds(50));
+        const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        ADAPM_CHECK(el < server_.options().wait_timeout_s, "watchdog: Set is waiting for a sync round that never completes");
+      }
+    }
+    res = acc;
+  } else {
+    ticket = server_.backend_->push(id_, keys, n, vals, set, &res, io);
+  }
   if (ticket == 0) {
     ADAPM_CHECK(res.n_failed == 0, "push failed for " << res.n_failed << " keys (protocol error)");
     num_push_params_local += res.n_local;

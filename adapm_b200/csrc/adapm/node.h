@@ -58,7 +58,9 @@ class SyncEngine {
 
  private:
   void loop();
+  void loop_fused();
   void round(bool sweep);
+  bool fused_ = false;
   void collect_intents(const std::vector<Clock>& clocks, const std::vector<Clock>& windows);
 
   Server* server_;

@@ -29,6 +29,7 @@ struct HostGroup {
   ADAPM_HD uint32_t bcast(uint32_t v) const { return v; }
   ADAPM_HD int32_t bcast(int32_t v) const { return v; }
   ADAPM_HD uint64_t bcast(uint64_t v) const { return v; }
+  ADAPM_HD uint32_t bcast_from(uint32_t v, int) const { return v; }
   ADAPM_HD double sum(double v) const { return v; }
 };
 
@@ -134,6 +135,174 @@ constexpr int kRowBatch = 8;
   ADAPM_UNROLL for (int u = 0; u < kRowBatch; ++u) \
     for (uint32_t i = i0_ + (uint32_t)u * (g).size(); i < (len); i = 0xffffffffu)
 
+// ---------------------------------------------------------------------------------------
+// Row primitives of the sync round: the only loops over row elements. On the device, float rows whose length is a
+// multiple of 4 take the 16-byte path (LDG.128 / REDG.F32x4 / STG.128, local HBM or an NVLink peer alike) with
+// kVecBatch independent 16-byte accesses per lane in flight: a 600-float word2vec row is ONE batch per array, i.e. one
+// NVLink round trip instead of the 19 dependent ones of an element-wise loop.
+#ifndef ADAPM_VEC_BATCH
+#define ADAPM_VEC_BATCH 5
+#endif
+constexpr int kVecBatch = ADAPM_VEC_BATCH;
+// (out of line on the device: the primitives are called from several branches of the slot functions; inlined, their
+// batches of 16-byte registers pushed the round kernels into spills)
+#if defined(__CUDA_ARCH__) && !defined(ADAPM_ROW_INLINE)
+#define ADAPM_ROWFN __device__ __noinline__
+#elif defined(__CUDA_ARCH__)
+#define ADAPM_ROWFN __device__ __forceinline__
+#else
+#define ADAPM_ROWFN inline
+#endif
+#if defined(__CUDA_ARCH__)
+template <class Val> ADAPM_D bool row_vec_ok(uint32_t, const void*, const void*, const void*) { return false; }
+template <> ADAPM_D bool row_vec_ok<float>(uint32_t len, const void* a, const void* b, const void* c) {
+#ifdef ADAPM_NO_VEC   // debugging: element-wise loops only
+  return false;
+#endif
+  return (len & 3u) == 0 && ((((uintptr_t)a) | ((uintptr_t)b) | ((uintptr_t)c)) & 15u) == 0;
+}
+#define ADAPM_VEC_BATCHES(g, nv) for (uint32_t j0_ = (g).lane(); j0_ < (nv); j0_ += (g).size() * kVecBatch)
+#define ADAPM_VEC_ELEMS(g, nv, u, j) \
+  _Pragma("unroll") for (int u = 0; u < kVecBatch; ++u) \
+    if (const uint32_t j = j0_ + (uint32_t)u * 32u; j < (nv))
+ADAPM_D bool f4_ne(const mem::F4& a, const mem::F4& b) { return a.x != b.x || a.y != b.y || a.z != b.z || a.w != b.w; }
+ADAPM_D mem::F4 f4_sub(const mem::F4& a, const mem::F4& b) { mem::F4 r; r.x = a.x - b.x; r.y = a.y - b.y; r.z = a.z - b.z; r.w = a.w - b.w; return r; }
+#endif
+
+// dst += (src - ref) where they differ; ref := (rebase ? src : 0).  Used by the refresh (dst = replica row,
+// ref = replica base, src = owner row or its published mirror) and by the relocation finalize (rebase = false).
+// Returns (via *ref_nonzero) whether any ref element was non-zero.
+template <class Val, class G>
+ADAPM_ROWFN void row_fold(const G& g, Val* dst, Val* ref, const Val* src, uint32_t len, bool rebase, bool* ref_nonzero) {
+  bool bnz = false;
+#if defined(__CUDA_ARCH__)
+  if (row_vec_ok<Val>(len, dst, ref, src)) {
+    float* d = reinterpret_cast<float*>(dst); float* r = reinterpret_cast<float*>(ref);
+    const float* s = reinterpret_cast<const float*>(src);
+    const uint32_t nv = len >> 2;
+    ADAPM_VEC_BATCHES(g, nv) {
+      mem::F4 S[kVecBatch], b[kVecBatch];
+      ADAPM_VEC_ELEMS(g, nv, u, j) S[u] = mem::ld_relaxed4(s + 4 * j);
+      ADAPM_VEC_ELEMS(g, nv, u, j) b[u] = mem::ld_relaxed4(r + 4 * j);
+      ADAPM_VEC_ELEMS(g, nv, u, j) {
+        const mem::F4 z = {0.f, 0.f, 0.f, 0.f};
+        bnz = bnz || f4_ne(b[u], z);
+        if (f4_ne(S[u], b[u])) {
+          mem::red_add4(d + 4 * j, f4_sub(S[u], b[u]));
+          if (rebase) mem::st_relaxed4(r + 4 * j, S[u]);
+        }
+        if (!rebase && f4_ne(b[u], z)) mem::st_relaxed4(r + 4 * j, z);
+      }
+    }
+    if (ref_nonzero) *ref_nonzero = g.any(bnz);
+    return;
+  }
+#endif
+  ADAPM_ROW_BATCHES(g, len) {
+    Val S[kRowBatch], b[kRowBatch];
+    ADAPM_ROW_ELEMS(g, len, u, i) S[u] = mem::ld_relaxed(src + i);
+    ADAPM_ROW_ELEMS(g, len, u, i) b[u] = mem::ld_relaxed(ref + i);
+    ADAPM_ROW_ELEMS(g, len, u, i) {
+      bnz = bnz || b[u] != (Val)0;
+      if (S[u] != b[u]) {
+        mem::red_add(dst + i, (Val)(S[u] - b[u]));
+        if (rebase) mem::st_relaxed(ref + i, S[u]);
+      }
+      if (!rebase && b[u] != (Val)0) mem::st_relaxed(ref + i, (Val)0);
+    }
+  }
+  if (ref_nonzero) *ref_nonzero = g.any(bnz);
+}
+
+// out += (row - base) where they differ (reductions into the owner's row); base := row if `rebase`.
+// Returns true if any element differed. (`all`: sys.sync.threshold < 0 - nothing changes for equal elements.)
+template <class Val, class G>
+ADAPM_ROWFN bool row_ship(const G& g, const Val* row, Val* base, Val* out, uint32_t len, bool rebase) {
+  bool nz = false;
+#if defined(__CUDA_ARCH__)
+  if (row_vec_ok<Val>(len, row, base, out)) {
+    const float* w = reinterpret_cast<const float*>(row); float* r = reinterpret_cast<float*>(base);
+    float* o = reinterpret_cast<float*>(out);
+    const uint32_t nv = len >> 2;
+    ADAPM_VEC_BATCHES(g, nv) {
+      mem::F4 v[kVecBatch], b[kVecBatch];
+      ADAPM_VEC_ELEMS(g, nv, u, j) v[u] = mem::ld_relaxed4(w + 4 * j);
+      ADAPM_VEC_ELEMS(g, nv, u, j) b[u] = mem::ld_relaxed4(r + 4 * j);
+      ADAPM_VEC_ELEMS(g, nv, u, j) {
+        if (f4_ne(v[u], b[u])) {
+          mem::red_add4(o + 4 * j, f4_sub(v[u], b[u]));
+          if (rebase) mem::st_relaxed4(r + 4 * j, v[u]);
+          nz = true;
+        }
+      }
+    }
+    return g.any(nz);
+  }
+#endif
+  ADAPM_ROW_BATCHES(g, len) {
+    Val v[kRowBatch], b[kRowBatch];
+    ADAPM_ROW_ELEMS(g, len, u, i) v[u] = mem::ld_relaxed(row + i);
+    ADAPM_ROW_ELEMS(g, len, u, i) b[u] = mem::ld_relaxed(base + i);
+    ADAPM_ROW_ELEMS(g, len, u, i) {
+      const Val d = v[u] - b[u];
+      if (d != (Val)0) {
+        mem::red_add(out + i, d);
+        if (rebase) mem::st_relaxed(base + i, v[u]);
+        nz = true;
+      }
+    }
+  }
+  return g.any(nz);
+}
+
+// sum over (row - base)^2   (sys.sync.threshold > 0: ship a replica delta only if its L2 norm is large enough)
+template <class Val, class G>
+ADAPM_ROWFN double row_delta_norm2(const G& g, const Val* row, const Val* base, uint32_t len) {
+  double acc = 0;
+#if defined(__CUDA_ARCH__)
+  if (row_vec_ok<Val>(len, row, base, row)) {
+    const float* w = reinterpret_cast<const float*>(row); const float* r = reinterpret_cast<const float*>(base);
+    const uint32_t nv = len >> 2;
+    float a = 0.f;
+    ADAPM_VEC_BATCHES(g, nv) {
+      mem::F4 v[kVecBatch], b[kVecBatch];
+      ADAPM_VEC_ELEMS(g, nv, u, j) v[u] = mem::ld_relaxed4(w + 4 * j);
+      ADAPM_VEC_ELEMS(g, nv, u, j) b[u] = mem::ld_relaxed4(r + 4 * j);
+      ADAPM_VEC_ELEMS(g, nv, u, j) {
+        const mem::F4 d = f4_sub(v[u], b[u]);
+        a += d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w;
+      }
+    }
+    return g.sum((double)a);
+  }
+#endif
+  ADAPM_ROW_BATCHES(g, len) {
+    Val v[kRowBatch];
+    ADAPM_ROW_ELEMS(g, len, u, i) v[u] = mem::ld_relaxed(row + i);
+    ADAPM_ROW_ELEMS(g, len, u, i) v[u] -= mem::ld_relaxed(base + i);
+    ADAPM_ROW_ELEMS(g, len, u, i) acc += (double)v[u] * (double)v[u];
+  }
+  return g.sum(acc);
+}
+
+// dst := src  (len values; owner row -> published mirror row)
+template <class Val, class G>
+ADAPM_ROWFN void row_copy(const G& g, Val* dst, const Val* src, uint32_t len) {
+#if defined(__CUDA_ARCH__)
+  if (row_vec_ok<Val>(len, dst, src, src)) {
+    float* d = reinterpret_cast<float*>(dst); const float* s = reinterpret_cast<const float*>(src);
+    const uint32_t nv = len >> 2;
+    ADAPM_VEC_BATCHES(g, nv) {
+      mem::F4 v[kVecBatch];
+      ADAPM_VEC_ELEMS(g, nv, u, j) v[u] = mem::ld_relaxed4(s + 4 * j);
+      ADAPM_VEC_ELEMS(g, nv, u, j) mem::st_relaxed4(d + 4 * j, v[u]);
+    }
+    return;
+  }
+#endif
+  for (uint32_t i = g.lane(); i < len; i += g.size()) mem::st_relaxed(dst + i, mem::ld_relaxed(src + i));
+}
+
 // Copy the located row into `out` (len values). Returns false if a SUM3 read raced with the
 // finalize step and must be retried by the caller.
 template <class Val, class G>
@@ -228,12 +397,16 @@ ADAPM_HD bool push_key(const Ctx& c, const G& g, Key key, const Val* vals, bool*
 // Set (assignment) goes to the owner's row. Mirrors the reference's `set` flag of Push
 // (coloc_kv_worker.h:223-239, coloc_kv_server_handle.h:404-415); on a replica the reference
 // only asserts, we route the store to the owner and re-base the local replica.
+// A key whose relocation is in flight cannot be assigned exactly (its value is spread over two rows until phase C
+// folds them). The op must NOT wait for that inside a grace-tracked kernel / op - the grace period waits for the op -
+// so set_key reports SET_RETRY and the caller (Worker::Push) repeats the key after the next sync round.
+enum SetResult : int { SET_FAIL = 0, SET_OK = 1, SET_RETRY = 2 };
 template <class Val, class G>
-ADAPM_HD bool set_key(const Ctx& c, const G& g, Key key, const Val* vals, bool* was_local) {
+ADAPM_HD int set_key(const Ctx& c, const G& g, Key key, const Val* vals, bool* was_local) {
   const int me = c.rank;
   const int cls = class_of_key(c, key);
   const uint32_t len = c.L.cls[cls].len;
-  for (int attempt = 0; attempt < kMaxAttempts; ++attempt) {
+  for (int attempt = 0; attempt < 256; ++attempt) {
     int32_t s = g.bcast(g.lane() == 0 ? mem::ld_relaxed(slot_of(c, me) + key) : 0);
     uint32_t st = S_FREE;
     if (s >= 0) st = meta_state(g.bcast(g.lane() == 0 ? mem::ld_acquire(meta_of(c, me) + s) : 0u));
@@ -242,15 +415,15 @@ ADAPM_HD bool set_key(const Ctx& c, const G& g, Key key, const Val* vals, bool* 
       for (uint32_t i = g.lane(); i < len; i += g.size()) mem::st_relaxed(row + i, vals[i]);
       if (g.lane() == 0) mem::red_add(version_of(c, me) + s, 1u);
       if (was_local) *was_local = true;
-      return true;
+      return SET_OK;
     }
-    if (state_is_incoming(st) || st == S_FINALIZING) { mem::cpu_relax(); continue; }  // wait for the transfer
+    if (state_is_incoming(st) || st == S_FINALIZING) return SET_RETRY;   // transfer in flight: after the next round
     int o = (int)g.bcast((uint32_t)(g.lane() == 0 ? mem::ld_relaxed(dir_of(c, me) + key) : 0));
-    if (o == me) { mem::cpu_relax(); continue; }
+    if (o == me) { mem::cpu_relax(); continue; }   // directory store and state word are a few stores apart
     int32_t ps = g.bcast(g.lane() == 0 ? mem::ld_relaxed(slot_of(c, o) + key) : 0);
     if (ps < 0) { mem::cpu_relax(); continue; }
     uint32_t pst = meta_state(g.bcast(g.lane() == 0 ? mem::ld_acquire(meta_of(c, o) + ps) : 0u));
-    if (pst != S_OWNED) { mem::cpu_relax(); continue; }
+    if (pst != S_OWNED) return SET_RETRY;
     Val* row = row_ptr<Val>(c, o, cls, ps);
     for (uint32_t i = g.lane(); i < len; i += g.size()) mem::st_relaxed(row + i, vals[i]);
     if (g.lane() == 0) mem::red_add(version_of(c, o) + ps, 1u);
@@ -263,9 +436,9 @@ ADAPM_HD bool set_key(const Ctx& c, const G& g, Key key, const Val* vals, bool* 
       }
     }
     if (was_local) *was_local = false;
-    return true;
+    return SET_OK;
   }
-  return false;
+  return SET_RETRY;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -412,8 +585,24 @@ ADAPM_HD bool phase_c_wants(const Ctx& c, uint32_t s, const RoundParams& rp) {
   return slot_swept(s, rp) || round_due(s, rp.round_no, rp.idle_period);
 }
 
+// The key's slot id at its owner `o` as seen from holder slot `s`: cached next to the standing want-bit (the owner's
+// slot of a key cannot change while it stays the owner), otherwise ONE NVLink load. All lanes get the same answer.
+template <class G>
+ADAPM_HD int32_t owner_slot_of(const Ctx& c, const G& g, uint32_t s, Key key, int o) {
+  int32_t ps = -1;
+  if (g.lane() == 0) {
+    const int me = c.rank;
+    if ((mem::ld_relaxed(flags_of(c, me) + s) & F_WANT_SET) && (int)mem::ld_relaxed(want_owner_of(c, me) + s) == o)
+      ps = mem::ld_relaxed(peer_slot_of(c, me) + s);
+    else
+      ps = mem::ld_relaxed(slot_of(c, o) + key);
+  }
+  return g.bcast(ps);
+}
+
 // Phase A, step 2: visit one non-owned slot: ship the replica delta to the owner, decide
-// whether the replica is still needed, request a refresh.
+// whether the replica is still needed, request a refresh. In steady state (want-bit standing, owner unchanged) this
+// issues only fire-and-forget reductions over NVLink: no remote load, nothing to wait for.
 template <class Val, class G>
 ADAPM_HD void phase_a_slot(const Ctx& c, const G& g, uint32_t s, const RoundParams& rp) {
   const int me = c.rank;
@@ -427,7 +616,7 @@ ADAPM_HD void phase_a_slot(const Ctx& c, const G& g, uint32_t s, const RoundPara
   const bool active = g.bcast((uint32_t)(g.lane() == 0 ? (intent_active(c, s, rp.clocks) ? 1u : 0u) : 0u)) != 0;
   const int o = (int)g.bcast((uint32_t)(g.lane() == 0 ? mem::ld_relaxed(dir_of(c, me) + key) : 0));
   int32_t ps = -1;
-  if (o != me) ps = g.bcast(g.lane() == 0 ? mem::ld_relaxed(slot_of(c, o) + key) : 0);
+  if (o != me) ps = owner_slot_of(c, g, s, key, o);
   if (ps < 0) { if (g.lane() == 0) count(c, C_PROTOCOL_ERRORS); return; }
   uint8_t* fl = flags_of(c, me) + s;
   if (st == S_REPLICA) {
@@ -440,40 +629,18 @@ ADAPM_HD void phase_a_slot(const Ctx& c, const G& g, uint32_t s, const RoundPara
       Val* row = row_ptr<Val>(c, me, cls, s);
       Val* base = base_ptr<Val>(c, me, cls, s);
       bool ship = true;
-      if (rp.threshold > 0 && active && !swept) {
-        double acc = 0;
-        ADAPM_ROW_BATCHES(g, len) {
-          Val v[kRowBatch];
-          ADAPM_ROW_ELEMS(g, len, u, i) v[u] = mem::ld_relaxed(row + i);
-          ADAPM_ROW_ELEMS(g, len, u, i) v[u] -= mem::ld_relaxed(base + i);
-          ADAPM_ROW_ELEMS(g, len, u, i) acc += (double)v[u] * (double)v[u];
-        }
-        acc = g.sum(acc);
-        ship = acc >= rp.threshold * rp.threshold;
-      }
+      if (rp.threshold > 0 && active && !swept)
+        ship = row_delta_norm2<Val>(g, row, base, len) >= rp.threshold * rp.threshold;
       if (ship) {
         if (g.lane() == 0) mem::st_relaxed(dp, (uint8_t)0);
         mem::fence();
-        Val* orow = row_ptr<Val>(c, o, cls, ps);
-        bool nz = false;
-        ADAPM_ROW_BATCHES(g, len) {
-          Val v[kRowBatch], b[kRowBatch];
-          ADAPM_ROW_ELEMS(g, len, u, i) v[u] = mem::ld_relaxed(row + i);
-          ADAPM_ROW_ELEMS(g, len, u, i) b[u] = mem::ld_relaxed(base + i);
-          ADAPM_ROW_ELEMS(g, len, u, i) {
-            const Val d = v[u] - b[u];
-            if (d != (Val)0 || rp.threshold < 0) {
-              if (d != (Val)0) mem::red_add(orow + i, d);
-              mem::st_relaxed(base + i, v[u]);
-              nz = nz || (d != (Val)0);
-            }
-          }
-        }
-        nz = g.any(nz);
+        const bool nz = row_ship<Val>(g, row, base, row_ptr<Val>(c, o, cls, ps), len, true);
         if (nz && g.lane() == 0) {
-          uint32_t old = mem::fetch_add(version_of(c, o) + ps, 1u);
+          // the owner's version counts applied updates; this replica accounts for its own bump locally, so that in
+          // phase C "owner version == ver_seen" still means "nothing but my own deltas arrived" (no round trip)
+          mem::red_add(version_of(c, o) + ps, 1u);
           uint32_t* vs = ver_seen_of(c, me) + s;
-          if (mem::ld_relaxed(vs) == old) mem::st_relaxed(vs, old + 1);
+          mem::st_relaxed(vs, mem::ld_relaxed(vs) + 1u);
           count(c, C_DELTAS_SHIPPED);
         }
       }
@@ -484,7 +651,7 @@ ADAPM_HD void phase_a_slot(const Ctx& c, const G& g, uint32_t s, const RoundPara
     if (g.lane() == 0) {
       // withdraw the standing request (the bit lives in the mask of the owner it was sent to; a relocation resets it)
       const uint8_t f = mem::ld_relaxed(fl);
-      if ((f & F_WANT_SET) && (int)mem::ld_relaxed(wo) == o) mem::fetch_and(want_of(c, o) + ps, ~((uint64_t)1 << me));
+      if ((f & F_WANT_SET) && (int)mem::ld_relaxed(wo) == o) mem::red_and(want_of(c, o) + ps, ~((uint64_t)1 << me));
       mem::st_relaxed(wo, (uint8_t)0xff);
       mem::st_relaxed(fl, (uint8_t)(f & ~(F_REQUESTED | F_WANT_SET)));
       mem::st_release(mp, meta_next(m, S_DROPPING, 0));
@@ -495,7 +662,8 @@ ADAPM_HD void phase_a_slot(const Ctx& c, const G& g, uint32_t s, const RoundPara
     // the request is sticky: it stands in the owner's want-mask until this rank drops the replica
     uint8_t f = mem::ld_relaxed(fl);
     if (!(f & F_WANT_SET) || (int)mem::ld_relaxed(wo) != o) {
-      mem::fetch_or(want_of(c, o) + ps, (uint64_t)1 << me);
+      mem::red_or(want_of(c, o) + ps, (uint64_t)1 << me);
+      mem::st_relaxed(peer_slot_of(c, me) + s, ps);
       mem::st_relaxed(wo, (uint8_t)o);
       f |= F_WANT_SET;
     }
@@ -547,6 +715,16 @@ template <class Val, class G>
 ADAPM_HD void clear_slot_rows(const Ctx& c, const G& g, int cls, uint32_t s, uint32_t len) {
   Val* row = row_ptr<Val>(c, c.rank, cls, s);
   Val* base = base_ptr<Val>(c, c.rank, cls, s);
+#if defined(__CUDA_ARCH__)
+  if (row_vec_ok<Val>(len, row, base, row)) {
+    const mem::F4 z = {0.f, 0.f, 0.f, 0.f};
+    for (uint32_t j = g.lane(); j < (len >> 2); j += g.size()) {
+      mem::st_relaxed4(reinterpret_cast<float*>(row) + 4 * j, z);
+      mem::st_relaxed4(reinterpret_cast<float*>(base) + 4 * j, z);
+    }
+    return;
+  }
+#endif
   for (uint32_t i = g.lane(); i < len; i += g.size()) {
     mem::st_relaxed(row + i, (Val)0);
     mem::st_relaxed(base + i, (Val)0);
@@ -572,23 +750,12 @@ ADAPM_HD void phase_c_slot(const Ctx& c, const G& g, uint32_t s, const RoundPara
     uint32_t m1 = meta_next(m, S_FINALIZING, (uint32_t)src);
     if (g.lane() == 0) mem::st_release(mp, m1);
     mem::fence(); g.sync();
-    Val* row = row_ptr<Val>(c, me, cls, s);
-    Val* base = base_ptr<Val>(c, me, cls, s);
-    const Val* srow = row_ptr<Val>(c, src, cls, ss);
     bool base_nonzero = false;
-    ADAPM_ROW_BATCHES(g, len) {
-      Val S[kRowBatch], b[kRowBatch];
-      ADAPM_ROW_ELEMS(g, len, u, i) S[u] = mem::ld_relaxed(srow + i);
-      ADAPM_ROW_ELEMS(g, len, u, i) b[u] = mem::ld_relaxed(base + i);
-      ADAPM_ROW_ELEMS(g, len, u, i) {
-        base_nonzero = base_nonzero || b[u] != (Val)0;
-        if (S[u] != b[u]) mem::red_add(row + i, (Val)(S[u] - b[u]));
-        mem::st_relaxed(base + i, (Val)0);
-      }
-    }
+    row_fold<Val>(g, row_ptr<Val>(c, me, cls, s), base_ptr<Val>(c, me, cls, s), row_ptr<Val>(c, src, cls, ss), len,
+                  false, &base_nonzero);
     // invariant used by the in-kernel read of in-flight rows (pm_kernels.cuh: value = local row + source row): a
     // placeholder that became the relocation target (INCOMING, not INCOMING_REPLICA) has an all-zero base
-    if (st == S_INCOMING && g.any(base_nonzero) && g.lane() == 0) count(c, C_PROTOCOL_ERRORS);
+    if (st == S_INCOMING && base_nonzero && g.lane() == 0) count(c, C_PROTOCOL_ERRORS);
     mem::fence(); g.sync();
     if (g.lane() == 0) {
       uint32_t sv = mem::ld_relaxed(version_of(c, src) + ss);
@@ -608,24 +775,22 @@ ADAPM_HD void phase_c_slot(const Ctx& c, const G& g, uint32_t s, const RoundPara
     if (c.technique == (int)MgmtTechniques::RELOCATION_ONLY) return;
     const int o = (int)g.bcast((uint32_t)(g.lane() == 0 ? mem::ld_relaxed(dir_of(c, me) + key) : 0));
     if (o == me) return;
-    int32_t ps = g.bcast(g.lane() == 0 ? mem::ld_relaxed(slot_of(c, o) + key) : 0);
+    const int32_t ps = owner_slot_of(c, g, s, key, o);
     if (ps < 0) return;
-    uint32_t pm = g.bcast(g.lane() == 0 ? mem::ld_acquire(meta_of(c, o) + ps) : 0u);
+    // owner state word and version in ONE round trip: lanes 0 and 1 of the same load instruction
+    uint32_t pv = 0;
+    if (g.size() > 1) {
+      if (g.lane() < 2) pv = mem::ld_acquire(g.lane() == 0 ? meta_of(c, o) + ps : version_of(c, o) + ps);
+    } else {
+      pv = mem::ld_acquire(meta_of(c, o) + ps);
+    }
+    const uint32_t pm = g.bcast(pv);
     if (meta_state(pm) != S_OWNED) return;  // owner is mid-relocation: ask again next round
-    uint32_t v = g.bcast(g.lane() == 0 ? mem::ld_acquire(version_of(c, o) + ps) : 0u);
+    const uint32_t v = g.size() > 1 ? g.bcast_from(pv, 1) : mem::ld_acquire(version_of(c, o) + ps);
     uint32_t seen = g.bcast(g.lane() == 0 ? mem::ld_relaxed(ver_seen_of(c, me) + s) : 0u);
     if (st == S_REPLICA && v == seen && !slot_swept(s, rp)) return;
-    Val* row = row_ptr<Val>(c, me, cls, s);
-    Val* base = base_ptr<Val>(c, me, cls, s);
-    const Val* orow = row_ptr<Val>(c, o, cls, ps);
-    ADAPM_ROW_BATCHES(g, len) {
-      Val S[kRowBatch], b[kRowBatch];
-      ADAPM_ROW_ELEMS(g, len, u, i) S[u] = mem::ld_relaxed(orow + i);
-      ADAPM_ROW_ELEMS(g, len, u, i) b[u] = mem::ld_relaxed(base + i);
-      ADAPM_ROW_ELEMS(g, len, u, i) {
-        if (S[u] != b[u]) { mem::red_add(row + i, (Val)(S[u] - b[u])); mem::st_relaxed(base + i, S[u]); }
-      }
-    }
+    row_fold<Val>(g, row_ptr<Val>(c, me, cls, s), base_ptr<Val>(c, me, cls, s), row_ptr<Val>(c, o, cls, ps), len, true,
+                  (bool*)nullptr);
     mem::fence(); g.sync();
     if (g.lane() == 0) {
       mem::st_relaxed(ver_seen_of(c, me) + s, v);
@@ -642,17 +807,8 @@ ADAPM_HD void phase_c_slot(const Ctx& c, const G& g, uint32_t s, const RoundPara
     int32_t ps = -1;
     if (o != me) ps = g.bcast(g.lane() == 0 ? mem::ld_relaxed(slot_of(c, o) + key) : 0);
     if (ps >= 0) {
-      Val* row = row_ptr<Val>(c, me, cls, s);
-      Val* base = base_ptr<Val>(c, me, cls, s);
-      Val* orow = row_ptr<Val>(c, o, cls, ps);
-      bool nz = false;
-      ADAPM_ROW_BATCHES(g, len) {
-        Val v[kRowBatch];
-        ADAPM_ROW_ELEMS(g, len, u, i) v[u] = mem::ld_relaxed(row + i);
-        ADAPM_ROW_ELEMS(g, len, u, i) v[u] -= mem::ld_relaxed(base + i);
-        ADAPM_ROW_ELEMS(g, len, u, i) if (v[u] != (Val)0) { mem::red_add(orow + i, v[u]); nz = true; }
-      }
-      nz = g.any(nz);
+      const bool nz = row_ship<Val>(g, row_ptr<Val>(c, me, cls, s), base_ptr<Val>(c, me, cls, s),
+                                    row_ptr<Val>(c, o, cls, ps), len, false);
       if (nz && g.lane() == 0) mem::red_add(version_of(c, o) + ps, 1u);
     } else if (g.lane() == 0) {
       count(c, C_PROTOCOL_ERRORS);

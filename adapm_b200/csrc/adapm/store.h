@@ -108,10 +108,12 @@ inline Layout build_layout(const ValueSpec& spec, const Options& opt, std::vecto
   L.off_flags = take((uint64_t)L.total_slots);
   L.off_dirty = take((uint64_t)L.total_slots);
   L.off_want_owner = take((uint64_t)L.total_slots);
+  L.off_peer_slot = take((uint64_t)L.total_slots * 4);
   L.off_free_top = take(MAX_CLASSES * 4);
   L.off_counters = take(C_NUM_COUNTERS * 8);
   L.locality_stats = opt.locality_stats ? 1u : 0u;
   L.off_access = opt.locality_stats ? take((uint64_t)L.num_keys * 8) : 0;
+  L.off_sync = take(sizeof(SyncArea));
   for (int c = 0; c < L.num_classes; ++c) {
     uint64_t row_bytes = (uint64_t)L.cls[c].len * L.val_bytes;
     L.cls[c].rows_off = take((uint64_t)L.cls[c].cap * row_bytes);
@@ -127,6 +129,7 @@ struct OpResult {
   uint64_t n_local = 0;
   uint64_t n_remote = 0;
   uint64_t n_failed = 0;
+  uint64_t n_retry = 0;   // Set only: keys whose relocation is in flight - repeat them after the next sync round
 };
 
 // Where the caller's key/value buffers live and how the op is ordered.
@@ -139,6 +142,20 @@ struct IoDesc {
   bool has_stream = false;   // false: use the worker's own stream
   void* stream = nullptr;    // cudaStream_t (0 is the legacy default stream, hence has_stream)
   const int64_t* offsets = nullptr;  // device path on mixed-length stores: value offset of every key (device ptr)
+};
+
+// A whole sync round as one request (backends whose rounds run without host sequencing, see has_fused_round).
+struct RoundRequest {
+  RoundParams rp;            // rp.sweep is decided by the backend (any rank's want_sweep)
+  const IntentRec* recs = nullptr;
+  size_t n_recs = 0;
+  uint8_t* status = nullptr; // [n_recs] 0 registered, 1 deferred, 2 dropped
+  bool want_stop = false;    // this rank would like to leave the round loop
+  bool want_sweep = false;   // this rank needs a guaranteed-propagation round (WaitSync)
+};
+struct RoundOutcome {
+  bool all_stop = false;     // every rank wanted to stop: nothing was done, leave the loop
+  bool any_sweep = false;
 };
 
 // One backend instance per rank. Thread-safety: worker ops may be called concurrently from
@@ -158,8 +175,11 @@ class Backend {
   // Return value: 0 = completed inline, otherwise a ticket for wait_ticket()/ticket_done().
   virtual uint64_t pull(int worker, const Key* keys, size_t n, void* vals, bool local_only, uint8_t* ok,
                         OpResult* res, const IoDesc& io) = 0;
+  // `todo` (Set with retry, host array of n bytes or nullptr): only keys with todo[i] != 0 are processed; completed
+  // keys are cleared, keys that must be repeated after the next sync round stay set (res->n_retry of them). With
+  // `todo` the op is synchronous on every backend.
   virtual uint64_t push(int worker, const Key* keys, size_t n, const void* vals, bool set, OpResult* res,
-                        const IoDesc& io) = 0;
+                        const IoDesc& io, uint8_t* todo = nullptr) = 0;
   virtual void wait_ticket(uint64_t) {}
   virtual bool ticket_done(uint64_t) { return true; }
   virtual void wait_worker(int /*worker*/) {}   // all ops issued by this worker are complete
@@ -176,6 +196,10 @@ class Backend {
   virtual void round_fence() = 0;   // wait until the round work issued so far is complete and visible
   // Grace period: returns when every worker op of THIS rank that started before the call is done.
   virtual void grace() = 0;
+  // Device-resident round: stop/sweep agreement, the barriers between the phases and the grace period all happen
+  // inside the backend (cuda: on the device, one enqueue per round); the sync thread only feeds intents.
+  virtual bool has_fused_round() const { return false; }
+  virtual RoundOutcome fused_round(const RoundRequest&) { throw Error("this backend has no fused round"); }
   virtual void read_counters(uint64_t* out) = 0;
   virtual void reset_counters() = 0;
   // copy `bytes` at heap offset `off` of THIS rank into host memory (statistics / debugging)

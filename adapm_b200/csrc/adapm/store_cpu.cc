@@ -85,24 +85,30 @@ class CpuBackend : public Backend {
   }
 
   uint64_t push(int worker, const Key* keys, size_t n, const void* vals, bool set, OpResult* res,
-                const IoDesc& io) override {
+                const IoDesc& io, uint8_t* todo) override {
     ADAPM_CHECK(!io.on_device, "the cpu backend takes host pointers");
     OpGuard guard(op_seq_[worker]);
     HostGroup g;
     const Val* in = reinterpret_cast<const Val*>(vals);
-    uint64_t nl = 0, nr = 0, nf = 0;
+    uint64_t nl = 0, nr = 0, nf = 0, nretry = 0;
     for (size_t i = 0; i < n; ++i) {
       const Key key = keys[i];
       ADAPM_CHECK(key >= 0 && key < ctx_.L.num_keys, "[ERROR] Push key " << key << ", which is outside the configured key range [0," << ctx_.L.num_keys << ")");
       bool local = false;
-      bool good = set ? set_key<Val>(ctx_, g, key, in, &local) : push_key<Val>(ctx_, g, key, in, &local);
-      if (!good) ++nf; else if (local) ++nl; else ++nr;
+      if (!todo || todo[i]) {
+        int good = set ? set_key<Val>(ctx_, g, key, in, &local) : (push_key<Val>(ctx_, g, key, in, &local) ? SET_OK : SET_FAIL);
+        if (good == SET_RETRY && todo) ++nretry;
+        else {
+          if (todo) todo[i] = 0;
+          if (good != SET_OK) ++nf; else if (local) ++nl; else ++nr;
+        }
+      }
       in += ctx_.L.cls[class_of_key(ctx_, key)].len;
     }
     mem::fence();
     count(ctx_, C_PUSH_LOCAL, nl);
     count(ctx_, C_PUSH_REMOTE, nr);
-    if (res) { res->n_local = nl; res->n_remote = nr; res->n_failed = nf; }
+    if (res) { res->n_local = nl; res->n_remote = nr; res->n_failed = nf; res->n_retry = nretry; }
     return 0;
   }
 

@@ -263,7 +263,73 @@ void SyncEngine::round(bool sweep) {
   if (server_->tracing()) server_->observe_traced_keys();
 }
 
+// The same loop for backends that run a whole round by themselves (cuda: device-side barriers, grace period and
+// stop/sweep agreement - the round is one enqueue): this thread only feeds intents and reads the outcome back.
+void SyncEngine::loop_fused() {
+  const Options& opt = server_->options();
+  Backend& be = server_->backend();
+  RankControl& rc = server_->my_control();
+  sw_total_.start();
+  for (;;) {
+    sw_pausing_.resume();
+    const bool urgent = rc.sweep_requested.load() > 0 || rc.stop_requested.load() > 0;
+    if (round_no_ > 0 && !urgent) {
+      if (opt.sync_pause_ms > 0) {
+        std::this_thread::sleep_for(std::chrono::milliseconds(opt.sync_pause_ms));
+      } else if (opt.sync_max_per_sec > 0) {
+        auto target = last_run_ + std::chrono::nanoseconds((int64_t)(1e9 / opt.sync_max_per_sec));
+        if (std::chrono::steady_clock::now() < target) std::this_thread::sleep_until(target);
+      }
+    }
+    last_run_ = std::chrono::steady_clock::now();
+    sw_pausing_.stop();
+
+    RoundRequest rq;
+    rq.want_stop = rc.stop_requested.load(std::memory_order_acquire) != 0;
+    rq.want_sweep = rc.sweep_requested.load(std::memory_order_acquire) > 0;
+    std::vector<Clock> clocks = server_->worker_clocks();
+    std::vector<Clock> windows(clocks.size(), WINDOW_MAX);
+    if (opt.time_intent_actions) windows = timer_.estimate_windows_and_tune(clocks, round_no_.load(std::memory_order_relaxed));
+    memset(&rq.rp, 0, sizeof(rq.rp));
+    for (size_t w = 0; w < clocks.size(); ++w) rq.rp.clocks[w] = clocks[w];
+    rq.rp.threshold = opt.sync_threshold;
+    rq.rp.round_no = (uint32_t)round_no_.load(std::memory_order_relaxed);
+    rq.rp.sweep_period = opt.sweep_period;
+    rq.rp.idle_period = opt.idle_period;
+
+    sw_register_.resume();
+    sw_collect_.resume();
+    collect_intents(clocks, windows);
+    sw_collect_.stop();
+    sw_register_.stop();
+    status_.assign(recs_.size(), 0);
+    rq.recs = recs_.data();
+    rq.n_recs = recs_.size();
+    rq.status = status_.data();
+
+    sw_phase_a_.resume();   // (the whole device round is accounted here)
+    RoundOutcome out = be.fused_round(rq);
+    sw_phase_a_.stop();
+    if (out.all_stop) break;
+    for (size_t i = 0; i < recs_.size(); ++i) {
+      if (status_[i] == 1) deferred_.push_back(recs_[i]);
+      else if (status_[i] == 0) ++recs_registered_;
+    }
+    deferred_pending_.store(deferred_.size(), std::memory_order_release);
+    if (server_->tracing()) server_->observe_traced_keys();
+
+    if (rq.want_sweep) {
+      int32_t cur = rc.sweep_requested.load();
+      while (cur > 0 && !rc.sweep_requested.compare_exchange_weak(cur, cur - 1)) {}
+    }
+    ++round_no_;
+    rc.rounds_done.fetch_add(1, std::memory_order_acq_rel);
+  }
+  sw_total_.stop();
+}
+
 void SyncEngine::loop() {
+  if (server_->backend().has_fused_round()) { fused_ = true; loop_fused(); return; }
   const Options& opt = server_->options();
   ControlBlock* ctl = server_->control();
   RankControl& rc = server_->my_control();
@@ -317,7 +383,7 @@ std::string SyncEngine::report() const {
      << (tot > 0 ? rounds / tot : 0) << "/s), intents " << intents_seen_.load() << " (" << recs_registered_.load()
      << " key registrations), clocks/round estimate " << timer_.avg_estimate() << "; time: pausing "
      << sw_pausing_.elapsed_s() << "s, register " << sw_register_.elapsed_s() << "s (of which host-side intent collection "
-     << sw_collect_.elapsed_s() << "s), phaseA "
+     << sw_collect_.elapsed_s() << "s), " << (fused_ ? "device round (enqueue + wait) " : "phaseA ")
      << sw_phase_a_.elapsed_s() << "s, phaseB " << sw_phase_b_.elapsed_s() << "s, grace " << sw_grace_.elapsed_s()
      << "s, phaseC " << sw_phase_c_.elapsed_s() << "s, barriers " << sw_barriers_.elapsed_s() << "s";
   return os.str();

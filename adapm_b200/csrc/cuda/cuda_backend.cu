@@ -58,6 +58,7 @@ pull_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ keys, size_t 
             const int64_t* __restrict__ offsets, uint32_t uniform_len, int local_only, uint8_t* ok,
             unsigned long long* result) {
   WarpGroup g;
+  dev::cta_enter(c);
   const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
   unsigned nl = 0, nr = 0, nf = 0;
@@ -95,25 +96,32 @@ pull_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ keys, size_t 
     uint64_t* cn = counters_of(c, c.rank);
     if (nl) atomicAdd((unsigned long long*)(cn + C_PULL_LOCAL), (unsigned long long)nl);
     if (nr) atomicAdd((unsigned long long*)(cn + C_PULL_REMOTE), (unsigned long long)nr);
-    if (nf) atomicAdd((unsigned long long*)(cn + C_PROTOCOL_ERRORS), (unsigned long long)nf);
+    // a local_only miss (PullIfLocal, local sampling) is an ordinary outcome, not a protocol error (cpu backend: same)
+    if (nf && !local_only) atomicAdd((unsigned long long*)(cn + C_PROTOCOL_ERRORS), (unsigned long long)nf);
   }
+  dev::cta_exit(c);
 }
 
 // ------------------------------------------------------------------------------ K2
 __global__ void __launch_bounds__(kThreads)
 push_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ keys, size_t n, const float* __restrict__ vals,
-            const int64_t* __restrict__ offsets, uint32_t uniform_len, int set, unsigned long long* result) {
+            const int64_t* __restrict__ offsets, uint32_t uniform_len, int set, unsigned long long* result,
+            uint8_t* __restrict__ todo) {
   WarpGroup g;
+  dev::cta_enter(c);
   const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
-  unsigned nl = 0, nr = 0, nf = 0;
+  unsigned nl = 0, nr = 0, nf = 0, nretry = 0;
   for (size_t i = warp; i < n; i += nwarps) {
+    if (todo && !todo[i]) continue;   // Set with retry: this key is already done
     const Key key = keys[i];
     const float* v = vals + (offsets ? (size_t)offsets[i] : i * (size_t)uniform_len);
     bool good = false, local = false;
     if (key >= 0 && key < c.L.num_keys) {
       if (set) {
-        good = set_key<float>(c, g, key, v, &local);
+        const int r = set_key<float>(c, g, key, v, &local);
+        if (r == SET_RETRY && todo) { ++nretry; continue; }   // relocation in flight: the host repeats it after a round
+        good = r == SET_OK;
       } else {
         const uint32_t len = c.L.cls[class_of_key(c, key)].len;
         PushLoc<float> loc = locate_push<float>(c, g, key);
@@ -133,6 +141,7 @@ push_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ keys, size_t 
         }
       }
     }
+    if (todo && g.lane() == 0) todo[i] = 0;
     if (!good) ++nf; else if (local) ++nl; else ++nr;
   }
   if (g.lane() == 0) {
@@ -140,12 +149,14 @@ push_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ keys, size_t 
       if (nl) atomicAdd(result + 0, (unsigned long long)nl);
       if (nr) atomicAdd(result + 1, (unsigned long long)nr);
       if (nf) atomicAdd(result + 2, (unsigned long long)nf);
+      if (nretry) atomicAdd(result + 3, (unsigned long long)nretry);
     }
     uint64_t* cn = counters_of(c, c.rank);
     if (nl) atomicAdd((unsigned long long*)(cn + C_PUSH_LOCAL), (unsigned long long)nl);
     if (nr) atomicAdd((unsigned long long*)(cn + C_PUSH_REMOTE), (unsigned long long)nr);
     if (nf) atomicAdd((unsigned long long*)(cn + C_PROTOCOL_ERRORS), (unsigned long long)nf);
   }
+  dev::cta_exit(c);
 }
 
 __global__ void peek_kernel(const __grid_constant__ Ctx c, const Key* keys, size_t n, uint8_t* state_out, uint8_t* owner_out) {
@@ -158,10 +169,15 @@ __global__ void peek_kernel(const __grid_constant__ Ctx c, const Key* keys, size
 }
 
 // ------------------------------------------------------------------------------ sync round
-__global__ void register_kernel(const __grid_constant__ Ctx c, const IntentRec* recs, size_t n, RoundParams rp, uint8_t* status) {
+// All round kernels read their parameters from a device-resident RoundDev (cuda_backend.h): the host uploads it once
+// per round, the first cross-rank barrier of the round fills in what the ranks agreed on (sweep / stop).
+__global__ void register_kernel(const __grid_constant__ Ctx c, const IntentRec* recs, const RoundDev* __restrict__ rd,
+                                uint8_t* status) {
+  if (rd->stop) return;
+  const size_t n = rd->n_recs;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  int st = register_intent<float>(c, recs[i], rp.clocks);
+  int st = register_intent<float>(c, recs[i], rd->rp.clocks);
   status[i] = (uint8_t)st;
   if (st == 0) count(c, C_INTENTS_REGISTERED);
   else if (st == 1) count(c, C_INTENTS_DEFERRED);
@@ -172,9 +188,11 @@ __global__ void register_kernel(const __grid_constant__ Ctx c, const IntentRec* 
 // would leave most warps idle), (2) one warp per worklist item, grid-strided, so that the long
 // dependent-load chains of many slots overlap.
 template <int PHASE>
-__global__ void __launch_bounds__(kThreads) phase_scan_kernel(const __grid_constant__ Ctx c, RoundParams rp,
+__global__ void __launch_bounds__(kThreads) phase_scan_kernel(const __grid_constant__ Ctx c, const RoundDev* __restrict__ rd,
                                                               uint32_t* __restrict__ worklist,
                                                               unsigned int* __restrict__ count) {
+  if (rd->stop) return;
+  const RoundParams& rp = rd->rp;
   const uint32_t S = c.L.total_slots;
   const uint32_t* meta = meta_of(c, c.rank);
   const int lane = threadIdx.x & 31;
@@ -194,14 +212,20 @@ __global__ void __launch_bounds__(kThreads) phase_scan_kernel(const __grid_const
   }
 }
 
-// 128-thread blocks: at ~80 registers one block fits into the 12 K registers per SM that the lean training kernels
+// 128-thread blocks at <= 80 registers: one block fits into the 12 K registers per SM that the lean training kernels
 // (ops_sgns_tma.cu, 104 registers x 512 threads) leave free, so the round's row work runs next to them
 constexpr int kWorkThreads = 128;
 template <int PHASE>
-__global__ void __launch_bounds__(kWorkThreads) phase_work_kernel(const __grid_constant__ Ctx c, RoundParams rp,
-                                                              const uint32_t* __restrict__ worklist,
-                                                              const unsigned int* __restrict__ count) {
+#ifndef ADAPM_WORK_MINB
+#define ADAPM_WORK_MINB 5   // <= 96 registers: 128 threads x 96 = the 12 K registers a lean training kernel leaves free per SM
+#endif
+__global__ void __launch_bounds__(kWorkThreads, ADAPM_WORK_MINB) phase_work_kernel(const __grid_constant__ Ctx c,
+                                                                  const RoundDev* __restrict__ rd,
+                                                                  const uint32_t* __restrict__ worklist,
+                                                                  const unsigned int* __restrict__ count) {
+  if (rd->stop) return;
   WarpGroup g;
+  const RoundParams& rp = rd->rp;
   const unsigned n = *count;
   const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -213,11 +237,82 @@ __global__ void __launch_bounds__(kWorkThreads) phase_work_kernel(const __grid_c
   }
 }
 
-__global__ void __launch_bounds__(kThreads) phase_b_kernel(const __grid_constant__ Ctx c, RoundParams rp) {
+__global__ void __launch_bounds__(kThreads) phase_b_kernel(const __grid_constant__ Ctx c, const RoundDev* __restrict__ rd) {
+  if (rd->stop) return;
   const uint32_t S = c.L.total_slots;
   const uint64_t* want = want_of(c, c.rank);
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x)
-    if (__ldcg(want + s) != 0) phase_b_slot(c, s, rp);
+    if (__ldcg(want + s) != 0) phase_b_slot(c, s, rd->rp);
+}
+
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Cross-rank barrier on the device (layout.h: SyncArea). One thread per rank: publish my arrival (and, for the first
+// barrier of a round, my stop/sweep request word) in that rank's area with a system-scope release store over NVLink,
+// then wait until that rank's arrival shows up in my own area. No host thread is involved: the round is ONE enqueue.
+// Every wait is bounded (timeout_ns, and the host's abort word in mapped pinned memory): a dead peer produces an
+// error code in RoundDev, never a kernel that spins forever.
+__global__ void __launch_bounds__(64) xbar_kernel(const __grid_constant__ Ctx c, uint32_t seq, uint32_t parity, RoundDev* rd,
+                                                  int gather, const volatile uint32_t* abort_word,
+                                                  unsigned long long timeout_ns) {
+  if (!gather && rd->stop) return;   // all ranks agreed to stop in the first barrier of this round
+  const int r = threadIdx.x;
+  const int me = c.rank;
+  __shared__ uint32_t failed;
+  if (r == 0) failed = 0;
+  __syncthreads();
+  if (r < c.L.world) {
+    __threadfence_system();          // everything the earlier kernels of this round wrote (anywhere) is performed
+    SyncArea* theirs = sync_area_of(c, r);
+    if (gather) mem::st_relaxed(&theirs->flag_word[parity][me], rd->my_flags);
+    mem::st_release(&theirs->bar_arrive[me], seq);
+    const uint32_t* mine = &sync_area_of(c, me)->bar_arrive[r];
+    const unsigned long long t0 = global_ns();
+    unsigned spins = 0;
+    while ((int32_t)(mem::ld_acquire(mine) - seq) < 0) {
+      __nanosleep(100);
+      if ((++spins & 63u) == 0 && ((abort_word && *abort_word) || global_ns() - t0 > timeout_ns)) { failed = 1; break; }
+    }
+  }
+  __syncthreads();
+  if (r == 0) {
+    if (failed) rd->error = 1;
+    if (gather) {
+      const uint32_t* w = sync_area_of(c, me)->flag_word[parity];
+      uint32_t all_stop = 1, any_sweep = 0;
+      for (int k = 0; k < c.L.world; ++k) {
+        const uint32_t f = mem::ld_relaxed(w + k);
+        all_stop &= f & 1u;
+        any_sweep |= (f >> 1) & 1u;
+      }
+      rd->stop = (all_stop && !failed) ? 1u : 0u;
+      rd->any_sweep = any_sweep;
+      rd->rp.sweep = (int32_t)any_sweep;
+    }
+    __threadfence_system();
+  }
+}
+
+// Grace period on the device: flip the epoch, wait until every CTA that registered on the old side (and may have
+// read the directory before phase B changed it) has left. Replaces one event record + host wait per tracked stream.
+__global__ void grace_kernel(const __grid_constant__ Ctx c, RoundDev* rd, const volatile uint32_t* abort_word,
+                             unsigned long long timeout_ns) {
+  if (rd->stop) return;
+  SyncArea* sa = sync_area_of(c, c.rank);
+  const uint32_t old = mem::ld_relaxed(&sa->epoch);
+  mem::st_release(&sa->epoch, old + 1u);
+  __threadfence();
+  const unsigned long long t0 = global_ns();
+  unsigned spins = 0;
+  while (mem::ld_acquire(&sa->active[old & 1u]) != 0u) {
+    __nanosleep(200);
+    if ((++spins & 63u) == 0 && ((abort_word && *abort_word) || global_ns() - t0 > timeout_ns)) { rd->error = 2; break; }
+  }
+  __threadfence_system();
 }
 
 }  // namespace
@@ -256,6 +351,16 @@ CudaBackend::CudaBackend(const Options& opt, const Layout& L, std::shared_ptr<Fa
   }
   ADAPM_CUDA_CHECK(cudaMalloc((void**)&worklist_, (size_t)(L.total_slots + 32) * sizeof(uint32_t)));
   ADAPM_CUDA_CHECK(cudaMalloc((void**)&work_count_, 64));
+  ADAPM_CUDA_CHECK(cudaMalloc((void**)&round_dev_, sizeof(RoundDev)));
+  ADAPM_CUDA_CHECK(cudaMemset(round_dev_, 0, sizeof(RoundDev)));
+  ADAPM_CUDA_CHECK(cudaHostAlloc((void**)&round_host_, 2 * sizeof(RoundDev), cudaHostAllocDefault));
+  memset(round_host_, 0, 2 * sizeof(RoundDev));
+  ADAPM_CUDA_CHECK(cudaHostAlloc((void**)&abort_word_, 64, cudaHostAllocMapped));
+  *abort_word_ = 0;
+  ADAPM_CUDA_CHECK(cudaEventCreateWithFlags(&round_done_, cudaEventDisableTiming));
+  fused_round_ = L.world > 1;
+  if (const char* e = getenv("ADAPM_HOST_ROUND")) fused_round_ = fused_round_ && atoi(e) == 0;
+  dev_timeout_ns_ = (unsigned long long)(std::min(opt.wait_timeout_s, 20.0) * 1e9);
 }
 
 CudaBackend::~CudaBackend() {
@@ -266,6 +371,14 @@ CudaBackend::~CudaBackend() {
   if (sync_staging_.dev) cudaFree(sync_staging_.dev);
   if (worklist_) cudaFree(worklist_);
   if (work_count_) cudaFree(work_count_);
+  if (round_dev_) cudaFree(round_dev_);
+  if (round_host_) cudaFreeHost(round_host_);
+  if (abort_word_) cudaFreeHost(abort_word_);
+  if (recs_dev_) cudaFree(recs_dev_);
+  if (recs_host_) cudaFreeHost(recs_host_);
+  if (status_dev_) cudaFree(status_dev_);
+  if (status_host_) cudaFreeHost(status_host_);
+  if (round_done_) cudaEventDestroy(round_done_);
   for (auto& kv : tickets_) cudaEventDestroy(kv.second);
   for (auto e : event_pool_) cudaEventDestroy(e);
   for (auto s : worker_streams_) cudaStreamDestroy(s);
@@ -454,7 +567,7 @@ uint64_t CudaBackend::pull(int worker, const Key* keys, size_t n, void* vals, bo
 }
 
 uint64_t CudaBackend::push(int worker, const Key* keys, size_t n, const void* vals, bool set, OpResult* res,
-                           const IoDesc& io) {
+                           const IoDesc& io, uint8_t* todo) {
   use_device();
   if (n == 0) { if (res) *res = OpResult(); return 0; }
   const Layout& L = ctx_.L;
@@ -462,11 +575,32 @@ uint64_t CudaBackend::push(int worker, const Key* keys, size_t n, const void* va
   if (io.on_device) {
     ADAPM_CHECK(uniform || io.offsets, "device-pointer push on a mixed-length store needs per-key value offsets");
     cudaStream_t s = resolve_stream(worker, io);
+    if (!todo) {
+      push_kernel<<<grid_for_warps(n, num_sms_), kThreads, 0, s>>>(ctx_, keys, n, (const float*)vals, uniform ? nullptr : io.offsets, L.cls[0].len,
+                                                                   set ? 1 : 0, nullptr, nullptr);
+      ADAPM_COUNT_LAUNCH();
+      ADAPM_CUDA_CHECK(cudaGetLastError());
+      return record_ticket(s);
+    }
+    // Set with retry: keys and values stay on the device, the todo mask and the counts go through pinned memory;
+    // synchronous (the caller decides from the counts whether to repeat after the next sync round)
+    Staging& st = *staging_[worker];
+    std::lock_guard<std::mutex> lk(st.mu);
+    const size_t o_todo = 256;
+    ensure_staging(st, o_todo + n + 256);
+    memset(st.host, 0, 64);
+    memcpy(st.host + o_todo, todo, n);
+    ADAPM_CUDA_CHECK(cudaMemcpyAsync(st.dev, st.host, o_todo + n, cudaMemcpyHostToDevice, s));
     push_kernel<<<grid_for_warps(n, num_sms_), kThreads, 0, s>>>(ctx_, keys, n, (const float*)vals, uniform ? nullptr : io.offsets, L.cls[0].len,
-                                                                 set ? 1 : 0, nullptr);
+                                                                 set ? 1 : 0, (unsigned long long*)st.dev, (uint8_t*)(st.dev + o_todo));
     ADAPM_COUNT_LAUNCH();
-  ADAPM_CUDA_CHECK(cudaGetLastError());
-    return record_ticket(s);
+    ADAPM_CUDA_CHECK(cudaGetLastError());
+    ADAPM_CUDA_CHECK(cudaMemcpyAsync(st.host, st.dev, o_todo + n, cudaMemcpyDeviceToHost, s));
+    ADAPM_CUDA_CHECK(cudaStreamSynchronize(s));
+    const unsigned long long* r = (const unsigned long long*)st.host;
+    if (res) { res->n_local = r[0]; res->n_remote = r[1]; res->n_failed = r[2]; res->n_retry = r[3]; }
+    memcpy(todo, st.host + o_todo, n);
+    return 0;
   }
   Staging& st = *staging_[worker];
   std::lock_guard<std::mutex> lk(st.mu);
@@ -487,22 +621,25 @@ uint64_t CudaBackend::push(int worker, const Key* keys, size_t n, const void* va
   const size_t o_keys = 0;
   const size_t o_offs = align_up(o_keys + n * 8, 256);
   const size_t o_res = align_up(o_offs + n * 8, 256);
-  const size_t o_vals = align_up(o_res + 64, 256);
+  const size_t o_todo = align_up(o_res + 64, 256);
+  const size_t o_vals = align_up(o_todo + (todo ? n : 0), 256);
   ensure_staging(st, o_vals + bytes_vals + 256);
   memcpy(st.host + o_keys, keys, n * 8);
   if (!uniform) memcpy(st.host + o_offs, prefix.data(), n * 8);
   memset(st.host + o_res, 0, 64);
+  if (todo) memcpy(st.host + o_todo, todo, n);
   memcpy(st.host + o_vals, vals, bytes_vals);
   ADAPM_CUDA_CHECK(cudaMemcpyAsync(st.dev, st.host, o_vals + bytes_vals, cudaMemcpyHostToDevice, s));
   push_kernel<<<grid_for_warps(n, num_sms_), kThreads, 0, s>>>(
       ctx_, (const Key*)(st.dev + o_keys), n, (const float*)(st.dev + o_vals), uniform ? nullptr : (const int64_t*)(st.dev + o_offs),
-      L.cls[0].len, set ? 1 : 0, (unsigned long long*)(st.dev + o_res));
+      L.cls[0].len, set ? 1 : 0, (unsigned long long*)(st.dev + o_res), todo ? (uint8_t*)(st.dev + o_todo) : nullptr);
   ADAPM_COUNT_LAUNCH();
   ADAPM_CUDA_CHECK(cudaGetLastError());
-  ADAPM_CUDA_CHECK(cudaMemcpyAsync(st.host + o_res, st.dev + o_res, 64, cudaMemcpyDeviceToHost, s));
+  ADAPM_CUDA_CHECK(cudaMemcpyAsync(st.host + o_res, st.dev + o_res, (o_todo - o_res) + (todo ? n : 0), cudaMemcpyDeviceToHost, s));
   ADAPM_CUDA_CHECK(cudaStreamSynchronize(s));
   const unsigned long long* r = (const unsigned long long*)(st.host + o_res);
-  if (res) { res->n_local = r[0]; res->n_remote = r[1]; res->n_failed = r[2]; }
+  if (res) { res->n_local = r[0]; res->n_remote = r[1]; res->n_failed = r[2]; res->n_retry = r[3]; }
+  if (todo) memcpy(todo, st.host + o_todo, n);
   return 0;
 }
 
@@ -531,6 +668,17 @@ bool CudaBackend::key_is_local(Key k) {
   return st == S_OWNED || st == S_REPLICA || st == S_INCOMING_REPLICA;
 }
 
+void CudaBackend::upload_round(const RoundParams& rp, uint32_t n_recs, uint32_t flags) {
+  RoundDev& h = round_host_[0];
+  h.rp = rp;
+  h.n_recs = n_recs;
+  h.my_flags = flags;
+  h.stop = 0; h.any_sweep = 0; h.error = 0;
+  ADAPM_CUDA_CHECK(cudaMemcpyAsync(round_dev_, &h, sizeof(RoundDev), cudaMemcpyHostToDevice, sync_stream_));
+}
+
+// ---- host-sequenced round (ADAPM_HOST_ROUND=1): the sync thread waits for every phase and the ranks meet at
+// control-plane barriers; the kernels are the same as in the device-resident round
 void CudaBackend::register_intents(const IntentRec* recs, size_t n, const RoundParams& rp, uint8_t* status) {
   use_device();
   if (n == 0) return;
@@ -540,8 +688,9 @@ void CudaBackend::register_intents(const IntentRec* recs, size_t n, const RoundP
   Staging& st = sync_staging_;
   memcpy(st.host, recs, n * sizeof(IntentRec));
   TraceScope ts_(this, "register", sync_stream_);
+  upload_round(rp, (uint32_t)n, 0);
   ADAPM_CUDA_CHECK(cudaMemcpyAsync(st.dev, st.host, n * sizeof(IntentRec), cudaMemcpyHostToDevice, sync_stream_));
-  register_kernel<<<(int)((n + 255) / 256), 256, 0, sync_stream_>>>(ctx_, (const IntentRec*)st.dev, n, rp, (uint8_t*)(st.dev + o_st));
+  register_kernel<<<(int)((n + 255) / 256), 256, 0, sync_stream_>>>(ctx_, (const IntentRec*)st.dev, round_dev_, (uint8_t*)(st.dev + o_st));
   ADAPM_COUNT_LAUNCH();
   ADAPM_CUDA_CHECK(cudaGetLastError());
   ADAPM_CUDA_CHECK(cudaMemcpyAsync(st.host + o_st, st.dev + o_st, n, cudaMemcpyDeviceToHost, sync_stream_));
@@ -549,32 +698,117 @@ void CudaBackend::register_intents(const IntentRec* recs, size_t n, const RoundP
   memcpy(status, st.host + o_st, n);
 }
 
+void CudaBackend::launch_phase(int phase) {
+  if (phase == 1) {
+    TraceScope ts_(this, "phaseB", sync_stream_);
+    phase_b_kernel<<<num_sms_ * scan_blocks_per_sm_, kThreads, 0, sync_stream_>>>(ctx_, round_dev_);
+    ADAPM_COUNT_LAUNCH();
+    ADAPM_CUDA_CHECK(cudaGetLastError());
+    return;
+  }
+  TraceScope ts_(this, phase == 0 ? "phaseA" : "phaseC", sync_stream_);
+  ADAPM_CUDA_CHECK(cudaMemsetAsync(work_count_, 0, sizeof(unsigned int), sync_stream_));
+  if (phase == 0) {
+    phase_scan_kernel<0><<<num_sms_ * scan_blocks_per_sm_, kThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, work_count_);
+    phase_work_kernel<0><<<num_sms_ * work_blocks_per_sm_, kWorkThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, work_count_);
+  } else {
+    phase_scan_kernel<1><<<num_sms_ * scan_blocks_per_sm_, kThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, work_count_);
+    phase_work_kernel<1><<<num_sms_ * work_blocks_per_sm_, kWorkThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, work_count_);
+  }
+  ADAPM_COUNT_LAUNCH();
+  ADAPM_COUNT_LAUNCH();
+  ADAPM_CUDA_CHECK(cudaGetLastError());
+}
+
 void CudaBackend::phase_a(const RoundParams& rp) {
   use_device();
-  TraceScope ts_(this, "phaseA", sync_stream_);
-  ADAPM_CUDA_CHECK(cudaMemsetAsync(work_count_, 0, sizeof(unsigned int), sync_stream_));
-  phase_scan_kernel<0><<<num_sms_ * scan_blocks_per_sm_, kThreads, 0, sync_stream_>>>(ctx_, rp, worklist_, work_count_);
-  ADAPM_COUNT_LAUNCH();
-  phase_work_kernel<0><<<num_sms_ * work_blocks_per_sm_, kWorkThreads, 0, sync_stream_>>>(ctx_, rp, worklist_, work_count_);
-  ADAPM_COUNT_LAUNCH();
-  ADAPM_CUDA_CHECK(cudaGetLastError());
+  upload_round(rp, 0, 0);
+  launch_phase(0);
 }
-void CudaBackend::phase_b(const RoundParams& rp) {
+void CudaBackend::phase_b(const RoundParams&) {
   use_device();
-  TraceScope ts_(this, "phaseB", sync_stream_);
-  phase_b_kernel<<<num_sms_ * scan_blocks_per_sm_, kThreads, 0, sync_stream_>>>(ctx_, rp);
-  ADAPM_COUNT_LAUNCH();
-  ADAPM_CUDA_CHECK(cudaGetLastError());
+  launch_phase(1);
 }
-void CudaBackend::phase_c(const RoundParams& rp) {
+void CudaBackend::phase_c(const RoundParams&) {
   use_device();
-  TraceScope ts_(this, "phaseC", sync_stream_);
-  ADAPM_CUDA_CHECK(cudaMemsetAsync(work_count_, 0, sizeof(unsigned int), sync_stream_));
-  phase_scan_kernel<1><<<num_sms_ * scan_blocks_per_sm_, kThreads, 0, sync_stream_>>>(ctx_, rp, worklist_, work_count_);
-  ADAPM_COUNT_LAUNCH();
-  phase_work_kernel<1><<<num_sms_ * work_blocks_per_sm_, kWorkThreads, 0, sync_stream_>>>(ctx_, rp, worklist_, work_count_);
-  ADAPM_COUNT_LAUNCH();
+  launch_phase(2);
+}
+
+// ---- device-resident round: ONE enqueue per round, nothing in it waits for the host.
+//   upload {params, intent records} -> barrier 1 (+ stop/sweep agreement) -> register -> phase A -> barrier 2 ->
+//   phase B -> barrier 3 -> grace (epoch flip + drain) -> barrier 4 -> phase C -> download {agreement, status}
+// The ranks run the same sequence in lock-step; the barrier numbers derive from the round count.
+RoundOutcome CudaBackend::fused_round(const RoundRequest& rq) {
+  use_device();
+  cudaStream_t s = sync_stream_;
+  const size_t n = rq.n_recs;
+  if (n > recs_cap_) {
+    const size_t cap = std::max<size_t>(2 * n, 1 << 16);
+    if (recs_dev_) { cudaFree(recs_dev_); cudaFreeHost(recs_host_); cudaFree(status_dev_); cudaFreeHost(status_host_); }
+    ADAPM_CUDA_CHECK(cudaMalloc((void**)&recs_dev_, cap * sizeof(IntentRec)));
+    ADAPM_CUDA_CHECK(cudaHostAlloc((void**)&recs_host_, cap * sizeof(IntentRec), cudaHostAllocDefault));
+    ADAPM_CUDA_CHECK(cudaMalloc((void**)&status_dev_, cap));
+    ADAPM_CUDA_CHECK(cudaHostAlloc((void**)&status_host_, cap, cudaHostAllocDefault));
+    recs_cap_ = cap;
+  }
+  upload_round(rq.rp, (uint32_t)n, (rq.want_stop ? 1u : 0u) | (rq.want_sweep ? 2u : 0u));
+  if (n) {
+    memcpy(recs_host_, rq.recs, n * sizeof(IntentRec));
+    ADAPM_CUDA_CHECK(cudaMemcpyAsync(recs_dev_, recs_host_, n * sizeof(IntentRec), cudaMemcpyHostToDevice, s));
+  }
+  const uint32_t seq0 = (uint32_t)(fused_rounds_ * 4);
+  const uint32_t parity = (uint32_t)(fused_rounds_ & 1);
+  uint32_t* abort_dev = nullptr;
+  ADAPM_CUDA_CHECK(cudaHostGetDevicePointer((void**)&abort_dev, abort_word_, 0));
+  auto xbar = [&](uint32_t k, int gather) {
+    TraceScope ts_(this, "xbar", s);
+    xbar_kernel<<<1, 64, 0, s>>>(ctx_, seq0 + k, parity, round_dev_, gather, abort_dev, dev_timeout_ns_);
+    ADAPM_COUNT_LAUNCH();
+  };
+  xbar(1, 1);
+  if (n) {
+    TraceScope ts_(this, "register", s);
+    register_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(ctx_, recs_dev_, round_dev_, status_dev_);
+    ADAPM_COUNT_LAUNCH();
+  }
+  launch_phase(0);
+  xbar(2, 0);
+  launch_phase(1);
+  xbar(3, 0);
+  {
+    TraceScope ts_(this, "grace", s);
+    grace_kernel<<<1, 1, 0, s>>>(ctx_, round_dev_, abort_dev, dev_timeout_ns_);
+    ADAPM_COUNT_LAUNCH();
+  }
+  xbar(4, 0);
+  launch_phase(2);
   ADAPM_CUDA_CHECK(cudaGetLastError());
+  ADAPM_CUDA_CHECK(cudaMemcpyAsync(&round_host_[1], round_dev_, sizeof(RoundDev), cudaMemcpyDeviceToHost, s));
+  if (n) ADAPM_CUDA_CHECK(cudaMemcpyAsync(status_host_, status_dev_, n, cudaMemcpyDeviceToHost, s));
+  ADAPM_CUDA_CHECK(cudaEventRecord(round_done_, s));
+  ++fused_rounds_;
+  // wait for the round; a failed peer (the failure detector breaks the control-plane barriers) aborts the device waits
+  ControlBlock* ctl = fabric_->control();
+  unsigned spins = 0;
+  for (;;) {
+    cudaError_t e = cudaEventQuery(round_done_);
+    if (e == cudaSuccess) break;
+    if (e != cudaErrorNotReady) ADAPM_CUDA_CHECK(e);
+    if (++spins < 2000) std::this_thread::yield();
+    else std::this_thread::sleep_for(std::chrono::microseconds(20));
+    if ((spins & 255u) == 0 && ctl->sync_barrier.broken.load(std::memory_order_relaxed)) *abort_word_ = 1;
+  }
+  const RoundDev& res = round_host_[1];
+  if (res.error) {
+    ctl->sync_barrier.broken.store(1);
+    throw Error(res.error == 1 ? "sync round: a device-side cross-rank barrier timed out or was aborted (a peer died or hangs)"
+                               : "sync round: the grace period did not end (a kernel that touches the store hangs)");
+  }
+  if (n && rq.status) memcpy(rq.status, status_host_, n);
+  RoundOutcome out;
+  out.all_stop = res.stop != 0;
+  out.any_sweep = res.any_sweep != 0;
+  return out;
 }
 // ---------------------------------------------------------------------------------------- kernel timeline
 CudaBackend::TraceScope::TraceScope(CudaBackend* be, const char* name, cudaStream_t st) : b(be), idx(-1), s(st) {

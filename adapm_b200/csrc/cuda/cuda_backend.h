@@ -18,6 +18,18 @@ namespace adapm {
 std::atomic<uint64_t>& kernel_launch_counter();
 #define ADAPM_COUNT_LAUNCH() (::adapm::kernel_launch_counter().fetch_add(1, std::memory_order_relaxed))
 
+// Device-resident parameters and results of the round in flight: uploaded by the host once per round; the first
+// cross-rank barrier of the round fills in what the ranks agreed on.
+struct RoundDev {
+  RoundParams rp;
+  uint32_t n_recs;
+  uint32_t my_flags;    // in : bit 0 = this rank wants to stop, bit 1 = this rank wants a guaranteed-propagation round
+  uint32_t stop;        // out: every rank wants to stop -> the rest of the round is skipped on all ranks
+  uint32_t any_sweep;   // out
+  uint32_t error;       // out: 1 = a cross-rank barrier, 2 = the grace period timed out / was aborted
+  uint32_t pad[3];
+};
+
 class CudaBackend : public Backend {
  public:
   CudaBackend(const Options& opt, const Layout& L, std::shared_ptr<Fabric> fabric);
@@ -30,7 +42,7 @@ class CudaBackend : public Backend {
   uint64_t pull(int worker, const Key* keys, size_t n, void* vals, bool local_only, uint8_t* ok, OpResult* res,
                 const IoDesc& io) override;
   uint64_t push(int worker, const Key* keys, size_t n, const void* vals, bool set, OpResult* res,
-                const IoDesc& io) override;
+                const IoDesc& io, uint8_t* todo = nullptr) override;
   void wait_ticket(uint64_t t) override;
   bool ticket_done(uint64_t t) override;
   void wait_worker(int worker) override;
@@ -43,6 +55,8 @@ class CudaBackend : public Backend {
   void phase_c(const RoundParams& rp) override;
   void round_fence() override;
   void grace() override;
+  bool has_fused_round() const override { return fused_round_; }
+  RoundOutcome fused_round(const RoundRequest& rq) override;
   void read_counters(uint64_t* out) override;
   void reset_counters() override;
   void read_heap(uint64_t off, void* dst, size_t bytes) override;
@@ -105,6 +119,21 @@ class CudaBackend : public Backend {
   uint64_t next_ticket_ = 1;
   uint32_t* worklist_ = nullptr;       // slots that need work in the current phase (device)
   unsigned int* work_count_ = nullptr;
+  // device-resident round (default for world > 1; ADAPM_HOST_ROUND=1 selects the host-sequenced round)
+  void upload_round(const RoundParams& rp, uint32_t n_recs, uint32_t flags);
+  void launch_phase(int phase);   // 0 = A, 1 = B, 2 = C
+  bool fused_round_ = false;
+  RoundDev* round_dev_ = nullptr;      // device
+  RoundDev* round_host_ = nullptr;     // pinned: [0] = upload staging, [1] = results
+  uint32_t* abort_word_ = nullptr;     // pinned + mapped: set by the host to break device-side waits
+  IntentRec* recs_dev_ = nullptr;
+  IntentRec* recs_host_ = nullptr;     // pinned
+  uint8_t* status_dev_ = nullptr;
+  uint8_t* status_host_ = nullptr;     // pinned
+  size_t recs_cap_ = 0;
+  cudaEvent_t round_done_ = nullptr;
+  uint64_t fused_rounds_ = 0;          // barrier sequence numbers derive from it (same on every rank)
+  unsigned long long dev_timeout_ns_ = 20ull * 1000000000ull;
   std::vector<uint32_t> key_len_;   // host mirror of per-key lengths (mixed-length stores only)
 };
 

@@ -14,6 +14,7 @@ struct WarpGroup {
   __device__ __forceinline__ uint64_t bcast(uint64_t v) const {
     return (uint64_t)__shfl_sync(0xffffffffu, (unsigned long long)v, 0);
   }
+  __device__ __forceinline__ uint32_t bcast_from(uint32_t v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
   __device__ __forceinline__ double sum(double v) const {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -44,6 +44,7 @@ gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   const int lane = threadIdx.x & 31;
   const int tile_n = blockIdx.x, tile_m = blockIdx.y;
   const int num_kb = (K + BK_ELEMS - 1) / BK_ELEMS;
+  dev::cta_enter(c);   // the gather warps read store rows through the directory: count this CTA in the grace epoch
 
   if (warp == 1 && lane == 0) {
     // full: 1 arrival (TMA expect_tx for the Q tile) + 4 arrivals (one per gather warp)
@@ -176,6 +177,7 @@ gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
   }
+  dev::cta_exit(c);
 }
 
 template <int EPI>

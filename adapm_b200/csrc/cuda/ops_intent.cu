@@ -25,6 +25,7 @@ __global__ void __launch_bounds__(256)
 intent_prepass_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ keys, int64_t n, Clock end, int worker,
                       Key* __restrict__ out_keys, unsigned int* __restrict__ out_count) {
   const int lane = threadIdx.x & 31;
+  dev::cta_enter(c);
   for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x; i0 < n; i0 += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i = i0 + threadIdx.x;
     bool need = false;
@@ -42,6 +43,7 @@ intent_prepass_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ key
       if (need) out_keys[base + __popc(mask & ((1u << lane) - 1u))] = k;
     }
   }
+  dev::cta_exit(c);
 }
 
 }  // namespace

@@ -93,6 +93,7 @@ kge_step_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ subj, con
                 const Key* __restrict__ obj, const float* __restrict__ labels, int n_calls, int nh, float eta,
                 float gamma_e, float gamma_r, float* __restrict__ loss_out, unsigned long long* __restrict__ stats) {
   extern __shared__ float smem_f[];  // generic path: per warp 6*nh floats
+  dev::cta_enter(c);
   const int lane = threadIdx.x & 31;
   const int warp_in_block = threadIdx.x >> 5;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -185,6 +186,7 @@ kge_step_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ subj, con
     if (n_slow) atomicAdd(stats + 2, (unsigned long long)n_slow);
     if (n_upd) atomicAdd(stats + 3, (unsigned long long)n_upd);
   }
+  dev::cta_exit(c);
 }
 
 }  // namespace

@@ -50,6 +50,7 @@ mf_step_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ row_keys, 
                const float* __restrict__ xs, const int* __restrict__ row_nnz, const int* __restrict__ col_nnz, int n,
                int rank, float eps, float lambda, float* __restrict__ loss_out, unsigned long long* __restrict__ stats) {
   extern __shared__ float smem_f[];
+  dev::cta_enter(c);
   const int lane = threadIdx.x & 31;
   const int warp_in_block = threadIdx.x >> 5;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -129,6 +130,7 @@ mf_step_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ row_keys, 
     if (n_slow) atomicAdd(stats + 2, (unsigned long long)n_slow);
     if (n_upd) atomicAdd(stats + 3, (unsigned long long)n_upd);
   }
+  dev::cta_exit(c);
 }
 
 }  // namespace

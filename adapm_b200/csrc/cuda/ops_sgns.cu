@@ -80,6 +80,7 @@ sgns_step_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ centers,
                  const Key* __restrict__ negatives, int n_pairs, int neg, int d, float alpha,
                  float* __restrict__ loss_out, unsigned long long* __restrict__ stats) {
   extern __shared__ float smem_f[];  // slow-path scratch: per warp 4*d floats
+  dev::cta_enter(c);
   const int lane = threadIdx.x & 31;
   const int warp_in_block = threadIdx.x >> 5;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -291,6 +292,7 @@ sgns_step_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ centers,
     if (n_slow) atomicAdd(stats + 2, (unsigned long long)n_slow);
     if (n_upd) atomicAdd(stats + 3, (unsigned long long)n_upd);
   }
+  dev::cta_exit(c);
 }
 
 }  // namespace

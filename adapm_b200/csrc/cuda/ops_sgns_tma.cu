@@ -105,6 +105,7 @@ sgns_step_tma_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ cent
   // per warp: RING row buffers of 2*d floats (16-byte aligned) | generic-path scratch is carved from the ring
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ WarpSmem wsm[kWarps];
+  dev::cta_enter(c);
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -358,6 +359,7 @@ sgns_step_tma_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ cent
     if (n_slow) atomicAdd(stats + 2, (unsigned long long)n_slow);
     if (n_upd) atomicAdd(stats + 3, (unsigned long long)n_upd);
   }
+  dev::cta_exit(c);
 }
 
 }  // namespace

@@ -26,6 +26,40 @@ __device__ __forceinline__ void red_row4(float* p, float4 v) {
                : "memory");
 }
 
+// Grace-period registration (layout.h: SyncArea). Every CTA of a kernel that reads the directory / touches rows brackets
+// its work with cta_enter / cta_exit: it is counted in active[epoch & 1] while it runs. The sync round flips the epoch
+// after it announced new owners (phase B) and waits until the old side has drained: everything that may still act on
+// the old directory is done before the relocation transfers start (phase C). One atomic pair per CTA; nothing on a
+// single-rank store. All threads of the CTA must call both (they contain __syncthreads()).
+__device__ __forceinline__ uint32_t& cta_epoch_ref() {
+  __shared__ uint32_t cta_epoch_;
+  return cta_epoch_;
+}
+// (out of line on purpose: the fused kernels sit exactly at their register budget)
+static __device__ __noinline__ void cta_register(SyncArea* sa) {
+  for (;;) {
+    const uint32_t e = mem::ld_acquire(&sa->epoch);
+    atomicAdd(&sa->active[e & 1u], 1u);
+    __threadfence();
+    if (mem::ld_acquire(&sa->epoch) == e) { cta_epoch_ref() = e; break; }
+    atomicSub(&sa->active[e & 1u], 1u);   // the round flipped the epoch in between: register on the new side
+  }
+}
+__device__ __forceinline__ void cta_deregister(SyncArea* sa) {
+  __threadfence_system();   // this CTA's reductions (local or NVLink) are performed before it counts as gone
+  atomicSub(&sa->active[cta_epoch_ref() & 1u], 1u);
+}
+__device__ __forceinline__ void cta_enter(const Ctx& c) {
+  if (c.L.world == 1) return;
+  if (threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0) cta_register(sync_area_of(c, c.rank));
+  __syncthreads();
+}
+__device__ __forceinline__ void cta_exit(const Ctx& c) {
+  if (c.L.world == 1) return;
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0) cta_deregister(sync_area_of(c, c.rank));
+}
+
 // Warp-cooperative: where does `key` live for a read? Wraps protocol.h's locate_pull and
 // returns raw pointers. All lanes get the same answer.
 struct RowRef {

@@ -4,6 +4,10 @@ import sys
 import pytest
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+# Several logical ranks share ONE GPU in the gpu tests, each with its own sync stream whose device-side barrier kernel
+# waits for the other ranks' kernels: give every stream its own hardware queue (default 8 connections would let one
+# rank's kernels queue up behind another rank's waiting barrier). Must be set before CUDA initialises.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 
 def pytest_configure(config):

@@ -112,3 +112,56 @@ def test_set_operation(mode):
     res = run_cluster(_set_worker, world=4, workers=2, mode=mode, value_lengths=2, num_keys=20, dtype="int64")
     errs = [e for r in res.values() for k, v in r.items() if k != "counters" for e in v]
     assert not errs, "\n".join(errs)
+
+
+# ---- Set while the keys are moving (round-1 advisor finding: Set used to spin for a state that only phase C of the
+# sync round produces, inside an op that the round's grace period waits for). Two ranks pass a block of keys back and
+# forth with intents, the third one assigns them all the time: every Set must complete (no protocol error), and the
+# value read afterwards is the last assignment.
+SET_KEYS = 64
+
+
+def _set_under_relocation_worker(kv, server, wid):
+    rank = server.my_rank()
+    keys = torch.arange(SET_KEYS, dtype=torch.int64)
+    errors = []
+    kv.barrier()
+    if rank < 2:
+        for it in range(300):
+            if (it % 2) == rank:
+                kv.intent(keys, kv.current_clock(), kv.current_clock() + 3)
+            for _ in range(3):
+                kv.advance_clock()
+            kv.wait(kv.pull(keys[:4], torch.zeros(4 * 2, dtype=server.dtype)))
+    else:
+        for it in range(1500):
+            v = torch.full((SET_KEYS * 2,), float(it), dtype=server.dtype)
+            try:
+                kv.wait(kv.set(keys, v))
+            except Exception as e:  # noqa
+                errors.append(f"set {it} failed: {e}")
+                break
+    kv.barrier()
+    for _ in range(8):
+        kv.advance_clock()
+    kv.wait_sync(); kv.barrier()
+    kv.wait_sync(); kv.barrier()
+    if rank == 2:
+        v = torch.full((SET_KEYS * 2,), 4242.0, dtype=server.dtype)
+        kv.wait(kv.set(keys, v))
+        t = torch.zeros(SET_KEYS * 2, dtype=server.dtype)
+        kv.wait(kv.pull(keys, t))
+        if not torch.equal(t, v):
+            errors.append(f"read after set: {t[:6].tolist()}")
+    kv.barrier()
+    kv.finalize()
+    return errors
+
+
+def test_set_under_relocation():
+    res = run_cluster(_set_under_relocation_worker, world=3, workers=1, mode="threads", value_lengths=2,
+                      num_keys=SET_KEYS + 8, dtype="float32")
+    errs = [e for r in res.values() for k, v in r.items() if k != "counters" for e in v]
+    assert not errs, "\n".join(errs)
+    assert all(r["counters"]["protocol_errors"] == 0 for r in res.values())
+    assert sum(r["counters"]["relocations"] for r in res.values()) > 0

@@ -48,3 +48,20 @@ def test_set_operation_cuda():
     res = run_cluster(dyn._set_worker, world=4, workers=2, mode="threads", value_lengths=2, num_keys=20,
                       dtype="float32", backend="cuda")
     assert not _errs(res), "\n".join(_errs(res))
+
+
+def test_set_under_relocation_cuda():
+    """Set on keys that two other ranks keep relocating: the kernel reports keys in flight and the worker repeats them
+    after a round (the device-side grace period would otherwise wait for a kernel that waits for the round)."""
+    res = run_cluster(dyn._set_under_relocation_worker, world=3, workers=1, mode="threads", value_lengths=2,
+                      num_keys=dyn.SET_KEYS + 8, dtype="float32", backend="cuda")
+    assert not _errs(res), "\n".join(_errs(res))
+    assert all(r["counters"]["protocol_errors"] == 0 for r in res.values())
+
+
+def test_host_sequenced_round_cuda(monkeypatch):
+    """ADAPM_HOST_ROUND=1 keeps the host-sequenced round (control-plane barriers, event-based grace) working."""
+    monkeypatch.setenv("ADAPM_HOST_ROUND", "1")
+    res = run_cluster(mk._worker, world=3, workers=2, mode="threads", value_lengths=mk.VPK, num_keys=mk.NUM_KEYS,
+                      dtype="float32", backend="cuda")
+    assert not _errs(res), "\n".join(_errs(res))
