@@ -121,9 +121,9 @@ ADAPM_D void red_and(uint64_t* p, uint64_t v) {
 // 16-byte row accesses (local HBM or an NVLink peer: same instructions)
 struct alignas(16) F4 { float x, y, z, w; };
 ADAPM_D F4 ld_relaxed4(const float* p) {
-  F4 v;
-  asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  float x, y, z, w;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x), "=f"(y), "=f"(z), "=f"(w) : "l"(p) : "memory");
+  F4 v; v.x = x; v.y = y; v.z = z; v.w = w;
   return v;
 }
 ADAPM_D void st_relaxed4(float* p, F4 v) {

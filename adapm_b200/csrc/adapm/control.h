@@ -64,6 +64,8 @@ struct alignas(64) RankControl {
   uint64_t heap_bytes;
   int32_t device;
   int32_t pid;
+  int32_t vmm_ok;                        // this rank can allocate its heap with the VMM API and pass it as a POSIX fd
+  int32_t mc_ok;                         // ... and its device supports NVLS multicast objects
 };
 
 // Host RPC mailboxes (rpc.h): one multi-producer / single-consumer ring of fragments per rank.

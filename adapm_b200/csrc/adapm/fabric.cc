@@ -4,7 +4,10 @@
 #include <fcntl.h>
 #include <signal.h>
 #include <sys/mman.h>
+#include <sys/socket.h>
 #include <sys/stat.h>
+#include <sys/un.h>
+#include <poll.h>
 #include <unistd.h>
 
 #include <map>
@@ -160,6 +163,68 @@ void gc_stale_shm_segments() {
   }
 }
 
+// ---- passing file descriptors between the ranks of a box (VMM heap handles, the multicast object): one unix
+// datagram socket per rank in the abstract namespace (nothing to clean up on the file system), SCM_RIGHTS messages
+struct FdMsg { int32_t sender; int32_t kind; };
+enum FdKind : int32_t { FD_HEAP = 1, FD_MULTICAST = 2 };
+
+sockaddr_un fdx_addr(const std::string& name, socklen_t* len) {
+  sockaddr_un a;
+  memset(&a, 0, sizeof(a));
+  a.sun_family = AF_UNIX;
+  const size_t n = std::min(name.size(), sizeof(a.sun_path) - 2);
+  memcpy(a.sun_path + 1, name.data(), n);   // sun_path[0] == 0: abstract socket
+  *len = (socklen_t)(offsetof(sockaddr_un, sun_path) + 1 + n);
+  return a;
+}
+int fdx_bind(const std::string& name) {
+  int s = socket(AF_UNIX, SOCK_DGRAM | SOCK_CLOEXEC, 0);
+  ADAPM_CHECK(s >= 0, "socket(AF_UNIX) failed: " << strerror(errno));
+  socklen_t len;
+  sockaddr_un a = fdx_addr(name, &len);
+  ADAPM_CHECK(bind(s, (sockaddr*)&a, len) == 0, "bind(" << name << ") failed: " << strerror(errno));
+  return s;
+}
+void fdx_send(int sock, const std::string& to, int fd, FdMsg msg) {
+  socklen_t len;
+  sockaddr_un a = fdx_addr(to, &len);
+  iovec iov{&msg, sizeof(msg)};
+  alignas(cmsghdr) char ctl[CMSG_SPACE(sizeof(int))];
+  memset(ctl, 0, sizeof(ctl));
+  msghdr mh;
+  memset(&mh, 0, sizeof(mh));
+  mh.msg_name = &a; mh.msg_namelen = len;
+  mh.msg_iov = &iov; mh.msg_iovlen = 1;
+  mh.msg_control = ctl; mh.msg_controllen = sizeof(ctl);
+  cmsghdr* cm = CMSG_FIRSTHDR(&mh);
+  cm->cmsg_level = SOL_SOCKET; cm->cmsg_type = SCM_RIGHTS; cm->cmsg_len = CMSG_LEN(sizeof(int));
+  memcpy(CMSG_DATA(cm), &fd, sizeof(int));
+  for (int attempt = 0;; ++attempt) {
+    if (sendmsg(sock, &mh, 0) == (ssize_t)sizeof(msg)) return;
+    ADAPM_CHECK((errno == EAGAIN || errno == ENOBUFS || errno == ECONNREFUSED || errno == ENOENT) && attempt < 2000,
+                "sendmsg(fd) to " << to << " failed: " << strerror(errno));
+    std::this_thread::sleep_for(std::chrono::milliseconds(5));
+  }
+}
+int fdx_recv(int sock, FdMsg* msg, double timeout_s) {
+  pollfd pf{sock, POLLIN, 0};
+  int pr = poll(&pf, 1, (int)(timeout_s * 1000));
+  ADAPM_CHECK(pr > 0, "timed out waiting for a peer's memory handle");
+  iovec iov{msg, sizeof(*msg)};
+  alignas(cmsghdr) char ctl[CMSG_SPACE(sizeof(int))];
+  msghdr mh;
+  memset(&mh, 0, sizeof(mh));
+  mh.msg_iov = &iov; mh.msg_iovlen = 1;
+  mh.msg_control = ctl; mh.msg_controllen = sizeof(ctl);
+  ssize_t n = recvmsg(sock, &mh, MSG_CMSG_CLOEXEC);
+  ADAPM_CHECK(n == (ssize_t)sizeof(*msg), "recvmsg(fd) failed: " << strerror(errno));
+  cmsghdr* cm = CMSG_FIRSTHDR(&mh);
+  ADAPM_CHECK(cm && cm->cmsg_level == SOL_SOCKET && cm->cmsg_type == SCM_RIGHTS, "peer message carries no file descriptor");
+  int fd = -1;
+  memcpy(&fd, CMSG_DATA(cm), sizeof(int));
+  return fd;
+}
+
 class ShmFabric : public Fabric {
  public:
   ShmFabric(const Options& opt) {
@@ -223,6 +288,12 @@ class ShmFabric : public Fabric {
 
   ~ShmFabric() override {
     stop_failure_detector();
+    if (cuda_ && !vmm_.empty()) {
+      cudamem::set_device(device_);
+      if (mc_handle_) cudamem::mc_unmap(mc_handle_, device_, mc_heap_, vmm_[rank_].size);
+      for (auto& h : vmm_) cudamem::vmm_free(h);
+      for (int r = 0; r < world_; ++r) heaps_[r] = nullptr;
+    }
     for (int r = 0; r < world_; ++r) {
       if (!heaps_[r]) continue;
       if (cuda_) {
@@ -240,6 +311,7 @@ class ShmFabric : public Fabric {
   void allocate_heaps(uint64_t bytes) override {
     const uint64_t b = (bytes + 4095) / 4096 * 4096;
     RankControl& me = ctl_->ranks[rank_];
+    if (cuda_ && allocate_vmm_heaps(b)) return;
     if (cuda_) {
       cudamem::set_device(device_);
       heaps_[rank_] = cudamem::alloc_zeroed(b);
@@ -280,14 +352,101 @@ class ShmFabric : public Fabric {
     node_barrier("shm heap mapped");
   }
 
+  // Heaps as VMM allocations that peers import through POSIX file descriptors, bound to one NVLS multicast object
+  // when every device of the job supports it (NVSwitch boxes): mc_heap() + off then addresses offset `off` of ALL
+  // heaps at once. Returns false (nothing allocated) when some rank lacks VMM support or ADAPM_VMM=0: the caller
+  // falls back to cudaMalloc + CUDA IPC.
+  bool allocate_vmm_heaps(uint64_t b) {
+    RankControl& me = ctl_->ranks[rank_];
+    cudamem::set_device(device_);
+    bool mc = false;
+    bool vmm = cudamem::vmm_supported(device_, &mc);
+    if (const char* e = getenv("ADAPM_VMM")) vmm = vmm && atoi(e) != 0;
+    if (const char* e = getenv("ADAPM_MULTICAST")) mc = mc && atoi(e) != 0;
+    me.vmm_ok = vmm ? 1 : 0;
+    me.mc_ok = (vmm && mc) ? 1 : 0;
+    me.device = device_;
+    node_barrier("vmm capabilities");
+    bool all_vmm = true, all_mc = world_ > 1;
+    for (int r = 0; r < world_; ++r) { all_vmm = all_vmm && ctl_->ranks[r].vmm_ok; all_mc = all_mc && ctl_->ranks[r].mc_ok; }
+    for (int r = 0; r < world_ && all_mc; ++r)     // one device per rank: a device cannot join a multicast object twice
+      for (int q = 0; q < r; ++q) if (ctl_->ranks[q].device == ctl_->ranks[r].device) all_mc = false;
+    if (!all_vmm) return false;
+    const uint64_t gran = cudamem::vmm_granularity(device_, world_, all_mc);
+    const uint64_t size = (b + gran - 1) / gran * gran;
+    vmm_.assign(world_, cudamem::VmmHeap());
+    vmm_[rank_] = cudamem::vmm_alloc(device_, size);
+    heaps_[rank_] = vmm_[rank_].va;
+    me.heap_bytes = size;
+    heap_bytes_[rank_] = size;
+    auto sock_name = [&](int r) { return prefix_.substr(1) + "_fd" + std::to_string(r); };
+    const int sock = fdx_bind(sock_name(rank_));
+    node_barrier("vmm sockets bound");
+    for (int r = 0; r < world_; ++r) {
+      if (r == rank_) continue;
+      const int fd = cudamem::vmm_export_fd(vmm_[rank_]);
+      fdx_send(sock, sock_name(r), fd, FdMsg{rank_, FD_HEAP});
+      close(fd);
+    }
+    if (all_mc && rank_ == 0) {
+      int fd = -1;
+      mc_handle_ = cudamem::mc_create(world_, size, &fd);
+      for (int r = 1; r < world_; ++r) fdx_send(sock, sock_name(r), fd, FdMsg{0, FD_MULTICAST});
+      close(fd);
+    }
+    int expect = (world_ - 1) + ((all_mc && rank_ != 0) ? 1 : 0);
+    while (expect-- > 0) {
+      FdMsg m;
+      const int fd = fdx_recv(sock, &m, timeout_s_);
+      if (m.kind == FD_MULTICAST) {
+        mc_handle_ = cudamem::mc_import_fd(fd);
+      } else {
+        ADAPM_CHECK(m.kind == FD_HEAP && m.sender >= 0 && m.sender < world_ && m.sender != rank_, "unexpected handle message");
+        vmm_[m.sender] = cudamem::vmm_import_fd(device_, fd, size);
+        heaps_[m.sender] = vmm_[m.sender].va;
+        heap_bytes_[m.sender] = size;
+      }
+    }
+    close(sock);
+    if (all_mc) {
+      cudamem::mc_add_device(mc_handle_, device_);
+      node_barrier("multicast devices added");
+      mc_heap_ = cudamem::mc_bind_and_map(mc_handle_, device_, vmm_[rank_]);
+    }
+    node_barrier("vmm heaps mapped");
+    VLOG(1, "rank " << rank_ << ": VMM heap " << (size >> 20) << " MiB" << (mc_heap_ ? ", bound to an NVLS multicast object" : ""));
+    return true;
+  }
+
  private:
   std::string prefix_;
   size_t ctl_sz_ = 0;
   std::vector<uint64_t> heap_bytes_;
   bool my_heap_created_ = false;
+  std::vector<cudamem::VmmHeap> vmm_;
+  unsigned long long mc_handle_ = 0;
 };
 
 }  // namespace
+
+// Self-test of the file-descriptor channel (no GPU needed): a pipe's read end travels from one abstract unix socket to
+// another; the bytes written into the pipe must come out of the received descriptor.
+bool fabric_fdpass_selftest() {
+  const std::string a = "adapm_selftest_a_" + std::to_string((long)getpid()), b = "adapm_selftest_b_" + std::to_string((long)getpid());
+  int sa = fdx_bind(a), sb = fdx_bind(b);
+  int p[2];
+  if (pipe(p) != 0) return false;
+  fdx_send(sa, b, p[0], FdMsg{7, FD_HEAP});
+  FdMsg m;
+  int fd = fdx_recv(sb, &m, 5.0);
+  const char msg[] = "adapm";
+  bool ok = write(p[1], msg, sizeof(msg)) == (ssize_t)sizeof(msg);
+  char buf[16] = {0};
+  ok = ok && read(fd, buf, sizeof(msg)) == (ssize_t)sizeof(msg) && memcmp(buf, msg, sizeof(msg)) == 0;
+  ok = ok && m.sender == 7 && m.kind == FD_HEAP && fd != p[0];
+  close(fd); close(p[0]); close(p[1]); close(sa); close(sb);
+  return ok;
+}
 
 std::shared_ptr<Fabric> Fabric::create(const Options& opt) {
   ADAPM_CHECK(opt.world >= 1 && opt.world <= MAX_RANKS, "world size must be in [1," << MAX_RANKS << "]");

@@ -30,11 +30,15 @@ class Fabric {
   int rank() const { return rank_; }
   int world() const { return world_; }
   bool cuda() const { return cuda_; }
+  bool peers_are_processes() const { return peers_are_processes_; }   // one process (and GPU) per rank
   int device() const { return device_; }
 
   // Collective: allocate `bytes` for this rank (zero-filled) and map all peers' heaps.
   virtual void allocate_heaps(uint64_t bytes) = 0;
   char* heap(int r) const { return heaps_[r]; }
+  // NVLS multicast mapping of the heaps (cuda, one process per GPU, NVSwitch): a store / reduction to mc_heap() + off
+  // reaches offset `off` of EVERY rank's heap in one NVLink transaction. nullptr when the box has no multicast support.
+  char* mc_heap() const { return mc_heap_; }
 
   void node_barrier(const char* what) {
     ctl_->node_barrier.wait(world_, timeout_s_, what);
@@ -54,11 +58,14 @@ class Fabric {
   bool cuda_ = false;
   double timeout_s_ = 300;
   std::vector<char*> heaps_;
+  char* mc_heap_ = nullptr;
   bool peers_are_processes_ = false;
   std::thread fd_thread_;
   std::atomic<bool> fd_stop_{false};
   std::atomic<int> dead_peer_{-1};
 };
+
+bool fabric_fdpass_selftest();   // unit test hook of the descriptor channel between ranks (fabric.cc)
 
 // device helpers implemented in cuda/device_mem.cu (only linked in the cuda build)
 namespace cudamem {
@@ -71,6 +78,29 @@ void export_handle(char* p, unsigned char* out128);   // cudaIpcGetMemHandle
 char* import_handle(const unsigned char* in128);      // cudaIpcOpenMemHandle
 void close_handle(char* p);
 void enable_peer(int my_dev, int peer_dev);
+
+// ---- CUDA virtual memory management (cuMemCreate / cuMemMap) + NVLS multicast objects (cuMulticastCreate), used by
+// the shm fabric when the driver supports them: the heap of a rank is ONE physical allocation that peers import through
+// a POSIX file descriptor (sent over a unix socket) and that is bound to a multicast object spanning all ranks.
+// All driver entry points are resolved at run time (cudaGetDriverEntryPoint): no link-time dependency on libcuda.
+struct VmmHeap {
+  char* va = nullptr;          // mapping in this process
+  uint64_t size = 0;           // padded to the allocation / multicast granularity
+  unsigned long long handle = 0;   // CUmemGenericAllocationHandle
+};
+bool vmm_supported(int dev, bool* multicast);        // VMM + POSIX-fd handles (and multicast objects) on this device
+uint64_t vmm_granularity(int dev, int world, bool multicast);
+VmmHeap vmm_alloc(int dev, uint64_t size);           // zero-filled, mapped read/write for `dev`
+int vmm_export_fd(const VmmHeap& h);
+VmmHeap vmm_import_fd(int dev, int fd, uint64_t size);   // peer's allocation mapped read/write for `dev` (closes fd)
+void vmm_free(VmmHeap& h);
+// multicast object: created by one rank, imported by the others through an fd, every rank adds its device, then binds
+// its heap and maps the object
+unsigned long long mc_create(int world, uint64_t size, int* fd_out);
+unsigned long long mc_import_fd(int fd);
+void mc_add_device(unsigned long long mc, int dev);
+char* mc_bind_and_map(unsigned long long mc, int dev, const VmmHeap& heap);
+void mc_unmap(unsigned long long mc, int dev, char* va, uint64_t size);
 }  // namespace cudamem
 
 }  // namespace adapm

@@ -285,6 +285,25 @@ ADAPM_ROWFN double row_delta_norm2(const G& g, const Val* row, const Val* base, 
   return g.sum(acc);
 }
 
+// row := 0, base := 0   (a slot goes back to the pool with all-zero rows: register_intent relies on it)
+template <class Val, class G>
+ADAPM_ROWFN void row_clear(const G& g, Val* row, Val* base, uint32_t len) {
+#if defined(__CUDA_ARCH__)
+  if (row_vec_ok<Val>(len, row, base, row)) {
+    const mem::F4 z = {0.f, 0.f, 0.f, 0.f};
+    for (uint32_t j = g.lane(); j < (len >> 2); j += g.size()) {
+      mem::st_relaxed4(reinterpret_cast<float*>(row) + 4 * j, z);
+      mem::st_relaxed4(reinterpret_cast<float*>(base) + 4 * j, z);
+    }
+    return;
+  }
+#endif
+  for (uint32_t i = g.lane(); i < len; i += g.size()) {
+    mem::st_relaxed(row + i, (Val)0);
+    mem::st_relaxed(base + i, (Val)0);
+  }
+}
+
 // dst := src  (len values; owner row -> published mirror row)
 template <class Val, class G>
 ADAPM_ROWFN void row_copy(const G& g, Val* dst, const Val* src, uint32_t len) {
@@ -585,90 +604,119 @@ ADAPM_HD bool phase_c_wants(const Ctx& c, uint32_t s, const RoundParams& rp) {
   return slot_swept(s, rp) || round_due(s, rp.round_no, rp.idle_period);
 }
 
+// ---------------------------------------------------------------------------------------
+// Phases A and C are written as THREE steps per slot, so that the device can run each step as its own grid-wide pass:
+//   resolve  (one lane per slot)   all the metadata work: states, directory, owner slot, versions - including the
+//                                  remote (NVLink) metadata loads, of which a thread-per-slot pass keeps 100 000s in flight;
+//                                  produces at most one row operation (SlotWork::op with its three row pointers)
+//   row op   (one group per slot)  the only step that touches row data: 16-byte loads / reductions, no metadata, no fence
+//   commit   (one lane per slot)   versions, flags, state transitions, slot recycling
+// The kernel boundaries between the passes order them (plus the cross-rank barriers of the round); on the CPU the three
+// steps of a slot run back to back. Nothing in here spins or waits.
+enum RowOpKind : uint8_t { OP_NONE = 0, OP_SHIP = 1, OP_FINALIZE = 2, OP_REFRESH = 3, OP_DROP = 4, OP_CLEAR = 5 };
+constexpr uint8_t W_ACTIVE = 1, W_NZ = 2, W_REF_NONZERO = 4, W_SKIP_COMMIT = 8, W_WAS_PENDING = 16;
+
+struct SlotWork {
+  uint32_t slot;
+  uint32_t m;       // the slot's meta word as left by resolve
+  int32_t ps;       // the key's slot at the peer (owner / relocation source)
+  uint32_t v;       // owner version seen by resolve (refresh)
+  uint32_t len;
+  uint8_t st;       // slot state seen by resolve
+  uint8_t peer;     // owner / source rank
+  uint8_t op;       // RowOpKind
+  uint8_t flags;    // W_*
+  int32_t cls;
+  float thresh2;    // OP_SHIP: ship only if |row - base|^2 >= thresh2 (0 = always)
+  Key key;
+  void* dst;        // OP_SHIP: owner row (reduction target) | FINALIZE/REFRESH: local row | DROP: owner row | CLEAR: local row
+  void* ref;        // local base row
+  const void* src;  // OP_SHIP/DROP: local row | FINALIZE: source rank's row | REFRESH: owner row (or its published mirror)
+};
+
 // The key's slot id at its owner `o` as seen from holder slot `s`: cached next to the standing want-bit (the owner's
-// slot of a key cannot change while it stays the owner), otherwise ONE NVLink load. All lanes get the same answer.
-template <class G>
-ADAPM_HD int32_t owner_slot_of(const Ctx& c, const G& g, uint32_t s, Key key, int o) {
-  int32_t ps = -1;
-  if (g.lane() == 0) {
-    const int me = c.rank;
-    if ((mem::ld_relaxed(flags_of(c, me) + s) & F_WANT_SET) && (int)mem::ld_relaxed(want_owner_of(c, me) + s) == o)
-      ps = mem::ld_relaxed(peer_slot_of(c, me) + s);
-    else
-      ps = mem::ld_relaxed(slot_of(c, o) + key);
-  }
-  return g.bcast(ps);
+// slot of a key cannot change while it stays the owner), otherwise ONE NVLink load.
+ADAPM_HD int32_t owner_slot_of(const Ctx& c, uint32_t s, Key key, int o) {
+  const int me = c.rank;
+  if ((mem::ld_relaxed(flags_of(c, me) + s) & F_WANT_SET) && (int)mem::ld_relaxed(want_owner_of(c, me) + s) == o)
+    return mem::ld_relaxed(peer_slot_of(c, me) + s);
+  return mem::ld_relaxed(slot_of(c, o) + key);
 }
 
-// Phase A, step 2: visit one non-owned slot: ship the replica delta to the owner, decide
-// whether the replica is still needed, request a refresh. In steady state (want-bit standing, owner unchanged) this
-// issues only fire-and-forget reductions over NVLink: no remote load, nothing to wait for.
-template <class Val, class G>
-ADAPM_HD void phase_a_slot(const Ctx& c, const G& g, uint32_t s, const RoundParams& rp) {
+// ---- Phase A: replicas ship their deltas to the owners, expired replicas start dropping, live ones (re)request.
+// In steady state (want-bit standing, owner unchanged) this issues only fire-and-forget reductions over NVLink.
+template <class Val>
+ADAPM_HD void phase_a_resolve(const Ctx& c, SlotWork& w, const RoundParams& rp) {
   const int me = c.rank;
-  uint32_t* mp = meta_of(c, me) + s;
-  uint32_t m = g.bcast(g.lane() == 0 ? mem::ld_acquire(mp) : 0u);
-  uint32_t st = meta_state(m);
+  const uint32_t s = w.slot;
+  w.op = OP_NONE; w.flags = W_SKIP_COMMIT; w.ps = -1; w.v = 0; w.thresh2 = 0.f;
+  const uint32_t m = mem::ld_acquire(meta_of(c, me) + s);
+  const uint32_t st = meta_state(m);
+  w.m = m; w.st = (uint8_t)st;
   if (st != S_REPLICA && st != S_REPLICA_PENDING) return;
-  const Key key = (Key)g.bcast((uint64_t)(g.lane() == 0 ? (uint64_t)mem::ld_relaxed(slot_key_of(c, me) + s) : 0));
+  const Key key = mem::ld_relaxed(slot_key_of(c, me) + s);
   const int cls = class_of_key(c, key);
   const uint32_t len = c.L.cls[cls].len;
-  const bool active = g.bcast((uint32_t)(g.lane() == 0 ? (intent_active(c, s, rp.clocks) ? 1u : 0u) : 0u)) != 0;
-  const int o = (int)g.bcast((uint32_t)(g.lane() == 0 ? mem::ld_relaxed(dir_of(c, me) + key) : 0));
+  const bool active = intent_active(c, s, rp.clocks);
+  const int o = (int)mem::ld_relaxed(dir_of(c, me) + key);
   int32_t ps = -1;
-  if (o != me) ps = owner_slot_of(c, g, s, key, o);
-  if (ps < 0) { if (g.lane() == 0) count(c, C_PROTOCOL_ERRORS); return; }
-  uint8_t* fl = flags_of(c, me) + s;
+  if (o != me) ps = owner_slot_of(c, s, key, o);
+  if (ps < 0) { count(c, C_PROTOCOL_ERRORS); return; }
+  w.key = key; w.cls = cls; w.len = len; w.peer = (uint8_t)o; w.ps = ps;
+  w.flags = active ? W_ACTIVE : 0;
   if (st == S_REPLICA) {
     uint8_t* dp = dirty_of(c, me) + s;
-    uint8_t f = (uint8_t)g.bcast((uint32_t)(g.lane() == 0 ? mem::ld_relaxed(dp) : 0));
+    const uint8_t f = mem::ld_relaxed(dp);
     const bool swept = slot_swept(s, rp);
-    bool consider = (f != 0) || swept || !active;
-    bool never = rp.threshold > 1e300;  // inf: replicas never synchronise (except on drop)
+    const bool consider = (f != 0) || swept || !active;
+    const bool never = rp.threshold > 1e300;  // inf: replicas never synchronise (except on drop)
     if (consider && (!never || !active)) {
-      Val* row = row_ptr<Val>(c, me, cls, s);
-      Val* base = base_ptr<Val>(c, me, cls, s);
-      bool ship = true;
-      if (rp.threshold > 0 && active && !swept)
-        ship = row_delta_norm2<Val>(g, row, base, len) >= rp.threshold * rp.threshold;
-      if (ship) {
-        if (g.lane() == 0) mem::st_relaxed(dp, (uint8_t)0);
-        mem::fence();
-        const bool nz = row_ship<Val>(g, row, base, row_ptr<Val>(c, o, cls, ps), len, true);
-        if (nz && g.lane() == 0) {
-          // the owner's version counts applied updates; this replica accounts for its own bump locally, so that in
-          // phase C "owner version == ver_seen" still means "nothing but my own deltas arrived" (no round trip)
-          mem::red_add(version_of(c, o) + ps, 1u);
-          uint32_t* vs = ver_seen_of(c, me) + s;
-          mem::st_relaxed(vs, mem::ld_relaxed(vs) + 1u);
-          count(c, C_DELTAS_SHIPPED);
-        }
-      }
+      // clear the hint BEFORE the row is read (next pass): a push that lands later sets it again
+      mem::st_relaxed(dp, (uint8_t)0);
+      w.op = OP_SHIP;
+      w.src = row_ptr<Val>(c, me, cls, s);
+      w.ref = base_ptr<Val>(c, me, cls, s);
+      w.dst = row_ptr<Val>(c, o, cls, ps);
+      if (rp.threshold > 0 && active && !swept) w.thresh2 = (float)(rp.threshold * rp.threshold);
     }
   }
+}
+
+template <class Val>
+ADAPM_HD void phase_a_commit(const Ctx& c, const SlotWork& w) {
+  if (w.flags & W_SKIP_COMMIT) return;
+  const int me = c.rank;
+  const uint32_t s = w.slot;
+  const int o = w.peer;
+  const int32_t ps = w.ps;
+  if (w.op == OP_SHIP && (w.flags & W_NZ)) {
+    // the owner's version counts applied updates; this replica accounts for its own bump locally, so that in
+    // phase C "owner version == ver_seen" still means "nothing but my own deltas arrived" (no round trip)
+    mem::red_add(version_of(c, o) + ps, 1u);
+    uint32_t* vs = ver_seen_of(c, me) + s;
+    mem::st_relaxed(vs, mem::ld_relaxed(vs) + 1u);
+    count(c, C_DELTAS_SHIPPED);
+  }
+  uint8_t* fl = flags_of(c, me) + s;
   uint8_t* wo = want_owner_of(c, me) + s;
-  if (!active) {
-    if (g.lane() == 0) {
-      // withdraw the standing request (the bit lives in the mask of the owner it was sent to; a relocation resets it)
-      const uint8_t f = mem::ld_relaxed(fl);
-      if ((f & F_WANT_SET) && (int)mem::ld_relaxed(wo) == o) mem::red_and(want_of(c, o) + ps, ~((uint64_t)1 << me));
-      mem::st_relaxed(wo, (uint8_t)0xff);
-      mem::st_relaxed(fl, (uint8_t)(f & ~(F_REQUESTED | F_WANT_SET)));
-      mem::st_release(mp, meta_next(m, S_DROPPING, 0));
-    }
+  if (!(w.flags & W_ACTIVE)) {
+    // withdraw the standing request (the bit lives in the mask of the owner it was sent to; a relocation resets it)
+    const uint8_t f = mem::ld_relaxed(fl);
+    if ((f & F_WANT_SET) && (int)mem::ld_relaxed(wo) == o) mem::red_and(want_of(c, o) + ps, ~((uint64_t)1 << me));
+    mem::st_relaxed(wo, (uint8_t)0xff);
+    mem::st_relaxed(fl, (uint8_t)(f & ~(F_REQUESTED | F_WANT_SET)));
+    mem::st_release(meta_of(c, me) + s, meta_next(w.m, S_DROPPING, 0));
     return;
   }
-  if (g.lane() == 0) {
-    // the request is sticky: it stands in the owner's want-mask until this rank drops the replica
-    uint8_t f = mem::ld_relaxed(fl);
-    if (!(f & F_WANT_SET) || (int)mem::ld_relaxed(wo) != o) {
-      mem::red_or(want_of(c, o) + ps, (uint64_t)1 << me);
-      mem::st_relaxed(peer_slot_of(c, me) + s, ps);
-      mem::st_relaxed(wo, (uint8_t)o);
-      f |= F_WANT_SET;
-    }
-    mem::st_relaxed(fl, (uint8_t)(f | F_REQUESTED));
+  // the request is sticky: it stands in the owner's want-mask until this rank drops the replica
+  uint8_t f = mem::ld_relaxed(fl);
+  if (!(f & F_WANT_SET) || (int)mem::ld_relaxed(wo) != o) {
+    mem::red_or(want_of(c, o) + ps, (uint64_t)1 << me);
+    mem::st_relaxed(peer_slot_of(c, me) + s, ps);
+    mem::st_relaxed(wo, (uint8_t)o);
+    f |= F_WANT_SET;
   }
+  mem::st_relaxed(fl, (uint8_t)(f | F_REQUESTED));
 }
 
 // Phase B: the owner decides relocate vs replicate for one owned slot (ONE lane).
@@ -710,134 +758,152 @@ ADAPM_HD void phase_b_slot(const Ctx& c, uint32_t s, const RoundParams& rp) {
   count(c, C_RELOCATIONS);
 }
 
-// A slot goes back to the pool with all-zero row and base (register_intent relies on it).
-template <class Val, class G>
-ADAPM_HD void clear_slot_rows(const Ctx& c, const G& g, int cls, uint32_t s, uint32_t len) {
-  Val* row = row_ptr<Val>(c, c.rank, cls, s);
-  Val* base = base_ptr<Val>(c, c.rank, cls, s);
-#if defined(__CUDA_ARCH__)
-  if (row_vec_ok<Val>(len, row, base, row)) {
-    const mem::F4 z = {0.f, 0.f, 0.f, 0.f};
-    for (uint32_t j = g.lane(); j < (len >> 2); j += g.size()) {
-      mem::st_relaxed4(reinterpret_cast<float*>(row) + 4 * j, z);
-      mem::st_relaxed4(reinterpret_cast<float*>(base) + 4 * j, z);
-    }
-    return;
-  }
-#endif
-  for (uint32_t i = g.lane(); i < len; i += g.size()) {
-    mem::st_relaxed(row + i, (Val)0);
-    mem::st_relaxed(base + i, (Val)0);
-  }
-}
-
-// Phase C: transfers, refreshes, drops.  (after the grace period)
-template <class Val, class G>
-ADAPM_HD void phase_c_slot(const Ctx& c, const G& g, uint32_t s, const RoundParams& rp) {
+// ---- Phase C: transfers, refreshes, drops.  (after the grace period)
+template <class Val>
+ADAPM_HD void phase_c_resolve(const Ctx& c, SlotWork& w, const RoundParams& rp) {
   const int me = c.rank;
+  const uint32_t s = w.slot;
+  w.op = OP_NONE; w.flags = W_SKIP_COMMIT; w.ps = -1; w.v = 0; w.thresh2 = 0.f;
   uint32_t* mp = meta_of(c, me) + s;
-  uint32_t m = g.bcast(g.lane() == 0 ? mem::ld_acquire(mp) : 0u);
-  uint32_t st = meta_state(m);
+  const uint32_t m = mem::ld_acquire(mp);
+  const uint32_t st = meta_state(m);
+  w.m = m; w.st = (uint8_t)st;
   if (st == S_FREE || st == S_OWNED) return;
-  const Key key = (Key)g.bcast((uint64_t)(g.lane() == 0 ? (uint64_t)mem::ld_relaxed(slot_key_of(c, me) + s) : 0));
+  const Key key = mem::ld_relaxed(slot_key_of(c, me) + s);
   const int cls = class_of_key(c, key);
   const uint32_t len = c.L.cls[cls].len;
+  w.key = key; w.cls = cls; w.len = len;
   uint8_t* fl = flags_of(c, me) + s;
   if (state_is_incoming(st)) {
     const int src = (int)meta_peer(m);
-    int32_t ss = (int32_t)g.bcast(g.lane() == 0 ? mem::ld_relaxed(ver_seen_of(c, me) + s) : 0u);
-    if (ss < 0) { if (g.lane() == 0) count(c, C_PROTOCOL_ERRORS); return; }
-    uint32_t m1 = meta_next(m, S_FINALIZING, (uint32_t)src);
-    if (g.lane() == 0) mem::st_release(mp, m1);
-    mem::fence(); g.sync();
-    bool base_nonzero = false;
-    row_fold<Val>(g, row_ptr<Val>(c, me, cls, s), base_ptr<Val>(c, me, cls, s), row_ptr<Val>(c, src, cls, ss), len,
-                  false, &base_nonzero);
-    // invariant used by the in-kernel read of in-flight rows (pm_kernels.cuh: value = local row + source row): a
-    // placeholder that became the relocation target (INCOMING, not INCOMING_REPLICA) has an all-zero base
-    if (st == S_INCOMING && base_nonzero && g.lane() == 0) count(c, C_PROTOCOL_ERRORS);
-    mem::fence(); g.sync();
-    if (g.lane() == 0) {
-      uint32_t sv = mem::ld_relaxed(version_of(c, src) + ss);
-      mem::red_add(version_of(c, me) + s, sv + 1u);
-      mem::st_relaxed(ver_seen_of(c, me) + s, 0xffffffffu);
-      mem::st_relaxed(fl, (uint8_t)0);
-      mem::st_relaxed(want_owner_of(c, me) + s, (uint8_t)0xff);
-      mem::st_release(mp, meta_next(m1, S_OWNED, 0));
-    }
+    const int32_t ss = (int32_t)mem::ld_relaxed(ver_seen_of(c, me) + s);
+    if (ss < 0) { count(c, C_PROTOCOL_ERRORS); return; }
+    w.m = meta_next(m, S_FINALIZING, (uint32_t)src);
+    mem::st_release(mp, w.m);   // readers of the in-flight value (row - base + source row) re-validate this word
+    w.peer = (uint8_t)src; w.ps = ss;
+    w.op = OP_FINALIZE; w.flags = 0;
+    w.dst = row_ptr<Val>(c, me, cls, s); w.ref = base_ptr<Val>(c, me, cls, s); w.src = row_ptr<Val>(c, src, cls, ss);
     return;
   }
   if (st == S_REPLICA || st == S_REPLICA_PENDING) {
-    uint8_t f = (uint8_t)g.bcast((uint32_t)(g.lane() == 0 ? mem::ld_relaxed(fl) : 0));
+    const uint8_t f = mem::ld_relaxed(fl);
     const bool requested = (f & F_REQUESTED) != 0;
-    if (requested && g.lane() == 0) mem::st_relaxed(fl, (uint8_t)(f & ~F_REQUESTED));
+    if (requested) mem::st_relaxed(fl, (uint8_t)(f & ~F_REQUESTED));
     if (st == S_REPLICA_PENDING && !requested) return;  // the owner has not seen the request yet
     if (c.technique == (int)MgmtTechniques::RELOCATION_ONLY) return;
-    const int o = (int)g.bcast((uint32_t)(g.lane() == 0 ? mem::ld_relaxed(dir_of(c, me) + key) : 0));
+    const int o = (int)mem::ld_relaxed(dir_of(c, me) + key);
     if (o == me) return;
-    const int32_t ps = owner_slot_of(c, g, s, key, o);
+    const int32_t ps = owner_slot_of(c, s, key, o);
     if (ps < 0) return;
-    // owner state word and version in ONE round trip: lanes 0 and 1 of the same load instruction
-    uint32_t pv = 0;
-    if (g.size() > 1) {
-      if (g.lane() < 2) pv = mem::ld_acquire(g.lane() == 0 ? meta_of(c, o) + ps : version_of(c, o) + ps);
-    } else {
-      pv = mem::ld_acquire(meta_of(c, o) + ps);
-    }
-    const uint32_t pm = g.bcast(pv);
+    // owner state word and version: two independent loads, one NVLink round trip
+    const uint32_t pm = mem::ld_relaxed(meta_of(c, o) + ps);
+    const uint32_t v = mem::ld_relaxed(version_of(c, o) + ps);
     if (meta_state(pm) != S_OWNED) return;  // owner is mid-relocation: ask again next round
-    const uint32_t v = g.size() > 1 ? g.bcast_from(pv, 1) : mem::ld_acquire(version_of(c, o) + ps);
-    uint32_t seen = g.bcast(g.lane() == 0 ? mem::ld_relaxed(ver_seen_of(c, me) + s) : 0u);
+    const uint32_t seen = mem::ld_relaxed(ver_seen_of(c, me) + s);
     if (st == S_REPLICA && v == seen && !slot_swept(s, rp)) return;
-    row_fold<Val>(g, row_ptr<Val>(c, me, cls, s), base_ptr<Val>(c, me, cls, s), row_ptr<Val>(c, o, cls, ps), len, true,
-                  (bool*)nullptr);
-    mem::fence(); g.sync();
-    if (g.lane() == 0) {
-      mem::st_relaxed(ver_seen_of(c, me) + s, v);
-      count(c, C_REFRESHES);
-      if (st == S_REPLICA_PENDING) {
-        mem::st_release(mp, meta_next(m, S_REPLICA, 0));
-        count(c, C_REPLICA_SETUPS);
-      }
-    }
+    w.peer = (uint8_t)o; w.ps = ps; w.v = v;
+    w.op = OP_REFRESH; w.flags = (st == S_REPLICA_PENDING) ? W_WAS_PENDING : 0;
+    w.dst = row_ptr<Val>(c, me, cls, s); w.ref = base_ptr<Val>(c, me, cls, s); w.src = row_ptr<Val>(c, o, cls, ps);
     return;
   }
   if (st == S_DROPPING) {
-    const int o = (int)g.bcast((uint32_t)(g.lane() == 0 ? mem::ld_relaxed(dir_of(c, me) + key) : 0));
+    const int o = (int)mem::ld_relaxed(dir_of(c, me) + key);
     int32_t ps = -1;
-    if (o != me) ps = g.bcast(g.lane() == 0 ? mem::ld_relaxed(slot_of(c, o) + key) : 0);
-    if (ps >= 0) {
-      const bool nz = row_ship<Val>(g, row_ptr<Val>(c, me, cls, s), base_ptr<Val>(c, me, cls, s),
-                                    row_ptr<Val>(c, o, cls, ps), len, false);
-      if (nz && g.lane() == 0) mem::red_add(version_of(c, o) + ps, 1u);
-    } else if (g.lane() == 0) {
-      count(c, C_PROTOCOL_ERRORS);
-    }
-    clear_slot_rows<Val>(c, g, cls, s, len);
-    mem::fence(); g.sync();
-    if (g.lane() == 0) {
-      mem::st_release(slot_of(c, me) + key, (int32_t)-1);
-      mem::st_release(mp, meta_next(m, S_FREE, 0));
-      free_slot(c, cls, (int32_t)s);
-      count(c, C_REPLICA_DROPS);
-    }
+    if (o != me) ps = mem::ld_relaxed(slot_of(c, o) + key);
+    w.peer = (uint8_t)o; w.ps = ps; w.flags = 0;
+    w.src = row_ptr<Val>(c, me, cls, s); w.ref = base_ptr<Val>(c, me, cls, s);
+    if (ps >= 0) { w.op = OP_DROP; w.dst = row_ptr<Val>(c, o, cls, ps); }
+    else { count(c, C_PROTOCOL_ERRORS); w.op = OP_CLEAR; w.dst = const_cast<void*>(w.src); }
     return;
   }
   if (st == S_OUTGOING) {
-    if (g.lane() == 0) mem::st_release(mp, meta_next(m, S_DEAD, meta_peer(m)));
+    mem::st_release(mp, meta_next(m, S_DEAD, meta_peer(m)));
     return;
   }
   if (st == S_DEAD) {
-    clear_slot_rows<Val>(c, g, cls, s, len);
-    mem::fence(); g.sync();
-    if (g.lane() == 0) {
-      // the key may already have a fresh slot on this rank (it was requested back)
-      cas_i32(slot_of(c, me) + key, (int32_t)s, (int32_t)-1);
-      mem::st_release(mp, meta_next(m, S_FREE, 0));
-      free_slot(c, cls, (int32_t)s);
+    w.op = OP_CLEAR; w.flags = 0;
+    w.dst = row_ptr<Val>(c, me, cls, s); w.ref = base_ptr<Val>(c, me, cls, s); w.src = w.dst;
+    return;
+  }
+}
+
+template <class Val>
+ADAPM_HD void phase_c_commit(const Ctx& c, const SlotWork& w) {
+  if (w.flags & W_SKIP_COMMIT) return;
+  const int me = c.rank;
+  const uint32_t s = w.slot;
+  uint32_t* mp = meta_of(c, me) + s;
+  if (w.op == OP_FINALIZE) {
+    // invariant used by the in-kernel read of in-flight rows (pm_kernels.cuh: value = local row + source row): a
+    // placeholder that became the relocation target (INCOMING, not INCOMING_REPLICA) has an all-zero base
+    if (w.st == S_INCOMING && (w.flags & W_REF_NONZERO)) count(c, C_PROTOCOL_ERRORS);
+    const uint32_t sv = mem::ld_relaxed(version_of(c, w.peer) + w.ps);
+    mem::red_add(version_of(c, me) + s, sv + 1u);
+    mem::st_relaxed(ver_seen_of(c, me) + s, 0xffffffffu);
+    mem::st_relaxed(flags_of(c, me) + s, (uint8_t)0);
+    mem::st_relaxed(want_owner_of(c, me) + s, (uint8_t)0xff);
+    mem::st_release(mp, meta_next(w.m, S_OWNED, 0));
+    return;
+  }
+  if (w.op == OP_REFRESH) {
+    mem::st_relaxed(ver_seen_of(c, me) + s, w.v);
+    count(c, C_REFRESHES);
+    if (w.flags & W_WAS_PENDING) {
+      mem::st_release(mp, meta_next(w.m, S_REPLICA, 0));
+      count(c, C_REPLICA_SETUPS);
     }
     return;
   }
+  if (w.op == OP_DROP || (w.op == OP_CLEAR && w.st == S_DROPPING)) {
+    if (w.op == OP_DROP && (w.flags & W_NZ)) mem::red_add(version_of(c, w.peer) + w.ps, 1u);
+    mem::st_release(slot_of(c, me) + w.key, (int32_t)-1);
+    mem::st_release(mp, meta_next(w.m, S_FREE, 0));
+    free_slot(c, w.cls, (int32_t)s);
+    count(c, C_REPLICA_DROPS);
+    return;
+  }
+  if (w.op == OP_CLEAR) {   // DEAD relocation source
+    // the key may already have a fresh slot on this rank (it was requested back)
+    cas_i32(slot_of(c, me) + w.key, (int32_t)s, (int32_t)-1);
+    mem::st_release(mp, meta_next(w.m, S_FREE, 0));
+    free_slot(c, w.cls, (int32_t)s);
+    return;
+  }
+}
+
+// The row operation of one slot (one group of lanes; the only code of the round that touches row data).
+template <class Val, class G>
+ADAPM_HD void row_op_execute(const G& g, SlotWork& w) {
+  Val* dst = reinterpret_cast<Val*>(w.dst);
+  Val* ref = reinterpret_cast<Val*>(w.ref);
+  const Val* src = reinterpret_cast<const Val*>(w.src);
+  uint8_t out = 0;
+  switch (w.op) {
+    case OP_SHIP: {
+      bool ship = true;
+      if (w.thresh2 > 0.f) ship = row_delta_norm2<Val>(g, src, ref, w.len) >= (double)w.thresh2;
+      if (ship && row_ship<Val>(g, src, ref, dst, w.len, true)) out = W_NZ;
+      break;
+    }
+    case OP_FINALIZE: {
+      bool rnz = false;
+      row_fold<Val>(g, dst, ref, src, w.len, false, &rnz);
+      if (rnz) out = W_REF_NONZERO;
+      break;
+    }
+    case OP_REFRESH:
+      row_fold<Val>(g, dst, ref, src, w.len, true, (bool*)nullptr);
+      break;
+    case OP_DROP:
+      if (row_ship<Val>(g, src, ref, dst, w.len, false)) out = W_NZ;
+      row_clear<Val>(g, const_cast<Val*>(src), ref, w.len);   // a slot returns to the pool with all-zero row and base
+      break;
+    case OP_CLEAR:
+      row_clear<Val>(g, dst, ref, w.len);
+      break;
+    default: break;
+  }
+  if (out && g.lane() == 0) w.flags |= out;
 }
 
 // Intent pre-pass for one key (ONE lane, any thread, any time): if the key already has a usable local slot, extending

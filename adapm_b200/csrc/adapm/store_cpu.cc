@@ -135,7 +135,13 @@ class CpuBackend : public Backend {
     HostGroup g;
     const uint32_t S = ctx_.L.total_slots;
     for (uint32_t s = 0; s < S; ++s)
-      if (phase_a_wants(ctx_, s, rp)) phase_a_slot<Val>(ctx_, g, s, rp);
+      if (phase_a_wants(ctx_, s, rp)) {
+        SlotWork w;
+        w.slot = s;
+        phase_a_resolve<Val>(ctx_, w, rp);
+        if (w.op != OP_NONE) { mem::fence(); row_op_execute<Val>(g, w); mem::fence(); }
+        phase_a_commit<Val>(ctx_, w);
+      }
     mem::fence();
   }
   void phase_b(const RoundParams& rp) override {
@@ -149,7 +155,13 @@ class CpuBackend : public Backend {
     HostGroup g;
     const uint32_t S = ctx_.L.total_slots;
     for (uint32_t s = 0; s < S; ++s)
-      if (phase_c_wants(ctx_, s, rp)) phase_c_slot<Val>(ctx_, g, s, rp);
+      if (phase_c_wants(ctx_, s, rp)) {
+        SlotWork w;
+        w.slot = s;
+        phase_c_resolve<Val>(ctx_, w, rp);
+        if (w.op != OP_NONE) { mem::fence(); row_op_execute<Val>(g, w); mem::fence(); }
+        phase_c_commit<Val>(ctx_, w);
+      }
     mem::fence();
   }
   void round_fence() override { mem::fence(); }

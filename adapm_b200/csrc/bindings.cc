@@ -46,6 +46,7 @@ PYBIND11_MODULE(_C, m) {
   m.attr("CLOCK_MAX") = (int64_t)CLOCK_MAX;
   m.attr("MAX_RANKS") = (int)MAX_RANKS;
   m.def("cuda_available", [] { return cudamem::available(); });
+  m.def("_fdpass_selftest", [] { return fabric_fdpass_selftest(); });
   m.def("cuda_device_count", [] { return cudamem::available() ? cudamem::device_count() : 0; });
   m.def("poisson_quantile", &poisson_quantile);
 

@@ -189,7 +189,7 @@ __global__ void register_kernel(const __grid_constant__ Ctx c, const IntentRec* 
 // dependent-load chains of many slots overlap.
 template <int PHASE>
 __global__ void __launch_bounds__(kThreads) phase_scan_kernel(const __grid_constant__ Ctx c, const RoundDev* __restrict__ rd,
-                                                              uint32_t* __restrict__ worklist,
+                                                              SlotWork* __restrict__ worklist,
                                                               unsigned int* __restrict__ count) {
   if (rd->stop) return;
   const RoundParams& rp = rd->rp;
@@ -207,32 +207,46 @@ __global__ void __launch_bounds__(kThreads) phase_scan_kernel(const __grid_const
       unsigned base = 0;
       if (lane == 0) base = atomicAdd(count, (unsigned)__popc(mask));
       base = __shfl_sync(0xffffffffu, base, 0);
-      if (hit) worklist[base + __popc(mask & ((1u << lane) - 1u))] = s;
+      if (hit) worklist[base + __popc(mask & ((1u << lane) - 1u))].slot = s;
     }
   }
 }
 
-// 128-thread blocks at <= 80 registers: one block fits into the 12 K registers per SM that the lean training kernels
-// (ops_sgns_tma.cu, 104 registers x 512 threads) leave free, so the round's row work runs next to them
+// resolve / commit: one thread per worklist entry (all the metadata work, including the NVLink metadata loads: a
+// thread-per-slot pass keeps as many of them in flight as there are entries). STEP 0 = resolve, 1 = commit.
+template <int PHASE, int STEP>
+__global__ void __launch_bounds__(kThreads) phase_meta_kernel(const __grid_constant__ Ctx c, const RoundDev* __restrict__ rd,
+                                                              SlotWork* __restrict__ worklist,
+                                                              const unsigned int* __restrict__ count) {
+  if (rd->stop) return;
+  const unsigned n = *count;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (PHASE == 0) {
+      if (STEP == 0) phase_a_resolve<float>(c, worklist[i], rd->rp); else phase_a_commit<float>(c, worklist[i]);
+    } else {
+      if (STEP == 0) phase_c_resolve<float>(c, worklist[i], rd->rp); else phase_c_commit<float>(c, worklist[i]);
+    }
+  }
+}
+
+// row pass: one warp per worklist entry that has a row operation; 16-byte loads / reductions only, no metadata, no
+// fence (the kernel boundary orders it against resolve and commit). 128-thread blocks at <= 64 registers: one block
+// fits into the registers a lean training kernel (104 x 512) leaves free per SM, so the pass runs NEXT to the
+// training kernels instead of taking one of their two block slots.
 constexpr int kWorkThreads = 128;
-template <int PHASE>
 #ifndef ADAPM_WORK_MINB
-#define ADAPM_WORK_MINB 5   // <= 96 registers: 128 threads x 96 = the 12 K registers a lean training kernel leaves free per SM
+#define ADAPM_WORK_MINB 6   // <= 80 registers x 128 threads = 10 K of the 12 K registers a lean training kernel leaves free per SM
 #endif
-__global__ void __launch_bounds__(kWorkThreads, ADAPM_WORK_MINB) phase_work_kernel(const __grid_constant__ Ctx c,
-                                                                  const RoundDev* __restrict__ rd,
-                                                                  const uint32_t* __restrict__ worklist,
-                                                                  const unsigned int* __restrict__ count) {
+__global__ void __launch_bounds__(kWorkThreads, ADAPM_WORK_MINB) phase_row_kernel(const RoundDev* __restrict__ rd,
+                                                                               SlotWork* __restrict__ worklist,
+                                                                               const unsigned int* __restrict__ count) {
   if (rd->stop) return;
   WarpGroup g;
-  const RoundParams& rp = rd->rp;
   const unsigned n = *count;
   const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
   for (unsigned i = warp; i < n; i += nwarps) {
-    const uint32_t s = worklist[i];
-    if (PHASE == 0) phase_a_slot<float>(c, g, s, rp);
-    else phase_c_slot<float>(c, g, s, rp);
+    if (worklist[i].op != OP_NONE) row_op_execute<float>(g, worklist[i]);
     __syncwarp();
   }
 }
@@ -340,6 +354,7 @@ CudaBackend::CudaBackend(const Options& opt, const Layout& L, std::shared_ptr<Fa
   if (const char* e = getenv("ADAPM_SYNC_TRACE")) trace_on_ = atoi(e) != 0;
   if (const char* e = getenv("ADAPM_SYNC_SCAN_BLOCKS")) scan_blocks_per_sm_ = std::max(1, atoi(e));
   if (const char* e = getenv("ADAPM_SYNC_WORK_BLOCKS")) work_blocks_per_sm_ = std::max(1, atoi(e));
+  if (const char* e = getenv("ADAPM_SYNC_META_BLOCKS")) meta_blocks_per_sm_ = std::max(1, atoi(e));
   int lo = 0, hi = 0;
   ADAPM_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
   ADAPM_CUDA_CHECK(cudaStreamCreateWithPriority(&sync_stream_, cudaStreamNonBlocking, hi));
@@ -349,7 +364,7 @@ CudaBackend::CudaBackend(const Options& opt, const Layout& L, std::shared_ptr<Fa
     tracked_.insert(worker_streams_[w]);
     staging_.emplace_back(new Staging());
   }
-  ADAPM_CUDA_CHECK(cudaMalloc((void**)&worklist_, (size_t)(L.total_slots + 32) * sizeof(uint32_t)));
+  ADAPM_CUDA_CHECK(cudaMalloc((void**)&worklist_, (size_t)(L.total_slots + 32) * sizeof(SlotWork)));
   ADAPM_CUDA_CHECK(cudaMalloc((void**)&work_count_, 64));
   ADAPM_CUDA_CHECK(cudaMalloc((void**)&round_dev_, sizeof(RoundDev)));
   ADAPM_CUDA_CHECK(cudaMemset(round_dev_, 0, sizeof(RoundDev)));
@@ -358,7 +373,13 @@ CudaBackend::CudaBackend(const Options& opt, const Layout& L, std::shared_ptr<Fa
   ADAPM_CUDA_CHECK(cudaHostAlloc((void**)&abort_word_, 64, cudaHostAllocMapped));
   *abort_word_ = 0;
   ADAPM_CUDA_CHECK(cudaEventCreateWithFlags(&round_done_, cudaEventDisableTiming));
-  fused_round_ = L.world > 1;
+  // The device-resident round needs the ranks' kernels to run concurrently (a barrier kernel waits for its peers'
+  // barrier kernels): guaranteed with one process and GPU per rank. Logical ranks that share ONE device (inproc fabric,
+  // the single-GPU tests) can starve each other - any implicitly synchronising call of one rank's host thread
+  // (cudaFree, cudaDeviceSynchronize, ...) waits for another rank's waiting barrier - so they default to the
+  // host-sequenced round; ADAPM_DEVICE_ROUND=1 / ADAPM_HOST_ROUND=1 force either.
+  fused_round_ = L.world > 1 && fabric_->peers_are_processes();
+  if (const char* e = getenv("ADAPM_DEVICE_ROUND")) fused_round_ = L.world > 1 && atoi(e) != 0;
   if (const char* e = getenv("ADAPM_HOST_ROUND")) fused_round_ = fused_round_ && atoi(e) == 0;
   dev_timeout_ns_ = (unsigned long long)(std::min(opt.wait_timeout_s, 20.0) * 1e9);
 }
@@ -708,15 +729,19 @@ void CudaBackend::launch_phase(int phase) {
   }
   TraceScope ts_(this, phase == 0 ? "phaseA" : "phaseC", sync_stream_);
   ADAPM_CUDA_CHECK(cudaMemsetAsync(work_count_, 0, sizeof(unsigned int), sync_stream_));
+  const int gs = num_sms_ * scan_blocks_per_sm_, gm = num_sms_ * meta_blocks_per_sm_, gw = num_sms_ * work_blocks_per_sm_;
   if (phase == 0) {
-    phase_scan_kernel<0><<<num_sms_ * scan_blocks_per_sm_, kThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, work_count_);
-    phase_work_kernel<0><<<num_sms_ * work_blocks_per_sm_, kWorkThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, work_count_);
+    phase_scan_kernel<0><<<gs, kThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, work_count_);
+    phase_meta_kernel<0, 0><<<gm, kThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, work_count_);
+    phase_row_kernel<<<gw, kWorkThreads, 0, sync_stream_>>>(round_dev_, worklist_, work_count_);
+    phase_meta_kernel<0, 1><<<gm, kThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, work_count_);
   } else {
-    phase_scan_kernel<1><<<num_sms_ * scan_blocks_per_sm_, kThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, work_count_);
-    phase_work_kernel<1><<<num_sms_ * work_blocks_per_sm_, kWorkThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, work_count_);
+    phase_scan_kernel<1><<<gs, kThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, work_count_);
+    phase_meta_kernel<1, 0><<<gm, kThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, work_count_);
+    phase_row_kernel<<<gw, kWorkThreads, 0, sync_stream_>>>(round_dev_, worklist_, work_count_);
+    phase_meta_kernel<1, 1><<<gm, kThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, work_count_);
   }
-  ADAPM_COUNT_LAUNCH();
-  ADAPM_COUNT_LAUNCH();
+  for (int i = 0; i < 4; ++i) ADAPM_COUNT_LAUNCH();
   ADAPM_CUDA_CHECK(cudaGetLastError());
 }
 

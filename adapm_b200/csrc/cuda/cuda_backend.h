@@ -106,7 +106,8 @@ class CudaBackend : public Backend {
   std::vector<TraceRec> trace_;
   std::mutex trace_mu_;
   int scan_blocks_per_sm_ = 1;   // ADAPM_SYNC_SCAN_BLOCKS
-  int work_blocks_per_sm_ = 2;   // ADAPM_SYNC_WORK_BLOCKS (blocks of 128 threads)
+  int work_blocks_per_sm_ = 1;   // ADAPM_SYNC_WORK_BLOCKS (row pass: blocks of 128 threads)
+  int meta_blocks_per_sm_ = 1;   // ADAPM_SYNC_META_BLOCKS (resolve / commit passes: blocks of 256 threads)
   cudaStream_t sync_stream_ = nullptr;
   std::vector<cudaStream_t> worker_streams_;
   std::vector<std::unique_ptr<Staging>> staging_;  // per worker
@@ -117,7 +118,7 @@ class CudaBackend : public Backend {
   std::unordered_map<uint64_t, cudaEvent_t> tickets_;
   std::vector<cudaEvent_t> event_pool_;
   uint64_t next_ticket_ = 1;
-  uint32_t* worklist_ = nullptr;       // slots that need work in the current phase (device)
+  SlotWork* worklist_ = nullptr;       // slots that need work in the current phase (device), one record each
   unsigned int* work_count_ = nullptr;
   // device-resident round (default for world > 1; ADAPM_HOST_ROUND=1 selects the host-sequenced round)
   void upload_round(const RoundParams& rp, uint32_t n_recs, uint32_t flags);

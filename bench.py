@@ -42,6 +42,9 @@ def parse_args():
     ap.add_argument("--negative", type=int, default=25)
     ap.add_argument("--batch-pairs", type=int, default=32768)
     ap.add_argument("--read-ahead", type=int, default=32, help="intent look-ahead in steps (the reference reads 1000 sentences ahead)")
+    ap.add_argument("--placement-steps", type=int, default=-1,
+                    help="untimed training steps before the W warm-up steps that let the adaptive placement reach its steady "
+                         "state (N > 1 only; default: 3 x read-ahead, 0 for N = 1)")
     ap.add_argument("--max-inflight", type=int, default=3, help="steps the host may run ahead of the GPU")
     ap.add_argument("--sampling", default="local", choices=["local", "naive"])
     ap.add_argument("--techniques", default="all")
@@ -161,10 +164,17 @@ def main():
     data = SyntheticPairs(cfg, counts, rank, seed=1)
 
     K, W, RA = args.steps, args.warmup, cfg.read_ahead
-    total_steps = W + 2 * K + 640   # e2e loop + device-resident loop (+ profiling)
-    # data loader: pre-read all batches into pinned host memory (the reference reads sentences ahead too)
-    RING = 64  # distinct pinned batches, cycled (64 x 32768 pairs x 27 rows touch far more than L2 holds)
-    ring = [data.batch(s).pin_memory() for s in range(min(RING, total_steps + RA + 1))]
+    # Steady state: a parameter manager adapts its placement to the access pattern, so the first steps of a job run on
+    # a cold placement (every non-home row has to be requested once). P untimed training steps - same loop, same API -
+    # precede the W warm-up steps; nothing is pre-localised outside the loop and timing starts more than RA steps after
+    # the first intent, i.e. every timed step works on rows whose intent was signalled RA steps earlier INSIDE the loop.
+    P = args.placement_steps if args.placement_steps >= 0 else (3 * RA if world > 1 else 0)
+    n_prof = 640 if args.profile else 0
+    total_steps = P + W + K + 3 + K + n_prof   # placement + warm-up + e2e loop + device-resident loop (+ profiling)
+    # data loader: batches are read ahead into pinned host memory (the reference reads sentences ahead too). Every step
+    # has its own batch (no ring that would re-use localised rows) up to 2048 batches = 1 GB of pinned keys.
+    n_batches = min(total_steps + RA + 2, 2048)
+    ring = [data.batch(s).pin_memory() for s in range(n_batches)]
     for b_ in ring:
         # like the native loader (utils.text.NativeCorpus.pair_batches): every batch carries its distinct keys, which is
         # what Intent() is called with - deduplication belongs to the loader thread, not to the training loop
@@ -172,7 +182,7 @@ def main():
 
     class _Batches:
         def __len__(self):
-            return total_steps + RA + 1
+            return total_steps + RA + 2
 
         def __getitem__(self, i):
             if isinstance(i, slice):
@@ -183,8 +193,14 @@ def main():
     loss_host = torch.zeros(total_steps + 1, dtype=torch.float32).pin_memory()
     stream = torch.cuda.current_stream()
 
-    dev_ring = [b.to(dev) for b in ring]
+    # device-resident inputs of the second timed loop: exactly the batches of its steps (+ profiling windows)
+    dev_first = P + W + K
+    dev_ring = {s: batches[s].to(dev) for s in range(dev_first, min(total_steps, dev_first + 3 + K + n_prof))}
     from adapm_b200.ops import sgns_step
+
+    def dev_batch(s):
+        t = dev_ring.get(s)
+        return t if t is not None else batches[s].to(dev)
 
     def train_step(s, resident):
         """One training step through the public API. resident=False: this step's key batch is copied
@@ -194,21 +210,21 @@ def main():
             model.signal_intent(batches[s + RA], worker.current_clock() + RA)
         model.loss.zero_()
         if resident:
-            model.step_resident(dev_ring[s % len(dev_ring)])
+            model.step_resident(dev_batch(s))
         else:
             model.step(batches[s])                                       # (prefetched) H2D copy + sampler + fused step
             loss_host[s:s + 1].copy_(model.loss, non_blocking=True)      # D2H read of the step result
             model.prefetch(batches[s + 1])                               # H2D of the next step's keys (copy stream)
         worker.advance_clock()
 
-    # ---------------- warm-up (also lets the sync engine localise the first batches)
-    for s in range(RA):
-        model.signal_intent(batches[s], worker.current_clock() + s)
-    if world > 1:
-        worker.wait_sync()
-    for s in range(W):
+    # ---------------- placement steps + warm-up: the same loop as the timed one
+    for s in range(min(RA, len(batches))):
+        model.signal_intent(batches[s], worker.current_clock() + s)     # the first RA steps have no earlier step to signal them
+    for s in range(P + W):
         train_step(s, False)
     barrier()
+    counters0 = server.counters()
+    stats0 = model.stats.tolist()
 
     sampler = ClockSampler(local_rank)
     if rank == 0 and not os.environ.get("ADAPM_BENCH_NO_SMI"):
@@ -220,7 +236,7 @@ def main():
     barrier()
     ev0.record(stream)
     t_host0 = time.perf_counter()
-    for s in range(W, W + K):
+    for s in range(P + W, P + W + K):
         train_step(s, False)
     host_ms = (time.perf_counter() - t_host0) * 1e3 / K
     ev1.record(stream)
@@ -229,19 +245,21 @@ def main():
     launches_e2e = _C.kernel_launches() - launches0
 
     # ---------------- device-resident timed region (same loop, inputs already on the device)
-    for s in range(W + K, W + K + 3):
+    for s in range(P + W + K, P + W + K + 3):
         train_step(s, True)
     barrier()
     launches1 = _C.kernel_launches()
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev2.record(stream)
-    for s in range(W + K + 3, W + 2 * K + 3):
+    for s in range(P + W + K + 3, P + W + 2 * K + 3):
         train_step(s, True)
     ev3.record(stream)
     barrier()
     dev_ms = ev2.elapsed_time(ev3)
     launches_dev = _C.kernel_launches() - launches1
+    counters1 = server.counters()
+    stats1 = model.stats.tolist()
     clocks = sampler.stop() if rank == 0 else None
     if rank == 0 and sampler.p is None:
         clocks = {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling disabled (ADAPM_BENCH_NO_SMI)"]}
@@ -250,7 +268,8 @@ def main():
     prof = None
     if args.profile:
         # diagnostic: the device-resident loop once more, now without the nvidia-smi clock sampler running
-        base = W + 2 * K + 3
+        PB = P + W + 2 * K
+        base = PB + 3
         ev4, ev5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         ev4.record(stream)
@@ -260,11 +279,11 @@ def main():
         barrier()
         second_pass_ms = ev4.elapsed_time(ev5) / 100
         evs = []
-        for s in range(W + 2 * K + 103, W + 2 * K + 143):
+        for s in range(PB + 103, PB + 143):
             a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             if s + RA < len(batches):
                 model.signal_intent(batches[s + RA], worker.current_clock() + RA)
-            kb = dev_ring[s % len(dev_ring)]
+            kb = dev_batch(s)
             a.record(stream)
             model.sample_negatives()
             b.record(stream)
@@ -282,7 +301,7 @@ def main():
         sec = {"intent": 0.0, "wait_gpu": 0.0, "launch": 0.0, "d2h": 0.0, "prefetch": 0.0, "clock": 0.0}
         NP = 100
         pc = time.perf_counter
-        for s in range(W + 2 * K + 143, W + 2 * K + 143 + NP):
+        for s in range(PB + 143, PB + 143 + NP):
             t0 = pc()
             if s + RA < len(batches):
                 model.signal_intent(batches[s + RA], worker.current_clock() + RA)
@@ -321,7 +340,7 @@ def main():
                 model.loss.zero_()
                 if tracing:
                     server._impl.trace_mark("step_begin", stream.cuda_stream)
-                model.step_resident(dev_ring[s % len(dev_ring)])
+                model.step_resident(dev_batch(s))
                 if tracing:
                     server._impl.trace_mark("step_end", stream.cuda_stream)
                 worker.advance_clock()
@@ -333,7 +352,7 @@ def main():
             return {"mean": round(sum(ts) / n, 4), "p10": round(ts[n // 10], 4), "p50": round(ts[n // 2], 4),
                     "p90": round(ts[9 * n // 10], 4), "max": round(ts[-1], 4),
                     "rows_local_remote_slow": rows}
-        first = W + 2 * K + 243
+        first = PB + 243
         prof["steps_with_intent"] = per_step(first, 192, True)
         if tracing:   # kernel timeline of the round kernels and the steps, one file per rank
             os.makedirs("gpurun_out", exist_ok=True)
@@ -353,17 +372,39 @@ def main():
     e2e_value = updates_per_step * K / (e2e_ms * 1e-3)
     h2d = cfg.batch_pairs * 2 * 8
     if rank == 0:
-        bytes_per_update = 2 * cfg.row_len * 4  # read row + reduce row
+        here = os.path.dirname(os.path.abspath(__file__))
+        row_bytes = cfg.row_len * 4
+        bytes_per_update = 2 * row_bytes  # read row + reduce row
         try:
-            peaks = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")))
+            peaks = json.load(open(os.path.join(here, "MEASURED_PEAKS.json")))
             hbm = peaks["hbm_gbs"]
             denom = "measured"
         except Exception:
             hbm, denom = 6650.0, "fallback"
+        # same-box anchor: the NCCL-only arm (bench.py --impl nccl, stock PyTorch ops + all_to_all), measured on this pool
+        # and recorded in baseline/nccl_arm.json by N; the reference itself cannot be built
+        vs_baseline, anchor = None, None
+        try:
+            arm = json.load(open(os.path.join(here, "baseline", "nccl_arm.json")))
+            anchor = arm["updates_per_s"].get(str(world))
+            if anchor:
+                vs_baseline = value / anchor
+        except Exception:
+            pass
+        # traffic of rank 0 inside the two timed loops (+ 3 steps between them), per step
+        n_steps_win = 2 * K + 3
+        dstat = [b_ - a_ for a_, b_ in zip(stats0, stats1)]
+        dcnt = {k: counters1[k] - counters0[k] for k in counters1 if isinstance(counters1[k], int) and k in counters0}
+        nv_step = (2 * dstat[1] * row_bytes                                             # fused step: remote row load + reduction
+                   + (dcnt.get("refreshes", 0) + dcnt.get("relocations", 0)) * row_bytes  # round: owner row reads
+                   + dcnt.get("deltas_shipped", 0) * row_bytes) / n_steps_win            # round: replica deltas (reductions)
+        link_gbs = 770.0   # measured peer copy, one direction, per GPU (B200_PROFILING.md)
+        nv_time_ms = nv_step / (link_gbs * 1e9) * 1e3
+        hbm_time_ms = cfg.batch_pairs * cfg.updates_per_pair * bytes_per_update / (hbm * 1e9) * 1e3
         out = {
             "metric": "word2vec SGNS updates/sec (device-timed, max over ranks)",
             "value": value, "unit": "updates/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": vs_baseline,
             "dtype": "fp32", "data": "synthetic", "impl": "native",
             "config": {"model": "word2vec SGNS 1M-vocab d=300 (rows = [embedding|AdaGrad], 2400 B fp32)",
                        "vocab": cfg.vocab_size, "embed_dim": cfg.embed_dim, "negative": cfg.negative,
@@ -371,8 +412,14 @@ def main():
                        "seq_len": None, "updates_per_pair": cfg.updates_per_pair,
                        "parallelism": f"pm{world} (key-sharded store, intent-driven relocation/replication)",
                        "sampling": cfg.sampling_scheme, "intent_read_ahead": RA,
+                       "placement_steps": P,
+                       "placement_note": "P untimed training steps (same loop) run before the W warm-up steps so that the "
+                                         "adaptive placement is in steady state; nothing is localised outside the loop",
                        "intent_keys": "distinct keys of the batch, prepared by the loader (outside the step loop)",
-                       "l2": "inputs larger than L2: 4.8 GB table; a ring of 64 distinct random batches (56M row touches) is cycled",
+                       "l2": f"inputs larger than L2: 4.8 GB table; every step has its own random batch "
+                             f"({len(ring)} distinct batches, {'no wrap' if len(ring) >= total_steps + RA + 2 else 'wraps'})",
+                       "vs_baseline_anchor": ("bench.py --impl nccl on the same pool: %.4g updates/s at N=%d "
+                                              "(baseline/nccl_arm.json)" % (anchor, world)) if anchor else None,
                        "note": "reference dtype is float32 (apps/word2vec.cc:40); rows stay fp32 for exact additive updates"},
             "e2e": {"value": e2e_value, "unit": "updates/s", "ms_per_step": e2e_ms / K,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
@@ -380,13 +427,19 @@ def main():
             "clocks": clocks,
             "roofline": {"hbm_bytes_per_update": bytes_per_update,
                          "achieved_hbm_gbs_per_gpu": value / world * bytes_per_update / 1e9,
-                         "fraction_of_hbm_peak": value / world * bytes_per_update / 1e9 / hbm, "peak": denom},
-            "locality": {"rows_local": stats[0], "rows_remote": stats[1], "rows_slow_path": stats[2]},
-            "pm": {k: counters[k] for k in ("relocations", "replica_setups", "replica_drops", "refreshes",
-                                            "deltas_shipped", "sync_rounds", "protocol_errors")},
+                         "fraction_of_hbm_peak": value / world * bytes_per_update / 1e9 / hbm, "peak": denom,
+                         "nvlink_bytes_per_step_per_gpu": nv_step, "nvlink_gbs_per_gpu": nv_step / (dev_ms / K * 1e-3) / 1e9,
+                         "nvlink_fraction_of_link": nv_step / (dev_ms / K * 1e-3) / 1e9 / link_gbs,
+                         "roofline_ms_per_step": max(nv_time_ms, hbm_time_ms),
+                         "fraction_of_roofline": max(nv_time_ms, hbm_time_ms) / (dev_ms / K),
+                         "note": "roofline = slower of (algorithmic HBM bytes / measured copy bandwidth) and (bytes that "
+                                 "crossed NVLink / 770 GB/s measured peer copy); rank 0's counters over both timed loops"},
+            "locality": {"rows_local": dstat[0], "rows_remote": dstat[1], "rows_slow_path": dstat[2]},
+            "pm": {k: dcnt.get(k, 0) for k in ("relocations", "replica_setups", "replica_drops", "refreshes",
+                                                "deltas_shipped", "sync_rounds", "protocol_errors")},
             "profile": prof, "host_loop_ms_per_step": host_ms,
             "sync_report": server._impl.sync_report() if world > 1 else None,
-            "loss_last": float(loss_host[W + K - 1]) / max(1, cfg.batch_pairs * (cfg.negative + 1)),
+            "loss_last": float(loss_host[P + W + K - 1]) / max(1, cfg.batch_pairs * (cfg.negative + 1)),
         }
         print(json.dumps(out))
     worker.finalize()

@@ -237,3 +237,10 @@ def test_control_block_allreduce(mode):
     res = run_cluster(_allreduce_sum_worker, world=3, workers=1, mode=mode, value_lengths=1, num_keys=8)
     for r in res.values():
         assert r[0][0] == [6.0, 1.5, -6.0] and r[0][1] == [3.0]
+
+
+def test_fd_channel_between_ranks():
+    """The unix-socket channel that carries VMM heap handles / the multicast object between the ranks of a box."""
+    from adapm_b200 import _C
+
+    assert _C._fdpass_selftest()
