@@ -110,9 +110,9 @@ def main(argv=None) -> int:
     known = torch.cat([tr, va, te])
     t0 = time.time()
     if args.eval_initial:
+        ev = model.evaluate_distributed(va, known)      # collective: every rank ranks its share (kge.cc:555-709)
         if rank == 0:
-            print(f"[kge] initial valid: {model.evaluate(va, known)}", flush=True)
-        kv.barrier()
+            print(f"[kge] initial valid: {ev}", flush=True)
     for epoch in range(1, args.num_epochs + 1):
         perm = mine[torch.randperm(mine.shape[0], generator=torch.Generator().manual_seed(epoch * 977 + rank))]
         starts = list(range(0, perm.shape[0], cfg.batch_triples))
@@ -138,11 +138,10 @@ def main(argv=None) -> int:
         if rank == 0:
             print(f"[kge] epoch {epoch}: bce loss {float(total[0]):.4f} ({time.time() - t0:.1f}s)", flush=True)
         if args.eval_freq > 0 and epoch % args.eval_freq == 0:
+            ev = model.evaluate_distributed(va, known)
+            trn = model.evaluate_distributed(tr, known, truncate=args.eval_truncate_tr) if args.eval_truncate_tr else None
             if rank == 0:
-                ev = model.evaluate(va, known)
-                trn = model.evaluate(tr[: args.eval_truncate_tr], known) if args.eval_truncate_tr else None
                 print(f"[kge] epoch {epoch} valid: {ev}" + (f" train: {trn}" if trn else ""), flush=True)
-            kv.barrier()
         if args.model_path and epoch % args.write_every == 0:
             model.save(args.model_path, epoch, write_checkpoint=bool(args.write_end_checkpoint) and epoch == args.num_epochs)
         if time.time() - t0 > args.max_runtime:
@@ -151,7 +150,9 @@ def main(argv=None) -> int:
         if model.cuda and cfg.algorithm == "ComplEx" and cfg.embed_dim % 4 == 0:
             # fused gather + tcgen05 GEMM + rank count: entity rows are read from every GPU's HBM in-kernel
             print(f"[kge] test (fused gather-GEMM eval): {evaluate_fused(model, te, known)}", flush=True)
-        print(f"[kge] test: {model.evaluate(te, known)}", flush=True)
+    ev = model.evaluate_distributed(te, known)
+    if rank == 0:
+        print(f"[kge] test: {ev}", flush=True)
     kv.barrier()
     kv.finalize()
     if rank == 0:

@@ -37,10 +37,18 @@ void bind(py::module_& m) {
                    ptr<unsigned int>(out_count));
   });
   m.def("kge_complex_step", [](uintptr_t be, uintptr_t stream, uintptr_t s, uintptr_t r, uintptr_t o, uintptr_t labels,
-                               int n, int nh, float eta, float gamma_e, float gamma_r, uintptr_t loss, uintptr_t stats) {
+                               int n, int nh, float eta, float gamma_e, float gamma_r, uintptr_t loss, uintptr_t stats,
+                               float dropout_e, float dropout_r, uint64_t seed) {
     kge_complex_step(backend_of(be), (cudaStream_t)stream, ptr<const Key>(s), ptr<const Key>(r), ptr<const Key>(o),
                      ptr<const float>(labels), n, nh, eta, gamma_e, gamma_r, ptr<float>(loss),
-                     ptr<unsigned long long>(stats));
+                     ptr<unsigned long long>(stats), dropout_e, dropout_r, seed);
+  });
+  m.def("kge_rescal_step", [](uintptr_t be, uintptr_t stream, uintptr_t s, uintptr_t r, uintptr_t o, uintptr_t labels,
+                              int n, int D, float eta, float gamma_e, float gamma_r, uintptr_t loss, uintptr_t stats,
+                              float dropout_e, float dropout_r, uint64_t seed) {
+    kge_rescal_step(backend_of(be), (cudaStream_t)stream, ptr<const Key>(s), ptr<const Key>(r), ptr<const Key>(o),
+                    ptr<const float>(labels), n, D, eta, gamma_e, gamma_r, ptr<float>(loss),
+                    ptr<unsigned long long>(stats), dropout_e, dropout_r, seed);
   });
   m.def("mf_step", [](uintptr_t be, uintptr_t stream, uintptr_t rows, uintptr_t cols, uintptr_t xs, uintptr_t rn,
                       uintptr_t cn, int n, int rank, float eps, float lambda, uintptr_t loss, uintptr_t stats) {

@@ -13,6 +13,8 @@
 #include <cuda_runtime.h>
 
 #include <cstdlib>
+#include <map>
+#include <mutex>
 
 #include "ops.h"
 #include "pm_kernels.cuh"
@@ -31,6 +33,28 @@ __device__ __forceinline__ float4 f4_fma(float4 a, float4 b, float4 c) {
 __device__ __forceinline__ float4 f4_sub(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
 __device__ __forceinline__ float f4_hsum(float4 a) { return a.x + a.y + a.z + a.w; }
 
+// Dropout on the pulled copies (reference kge.cc:405-413,478-484: Bernoulli(p) zero, others scaled by 1/(1-p); score,
+// gradients and L2 all see the masked copy; the AdaGrad half of a row is untouched). The mask is a pure function of
+// (seed, training call, which row of the call, element index) so that the PyTorch reference of the tests can
+// reproduce it (ops.kge_dropout_mask mirrors mask_keep bit by bit).
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+struct Dropout {
+  uint32_t seed;
+  float p, scale;   // scale = 1 / (1 - p)
+  __device__ __forceinline__ float keep(uint32_t call, uint32_t which, uint32_t elem) const {
+    const uint32_t u = mix32(mix32(seed + call * 3u + which) ^ (elem * 0x9E3779B9u));
+    return ((float)(u >> 8) * (1.0f / 16777216.0f)) >= p ? scale : 0.f;
+  }
+  __device__ __forceinline__ float4 apply4(float4 v, uint32_t call, uint32_t which, uint32_t elem0) const {
+    if (p <= 0.f) return v;
+    return make_float4(v.x * keep(call, which, elem0), v.y * keep(call, which, elem0 + 1),
+                       v.z * keep(call, which, elem0 + 2), v.w * keep(call, which, elem0 + 3));
+  }
+};
+
 // g = dl * d + (reg ? gamma * x : 0); returns AdaGrad update pair and issues the reductions.
 __device__ __forceinline__ void adagrad_push4(float* emb_ptr, float* acc_ptr, float4 d, float4 x, float dl, float gamma,
                                               float eta) {
@@ -46,11 +70,19 @@ __device__ __forceinline__ void adagrad_push4(float* emb_ptr, float* acc_ptr, fl
 
 // scalar generic path (any nh; also used when a row is in a transitional state): rows staged in smem
 __device__ __noinline__ float kge_call_generic(const Ctx& c, Key ks, Key kr, Key ko, float label, int nh, float eta,
-                                               float gamma_e, float gamma_r, float* stage, bool* applied) {
+                                               float gamma_e, float gamma_r, float* stage, bool* applied, uint32_t call,
+                                               Dropout de, Dropout dr) {
   const int lane = threadIdx.x & 31;
   float* S = stage; float* R = stage + 2 * nh; float* O = stage + 4 * nh;
   *applied = false;
   if (!dev::slow_pull(c, ks, S) || !dev::slow_pull(c, kr, R) || !dev::slow_pull(c, ko, O)) return 0.f;
+  if (de.p > 0.f || dr.p > 0.f) {
+    for (int i = lane; i < nh; i += 32) {
+      if (de.p > 0.f) { S[i] *= de.keep(call, 0, (uint32_t)i); O[i] *= de.keep(call, 2, (uint32_t)i); }
+      if (dr.p > 0.f) R[i] *= dr.keep(call, 1, (uint32_t)i);
+    }
+    __syncwarp();
+  }
   const int H = nh / 2;
   float sc = 0.f;
   for (int i = lane; i < H; i += 32)
@@ -91,7 +123,8 @@ template <int VPLH, int MAXREG>
 __global__ void __maxnreg__(MAXREG)
 kge_step_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ subj, const Key* __restrict__ rel,
                 const Key* __restrict__ obj, const float* __restrict__ labels, int n_calls, int nh, float eta,
-                float gamma_e, float gamma_r, float* __restrict__ loss_out, unsigned long long* __restrict__ stats) {
+                float gamma_e, float gamma_r, float* __restrict__ loss_out, unsigned long long* __restrict__ stats,
+                Dropout de, Dropout dr) {
   extern __shared__ float smem_f[];  // generic path: per warp 6*nh floats
   dev::cta_enter(c);
   const int lane = threadIdx.x & 31;
@@ -119,7 +152,7 @@ kge_step_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ subj, con
     if (VPLH == 0 || !ps || !pr || !po) {
       ++n_slow;
       bool applied;
-      loss_acc += kge_call_generic(c, ks, kr, ko, label, nh, eta, gamma_e, gamma_r, stage, &applied);
+      loss_acc += kge_call_generic(c, ks, kr, ko, label, nh, eta, gamma_e, gamma_r, stage, &applied, (uint32_t)p, de, dr);
       if (applied) n_upd += 3;
       continue;
     }
@@ -134,6 +167,12 @@ kge_step_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ subj, con
       sre[v] = in ? dev::ld_row4(ps + 4 * j) : z; sim[v] = in ? dev::ld_row4(ps + H + 4 * j) : z;
       rre[v] = in ? dev::ld_row4(pr + 4 * j) : z; rim[v] = in ? dev::ld_row4(pr + H + 4 * j) : z;
       ore[v] = in ? dev::ld_row4(po + 4 * j) : z; oim[v] = in ? dev::ld_row4(po + H + 4 * j) : z;
+      if (in && (de.p > 0.f || dr.p > 0.f)) {   // dropout on the pulled copies (uniform branch: kernel arguments)
+        const uint32_t e = 4u * (uint32_t)j, cp = (uint32_t)p;
+        sre[v] = de.apply4(sre[v], cp, 0, e); sim[v] = de.apply4(sim[v], cp, 0, (uint32_t)H + e);
+        rre[v] = dr.apply4(rre[v], cp, 1, e); rim[v] = dr.apply4(rim[v], cp, 1, (uint32_t)H + e);
+        ore[v] = de.apply4(ore[v], cp, 2, e); oim[v] = de.apply4(oim[v], cp, 2, (uint32_t)H + e);
+      }
     }
 #pragma unroll
     for (int v = 0; v < V; ++v) {
@@ -189,13 +228,156 @@ kge_step_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ subj, con
   dev::cta_exit(c);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// RESCAL (reference kge.cc:895-922): score = s^T R o with a D x D relation matrix (relation row = [R | AdaGrad] of
+// 2 D^2 floats), gradients d_s = R o, d_o = R^T s, d_R = s o^T (rank 1). One warp per training call:
+//   pass 1  stream R once (16-byte loads, local HBM or NVLink): per float4 a row-dot into ds[i] and four axpy terms
+//           into do[j..j+3] (shared-memory accumulators of the warp) -> score = s . ds
+//   entity rows: AdaGrad + 16-byte reductions for s and o
+//   pass 2  stream R's values + accumulators again (L2 hits), form dl * s_i * o_j (+ gamma R_ij), AdaGrad, 16-byte
+//           reductions into both halves of the relation row
+// Rows in a transitional protocol state go through the generic Pull/Push path with a global scratch buffer.
+__device__ __noinline__ bool rescal_slow_rows(const Ctx& c, Key ks, Key kr, Key ko, float* gs, float* gr, float* go) {
+  return dev::slow_pull(c, ks, gs) && dev::slow_pull(c, kr, gr) && dev::slow_pull(c, ko, go);
+}
+
+__global__ void __launch_bounds__(kThreads)
+kge_rescal_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ subj, const Key* __restrict__ rel,
+                  const Key* __restrict__ obj, const float* __restrict__ labels, int n_calls, int D, float eta,
+                  float gamma_e, float gamma_r, float* __restrict__ loss_out, unsigned long long* __restrict__ stats,
+                  Dropout de, Dropout dr, float* __restrict__ scratch) {
+  extern __shared__ float smem_f[];   // per warp: s[D] | o[D] | ds[D] | do[D]
+  dev::cta_enter(c);
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  float* sv = smem_f + (size_t)wib * 4 * D;
+  float* ov = sv + D; float* dsv = ov + D; float* dov = dsv + D;
+  const int DD = D * D;
+  const int nv = DD >> 2;          // float4 of the relation matrix
+  float* my_scratch = scratch + (size_t)warp * (size_t)(2 * DD + 4 * D);   // generic path: rel row | s row | o row
+  float loss_acc = 0.f;
+  unsigned n_local = 0, n_remote = 0, n_slow = 0, n_upd = 0;
+
+  for (int p = warp; p < n_calls; p += nwarps) {
+    const Key ks = subj[p], kr = rel[p], ko = obj[p];
+    const float label = labels[p];
+    dev::Target t;
+    t.row = nullptr; t.version = nullptr; t.flag = nullptr;
+    if (lane < 3) {
+      Key k = lane == 0 ? ks : (lane == 1 ? kr : ko);
+      t = dev::resolve_fast(c, k, class_of_key(c, k), &n_local, &n_remote);
+    }
+    float* ps = (float*)__shfl_sync(0xffffffffu, (unsigned long long)t.row, 0);
+    float* pr = (float*)__shfl_sync(0xffffffffu, (unsigned long long)t.row, 1);
+    float* po = (float*)__shfl_sync(0xffffffffu, (unsigned long long)t.row, 2);
+    const bool slow = !ps || !pr || !po;
+    if (slow) {   // stage the three rows in global scratch and run the same math on the copies
+      ++n_slow;
+      float* gr_ = my_scratch; float* gs_ = my_scratch + 2 * DD; float* go_ = gs_ + 2 * D;
+      if (!rescal_slow_rows(c, ks, kr, ko, gs_, gr_, go_)) continue;
+      ps = gs_; pr = gr_; po = go_;
+    }
+    const uint32_t cp = (uint32_t)p;
+    for (int i = lane; i < D; i += 32) {
+      float a = reinterpret_cast<const volatile float*>(ps)[i];
+      float b = reinterpret_cast<const volatile float*>(po)[i];
+      if (de.p > 0.f) { a *= de.keep(cp, 0, (uint32_t)i); b *= de.keep(cp, 2, (uint32_t)i); }
+      sv[i] = a; ov[i] = b; dsv[i] = 0.f; dov[i] = 0.f;
+    }
+    __syncwarp();
+    // ---- pass 1: ds = R o, do = R^T s
+    for (int q = lane; q < nv; q += 32) {
+      const int e = 4 * q, i = e / D, j = e - i * D;
+      float4 r4 = dev::ld_row4(pr + e);
+      if (dr.p > 0.f) r4 = dr.apply4(r4, cp, 1, (uint32_t)e);
+      const float si = sv[i];
+      atomicAdd(dsv + i, r4.x * ov[j] + r4.y * ov[j + 1] + r4.z * ov[j + 2] + r4.w * ov[j + 3]);
+      atomicAdd(dov + j, si * r4.x); atomicAdd(dov + j + 1, si * r4.y);
+      atomicAdd(dov + j + 2, si * r4.z); atomicAdd(dov + j + 3, si * r4.w);
+    }
+    __syncwarp();
+    float sc = 0.f;
+    for (int i = lane; i < D; i += 32) sc += sv[i] * dsv[i];
+    sc = dev::warp_sum(sc);
+    const float dl = 1.f / (1.f + __expf(-sc)) - label;
+    const bool pos = label > 0.5f;
+    const float ge = pos ? gamma_e : 0.f, grr = pos ? gamma_r : 0.f;
+    {
+      float z = pos ? sc : -sc;
+      loss_acc += __logf(1.f + __expf(-fminf(fmaxf(z, -30.f), 30.f)));
+    }
+    // ---- entity rows
+    for (int i = lane; i < D; i += 32) {
+      const float g_s = fmaf(ge, sv[i], dl * dsv[i]), g_o = fmaf(ge, ov[i], dl * dov[i]);
+      const float a_s = reinterpret_cast<const volatile float*>(ps)[D + i], a_o = reinterpret_cast<const volatile float*>(po)[D + i];
+      const float us = -eta * g_s * rsqrtf(a_s + g_s * g_s), uo = -eta * g_o * rsqrtf(a_o + g_o * g_o);
+      if (slow) { ps[i] = us; ps[D + i] = g_s * g_s; po[i] = uo; po[D + i] = g_o * g_o; }
+      else { mem::red_add(ps + i, us); mem::red_add(ps + D + i, g_s * g_s); mem::red_add(po + i, uo); mem::red_add(po + D + i, g_o * g_o); }
+    }
+    // ---- pass 2: relation matrix update (rank-1 gradient)
+    for (int q = lane; q < nv; q += 32) {
+      const int e = 4 * q, i = e / D, j = e - i * D;
+      float4 r4 = dev::ld_row4(pr + e);
+      if (dr.p > 0.f) r4 = dr.apply4(r4, cp, 1, (uint32_t)e);
+      const float4 a4 = dev::ld_row4(pr + DD + e);
+      const float w = dl * sv[i];
+      const float4 g = make_float4(fmaf(grr, r4.x, w * ov[j]), fmaf(grr, r4.y, w * ov[j + 1]), fmaf(grr, r4.z, w * ov[j + 2]),
+                                   fmaf(grr, r4.w, w * ov[j + 3]));
+      const float4 ua = f4_mul(g, g);
+      const float4 ue = make_float4(-eta * g.x * rsqrtf(a4.x + ua.x), -eta * g.y * rsqrtf(a4.y + ua.y),
+                                    -eta * g.z * rsqrtf(a4.z + ua.z), -eta * g.w * rsqrtf(a4.w + ua.w));
+      if (slow) { *reinterpret_cast<float4*>(pr + e) = ue; *reinterpret_cast<float4*>(pr + DD + e) = ua; }
+      else { dev::red_row4(pr + e, ue); dev::red_row4(pr + DD + e, ua); }
+    }
+    if (slow) {
+      __syncwarp();
+      bool ok = dev::slow_push(c, ks, ps);
+      ok = dev::slow_push(c, kr, pr) && ok;
+      ok = dev::slow_push(c, ko, po) && ok;
+      if (ok) n_upd += 3;
+    } else {
+      if (lane < 3) dev::mark_pushed(t);
+      n_upd += 3;
+    }
+    __syncwarp();
+  }
+
+  __syncwarp();
+  if (lane == 0 && loss_out) atomicAdd(loss_out, loss_acc);
+  unsigned sl = n_local, sr = n_remote;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sl += __shfl_xor_sync(0xffffffffu, sl, o);
+    sr += __shfl_xor_sync(0xffffffffu, sr, o);
+  }
+  if (lane == 0 && stats) {
+    if (sl) atomicAdd(stats + 0, (unsigned long long)sl);
+    if (sr) atomicAdd(stats + 1, (unsigned long long)sr);
+    if (n_slow) atomicAdd(stats + 2, (unsigned long long)n_slow);
+    if (n_upd) atomicAdd(stats + 3, (unsigned long long)n_upd);
+  }
+  dev::cta_exit(c);
+}
+
 }  // namespace
 
 // n_calls training calls (s[i], r[i], o[i], label[i]); entity and relation rows must be 2*nh floats.
+static Dropout make_dropout(float p, uint64_t seed, uint32_t salt) {
+  Dropout d;
+  d.p = p > 0.f ? p : 0.f;
+  ADAPM_CHECK(d.p < 1.f, "dropout probability must be < 1");
+  d.scale = 1.f / (1.f - d.p);
+  d.seed = (uint32_t)(seed ^ (seed >> 32)) * 2654435761u + salt;
+  return d;
+}
+
 void kge_complex_step(CudaBackend& be, cudaStream_t stream, const Key* subj, const Key* rel, const Key* obj,
                       const float* labels, int n_calls, int nh, float eta, float gamma_e, float gamma_r, float* loss_out,
-                      unsigned long long* stats) {
+                      unsigned long long* stats, float dropout_e, float dropout_r, uint64_t seed) {
   if (n_calls == 0) return;
+  const Dropout de = make_dropout(dropout_e, seed, 0x11u), dr = make_dropout(dropout_r, seed, 0x22u);
   ADAPM_CHECK(nh % 2 == 0, "ComplEx needs an even embedding size");
   be.track_stream(stream);
   const Ctx& c = be.ctx();
@@ -216,7 +398,7 @@ void kge_complex_step(CudaBackend& be, cudaStream_t stream, const Key* subj, con
       attr_set = true;                                                                                         \
     }                                                                                                          \
     kge_step_kernel<V, R><<<blocks, kThreads, smem, stream>>>(c, subj, rel, obj, labels, n_calls, nh, eta,     \
-                                                              gamma_e, gamma_r, loss_out, stats);              \
+                                                              gamma_e, gamma_r, loss_out, stats, de, dr);      \
   } while (0)
 #define ADAPM_LAUNCH_KGE(V)              \
   do {                                   \
@@ -228,6 +410,39 @@ void kge_complex_step(CudaBackend& be, cudaStream_t stream, const Key* subj, con
     case 2: ADAPM_LAUNCH_KGE(2); break;
     default: ADAPM_LAUNCH_KGE(0); break;
   }
+  ADAPM_COUNT_LAUNCH();
+  ADAPM_CUDA_CHECK(cudaGetLastError());
+}
+
+// RESCAL training calls: entity rows 2*D floats, relation rows 2*D*D floats (D % 4 == 0, D <= 128).
+void kge_rescal_step(CudaBackend& be, cudaStream_t stream, const Key* subj, const Key* rel, const Key* obj,
+                     const float* labels, int n_calls, int D, float eta, float gamma_e, float gamma_r, float* loss_out,
+                     unsigned long long* stats, float dropout_e, float dropout_r, uint64_t seed) {
+  if (n_calls == 0) return;
+  ADAPM_CHECK(D % 4 == 0 && D >= 4 && D <= 128, "kge_rescal_step: embedding size must be a multiple of 4 in [4, 128]");
+  be.track_stream(stream);
+  const Ctx& c = be.ctx();
+  const Dropout de = make_dropout(dropout_e, seed, 0x11u), dr = make_dropout(dropout_r, seed, 0x22u);
+  const int warps_per_block = kThreads / 32;
+  const int blocks = std::min((n_calls + warps_per_block - 1) / warps_per_block, be.num_sms() * 4);
+  const size_t smem = (size_t)warps_per_block * 4 * D * sizeof(float);
+  // generic-path scratch (rows in a transitional protocol state): one relation row + two entity rows per warp
+  static std::mutex mu;
+  static std::map<int, std::pair<float*, size_t>> scratch_by_dev;
+  float* scratch = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    const size_t need = (size_t)blocks * warps_per_block * (size_t)(2 * D * D + 4 * D) * sizeof(float);
+    auto& e = scratch_by_dev[be.device()];
+    if (e.second < need) {
+      if (e.first) cudaFree(e.first);
+      ADAPM_CUDA_CHECK(cudaMalloc((void**)&e.first, need));
+      e.second = need;
+    }
+    scratch = e.first;
+  }
+  kge_rescal_kernel<<<blocks, kThreads, smem, stream>>>(c, subj, rel, obj, labels, n_calls, D, eta, gamma_e, gamma_r,
+                                                        loss_out, stats, de, dr, scratch);
   ADAPM_COUNT_LAUNCH();
   ADAPM_CUDA_CHECK(cudaGetLastError());
 }

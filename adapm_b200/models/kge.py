@@ -17,8 +17,12 @@ Behavioural parity with the reference application ``apps/knowledge_graph_embeddi
   ``checkpoint.epoch.N.{entities,relations}[.adagrad].bin`` (raw float64) (kge.cc:327-401; the reference's
   byte-offset bug for the adagrad half is not replicated).
 
-The ComplEx train calls run as ONE fused kernel (``ops.kge_complex_step``); RESCAL uses the public
-Pull/Push API with PyTorch math (its relation rows are d x d matrices).
+On the GPU the train calls of a batch run as ONE fused kernel - ``ops.kge_complex_step`` or, for RESCAL (relation
+rows are d x d matrices), ``ops.kge_rescal_step`` - including dropout on the pulled copies (mask from a counter-based
+hash, reproducible by ``ops.kge_dropout_mask``). The evaluation ranks subject, relation and object of every test
+triple (kge.cc:716-774) and aggregates the reference's 19 metrics over the ranks through ``eval_key``
+(kge.cc:592-709). The CPU backend runs the same calls through the public Pull/Push API with PyTorch math
+(``kge_reference_step``, also the numerics oracle of the GPU tests).
 """
 from __future__ import annotations
 
@@ -198,16 +202,17 @@ class KGE:
         """One batch of positive triples ([B,3] int64 CPU tensor, pinned for the e2e path)."""
         cfg = self.cfg
         B = triples_host.shape[0]
-        if self.cuda and cfg.algorithm == "ComplEx" and cfg.dropout_entity == 0 and cfg.dropout_relation == 0:
-            from ..ops import kge_complex_step
+        if self.cuda:
+            from ..ops import kge_complex_step, kge_rescal_step
 
             tr = triples_host.to(self.server.device, non_blocking=True)
             local_only = cfg.sampling_scheme == "local" and self.server.num_servers() > 1
             seed = (cfg.model_seed * 7 + self.server.my_rank() * 7919 + self.step_no) & 0xFFFFFFFFFFFF
             neg = self.sampler.sample(B * 2 * cfg.neg_ratio, seed, local_only=local_only).view(B, 2 * cfg.neg_ratio)
             S, R, O, L = self._expand(tr, neg)
-            kge_complex_step(self.server, S, R, O, L, cfg.embed_dim, cfg.eta, cfg.gamma_entity, cfg.gamma_relation,
-                             self.loss, self.stats)
+            fused = kge_complex_step if cfg.algorithm == "ComplEx" else kge_rescal_step
+            fused(self.server, S, R, O, L, cfg.embed_dim, cfg.eta, cfg.gamma_entity, cfg.gamma_relation, self.loss,
+                  self.stats, cfg.dropout_entity, cfg.dropout_relation, seed)
             self.step_no += 1
             return self.loss
         neg = torch.randint(0, cfg.num_entities, (B, 2 * cfg.neg_ratio), generator=self._gen)
@@ -246,49 +251,57 @@ class KGE:
             Rg.numpy().astype(np.float64).tofile(f"{path_prefix}checkpoint.epoch.{epoch}.relations.adagrad.bin")
 
     # ------------------------------------------------------------------ evaluation
-    def evaluate(self, triples: torch.Tensor, known: torch.Tensor, batch: int = 2048, use_tensor_cores: bool = True):
-        """Filtered ranking (reference kge.cc:716-774): rank of the true object among all entities for
-        (s, r, ?) and of the true subject for (?, r, o); other known-true answers are filtered out.
-        Returns dict(mrr, mrr_raw, hits@1/3/10). ``known``: all true triples (train+valid+test)."""
+    EVAL_METRICS = ("mrr_s", "mrr_r", "mrr_o", "mrr_s_raw", "mrr_o_raw", "mr_s", "mr_r", "mr_o", "mr_s_raw", "mr_o_raw",
+                    "hits01_s", "hits01_r", "hits01_o", "hits03_s", "hits03_r", "hits03_o", "hits10_s", "hits10_r",
+                    "hits10_o")   # slots 0..18 of the eval_key row (reference kge.cc:94-112)
+
+    def rank_triples(self, triples: torch.Tensor, known: torch.Tensor, batch: int = 2048, use_tensor_cores: bool = True):
+        """Ranks of the true subject / relation / object of every triple among all candidates (reference
+        ``rank()``, kge.cc:716-774): subject and object ranks raw and filtered (other known-true answers do not count),
+        the relation rank unfiltered like in the reference. Returns a dict of int64 tensors
+        ``rank_s, rank_r, rank_o, rank_s_raw, rank_o_raw``. ``known``: all true triples (train+valid+test)."""
         cfg = self.cfg
         dev = self.server.device if self.cuda else torch.device("cpu")
         E, _, R, _ = self.pull_embeddings(dev)
         triples = triples.to(dev)
         known = torch.unique(known.to(dev), dim=0)   # duplicates must not be filtered twice
-        ne = cfg.num_entities
-        # index of known answers: key = (a * nr + r) -> list of entities
-        sr_key = known[:, 0] * cfg.num_relations + known[:, 1]
-        or_key = known[:, 2] * cfg.num_relations + known[:, 1]
-        ranks_f, ranks_r = [], []
-        tc = self.cuda and use_tensor_cores and cfg.algorithm == "ComplEx"
+        d = cfg.embed_dim
+        tc = self.cuda and use_tensor_cores
         if tc:
             from ..ops import gemm_nt_rank_count
 
-            E_s = E.to(torch.bfloat16).float()   # score with the operands the tensor cores see
+            bf = lambda x: x.to(torch.bfloat16).float()   # score with the operands the tensor cores see
         else:
-            E_s = E
+            bf = lambda x: x
+        E_s, R_s = bf(E), bf(R)
+        sr_key = known[:, 0] * cfg.num_relations + known[:, 1]
+        or_key = known[:, 2] * cfg.num_relations + known[:, 1]
         order = torch.argsort(sr_key)
         sr_sorted, sr_ent = sr_key[order], known[order, 2]
         order = torch.argsort(or_key)
         or_sorted, or_ent = or_key[order], known[order, 0]
+        out = {k: [] for k in ("rank_s", "rank_r", "rank_o", "rank_s_raw", "rank_o_raw")}
+
+        def count_better(q, cand, true_score, true_idx):
+            if tc:   # tcgen05 GEMM with the rank-count epilogue: the [B, candidates] scores never reach HBM
+                return gemm_nt_rank_count(q, cand, true_score, true_idx).long() + 1
+            scores = q @ cand.t()
+            scores.scatter_(1, true_idx.view(-1, 1), float("-inf"))
+            return (scores > true_score.view(-1, 1)).sum(1) + 1
+
         for i in range(0, triples.shape[0], batch):
             t = triples[i:i + batch]
+            Es, Eo, Rr = E[t[:, 0]], E[t[:, 2]], R[t[:, 1]]
             for side in (0, 1):  # 0: predict object, 1: predict subject
                 if cfg.algorithm == "ComplEx":
-                    q = complex_query(E[t[:, 0]] if side == 0 else E[t[:, 2]], R[t[:, 1]], conj=(side == 1))
+                    q = complex_query(Es if side == 0 else Eo, Rr, conj=(side == 1))
                 else:
-                    Rm = R[t[:, 1]].view(-1, cfg.embed_dim, cfg.embed_dim)
-                    q = torch.einsum("bi,bij->bj", E[t[:, 0]], Rm) if side == 0 else torch.einsum("bij,bj->bi", Rm, E[t[:, 2]])
-                if tc:
-                    q = q.to(torch.bfloat16).float()
+                    Rm = Rr.view(-1, d, d)
+                    q = torch.einsum("bi,bij->bj", Es, Rm) if side == 0 else torch.einsum("bij,bj->bi", Rm, Eo)
+                q = bf(q)
                 true_e = t[:, 2] if side == 0 else t[:, 0]
                 true_score = (q * E_s[true_e]).sum(1)
-                if tc:   # tcgen05 GEMM with the rank-count epilogue: the [B, ne] scores never reach HBM
-                    raw = gemm_nt_rank_count(q, E_s, true_score, true_e).long() + 1
-                else:
-                    scores = q @ E_s.t()
-                    scores.scatter_(1, true_e.view(-1, 1), float("-inf"))
-                    raw = (scores > true_score.view(-1, 1)).sum(1) + 1
+                raw = count_better(q, E_s, true_score, true_e)
                 # filtering: other known answers of the same query do not count
                 qkey = (t[:, 0] if side == 0 else t[:, 2]) * cfg.num_relations + t[:, 1]
                 kks, kes = (sr_sorted, sr_ent) if side == 0 else (or_sorted, or_ent)
@@ -301,13 +314,76 @@ class KGE:
                 ks = (q[rows] * E_s[ents]).sum(1)
                 better = (ks > true_score[rows]) & (ents != true_e[rows])
                 filt = raw - torch.zeros_like(raw).index_add_(0, rows, better.to(raw.dtype))
-                ranks_r.append(raw)
-                ranks_f.append(filt)
-        rf = torch.cat(ranks_f).double()
-        rr = torch.cat(ranks_r).double()
-        return {"mrr": float((1 / rf).mean()), "mrr_raw": float((1 / rr).mean()),
-                "hits@1": float((rf <= 1).double().mean()), "hits@3": float((rf <= 3).double().mean()),
-                "hits@10": float((rf <= 10).double().mean()), "n": int(rf.numel() // 2)}
+                out["rank_o_raw" if side == 0 else "rank_s_raw"].append(raw)
+                out["rank_o" if side == 0 else "rank_s"].append(filt)
+            # relation side: score(s, r', o) = <q_r, R[r']> for all relations r'
+            if cfg.algorithm == "ComplEx":
+                h = d // 2
+                sre, sim, ore, oim = Es[:, :h], Es[:, h:], Eo[:, :h], Eo[:, h:]
+                qr = torch.cat([sre * ore + sim * oim, sre * oim - sim * ore], 1)
+            else:
+                qr = torch.einsum("bi,bj->bij", Es, Eo).reshape(t.shape[0], d * d)
+            qr = bf(qr)
+            true_score = (qr * R_s[t[:, 1]]).sum(1)
+            out["rank_r"].append(count_better(qr, R_s, true_score, t[:, 1]))
+        return {k: torch.cat(v) if v else torch.zeros(0, dtype=torch.int64, device=dev) for k, v in out.items()}
+
+    @staticmethod
+    def _metric_sums(ranks: dict) -> torch.Tensor:
+        """The 19 partial sums of the reference (EVAL_METRICS order) as a float64 vector."""
+        f = {k: v.double() for k, v in ranks.items()}
+        s, r, o, sr, orr = f["rank_s"], f["rank_r"], f["rank_o"], f["rank_s_raw"], f["rank_o_raw"]
+        vals = [(1 / s).sum(), (1 / r).sum(), (1 / o).sum(), (1 / sr).sum(), (1 / orr).sum(),
+                s.sum(), r.sum(), o.sum(), sr.sum(), orr.sum()]
+        for k in (1, 3, 10):
+            vals += [(s <= k).double().sum(), (r <= k).double().sum(), (o <= k).double().sum()]
+        return torch.stack([v.cpu() for v in vals])
+
+    def evaluate(self, triples: torch.Tensor, known: torch.Tensor, batch: int = 2048, use_tensor_cores: bool = True):
+        """Filtered ranking evaluation of ``triples`` on THIS rank. Returns the reference's 19 metrics plus the usual
+        entity-side summary (``mrr`` / ``hits@k`` = mean over subject and object side)."""
+        ranks = self.rank_triples(triples, known, batch, use_tensor_cores)
+        return self._finish_metrics(self._metric_sums(ranks), triples.shape[0])
+
+    def _finish_metrics(self, sums: torch.Tensor, n: int) -> dict:
+        m = {k: float(v) / max(1, n) for k, v in zip(self.EVAL_METRICS, sums.tolist())}
+        m["mrr"] = 0.5 * (m["mrr_s"] + m["mrr_o"])
+        m["mrr_raw"] = 0.5 * (m["mrr_s_raw"] + m["mrr_o_raw"])
+        for k, name in ((1, "hits01"), (3, "hits03"), (10, "hits10")):
+            m[f"hits@{k}"] = 0.5 * (m[f"{name}_s"] + m[f"{name}_o"])
+        m["n"] = int(n)
+        return m
+
+    def evaluate_distributed(self, triples: torch.Tensor, known: torch.Tensor, truncate: int = 0, batch: int = 2048,
+                             use_tensor_cores: bool = True) -> dict:
+        """The reference's distributed evaluation (kge.cc:555-709): every rank ranks its share of the test triples, the
+        partial sums of the 19 metrics are aggregated through the ``eval_key`` row of the parameter manager (reset,
+        barrier, push, barrier, pull) and rank 0 returns the normalised metrics (other ranks return {}). Collective:
+        one call per rank, with the same ``triples`` everywhere."""
+        cfg, kv = self.cfg, self.worker
+        world, rank = self.server.num_servers(), self.server.my_rank()
+        N = triples.shape[0] if truncate <= 0 else min(triples.shape[0], truncate)
+        per = -(-N // world)
+        mine = triples[rank * per: min(N, (rank + 1) * per)]
+        ek = torch.tensor([cfg.eval_key], dtype=torch.int64)
+        row = torch.zeros(20, dtype=self.server.dtype)
+        if rank == 0:   # reset the aggregation row (it may hold the sums of the previous evaluation)
+            kv.wait(kv.pull(ek, row))
+            kv.wait(kv.push(ek, -row))
+        kv.wait_sync() if world > 1 else None
+        kv.barrier()
+        part = torch.zeros(20, dtype=self.server.dtype)
+        if mine.shape[0]:
+            part[:19] = self._metric_sums(self.rank_triples(mine, known, batch, use_tensor_cores)).to(part.dtype)
+        kv.wait(kv.push(ek, part))
+        kv.wait_sync() if world > 1 else None
+        kv.barrier()
+        if rank != 0:
+            kv.barrier()
+            return {}
+        kv.wait(kv.pull(ek, row))
+        kv.barrier()
+        return self._finish_metrics(row[:19].double(), N)
 
 
 def complex_query(a: torch.Tensor, r: torch.Tensor, conj: bool) -> torch.Tensor:
@@ -332,9 +408,10 @@ def score_all(q: torch.Tensor, E: torch.Tensor, server=None) -> torch.Tensor:
     return q @ E.t()
 
 
-def kge_reference_step(kv, S, R, O, L, cfg: KGEConfig) -> float:
+def kge_reference_step(kv, S, R, O, L, cfg: KGEConfig, masks=None) -> float:
     """Plain PyTorch fp32 training calls through Pull/Push with the reference's update rule
-    (all calls of the batch read the state at the start of the step)."""
+    (all calls of the batch read the state at the start of the step). ``masks`` = (subject, relation, object)
+    dropout scale masks [n, len] (``ops.kge_dropout_mask``) instead of fresh random ones."""
     d = cfg.embed_dim
     n = S.numel()
 
@@ -348,11 +425,13 @@ def kge_reference_step(kv, S, R, O, L, cfg: KGEConfig) -> float:
     Es, As, Eo, Ao = rs[:, :d], rs[:, d:], ro[:, :d], ro[:, d:]
     rd = cfg.relation_len // 2
     Er, Ar = rr[:, :rd], rr[:, rd:]
-    if cfg.dropout_entity > 0:      # Bernoulli mask + 1/(1-p) scaling, applied to the pulled copies only
+    if masks is not None:
+        Es, Er, Eo = Es * masks[0], Er * masks[1], Eo * masks[2]
+    elif cfg.dropout_entity > 0:      # Bernoulli mask + 1/(1-p) scaling, applied to the pulled copies only
         p = cfg.dropout_entity
         Es = Es * (torch.rand_like(Es) >= p) / (1 - p)
         Eo = Eo * (torch.rand_like(Eo) >= p) / (1 - p)
-    if cfg.dropout_relation > 0:
+    if masks is None and cfg.dropout_relation > 0:
         p = cfg.dropout_relation
         Er = Er * (torch.rand_like(Er) >= p) / (1 - p)
     if cfg.algorithm == "ComplEx":

@@ -99,16 +99,60 @@ def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
 
 def kge_complex_step(server, subj: torch.Tensor, rel: torch.Tensor, obj: torch.Tensor, labels: torch.Tensor,
                      embed_dim: int, eta: float, gamma_entity: float, gamma_relation: float, loss: torch.Tensor,
-                     stats: Optional[torch.Tensor] = None) -> None:
+                     stats: Optional[torch.Tensor] = None, dropout_entity: float = 0.0, dropout_relation: float = 0.0,
+                     seed: int = 0) -> None:
     """Fused ComplEx training calls: for every i, one Model::train(s[i], r[i], o[i], label[i]) of the
-    reference (pull 3 rows, score, BCE gradient, L2 on positives, AdaGrad, push 3 rows)."""
+    reference (pull 3 rows, optional dropout on the pulled copies, score, BCE gradient, L2 on positives, AdaGrad,
+    push 3 rows). The dropout mask is ``kge_dropout_mask(seed, ...)``."""
     _i64(subj, "subj"); _i64(rel, "rel"); _i64(obj, "obj"); _f32(labels, "labels"); _f32(loss, "loss")
     n = subj.numel()
     if not (rel.numel() == n and obj.numel() == n and labels.numel() == n):
         raise ValueError("subj, rel, obj and labels must have the same length")
     _C.kge_complex_step(server._impl.backend_handle(), _stream(subj), subj.data_ptr(), rel.data_ptr(), obj.data_ptr(),
                         labels.data_ptr(), n, int(embed_dim), float(eta), float(gamma_entity), float(gamma_relation),
-                        loss.data_ptr(), stats.data_ptr() if stats is not None else 0)
+                        loss.data_ptr(), stats.data_ptr() if stats is not None else 0, float(dropout_entity),
+                        float(dropout_relation), int(seed) & 0xFFFFFFFFFFFFFFFF)
+
+
+def kge_rescal_step(server, subj: torch.Tensor, rel: torch.Tensor, obj: torch.Tensor, labels: torch.Tensor,
+                    embed_dim: int, eta: float, gamma_entity: float, gamma_relation: float, loss: torch.Tensor,
+                    stats: Optional[torch.Tensor] = None, dropout_entity: float = 0.0, dropout_relation: float = 0.0,
+                    seed: int = 0) -> None:
+    """Fused RESCAL training calls (score s^T R o, rank-1 relation gradient; relation rows are 2*d*d floats)."""
+    _i64(subj, "subj"); _i64(rel, "rel"); _i64(obj, "obj"); _f32(labels, "labels"); _f32(loss, "loss")
+    n = subj.numel()
+    if not (rel.numel() == n and obj.numel() == n and labels.numel() == n):
+        raise ValueError("subj, rel, obj and labels must have the same length")
+    _C.kge_rescal_step(server._impl.backend_handle(), _stream(subj), subj.data_ptr(), rel.data_ptr(), obj.data_ptr(),
+                       labels.data_ptr(), n, int(embed_dim), float(eta), float(gamma_entity), float(gamma_relation),
+                       loss.data_ptr(), stats.data_ptr() if stats is not None else 0, float(dropout_entity),
+                       float(dropout_relation), int(seed) & 0xFFFFFFFFFFFFFFFF)
+
+
+def _mix32(x: torch.Tensor) -> torch.Tensor:
+    m = 0xFFFFFFFF
+    x = x & m
+    x = x ^ (x >> 16)
+    x = (x * 0x7FEB352D) & m
+    x = x ^ (x >> 15)
+    x = (x * 0x846CA68B) & m
+    x = x ^ (x >> 16)
+    return x
+
+
+def kge_dropout_mask(seed: int, n_calls: int, which: int, n_elems: int, p: float, relation: bool = False) -> torch.Tensor:
+    """The [n_calls, n_elems] scale mask (0 or 1/(1-p)) that the fused KGE kernels apply to the pulled copy of row
+    ``which`` (0 subject, 1 relation, 2 object) of every training call - bit-exact mirror of the device function
+    (csrc/cuda/ops_kge.cu: Dropout::keep), for the numerics tests."""
+    if p <= 0:
+        return torch.ones(n_calls, n_elems)
+    seed &= 0xFFFFFFFFFFFFFFFF
+    s32 = (((seed ^ (seed >> 32)) & 0xFFFFFFFF) * 2654435761 + (0x22 if relation else 0x11)) & 0xFFFFFFFF
+    call = torch.arange(n_calls, dtype=torch.int64).view(-1, 1)
+    elem = torch.arange(n_elems, dtype=torch.int64).view(1, -1)
+    u = _mix32(_mix32((s32 + call * 3 + which) & 0xFFFFFFFF) ^ ((elem * 0x9E3779B9) & 0xFFFFFFFF))
+    keep = ((u >> 8).to(torch.float32) * (1.0 / 16777216.0)) >= torch.tensor(p, dtype=torch.float32)
+    return keep.to(torch.float32) * (1.0 / (1.0 - torch.tensor(p, dtype=torch.float32)))
 
 
 def mf_step(server, row_keys: torch.Tensor, col_keys: torch.Tensor, x: torch.Tensor, row_nnz: torch.Tensor,

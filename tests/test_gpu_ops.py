@@ -221,6 +221,61 @@ def test_kge_complex_step_matches_pytorch_reference(cluster1, nh):
     assert stats.tolist()[3] == 3 * n
 
 
+@pytest.mark.parametrize("algo,d,p_e,p_r", [("RESCAL", 32, 0.0, 0.0), ("RESCAL", 64, 0.0, 0.0), ("RESCAL", 12, 0.0, 0.0),
+                                            ("RESCAL", 32, 0.3, 0.2), ("ComplEx", 128, 0.25, 0.4), ("ComplEx", 20, 0.5, 0.0)])
+def test_kge_rescal_and_dropout_match_pytorch_reference(cluster1, algo, d, p_e, p_r):
+    """The fused RESCAL kernel (s^T R o, rank-1 relation gradient) and the in-kernel dropout of both KGE kernels
+    against the reference formula in PyTorch; the dropout mask is a pure function of (seed, call, row, element) that
+    ``ops.kge_dropout_mask`` reproduces on the host, so the comparison is exact up to fp32 rounding."""
+    from adapm_b200.models.kge import KGEConfig, kge_reference_step
+    from adapm_b200.ops import kge_complex_step, kge_rescal_step, kge_dropout_mask
+    import adapm_b200 as ad
+
+    n = 40
+    cfg = KGEConfig(num_entities=2 * n + 5, num_relations=n + 3, embed_dim=d, neg_ratio=1, algorithm=algo,
+                    dropout_entity=p_e, dropout_relation=p_r)
+    server, kv = cluster1(cfg.value_lengths(), cfg.num_keys)
+    dev = server.device
+    g = torch.Generator().manual_seed(d + int(100 * p_e))
+    el, rl = cfg.entity_len // 2, cfg.relation_len // 2
+    ek = torch.arange(cfg.num_entities)
+    rk = torch.arange(cfg.num_entities, cfg.num_entities + cfg.num_relations)
+    erows = torch.cat([torch.randn(cfg.num_entities, el, generator=g) * 0.3, torch.rand(cfg.num_entities, el, generator=g) + 1e-3], 1)
+    rrows = torch.cat([torch.randn(cfg.num_relations, rl, generator=g) * 0.3, torch.rand(cfg.num_relations, rl, generator=g) + 1e-3], 1)
+    kv.set(ek, erows.clone().view(-1)); kv.set(rk, rrows.clone().view(-1))
+    perm = torch.randperm(cfg.num_entities, generator=g)
+    S, O = perm[:n], perm[n:2 * n]
+    R = torch.randperm(cfg.num_relations, generator=g)[:n] + cfg.num_entities
+    L = (torch.arange(n) % 3 == 0).float()
+    loss = torch.zeros(1, device=dev)
+    stats = torch.zeros(4, dtype=torch.int64, device=dev)
+    seed = 0x1234_5678_9ABC
+    fused = kge_complex_step if algo == "ComplEx" else kge_rescal_step
+    fused(server, S.to(dev), R.to(dev), O.to(dev), L.to(dev), d, cfg.eta, cfg.gamma_entity, cfg.gamma_relation, loss, stats,
+          p_e, p_r, seed)
+    torch.cuda.synchronize()
+    got_e = torch.empty(cfg.num_entities * 2 * el); kv.pull(ek, got_e)
+    got_r = torch.empty(cfg.num_relations * 2 * rl); kv.pull(rk, got_r)
+
+    masks = None
+    if p_e > 0 or p_r > 0:
+        masks = (kge_dropout_mask(seed, n, 0, el, p_e), kge_dropout_mask(seed, n, 1, rl, p_r, relation=True),
+                 kge_dropout_mask(seed, n, 2, el, p_e))
+        assert p_e == 0 or 0.0 < float((masks[0] == 0).float().mean()) < 1.0
+    ref_server = ad.Server(cfg.value_lengths(), num_keys=cfg.num_keys, num_threads=1, rank=0, world=1, backend="cpu",
+                           fabric="inproc", job=f"kgeref{algo}{d}{int(100 * p_e)}")
+    ref_kv = ad.Worker(0, ref_server)
+    ref_kv.set(ek, erows.clone().view(-1)); ref_kv.set(rk, rrows.clone().view(-1))
+    ref_loss = kge_reference_step(ref_kv, S, R, O, L, cfg, masks=masks)
+    ref_e = torch.empty_like(got_e); ref_kv.pull(ek, ref_e)
+    ref_r = torch.empty_like(got_r); ref_kv.pull(rk, ref_r)
+    ref_kv.finalize(); ref_server.shutdown()
+    torch.testing.assert_close(got_e, ref_e, rtol=5e-4, atol=5e-5)
+    torch.testing.assert_close(got_r, ref_r, rtol=5e-4, atol=5e-5)
+    torch.testing.assert_close(loss.cpu()[0], torch.tensor(ref_loss), rtol=1e-3, atol=1e-3)
+    assert stats.tolist()[3] == 3 * n
+
+
 @pytest.mark.parametrize("rank", [128, 64, 10])
 def test_mf_step_matches_pytorch_reference(cluster1, rank):
     from adapm_b200.models.mf import mf_reference_step

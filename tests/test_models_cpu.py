@@ -44,6 +44,9 @@ def test_word2vec_cpu(tmp_path, world):
     assert os.path.getsize(tmp_path / "vectors.bin") > 300 * (16 * 4 + 3)
 
 
+KGE_EVAL_KEYS = ("mrr_s", "mrr_r", "mrr_o", "mrr_s_raw", "mrr_o_raw", "mr_s", "mr_r", "mr_o", "hits01_s", "hits03_r", "hits10_o")
+
+
 def _kge_worker(kv, server, wid):
     from adapm_b200.models.kge import KGE, KGEConfig, synthetic_triples
 
@@ -67,6 +70,8 @@ def _kge_worker(kv, server, wid):
         out["eval"] = model.evaluate(tr[:100], tr)
         model.save(os.path.join(server._tmp, "m."), 6, write_checkpoint=True)
     kv.barrier()
+    # the reference's distributed evaluation: every rank ranks its share, the 19 metric sums meet in the eval_key row
+    out["eval_dist"] = model.evaluate_distributed(tr[:100], tr)
     kv.finalize()
     return out
 
@@ -89,6 +94,15 @@ def test_kge_cpu(tmp_path, algo, world):
     assert 0 < ev["mrr"] <= 1 and ev["mrr"] >= ev["mrr_raw"] - 1e-9 and ev["n"] == 100
     # chance level is ~0.08 for 60 entities; two asynchronous ranks (Hogwild) land between 0.18 and 0.36 after 6 epochs
     assert ev["mrr"] > (0.2 if world == 1 else 0.13), ev
+    # subject, relation and object are ranked (kge.cc:742-757); the distributed aggregation reproduces the local numbers
+    for k in ("mrr_s", "mrr_r", "mrr_o", "mr_r", "hits10_r", "mrr_s_raw", "mrr_o_raw"):
+        assert k in ev, k
+    assert 0 < ev["mrr_r"] <= 1 and ev["mr_r"] >= 1
+    evd = res[0][0]["eval_dist"]
+    for k in KGE_EVAL_KEYS:
+        assert abs(evd[k] - ev[k]) <= 1e-4 * max(1.0, abs(ev[k])), (k, evd[k], ev[k])
+    for r in range(1, world):
+        assert res[r][0]["eval_dist"] == {}
     e = np.fromfile(tmp_path / "m.export.epoch.6.entities.bin", dtype=np.float32)
     assert e.size == cfg.num_entities * cfg.embed_dim
     a = np.fromfile(tmp_path / "m.checkpoint.epoch.6.relations.adagrad.bin", dtype=np.float64)
