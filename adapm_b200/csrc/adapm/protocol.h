@@ -912,12 +912,21 @@ ADAPM_HD void row_op_execute(const G& g, SlotWork& w) {
 ADAPM_HD bool extend_intent_if_local(const Ctx& c, Key key, int worker, Clock end) {
   const int32_t s = mem::ld_relaxed(slot_of(c, c.rank) + key);
   if (s < 0) return false;
-  const uint32_t st = meta_state(mem::ld_acquire(meta_of(c, c.rank) + s));
-  if (st == S_OWNED || st == S_REPLICA || st == S_REPLICA_PENDING || state_is_incoming(st)) {
-    atomic_max_i64(intent_end_of(c, c.rank) + (size_t)s * c.L.workers + worker, end);
-    return true;
-  }
-  return false;
+  const uint32_t m = mem::ld_acquire(meta_of(c, c.rank) + s);
+  const uint32_t st = meta_state(m);
+  if (!(st == S_OWNED || st == S_REPLICA || st == S_REPLICA_PENDING || state_is_incoming(st))) return false;
+  atomic_max_i64(intent_end_of(c, c.rank) + (size_t)s * c.L.workers + worker, end);
+  // The sync round may have decided to drop this replica / to hand the key over (or may even have recycled the slot
+  // for another key) between the state check and the atomic max: the extension is then not (reliably) seen. Re-read:
+  // only an unchanged slot of this very key counts; everything else goes through the host path, which cannot lose it.
+  mem::fence();
+  const uint32_t m2 = mem::ld_acquire(meta_of(c, c.rank) + s);
+  const uint32_t st2 = meta_state(m2);
+  const bool still = (st2 == S_OWNED || st2 == S_REPLICA || st2 == S_REPLICA_PENDING || state_is_incoming(st2)) &&
+                     (meta_seq(m2) == meta_seq(m) || st2 == st) &&
+                     mem::ld_relaxed(slot_key_of(c, c.rank) + s) == key &&
+                     mem::ld_relaxed(slot_of(c, c.rank) + key) == s;
+  return still;
 }
 
 // Is `key` usable from local memory right now (owned or usable replica)?  (PullIfLocal / local sampling)

@@ -73,7 +73,10 @@ void MailRouter::send(int to, int app_id, int customer_id, int head, int timesta
     auto t0 = std::chrono::steady_clock::now();
     int spins = 0;
     // my turn on this slot: the consumer has passed ticket - MAIL_SLOTS and released the slot
+    const bool on_router = std::this_thread::get_id() == thread_.get_id();
     while (mb.head.load(std::memory_order_acquire) + MAIL_SLOTS <= ticket || s.state.load(std::memory_order_acquire) != 0) {
+      // a handler (router thread) that waits for a slot keeps emptying its own mailbox: the peer may be waiting for one
+      if (on_router) drain_ring(/*defer=*/true);
       if (++spins < 100) std::this_thread::yield();
       else std::this_thread::sleep_for(std::chrono::microseconds(50));
       if ((spins & 1023) == 0) {
@@ -90,7 +93,7 @@ void MailRouter::send(int to, int app_id, int customer_id, int head, int timesta
   } while (off < total);
 }
 
-bool MailRouter::drain_ring() {
+bool MailRouter::drain_ring(bool defer) {
   Mailbox& mb = server_->control()->mail[server_->my_rank()];
   bool any = false;
   for (;;) {
@@ -118,7 +121,12 @@ bool MailRouter::drain_ring() {
     if (complete) {
       Msg done = std::move(*m);
       partial_.erase(key);
-      dispatch(std::move(done));
+      if (defer) {
+        std::lock_guard<std::mutex> lk(mu_);
+        local_.push_back(std::move(done));
+      } else {
+        dispatch(std::move(done));
+      }
     }
   }
   return any;

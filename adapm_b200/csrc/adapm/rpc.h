@@ -58,7 +58,9 @@ class MailRouter {
   struct Msg { int app_id, customer_id; bool request; SimpleData d; };
   void loop();
   void dispatch(Msg&& m);
-  bool drain_ring();
+  // defer = true: completed messages are queued (local_) instead of dispatched - used while the router thread itself
+  // waits for a free slot in a peer's mailbox, so that two ranks answering each other never block each other
+  bool drain_ring(bool defer = false);
 
   Server* server_;
   std::thread thread_;

@@ -33,6 +33,7 @@ intent_prepass_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ key
     if (i < n) {
       k = keys[i];
       if (k >= 0 && k < c.L.num_keys) need = !extend_intent_if_local(c, k, worker, end);   // protocol.h, shared with the host
+      else need = true;   // out of range: hand it to the host path, whose Intent() raises for it (like Worker::Intent)
     }
     // warp-aggregated append of the keys that still need the sync thread
     const unsigned mask = __ballot_sync(0xffffffffu, need);

@@ -78,7 +78,8 @@ def run_nccl_word2vec(args, rank: int, world: int, local_rank: int) -> int:
         rank_of = torch.empty_like(order)
         rank_of[order] = torch.arange(order.numel())
         send_mat[s] = torch.bincount(owner, minlength=world)
-        prepared.append((shard_row(uk[order]).pin_memory(), rank_of[inv].pin_memory()))   # shard rows to request, position of every pair's row
+        # shard rows to request (owner order), position of every pair's row in that order
+        prepared.append((shard_row(uk[order]).pin_memory(), rank_of[inv].pin_memory()))
     if world > 1:
         # recv_mat[s][p] = number of rows rank p requests from me at step s (everybody's send matrix, column `rank`)
         sm = send_mat.to(dev)

@@ -32,29 +32,48 @@ def owned_keys(server, chunk: int = 1 << 20) -> torch.Tensor:
     return torch.cat(out) if out else torch.empty(0, dtype=torch.int64)
 
 
-def save_store(worker, prefix: str, chunk: int = 1 << 16) -> int:
-    """Collective (every worker 0 of every rank calls it). Returns the number of keys this rank wrote."""
+def save_store(worker, prefix: str, chunk: int = 1 << 16, attempts: int = 3) -> int:
+    """Collective over the RANKS: exactly one worker per rank calls it (worker 0 by convention; with
+    ``num_threads > 1`` the other workers of the rank must be idle - e.g. parked at their own barrier - while the
+    store is saved). Uses the node barrier, so it works for any number of workers per rank.
+
+    The sync thread keeps running during the save. After the quiescence idiom no relocation is pending, but to be
+    safe against a late one (an intent registered long ago that only now falls into the action window) the ownership
+    of every chunk is re-checked after its rows were pulled, and the ranks agree that exactly ``num_keys`` keys
+    were written; otherwise the save is repeated. Returns the number of keys this rank wrote."""
     server = worker.server
-    worker.waitall()
-    worker.wait_sync()
-    worker.barrier()
-    worker.wait_sync()
-    worker.barrier()                       # quiescent: no relocation in flight, replicas synchronised
-    keys = owned_keys(server)
-    lens = (torch.full((keys.numel(),), server._uniform_len, dtype=torch.int32) if server._uniform_len is not None
-            else server._lens_t[keys].to(torch.int32))
     np_dtype = {torch.float32: np.float32, torch.float64: np.float64, torch.int64: np.int64}[server.dtype]
-    with open(f"{prefix}.rank{server.my_rank()}.adapm", "wb") as f:
-        f.write(MAGIC + struct.pack("<qqi", server.num_keys(), keys.numel(), np.dtype(np_dtype).itemsize))
-        f.write(keys.numpy().tobytes())
-        f.write(lens.numpy().tobytes())
-        for a in range(0, keys.numel(), chunk):
-            k = keys[a:a + chunk]
-            vals = torch.empty(int(lens[a:a + chunk].sum()), dtype=server.dtype)
-            worker.wait(worker.pull(k, vals))
-            f.write(vals.numpy().tobytes())
-    worker.barrier()
-    return keys.numel()
+    fn = f"{prefix}.rank{server.my_rank()}.adapm"
+    for attempt in range(attempts):
+        worker.waitall()
+        worker.wait_sync()
+        server.barrier()
+        worker.wait_sync()
+        server.barrier()                       # quiescent: no relocation in flight, replicas synchronised
+        keys = owned_keys(server)
+        lens = (torch.full((keys.numel(),), server._uniform_len, dtype=torch.int32) if server._uniform_len is not None
+                else server._lens_t[keys].to(torch.int32))
+        moved = 0
+        with open(fn, "wb") as f:
+            f.write(MAGIC + struct.pack("<qqi", server.num_keys(), keys.numel(), np.dtype(np_dtype).itemsize))
+            f.write(keys.numpy().tobytes())
+            f.write(lens.numpy().tobytes())
+            me = server.my_rank()
+            for a in range(0, keys.numel(), chunk):
+                k = keys[a:a + chunk]
+                vals = torch.empty(int(lens[a:a + chunk].sum()), dtype=server.dtype)
+                worker.wait(worker.pull(k, vals))
+                f.write(vals.numpy().tobytes())
+                st = torch.empty(k.numel(), dtype=torch.uint8)
+                ow = torch.empty(k.numel(), dtype=torch.uint8)
+                server._impl.peek_into(k.data_ptr(), k.numel(), st.data_ptr(), ow.data_ptr())
+                moved += int((ow != me).sum())     # the key left this rank while it was being written
+        total, moved_all = server.allreduce_sum([float(keys.numel()), float(moved)])
+        if int(total) == server.num_keys() and int(moved_all) == 0:
+            server.barrier()
+            return keys.numel()
+    raise RuntimeError(f"save_store: the placement kept changing during {attempts} attempts "
+                       f"(keys written {int(total)} of {server.num_keys()}, moved {int(moved_all)}); quiesce the workers first")
 
 
 def load_store(worker, prefix: str, chunk: int = 1 << 16) -> int:

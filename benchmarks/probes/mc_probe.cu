@@ -6,12 +6,15 @@
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
-#define CK(x) do { CUresult r_ = (x); if (r_ != CUDA_SUCCESS) { const char* s_; cuGetErrorString(r_, &s_); printf("FAIL %s -> %d %s (line %d)\n", #x, (int)r_, s_ ? s_ : "?", __LINE__); return 1; } } while (0)
+#define CK(x) do { CUresult r_ = (x); if (r_ != CUDA_SUCCESS) { const char* s_; cuGetErrorString(r_, &s_); \
+  printf("FAIL %s -> %d %s (line %d)\n", #x, (int)r_, s_ ? s_ : "?", __LINE__); return 1; } } while (0)
 #define CR(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("FAIL %s -> %s (line %d)\n", #x, cudaGetErrorString(e_), __LINE__); return 1; } } while (0)
 
 __global__ void mc_store(float* mc, int n, float v) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i * 4 < n) asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc + 4 * i), "f"(v), "f"(v + 1), "f"(v + 2), "f"(v + 3) : "memory");
+  if (i * 4 < n)
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc + 4 * i), "f"(v), "f"(v + 1),
+                 "f"(v + 2), "f"(v + 3) : "memory");
 }
 __global__ void mc_red(float* mc, int n, float v) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;

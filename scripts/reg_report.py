@@ -14,4 +14,5 @@ for f in sorted(glob.glob("build/adapm_b200/cuda_*.o.log")):
         dn = dn.split("(")[0]
         if pat and not re.search(pat, dn):
             continue
-        print(f"{used.group(1) if used else '?':>4s} regs  stack {stack.group(1) if stack else '?':>4s}  spill {spill.group(1) if spill else '?'}/{spill.group(2) if spill else '?'}  {dn}")
+        g = lambda m, i=1: m.group(i) if m else "?"
+        print(f"{g(used):>4s} regs  stack {g(stack):>4s}  spill {g(spill)}/{g(spill, 2)}  {dn}")

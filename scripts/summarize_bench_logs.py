@@ -18,7 +18,8 @@ for f in sorted(glob.glob(os.path.join(d, "*.log"))):
     pm = j.get("pm") or {}
     nst = 2 * k + 3
     loc = j.get("locality") or {}
-    print(name, "| value %.3fG ms %.3f | e2e %.3fG | rem/slow per step %s/%s | reloc %s setup %s drop %s refr %s delta %s rounds %s err %s | host_ms %s" % (
+    print(name, "| value %.3fG ms %.3f | e2e %.3fG | rem/slow per step %s/%s | reloc %s setup %s drop %s refr %s "
+          "delta %s rounds %s err %s | host_ms %s" % (
         j["value"] / 1e9, j["ms_per_step"], (j.get("e2e") or {}).get("value", 0) / 1e9,
         loc.get("rows_remote", 0) // nst, loc.get("rows_slow_path", 0) // nst,
         pm.get("relocations", 0) // nst, pm.get("replica_setups", 0) // nst, pm.get("replica_drops", 0) // nst,
@@ -26,6 +27,7 @@ for f in sorted(glob.glob(os.path.join(d, "*.log"))):
         j.get("host_loop_ms_per_step")))
     if j.get("profile"):
         p = j["profile"]
-        print("    profile: sgns_ms %.3f max %.3f | with intent %s | without %s" % (p.get("sgns_ms", 0), p.get("sgns_ms_max", 0), p.get("steps_with_intent"), p.get("steps_without_intent")))
+        print("    profile: sgns_ms %.3f max %.3f | with intent %s | without %s" % (
+            p.get("sgns_ms", 0), p.get("sgns_ms_max", 0), p.get("steps_with_intent"), p.get("steps_without_intent")))
     if j.get("sync_report"):
         print("    " + j["sync_report"][:400])

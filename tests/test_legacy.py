@@ -113,3 +113,40 @@ def test_default_slicer():
     assert s[0].vals.tolist() == [0, 1] and s[2].vals.tolist() == [2, 3, 4] and s[2].lens.tolist() == [3]
     with pytest.raises(ValueError):
         default_slicer(KVPairs(np.array([5, 1], np.int64)), ranges)
+
+
+def _big_reply_worker(kv, server, wid):
+    """Two ranks answer each other with bodies far larger than a mailbox (64 slots x 976 B): the handlers run on the
+    router threads, which must keep emptying their own mailbox while they wait for a slot in the peer's."""
+    from adapm_b200.legacy import SimpleApp
+
+    world = server.num_servers()
+    app = SimpleApp(0, 0, server)
+    big = bytes((i * 13 + wid) % 251 for i in range(200_000))
+    got = []
+
+    def on_request(d, a):
+        a.response(d, big)
+
+    def on_response(d, a):
+        got.append((d.sender, len(d.body), bytes(d.body[:8])))
+
+    app.set_request_handle(on_request)
+    app.set_response_handle(on_response)
+    kv.barrier()
+    ts = [app.request(1, b"x" * 100_000, (wid + 1) % world) for _ in range(3)]
+    for t in ts:
+        app.wait(t)
+    kv.barrier()
+    peer = (wid + 1) % world
+    assert len(got) == 3 and all(s == peer and n == 200_000 for s, n, _ in got)
+    assert got[0][2] == bytes((i * 13 + peer) % 251 for i in range(8))
+    kv.barrier()
+    kv.finalize()
+    return len(got)
+
+
+def test_simple_app_large_mutual_replies():
+    res = run_cluster(_big_reply_worker, world=2, workers=1, mode="threads", value_lengths=1, num_keys=8,
+                      options={"wait_timeout_s": 30})
+    assert all(r[0] == 3 for r in res.values())
