@@ -719,6 +719,19 @@ ADAPM_HD void phase_a_commit(const Ctx& c, const SlotWork& w) {
   mem::st_relaxed(fl, (uint8_t)(f | F_REQUESTED));
 }
 
+// Phase B, filter (ONE lane, local reads only): can this owned slot relocate at all in this round? The standing (sticky)
+// want-bits make every replicated key a hit of a plain "want != 0" test in every round; relocation needs exactly one
+// requester (technique `all`), which only a few slots satisfy - the device compacts those into a worklist.
+ADAPM_HD bool phase_b_candidate(const Ctx& c, uint32_t s) {
+  uint64_t mask = mem::ld_relaxed(want_of(c, c.rank) + s);
+  if (mask == 0) return false;
+  mask &= ~((uint64_t)1 << c.rank);
+  if (mask == 0) return false;
+  if (c.technique == (int)MgmtTechniques::REPLICATION_ONLY) return false;
+  if (c.technique == (int)MgmtTechniques::RELOCATION_ONLY) return true;
+  return (mask & (mask - 1)) == 0;   // exactly one requester
+}
+
 // Phase B: the owner decides relocate vs replicate for one owned slot (ONE lane).
 // Decision rule = reference sync_manager.h:615-641: relocate iff no worker on the owner and no
 // other node has intent; the technique switch forces one side.
@@ -778,8 +791,8 @@ ADAPM_HD void phase_c_resolve(const Ctx& c, SlotWork& w, const RoundParams& rp) 
     const int src = (int)meta_peer(m);
     const int32_t ss = (int32_t)mem::ld_relaxed(ver_seen_of(c, me) + s);
     if (ss < 0) { count(c, C_PROTOCOL_ERRORS); return; }
-    w.m = meta_next(m, S_FINALIZING, (uint32_t)src);
-    mem::st_release(mp, w.m);   // readers of the in-flight value (row - base + source row) re-validate this word
+    // (the slot stays INCOMING - readable as row - base + source row - until the row pass folds it: FINALIZING, during
+    // which readers have to wait, only lasts for the few microseconds of that one row operation)
     w.peer = (uint8_t)src; w.ps = ss;
     w.op = OP_FINALIZE; w.flags = 0;
     w.dst = row_ptr<Val>(c, me, cls, s); w.ref = base_ptr<Val>(c, me, cls, s); w.src = row_ptr<Val>(c, src, cls, ss);
@@ -833,18 +846,7 @@ ADAPM_HD void phase_c_commit(const Ctx& c, const SlotWork& w) {
   const int me = c.rank;
   const uint32_t s = w.slot;
   uint32_t* mp = meta_of(c, me) + s;
-  if (w.op == OP_FINALIZE) {
-    // invariant used by the in-kernel read of in-flight rows (pm_kernels.cuh: value = local row + source row): a
-    // placeholder that became the relocation target (INCOMING, not INCOMING_REPLICA) has an all-zero base
-    if (w.st == S_INCOMING && (w.flags & W_REF_NONZERO)) count(c, C_PROTOCOL_ERRORS);
-    const uint32_t sv = mem::ld_relaxed(version_of(c, w.peer) + w.ps);
-    mem::red_add(version_of(c, me) + s, sv + 1u);
-    mem::st_relaxed(ver_seen_of(c, me) + s, 0xffffffffu);
-    mem::st_relaxed(flags_of(c, me) + s, (uint8_t)0);
-    mem::st_relaxed(want_owner_of(c, me) + s, (uint8_t)0xff);
-    mem::st_release(mp, meta_next(w.m, S_OWNED, 0));
-    return;
-  }
+  if (w.op == OP_FINALIZE) return;   // committed by the row operation itself (finalize_row)
   if (w.op == OP_REFRESH) {
     mem::st_relaxed(ver_seen_of(c, me) + s, w.v);
     count(c, C_REFRESHES);
@@ -871,9 +873,36 @@ ADAPM_HD void phase_c_commit(const Ctx& c, const SlotWork& w) {
   }
 }
 
+// Relocation transfer of one slot: fold the source row into the local one and take over the ownership - as ONE short
+// per-slot sequence (state FINALIZING only while it runs), because readers of an in-flight key have to wait it out.
+template <class Val, class G>
+ADAPM_HD void finalize_row(const Ctx& c, const G& g, SlotWork& w) {
+  const int me = c.rank;
+  const uint32_t s = w.slot;
+  uint32_t* mp = meta_of(c, me) + s;
+  const uint32_t m1 = meta_next(w.m, S_FINALIZING, (uint32_t)w.peer);
+  if (g.lane() == 0) mem::st_release(mp, m1);   // readers of row - base + source row re-validate this word
+  mem::fence(); g.sync();
+  bool rnz = false;
+  row_fold<Val>(g, reinterpret_cast<Val*>(w.dst), reinterpret_cast<Val*>(w.ref), reinterpret_cast<const Val*>(w.src), w.len,
+                false, &rnz);
+  mem::fence(); g.sync();
+  if (g.lane() == 0) {
+    // invariant used by the in-kernel read of in-flight rows (pm_kernels.cuh: value = local row + source row): a
+    // placeholder that became the relocation target (INCOMING, not INCOMING_REPLICA) has an all-zero base
+    if (w.st == S_INCOMING && rnz) count(c, C_PROTOCOL_ERRORS);
+    const uint32_t sv = mem::ld_relaxed(version_of(c, w.peer) + w.ps);
+    mem::red_add(version_of(c, me) + s, sv + 1u);
+    mem::st_relaxed(ver_seen_of(c, me) + s, 0xffffffffu);
+    mem::st_relaxed(flags_of(c, me) + s, (uint8_t)0);
+    mem::st_relaxed(want_owner_of(c, me) + s, (uint8_t)0xff);
+    mem::st_release(mp, meta_next(m1, S_OWNED, 0));
+  }
+}
+
 // The row operation of one slot (one group of lanes; the only code of the round that touches row data).
 template <class Val, class G>
-ADAPM_HD void row_op_execute(const G& g, SlotWork& w) {
+ADAPM_HD void row_op_execute(const Ctx& c, const G& g, SlotWork& w) {
   Val* dst = reinterpret_cast<Val*>(w.dst);
   Val* ref = reinterpret_cast<Val*>(w.ref);
   const Val* src = reinterpret_cast<const Val*>(w.src);
@@ -885,12 +914,9 @@ ADAPM_HD void row_op_execute(const G& g, SlotWork& w) {
       if (ship && row_ship<Val>(g, src, ref, dst, w.len, true)) out = W_NZ;
       break;
     }
-    case OP_FINALIZE: {
-      bool rnz = false;
-      row_fold<Val>(g, dst, ref, src, w.len, false, &rnz);
-      if (rnz) out = W_REF_NONZERO;
+    case OP_FINALIZE:
+      finalize_row<Val>(c, g, w);
       break;
-    }
     case OP_REFRESH:
       row_fold<Val>(g, dst, ref, src, w.len, true, (bool*)nullptr);
       break;

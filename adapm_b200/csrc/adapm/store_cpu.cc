@@ -139,16 +139,15 @@ class CpuBackend : public Backend {
         SlotWork w;
         w.slot = s;
         phase_a_resolve<Val>(ctx_, w, rp);
-        if (w.op != OP_NONE) { mem::fence(); row_op_execute<Val>(g, w); mem::fence(); }
+        if (w.op != OP_NONE) { mem::fence(); row_op_execute<Val>(ctx_, g, w); mem::fence(); }
         phase_a_commit<Val>(ctx_, w);
       }
     mem::fence();
   }
   void phase_b(const RoundParams& rp) override {
     const uint32_t S = ctx_.L.total_slots;
-    const uint64_t* want = want_of(ctx_, ctx_.rank);
     for (uint32_t s = 0; s < S; ++s)
-      if (mem::ld_relaxed(want + s) != 0) phase_b_slot(ctx_, s, rp);
+      if (phase_b_candidate(ctx_, s)) phase_b_slot(ctx_, s, rp);
     mem::fence();
   }
   void phase_c(const RoundParams& rp) override {
@@ -159,7 +158,7 @@ class CpuBackend : public Backend {
         SlotWork w;
         w.slot = s;
         phase_c_resolve<Val>(ctx_, w, rp);
-        if (w.op != OP_NONE) { mem::fence(); row_op_execute<Val>(g, w); mem::fence(); }
+        if (w.op != OP_NONE) { mem::fence(); row_op_execute<Val>(ctx_, g, w); mem::fence(); }
         phase_c_commit<Val>(ctx_, w);
       }
     mem::fence();

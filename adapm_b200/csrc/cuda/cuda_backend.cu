@@ -237,7 +237,8 @@ constexpr int kWorkThreads = 128;
 #ifndef ADAPM_WORK_MINB
 #define ADAPM_WORK_MINB 6   // <= 80 registers x 128 threads = 10 K of the 12 K registers a lean training kernel leaves free per SM
 #endif
-__global__ void __launch_bounds__(kWorkThreads, ADAPM_WORK_MINB) phase_row_kernel(const RoundDev* __restrict__ rd,
+__global__ void __launch_bounds__(kWorkThreads, ADAPM_WORK_MINB) phase_row_kernel(const __grid_constant__ Ctx c,
+                                                                               const RoundDev* __restrict__ rd,
                                                                                SlotWork* __restrict__ worklist,
                                                                                const unsigned int* __restrict__ count) {
   if (rd->stop) return;
@@ -246,17 +247,40 @@ __global__ void __launch_bounds__(kWorkThreads, ADAPM_WORK_MINB) phase_row_kerne
   const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
   for (unsigned i = warp; i < n; i += nwarps) {
-    if (worklist[i].op != OP_NONE) row_op_execute<float>(g, worklist[i]);
+    if (worklist[i].op != OP_NONE) row_op_execute<float>(c, g, worklist[i]);
     __syncwarp();
   }
 }
 
-__global__ void __launch_bounds__(kThreads) phase_b_kernel(const __grid_constant__ Ctx c, const RoundDev* __restrict__ rd) {
+// Phase B: (1) a streaming scan compacts the owned slots that can relocate in this round (exactly one requester) into
+// the worklist, (2) one THREAD per candidate decides and announces the new owner: the two NVLink round trips of a
+// relocation (target slot id, target state) overlap across tens of thousands of threads instead of queueing up inside
+// a few grid-striding ones.
+__global__ void __launch_bounds__(kThreads) phase_b_scan_kernel(const __grid_constant__ Ctx c, const RoundDev* __restrict__ rd,
+                                                                SlotWork* __restrict__ worklist,
+                                                                unsigned int* __restrict__ count) {
   if (rd->stop) return;
   const uint32_t S = c.L.total_slots;
   const uint64_t* want = want_of(c, c.rank);
-  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x)
-    if (__ldcg(want + s) != 0) phase_b_slot(c, s, rd->rp);
+  const int lane = threadIdx.x & 31;
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < ((S + 31u) & ~31u); s += gridDim.x * blockDim.x) {
+    const bool hit = s < S && __ldcg(want + s) != 0 && phase_b_candidate(c, s);
+    const unsigned mask = __ballot_sync(0xffffffffu, hit);
+    if (mask) {
+      unsigned base = 0;
+      if (lane == 0) base = atomicAdd(count, (unsigned)__popc(mask));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (hit) worklist[base + __popc(mask & ((1u << lane) - 1u))].slot = s;
+    }
+  }
+}
+__global__ void __launch_bounds__(kThreads) phase_b_kernel(const __grid_constant__ Ctx c, const RoundDev* __restrict__ rd,
+                                                           const SlotWork* __restrict__ worklist,
+                                                           const unsigned int* __restrict__ count) {
+  if (rd->stop) return;
+  const unsigned n = *count;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    phase_b_slot(c, worklist[i].slot, rd->rp);
 }
 
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -721,25 +745,29 @@ void CudaBackend::register_intents(const IntentRec* recs, size_t n, const RoundP
 
 void CudaBackend::launch_phase(int phase) {
   if (phase == 1) {
-    TraceScope ts_(this, "phaseB", sync_stream_);
-    phase_b_kernel<<<num_sms_ * scan_blocks_per_sm_, kThreads, 0, sync_stream_>>>(ctx_, round_dev_);
+    unsigned int* wc = work_count_ + 2;
+    ADAPM_CUDA_CHECK(cudaMemsetAsync(wc, 0, sizeof(unsigned int), sync_stream_));
+    { TraceScope t_(this, "B.scan", sync_stream_); phase_b_scan_kernel<<<num_sms_ * scan_blocks_per_sm_, kThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, wc); }
+    // one thread per candidate: the grid is sized for the worst case seen so far (the count lives on the device)
+    { TraceScope t_(this, "B.decide", sync_stream_); phase_b_kernel<<<num_sms_ * meta_blocks_per_sm_ * 4, kThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, wc); }
+    ADAPM_COUNT_LAUNCH();
     ADAPM_COUNT_LAUNCH();
     ADAPM_CUDA_CHECK(cudaGetLastError());
     return;
   }
-  TraceScope ts_(this, phase == 0 ? "phaseA" : "phaseC", sync_stream_);
-  ADAPM_CUDA_CHECK(cudaMemsetAsync(work_count_, 0, sizeof(unsigned int), sync_stream_));
+  unsigned int* wc = work_count_ + (phase == 0 ? 0 : 1);   // one counter per phase (read back by the kernel timeline)
+  ADAPM_CUDA_CHECK(cudaMemsetAsync(wc, 0, sizeof(unsigned int), sync_stream_));
   const int gs = num_sms_ * scan_blocks_per_sm_, gm = num_sms_ * meta_blocks_per_sm_, gw = num_sms_ * work_blocks_per_sm_;
   if (phase == 0) {
-    phase_scan_kernel<0><<<gs, kThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, work_count_);
-    phase_meta_kernel<0, 0><<<gm, kThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, work_count_);
-    phase_row_kernel<<<gw, kWorkThreads, 0, sync_stream_>>>(round_dev_, worklist_, work_count_);
-    phase_meta_kernel<0, 1><<<gm, kThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, work_count_);
+    { TraceScope t_(this, "A.scan", sync_stream_); phase_scan_kernel<0><<<gs, kThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, wc); }
+    { TraceScope t_(this, "A.resolve", sync_stream_); phase_meta_kernel<0, 0><<<gm, kThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, wc); }
+    { TraceScope t_(this, "A.row", sync_stream_); phase_row_kernel<<<gw, kWorkThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, wc); }
+    { TraceScope t_(this, "A.commit", sync_stream_); phase_meta_kernel<0, 1><<<gm, kThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, wc); }
   } else {
-    phase_scan_kernel<1><<<gs, kThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, work_count_);
-    phase_meta_kernel<1, 0><<<gm, kThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, work_count_);
-    phase_row_kernel<<<gw, kWorkThreads, 0, sync_stream_>>>(round_dev_, worklist_, work_count_);
-    phase_meta_kernel<1, 1><<<gm, kThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, work_count_);
+    { TraceScope t_(this, "C.scan", sync_stream_); phase_scan_kernel<1><<<gs, kThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, wc); }
+    { TraceScope t_(this, "C.resolve", sync_stream_); phase_meta_kernel<1, 0><<<gm, kThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, wc); }
+    { TraceScope t_(this, "C.row", sync_stream_); phase_row_kernel<<<gw, kWorkThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, wc); }
+    { TraceScope t_(this, "C.commit", sync_stream_); phase_meta_kernel<1, 1><<<gm, kThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, wc); }
   }
   for (int i = 0; i < 4; ++i) ADAPM_COUNT_LAUNCH();
   ADAPM_CUDA_CHECK(cudaGetLastError());
@@ -809,6 +837,7 @@ RoundOutcome CudaBackend::fused_round(const RoundRequest& rq) {
   launch_phase(2);
   ADAPM_CUDA_CHECK(cudaGetLastError());
   ADAPM_CUDA_CHECK(cudaMemcpyAsync(&round_host_[1], round_dev_, sizeof(RoundDev), cudaMemcpyDeviceToHost, s));
+  if (trace_on_) ADAPM_CUDA_CHECK(cudaMemcpyAsync(abort_word_ + 4, work_count_, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
   if (n) ADAPM_CUDA_CHECK(cudaMemcpyAsync(status_host_, status_dev_, n, cudaMemcpyDeviceToHost, s));
   ADAPM_CUDA_CHECK(cudaEventRecord(round_done_, s));
   ++fused_rounds_;
@@ -824,6 +853,10 @@ RoundOutcome CudaBackend::fused_round(const RoundRequest& rq) {
     if ((spins & 255u) == 0 && ctl->sync_barrier.broken.load(std::memory_order_relaxed)) *abort_word_ = 1;
   }
   const RoundDev& res = round_host_[1];
+  if (trace_on_) {
+    std::lock_guard<std::mutex> lk(trace_mu_);
+    if (trace_counts_.size() < ((size_t)1 << 20)) trace_counts_.push_back({(uint32_t)n, abort_word_[4], abort_word_[5]});
+  }
   if (res.error) {
     ctl->sync_barrier.broken.store(1);
     throw Error(res.error == 1 ? "sync round: a device-side cross-rank barrier timed out or was aborted (a peer died or hangs)"
@@ -880,6 +913,15 @@ void CudaBackend::dump_trace(const std::string& path) {
   }
   fclose(f);
   trace_.clear();
+  if (!trace_counts_.empty()) {   // per round: intent records registered, phase A worklist, phase C worklist
+    FILE* g = fopen((path + ".counts").c_str(), "w");
+    if (g) {
+      fprintf(g, "recs\tworkA\tworkC\n");
+      for (auto& c3 : trace_counts_) fprintf(g, "%u\t%u\t%u\n", c3[0], c3[1], c3[2]);
+      fclose(g);
+    }
+    trace_counts_.clear();
+  }
 }
 
 void CudaBackend::round_fence() {

@@ -6,6 +6,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <array>
 #include <mutex>
 #include <set>
 #include <unordered_map>
@@ -104,6 +105,7 @@ class CudaBackend : public Backend {
   bool trace_on_ = false;        // ADAPM_SYNC_TRACE
   cudaEvent_t trace_base_ = nullptr;
   std::vector<TraceRec> trace_;
+  std::vector<std::array<uint32_t, 3>> trace_counts_;
   std::mutex trace_mu_;
   int scan_blocks_per_sm_ = 1;   // ADAPM_SYNC_SCAN_BLOCKS
   int work_blocks_per_sm_ = 1;   // ADAPM_SYNC_WORK_BLOCKS (row pass: blocks of 128 threads)

@@ -96,6 +96,7 @@ class DeepFM:
         self.net = DenseNet(cfg, use_tensor_cores=self.cuda).to(self.dev)
         self.opt = torch.optim.Adam(self.net.parameters(), lr=cfg.lr_dense)
         self.step_no = 0
+        self.rows_pushed = 0      # (key,row) updates applied so far (distinct feature rows per batch)
 
     def init_model(self, chunk: int = 1 << 18) -> None:
         """v ~ N(0, 0.01), w = 0, accumulators 1e-6; every rank initialises the keys it is home for."""
@@ -117,8 +118,9 @@ class DeepFM:
         if self.server.num_servers() > 1:
             self.worker.intent(feat_ids.reshape(-1), clock, clock + 1)
 
-    def step(self, feat_ids: torch.Tensor, labels: torch.Tensor) -> float:
-        """feat_ids [B, F] int64 (global feature ids), labels [B] float (CPU or pinned tensors)."""
+    def step(self, feat_ids: torch.Tensor, labels: torch.Tensor, return_tensor: bool = False):
+        """feat_ids [B, F] int64 (global feature ids), labels [B] float (CPU / pinned / device tensors). Returns the
+        batch loss (a float, or the device tensor with ``return_tensor`` - no host synchronisation then)."""
         cfg, kv = self.cfg, self.worker
         B, F, k = feat_ids.shape[0], cfg.num_fields, cfg.embed_dim
         ids = feat_ids.to(self.dev, non_blocking=True).reshape(-1).contiguous()
@@ -146,7 +148,8 @@ class DeepFM:
         upd = torch.cat([-cfg.lr_sparse * g / torch.sqrt(acc + g * g), g * g], 1).contiguous()
         kv.push(uniq, upd.view(-1), True)
         self.step_no += 1
-        return float(loss.detach())
+        self.rows_pushed += int(uniq.numel())
+        return loss.detach() if return_tensor else float(loss.detach())
 
 
 def synthetic_ctr_batch(cfg: DeepFMConfig, step: int, rank: int = 0):

@@ -36,7 +36,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="native", choices=["native", "reference", "nccl"])
-    ap.add_argument("--config", default="word2vec", choices=["word2vec"])
+    ap.add_argument("--config", default="word2vec", choices=["word2vec", "kge", "mf", "ctr"],
+                    help="word2vec = BASELINE config #2 (the headline); kge / mf / ctr = configs #3 / #4 / #5 (benchmarks/configs.py)")
     ap.add_argument("--vocab", type=int, default=1_000_000)
     ap.add_argument("--dim", type=int, default=300)
     ap.add_argument("--negative", type=int, default=25)
@@ -144,6 +145,13 @@ def main():
         from adapm_b200.parallel.nccl_baseline import run_nccl_word2vec
 
         return run_nccl_word2vec(args, rank, world, local_rank)
+    if args.config != "word2vec":
+        from benchmarks.configs import run as run_config
+
+        rc = run_config(args.config, args, rank, world, local_rank, ClockSampler)
+        if world > 1:
+            dist.destroy_process_group()
+        return rc
 
     import adapm_b200 as ad
     from adapm_b200 import _C
