@@ -30,7 +30,7 @@ constexpr Clock WINDOW_MAX = CLOCK_MAX / 4;    // "act on every intent right awa
 constexpr int LOCAL = -1;                      // timestamp of an op that completed locally/inline
 
 constexpr int MAX_RANKS = 64;          // want-mask is one 64-bit word per slot
-constexpr int MAX_CLASSES = 8;         // distinct value lengths ("length classes")
+constexpr int MAX_CLASSES = 32;        // size classes of the row slabs (any number of distinct value lengths maps onto them)
 constexpr int MAX_LOCAL_WORKERS = 16;  // logical workers per rank (per GPU)
 
 // Which management techniques the sync engine may use (reference base.h:54).

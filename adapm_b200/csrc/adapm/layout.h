@@ -14,7 +14,7 @@
 namespace adapm {
 
 struct ClassInfo {
-  uint32_t len;         // values per row
+  uint32_t len;         // values per slot of this size class (= the row length of its keys unless Layout::per_key_len)
   uint32_t cap;         // slots of this class per rank
   uint32_t slot_begin;  // first global slot id of this class
   uint32_t pad;
@@ -33,7 +33,9 @@ struct Layout {
   uint32_t pad;
   uint64_t off_dir;        // uint8[num_keys]   owner rank of each key (replicated directory)
   uint64_t off_slot_of;    // int32[num_keys]   local slot of a key, -1 = not resident
-  uint64_t off_key_class;  // uint8[num_keys]   length class (only if num_classes > 1)
+  uint64_t off_key_class;  // uint8[num_keys]   size class (only if num_classes > 1)
+  uint64_t off_key_len;    // uint32[num_keys]  row length of every key (only if per_key_len: more distinct value
+                           //                   lengths than size classes, so a class holds keys of different lengths)
   uint64_t off_meta;       // uint32[S]         state | peer | seq
   uint64_t off_version;    // uint32[S]         owner: #pushes applied
   uint64_t off_ver_seen;   // uint32[S]         replica: owner version at last refresh
@@ -49,7 +51,7 @@ struct Layout {
   uint64_t off_access;     // uint32[2*num_keys] (accesses, local accesses) - only if locality stats are on, else 0
   uint64_t off_sync;       // SyncArea: device-side round state (grace epochs, cross-rank barrier flags)
   uint32_t locality_stats; // PS_LOCALITY_STATS equivalent (run-time switch sys.stats.locality)
-  uint32_t pad2;
+  uint32_t per_key_len;    // 1: row lengths come from off_key_len, the class only fixes the slot stride
   ClassInfo cls[MAX_CLASSES];
   uint64_t heap_bytes;
 };
@@ -107,6 +109,11 @@ ADAPM_HD SyncArea* sync_area_of(const Ctx& c, int r) { return at<SyncArea>(c, r,
 ADAPM_HD int class_of_key(const Ctx& c, Key k) {
   if (c.L.num_classes == 1) return 0;
   return at<uint8_t>(c, c.rank, c.L.off_key_class)[k];
+}
+// number of values of `key`'s row (<= the slot stride of its size class)
+ADAPM_HD uint32_t key_len(const Ctx& c, Key k, int cls) {
+  if (c.L.per_key_len) return at<uint32_t>(c, c.rank, c.L.off_key_len)[k];
+  return c.L.cls[cls].len;
 }
 template <class Val> ADAPM_HD Val* row_ptr(const Ctx& c, int r, int cls, uint32_t slot) {
   const ClassInfo& ci = c.L.cls[cls];

@@ -8,7 +8,8 @@ namespace adapm {
 // ======================================================================== Server
 Server::Server(const Options& opt, const ValueSpec& spec) : opt_(opt), spec_(spec) {
   ADAPM_CHECK(opt_.backend == "cpu" || opt_.backend == "cuda", "backend must be cpu or cuda");
-  if (opt_.backend == "cuda") ADAPM_CHECK(opt_.dtype == "float32", "the cuda backend stores float32 rows");
+  // (cuda: float32 rows for the fused application kernels; float64 / int64 rows - the reference's `double` apps and its
+  //  exact `long` contract tests - run through the generic Pull/Push/Set and the sync round)
   fabric_ = Fabric::create(opt_);
   std::vector<uint8_t> key_class;
   Layout L = build_layout(spec_, opt_, &key_class);
@@ -16,7 +17,7 @@ Server::Server(const Options& opt, const ValueSpec& spec) : opt_(opt), spec_(spe
                   << L.num_classes << " length classes");
   if (opt_.backend == "cuda") backend_ = make_cuda_backend(opt_, L, fabric_);
   else backend_ = make_cpu_backend(opt_, L, fabric_);
-  backend_->init_store(key_class);
+  backend_->init_store(key_class, spec_.lens);
   workers_.assign(opt_.workers, nullptr);
   parse_trace_keys();
   sync_.reset(new SyncEngine(this));

@@ -341,7 +341,7 @@ ADAPM_HD bool read_row(const G& g, const PullLoc<Val>& loc, Val* out, uint32_t l
 
 template <class Val, class G>
 ADAPM_HD bool pull_key(const Ctx& c, const G& g, Key key, Val* out, bool local_only, bool* was_local) {
-  const uint32_t len = c.L.cls[class_of_key(c, key)].len;
+  const uint32_t len = key_len(c, key, class_of_key(c, key));
   for (int attempt = 0; attempt < kMaxAttempts; ++attempt) {
     PullLoc<Val> loc = locate_pull<Val>(c, g, key, local_only);
     if (loc.kind == LOC_FAIL) return false;
@@ -401,7 +401,7 @@ ADAPM_HD PushLoc<Val> locate_push(const Ctx& c, const G& g, Key key) {
 
 template <class Val, class G>
 ADAPM_HD bool push_key(const Ctx& c, const G& g, Key key, const Val* vals, bool* was_local) {
-  const uint32_t len = c.L.cls[class_of_key(c, key)].len;
+  const uint32_t len = key_len(c, key, class_of_key(c, key));
   PushLoc<Val> loc = locate_push<Val>(c, g, key);
   if (!loc.row) return false;
   for (uint32_t i = g.lane(); i < len; i += g.size()) mem::red_add(loc.row + i, vals[i]);
@@ -424,7 +424,7 @@ template <class Val, class G>
 ADAPM_HD int set_key(const Ctx& c, const G& g, Key key, const Val* vals, bool* was_local) {
   const int me = c.rank;
   const int cls = class_of_key(c, key);
-  const uint32_t len = c.L.cls[cls].len;
+  const uint32_t len = key_len(c, key, cls);
   for (int attempt = 0; attempt < 256; ++attempt) {
     int32_t s = g.bcast(g.lane() == 0 ? mem::ld_relaxed(slot_of(c, me) + key) : 0);
     uint32_t st = S_FREE;
@@ -656,7 +656,7 @@ ADAPM_HD void phase_a_resolve(const Ctx& c, SlotWork& w, const RoundParams& rp) 
   if (st != S_REPLICA && st != S_REPLICA_PENDING) return;
   const Key key = mem::ld_relaxed(slot_key_of(c, me) + s);
   const int cls = class_of_key(c, key);
-  const uint32_t len = c.L.cls[cls].len;
+  const uint32_t len = key_len(c, key, cls);
   const bool active = intent_active(c, s, rp.clocks);
   const int o = (int)mem::ld_relaxed(dir_of(c, me) + key);
   int32_t ps = -1;
@@ -784,7 +784,7 @@ ADAPM_HD void phase_c_resolve(const Ctx& c, SlotWork& w, const RoundParams& rp) 
   if (st == S_FREE || st == S_OWNED) return;
   const Key key = mem::ld_relaxed(slot_key_of(c, me) + s);
   const int cls = class_of_key(c, key);
-  const uint32_t len = c.L.cls[cls].len;
+  const uint32_t len = key_len(c, key, cls);
   w.key = key; w.cls = cls; w.len = len;
   uint8_t* fl = flags_of(c, me) + s;
   if (state_is_incoming(st)) {

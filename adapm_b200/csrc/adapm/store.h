@@ -50,11 +50,41 @@ inline Layout build_layout(const ValueSpec& spec, const Options& opt, std::vecto
       home_count[0][r] = spec.num_keys / opt.world + ((spec.num_keys % opt.world) > r ? 1 : 0);
   } else {
     ADAPM_CHECK((int64_t)spec.lens.size() == spec.num_keys, "value_lengths must have one entry per key");
+    // Any number of distinct value lengths (reference: one allocation per key, coloc_kv_server_handle.h:162-170,
+    // 996-999) maps onto at most MAX_CLASSES size classes of the row slabs. Up to MAX_CLASSES distinct lengths: one
+    // exact class each. More: the sorted lengths are cut into MAX_CLASSES groups of bounded relative spread (the
+    // smallest ratio that fits, found by bisection); a class's slot holds its longest row (rounded up to 16 bytes), the
+    // keys keep their own length in a per-key table (Layout::per_key_len).
     std::map<uint32_t, int> idx;
     for (uint32_t l : spec.lens) idx.emplace(l, 0);
-    ADAPM_CHECK((int)idx.size() <= MAX_CLASSES, "at most " << MAX_CLASSES << " distinct value lengths are supported, got " << idx.size());
-    int i = 0;
-    for (auto& kv : idx) { kv.second = i++; class_len.push_back(kv.first); }
+    if ((int)idx.size() <= MAX_CLASSES) {
+      int i = 0;
+      for (auto& kv : idx) { kv.second = i++; class_len.push_back(kv.first); }
+    } else {
+      std::vector<uint32_t> d;
+      for (auto& kv : idx) d.push_back(kv.first);
+      auto groups_for = [&](double ratio, std::vector<size_t>* starts) {
+        int g = 0; double lo = 0;
+        for (size_t i = 0; i < d.size(); ++i) {
+          if (i == 0 || (double)d[i] > lo * ratio) { ++g; lo = (double)d[i]; if (starts) starts->push_back(i); }
+        }
+        return g;
+      };
+      double a = 1.0, b = (double)d.back() / (double)d.front() + 1.0;
+      for (int it = 0; it < 60; ++it) {
+        const double m = 0.5 * (a + b);
+        if (groups_for(m, nullptr) <= MAX_CLASSES) b = m; else a = m;
+      }
+      std::vector<size_t> starts;
+      groups_for(b, &starts);
+      for (size_t g = 0; g < starts.size(); ++g) {
+        const size_t end = g + 1 < starts.size() ? starts[g + 1] : d.size();
+        const uint32_t longest = d[end - 1];
+        class_len.push_back((longest + 3u) / 4u * 4u);
+        for (size_t i = starts[g]; i < end; ++i) idx[d[i]] = (int)g;
+      }
+      L.per_key_len = 1;
+    }
     home_count.assign(class_len.size(), std::vector<int64_t>(opt.world, 0));
     if (key_class_out) key_class_out->resize(spec.num_keys);
     for (int64_t k = 0; k < spec.num_keys; ++k) {
@@ -99,6 +129,7 @@ inline Layout build_layout(const ValueSpec& spec, const Options& opt, std::vecto
   L.off_dir = take((uint64_t)L.num_keys);
   L.off_slot_of = take((uint64_t)L.num_keys * 4);
   L.off_key_class = take(L.num_classes > 1 ? (uint64_t)L.num_keys : 1);
+  L.off_key_len = take(L.per_key_len ? (uint64_t)L.num_keys * 4 : 1);
   L.off_meta = take((uint64_t)L.total_slots * 4);
   L.off_version = take((uint64_t)L.total_slots * 4);
   L.off_ver_seen = take((uint64_t)L.total_slots * 4);
@@ -168,7 +199,8 @@ class Backend {
 
   // Populate directory + initial allocation (every key at its home rank key % world,
   // reference coloc_kv_server.h:86-90). Collective.
-  virtual void init_store(const std::vector<uint8_t>& key_class) = 0;
+  // key_lens: the per-key row lengths (only read when the layout has per_key_len set)
+  virtual void init_store(const std::vector<uint8_t>& key_class, const std::vector<uint32_t>& key_lens) = 0;
 
   // ---- worker data path. `vals` holds the concatenated rows in key order.
   // host pointers for the cpu backend; for cuda see cuda/cuda_backend.h (device or host).

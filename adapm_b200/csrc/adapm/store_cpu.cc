@@ -22,13 +22,14 @@ class CpuBackend : public Backend {
 
   const Ctx& ctx() const override { return ctx_; }
 
-  void init_store(const std::vector<uint8_t>& key_class) override {
+  void init_store(const std::vector<uint8_t>& key_class, const std::vector<uint32_t>& key_lens) override {
     const Ctx& c = ctx_;
     const int me = c.rank;
     const Layout& L = c.L;
     uint8_t* dir = dir_of(c, me);
     int32_t* so = slot_of(c, me);
     if (L.num_classes > 1) memcpy(at<uint8_t>(c, me, L.off_key_class), key_class.data(), (size_t)L.num_keys);
+    if (L.per_key_len) memcpy(at<uint32_t>(c, me, L.off_key_len), key_lens.data(), (size_t)L.num_keys * 4);
     std::vector<uint32_t> next(L.num_classes);
     for (int k = 0; k < L.num_classes; ++k) next[k] = L.cls[k].slot_begin;
     for (int64_t key = 0; key < L.num_keys; ++key) {
@@ -76,7 +77,7 @@ class CpuBackend : public Backend {
       bool good = pull_key<Val>(ctx_, g, key, out, local_only, &local);
       if (ok) ok[i] = good ? 1 : 0;
       if (!good) ++nf; else if (local) ++nl; else ++nr;
-      out += ctx_.L.cls[class_of_key(ctx_, key)].len;
+      out += key_len(ctx_, key, class_of_key(ctx_, key));
     }
     count(ctx_, C_PULL_LOCAL, nl);
     count(ctx_, C_PULL_REMOTE, nr);
@@ -103,7 +104,7 @@ class CpuBackend : public Backend {
           if (good != SET_OK) ++nf; else if (local) ++nl; else ++nr;
         }
       }
-      in += ctx_.L.cls[class_of_key(ctx_, key)].len;
+      in += key_len(ctx_, key, class_of_key(ctx_, key));
     }
     mem::fence();
     count(ctx_, C_PUSH_LOCAL, nl);

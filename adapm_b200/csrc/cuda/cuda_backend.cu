@@ -12,6 +12,7 @@
 
 #include <cstring>
 #include <sstream>
+#include <type_traits>
 
 #include "pm_kernels.cuh"
 
@@ -53,8 +54,11 @@ __global__ void init_uniform_kernel(const __grid_constant__ Ctx c) {
 }
 
 // ------------------------------------------------------------------------------ K1
+// (templated on the value type: float32 rows take the 16-byte fast paths, float64 / int64 rows - the reference's
+// `double` applications and its exact `long` contract tests - the element-wise protocol path)
+template <class Val>
 __global__ void __launch_bounds__(kThreads)
-pull_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ keys, size_t n, float* __restrict__ out,
+pull_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ keys, size_t n, Val* __restrict__ out,
             const int64_t* __restrict__ offsets, uint32_t uniform_len, int local_only, uint8_t* ok,
             unsigned long long* result) {
   WarpGroup g;
@@ -64,23 +68,25 @@ pull_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ keys, size_t 
   unsigned nl = 0, nr = 0, nf = 0;
   for (size_t i = warp; i < n; i += nwarps) {
     const Key key = keys[i];
-    float* o = out + (offsets ? (size_t)offsets[i] : i * (size_t)uniform_len);
+    Val* o = out + (offsets ? (size_t)offsets[i] : i * (size_t)uniform_len);
     bool good = false, local = false;
     if (key >= 0 && key < c.L.num_keys) {
-      const uint32_t len = c.L.cls[class_of_key(c, key)].len;
+      const uint32_t len = key_len(c, key, class_of_key(c, key));
       // fast path: directly readable row, 16-byte vectorised
       for (int attempt = 0; attempt < 1024 && !good; ++attempt) {
-        PullLoc<float> loc = locate_pull<float>(c, g, key, local_only != 0);
+        PullLoc<Val> loc = locate_pull<Val>(c, g, key, local_only != 0);
         if (loc.kind == LOC_FAIL) break;
-        if (loc.kind == LOC_DIRECT && (len & 3u) == 0 && ((((uintptr_t)loc.row) | ((uintptr_t)o)) & 15u) == 0) {
-          for (uint32_t j = g.lane() * 4; j < len; j += 128) {
-            float4 v = dev::ld_row4(loc.row + j);
-            *reinterpret_cast<float4*>(o + j) = v;
+        bool fast = false;
+        if constexpr (std::is_same<Val, float>::value) {
+          if (loc.kind == LOC_DIRECT && (len & 3u) == 0 && ((((uintptr_t)loc.row) | ((uintptr_t)o)) & 15u) == 0) {
+            for (uint32_t j = g.lane() * 4; j < len; j += 128) {
+              float4 v = dev::ld_row4(loc.row + j);
+              *reinterpret_cast<float4*>(o + j) = v;
+            }
+            fast = true;
           }
-          good = true;
-        } else {
-          good = read_row(g, loc, o, len);
         }
+        good = fast || read_row(g, loc, o, len);
         local = loc.local;
       }
     }
@@ -103,8 +109,9 @@ pull_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ keys, size_t 
 }
 
 // ------------------------------------------------------------------------------ K2
+template <class Val>
 __global__ void __launch_bounds__(kThreads)
-push_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ keys, size_t n, const float* __restrict__ vals,
+push_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ keys, size_t n, const Val* __restrict__ vals,
             const int64_t* __restrict__ offsets, uint32_t uniform_len, int set, unsigned long long* result,
             uint8_t* __restrict__ todo) {
   WarpGroup g;
@@ -115,23 +122,27 @@ push_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ keys, size_t 
   for (size_t i = warp; i < n; i += nwarps) {
     if (todo && !todo[i]) continue;   // Set with retry: this key is already done
     const Key key = keys[i];
-    const float* v = vals + (offsets ? (size_t)offsets[i] : i * (size_t)uniform_len);
+    const Val* v = vals + (offsets ? (size_t)offsets[i] : i * (size_t)uniform_len);
     bool good = false, local = false;
     if (key >= 0 && key < c.L.num_keys) {
       if (set) {
-        const int r = set_key<float>(c, g, key, v, &local);
+        const int r = set_key<Val>(c, g, key, v, &local);
         if (r == SET_RETRY && todo) { ++nretry; continue; }   // relocation in flight: the host repeats it after a round
         good = r == SET_OK;
       } else {
-        const uint32_t len = c.L.cls[class_of_key(c, key)].len;
-        PushLoc<float> loc = locate_push<float>(c, g, key);
+        const uint32_t len = key_len(c, key, class_of_key(c, key));
+        PushLoc<Val> loc = locate_push<Val>(c, g, key);
         if (loc.row) {
-          if ((len & 3u) == 0 && ((((uintptr_t)loc.row) | ((uintptr_t)v)) & 15u) == 0) {
-            for (uint32_t j = g.lane() * 4; j < len; j += 128)
-              dev::red_row4(loc.row + j, *reinterpret_cast<const float4*>(v + j));
-          } else {
-            for (uint32_t j = g.lane(); j < len; j += 32) mem::red_add(loc.row + j, v[j]);
+          bool fast = false;
+          if constexpr (std::is_same<Val, float>::value) {
+            if ((len & 3u) == 0 && ((((uintptr_t)loc.row) | ((uintptr_t)v)) & 15u) == 0) {
+              for (uint32_t j = g.lane() * 4; j < len; j += 128)
+                dev::red_row4(loc.row + j, *reinterpret_cast<const float4*>(v + j));
+              fast = true;
+            }
           }
+          if (!fast)
+            for (uint32_t j = g.lane(); j < len; j += 32) mem::red_add(loc.row + j, v[j]);
           if (g.lane() == 0) {
             if (loc.version) mem::red_add(loc.version, 1u);
             if (loc.flag) mem::st_relaxed(loc.flag, (uint8_t)1);
@@ -171,13 +182,14 @@ __global__ void peek_kernel(const __grid_constant__ Ctx c, const Key* keys, size
 // ------------------------------------------------------------------------------ sync round
 // All round kernels read their parameters from a device-resident RoundDev (cuda_backend.h): the host uploads it once
 // per round, the first cross-rank barrier of the round fills in what the ranks agreed on (sweep / stop).
+template <class Val>
 __global__ void register_kernel(const __grid_constant__ Ctx c, const IntentRec* recs, const RoundDev* __restrict__ rd,
                                 uint8_t* status) {
   if (rd->stop) return;
   const size_t n = rd->n_recs;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  int st = register_intent<float>(c, recs[i], rd->rp.clocks);
+  int st = register_intent<Val>(c, recs[i], rd->rp.clocks);
   status[i] = (uint8_t)st;
   if (st == 0) count(c, C_INTENTS_REGISTERED);
   else if (st == 1) count(c, C_INTENTS_DEFERRED);
@@ -214,7 +226,7 @@ __global__ void __launch_bounds__(kThreads) phase_scan_kernel(const __grid_const
 
 // resolve / commit: one thread per worklist entry (all the metadata work, including the NVLink metadata loads: a
 // thread-per-slot pass keeps as many of them in flight as there are entries). STEP 0 = resolve, 1 = commit.
-template <int PHASE, int STEP>
+template <class Val, int PHASE, int STEP>
 __global__ void __launch_bounds__(kThreads) phase_meta_kernel(const __grid_constant__ Ctx c, const RoundDev* __restrict__ rd,
                                                               SlotWork* __restrict__ worklist,
                                                               const unsigned int* __restrict__ count) {
@@ -222,9 +234,9 @@ __global__ void __launch_bounds__(kThreads) phase_meta_kernel(const __grid_const
   const unsigned n = *count;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     if (PHASE == 0) {
-      if (STEP == 0) phase_a_resolve<float>(c, worklist[i], rd->rp); else phase_a_commit<float>(c, worklist[i]);
+      if (STEP == 0) phase_a_resolve<Val>(c, worklist[i], rd->rp); else phase_a_commit<Val>(c, worklist[i]);
     } else {
-      if (STEP == 0) phase_c_resolve<float>(c, worklist[i], rd->rp); else phase_c_commit<float>(c, worklist[i]);
+      if (STEP == 0) phase_c_resolve<Val>(c, worklist[i], rd->rp); else phase_c_commit<Val>(c, worklist[i]);
     }
   }
 }
@@ -237,6 +249,7 @@ constexpr int kWorkThreads = 128;
 #ifndef ADAPM_WORK_MINB
 #define ADAPM_WORK_MINB 6   // <= 80 registers x 128 threads = 10 K of the 12 K registers a lean training kernel leaves free per SM
 #endif
+template <class Val>
 __global__ void __launch_bounds__(kWorkThreads, ADAPM_WORK_MINB) phase_row_kernel(const __grid_constant__ Ctx c,
                                                                                const RoundDev* __restrict__ rd,
                                                                                SlotWork* __restrict__ worklist,
@@ -247,7 +260,7 @@ __global__ void __launch_bounds__(kWorkThreads, ADAPM_WORK_MINB) phase_row_kerne
   const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
   for (unsigned i = warp; i < n; i += nwarps) {
-    if (worklist[i].op != OP_NONE) row_op_execute<float>(c, g, worklist[i]);
+    if (worklist[i].op != OP_NONE) row_op_execute<Val>(c, g, worklist[i]);
     __syncwarp();
   }
 }
@@ -355,6 +368,14 @@ __global__ void grace_kernel(const __grid_constant__ Ctx c, RoundDev* rd, const 
 
 }  // namespace
 
+// run `...` with the alias Val bound to the value type of the store (Options::dtype)
+#define ADAPM_DISPATCH_VAL(vb_is_int, vbytes, ...)                  \
+  do {                                                              \
+    if ((vbytes) == 4) { using Val = float; __VA_ARGS__; }          \
+    else if (vb_is_int) { using Val = int64_t; __VA_ARGS__; }       \
+    else { using Val = double; __VA_ARGS__; }                       \
+  } while (0)
+
 std::atomic<uint64_t>& kernel_launch_counter() {
   static std::atomic<uint64_t> c{0};
   return c;
@@ -368,6 +389,7 @@ CudaBackend::CudaBackend(const Options& opt, const Layout& L, std::shared_ptr<Fa
   ctx_.L = L;
   ctx_.rank = opt.rank;
   ctx_.technique = (int)opt.techniques;
+  int_rows_ = opt.dtype == "int64";
   fabric_->allocate_heaps(L.heap_bytes);
   device_ = fabric_->device();
   use_device();
@@ -440,7 +462,7 @@ void CudaBackend::ensure_staging(Staging& st, size_t bytes) {
   st.bytes = nb;
 }
 
-void CudaBackend::init_store(const std::vector<uint8_t>& key_class) {
+void CudaBackend::init_store(const std::vector<uint8_t>& key_class, const std::vector<uint32_t>& key_lens) {
   use_device();
   const Layout& L = ctx_.L;
   const int me = ctx_.rank;
@@ -460,7 +482,7 @@ void CudaBackend::init_store(const std::vector<uint8_t>& key_class) {
     for (int64_t key = 0; key < L.num_keys; ++key) {
       int home = (int)(key % L.world);
       dir[key] = (uint8_t)home;
-      key_len_[key] = L.cls[key_class[key]].len;
+      key_len_[key] = L.per_key_len ? key_lens[key] : L.cls[key_class[key]].len;
       if (home == me) {
         uint32_t s = next[key_class[key]]++;
         so[key] = (int32_t)s;
@@ -472,6 +494,7 @@ void CudaBackend::init_store(const std::vector<uint8_t>& key_class) {
     ADAPM_CUDA_CHECK(cudaMemcpy(h + L.off_dir, dir.data(), dir.size(), cudaMemcpyHostToDevice));
     ADAPM_CUDA_CHECK(cudaMemcpy(h + L.off_slot_of, so.data(), so.size() * 4, cudaMemcpyHostToDevice));
     ADAPM_CUDA_CHECK(cudaMemcpy(h + L.off_key_class, key_class.data(), key_class.size(), cudaMemcpyHostToDevice));
+    if (L.per_key_len) ADAPM_CUDA_CHECK(cudaMemcpy(h + L.off_key_len, key_lens.data(), key_lens.size() * 4, cudaMemcpyHostToDevice));
     ADAPM_CUDA_CHECK(cudaMemcpy(h + L.off_meta, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice));
     ADAPM_CUDA_CHECK(cudaMemcpy(h + L.off_slot_key, skey.data(), skey.size() * 8, cudaMemcpyHostToDevice));
     int32_t tops[MAX_CLASSES] = {0};
@@ -561,8 +584,8 @@ uint64_t CudaBackend::pull(int worker, const Key* keys, size_t n, void* vals, bo
   if (io.on_device) {
     ADAPM_CHECK(uniform || io.offsets, "device-pointer pull on a mixed-length store needs per-key value offsets");
     cudaStream_t s = resolve_stream(worker, io);
-    pull_kernel<<<grid_for_warps(n, num_sms_), kThreads, 0, s>>>(ctx_, keys, n, (float*)vals, uniform ? nullptr : io.offsets, L.cls[0].len,
-                                                                 local_only ? 1 : 0, ok, nullptr);
+    ADAPM_DISPATCH_VAL(int_rows_, L.val_bytes, pull_kernel<Val><<<grid_for_warps(n, num_sms_), kThreads, 0, s>>>(
+        ctx_, keys, n, (Val*)vals, uniform ? nullptr : io.offsets, L.cls[0].len, local_only ? 1 : 0, ok, nullptr));
     ADAPM_COUNT_LAUNCH();
   ADAPM_CUDA_CHECK(cudaGetLastError());
     return record_ticket(s);
@@ -580,7 +603,7 @@ uint64_t CudaBackend::pull(int worker, const Key* keys, size_t n, void* vals, bo
   // over the key lengths (host mirror of the class table, built in init_store)
   size_t bytes_vals;
   std::vector<int64_t> prefix;
-  if (uniform) bytes_vals = n * (size_t)L.cls[0].len * 4;
+  if (uniform) bytes_vals = n * (size_t)L.cls[0].len * L.val_bytes;
   else {
     prefix.resize(n);
     size_t acc = 0;
@@ -589,16 +612,16 @@ uint64_t CudaBackend::pull(int worker, const Key* keys, size_t n, void* vals, bo
       prefix[i] = (int64_t)acc;
       acc += (size_t)key_len_[keys[i]];
     }
-    bytes_vals = acc * 4;
+    bytes_vals = acc * L.val_bytes;
   }
   ensure_staging(st, o_vals + bytes_vals + 256);
   memcpy(st.host + o_keys, keys, n * 8);
   if (!uniform) memcpy(st.host + o_offs, prefix.data(), n * 8);
   memset(st.host + o_res, 0, 64);
   ADAPM_CUDA_CHECK(cudaMemcpyAsync(st.dev, st.host, o_ok, cudaMemcpyHostToDevice, s));
-  pull_kernel<<<grid_for_warps(n, num_sms_), kThreads, 0, s>>>(
-      ctx_, (const Key*)(st.dev + o_keys), n, (float*)(st.dev + o_vals), uniform ? nullptr : (const int64_t*)(st.dev + o_offs),
-      L.cls[0].len, local_only ? 1 : 0, (uint8_t*)(st.dev + o_ok), (unsigned long long*)(st.dev + o_res));
+  ADAPM_DISPATCH_VAL(int_rows_, L.val_bytes, pull_kernel<Val><<<grid_for_warps(n, num_sms_), kThreads, 0, s>>>(
+      ctx_, (const Key*)(st.dev + o_keys), n, (Val*)(st.dev + o_vals), uniform ? nullptr : (const int64_t*)(st.dev + o_offs),
+      L.cls[0].len, local_only ? 1 : 0, (uint8_t*)(st.dev + o_ok), (unsigned long long*)(st.dev + o_res)));
   ADAPM_COUNT_LAUNCH();
   ADAPM_CUDA_CHECK(cudaGetLastError());
   ADAPM_CUDA_CHECK(cudaMemcpyAsync(st.host + o_res, st.dev + o_res, (o_vals - o_res) + bytes_vals, cudaMemcpyDeviceToHost, s));
@@ -621,8 +644,8 @@ uint64_t CudaBackend::push(int worker, const Key* keys, size_t n, const void* va
     ADAPM_CHECK(uniform || io.offsets, "device-pointer push on a mixed-length store needs per-key value offsets");
     cudaStream_t s = resolve_stream(worker, io);
     if (!todo) {
-      push_kernel<<<grid_for_warps(n, num_sms_), kThreads, 0, s>>>(ctx_, keys, n, (const float*)vals, uniform ? nullptr : io.offsets, L.cls[0].len,
-                                                                   set ? 1 : 0, nullptr, nullptr);
+      ADAPM_DISPATCH_VAL(int_rows_, L.val_bytes, push_kernel<Val><<<grid_for_warps(n, num_sms_), kThreads, 0, s>>>(
+          ctx_, keys, n, (const Val*)vals, uniform ? nullptr : io.offsets, L.cls[0].len, set ? 1 : 0, nullptr, nullptr));
       ADAPM_COUNT_LAUNCH();
       ADAPM_CUDA_CHECK(cudaGetLastError());
       return record_ticket(s);
@@ -636,8 +659,9 @@ uint64_t CudaBackend::push(int worker, const Key* keys, size_t n, const void* va
     memset(st.host, 0, 64);
     memcpy(st.host + o_todo, todo, n);
     ADAPM_CUDA_CHECK(cudaMemcpyAsync(st.dev, st.host, o_todo + n, cudaMemcpyHostToDevice, s));
-    push_kernel<<<grid_for_warps(n, num_sms_), kThreads, 0, s>>>(ctx_, keys, n, (const float*)vals, uniform ? nullptr : io.offsets, L.cls[0].len,
-                                                                 set ? 1 : 0, (unsigned long long*)st.dev, (uint8_t*)(st.dev + o_todo));
+    ADAPM_DISPATCH_VAL(int_rows_, L.val_bytes, push_kernel<Val><<<grid_for_warps(n, num_sms_), kThreads, 0, s>>>(
+        ctx_, keys, n, (const Val*)vals, uniform ? nullptr : io.offsets, L.cls[0].len, set ? 1 : 0, (unsigned long long*)st.dev,
+        (uint8_t*)(st.dev + o_todo)));
     ADAPM_COUNT_LAUNCH();
     ADAPM_CUDA_CHECK(cudaGetLastError());
     ADAPM_CUDA_CHECK(cudaMemcpyAsync(st.host, st.dev, o_todo + n, cudaMemcpyDeviceToHost, s));
@@ -652,7 +676,7 @@ uint64_t CudaBackend::push(int worker, const Key* keys, size_t n, const void* va
   cudaStream_t s = worker_streams_[worker];
   std::vector<int64_t> prefix;
   size_t bytes_vals;
-  if (uniform) bytes_vals = n * (size_t)L.cls[0].len * 4;
+  if (uniform) bytes_vals = n * (size_t)L.cls[0].len * L.val_bytes;
   else {
     prefix.resize(n);
     size_t acc = 0;
@@ -661,7 +685,7 @@ uint64_t CudaBackend::push(int worker, const Key* keys, size_t n, const void* va
       prefix[i] = (int64_t)acc;
       acc += (size_t)key_len_[keys[i]];
     }
-    bytes_vals = acc * 4;
+    bytes_vals = acc * L.val_bytes;
   }
   const size_t o_keys = 0;
   const size_t o_offs = align_up(o_keys + n * 8, 256);
@@ -675,9 +699,9 @@ uint64_t CudaBackend::push(int worker, const Key* keys, size_t n, const void* va
   if (todo) memcpy(st.host + o_todo, todo, n);
   memcpy(st.host + o_vals, vals, bytes_vals);
   ADAPM_CUDA_CHECK(cudaMemcpyAsync(st.dev, st.host, o_vals + bytes_vals, cudaMemcpyHostToDevice, s));
-  push_kernel<<<grid_for_warps(n, num_sms_), kThreads, 0, s>>>(
-      ctx_, (const Key*)(st.dev + o_keys), n, (const float*)(st.dev + o_vals), uniform ? nullptr : (const int64_t*)(st.dev + o_offs),
-      L.cls[0].len, set ? 1 : 0, (unsigned long long*)(st.dev + o_res), todo ? (uint8_t*)(st.dev + o_todo) : nullptr);
+  ADAPM_DISPATCH_VAL(int_rows_, L.val_bytes, push_kernel<Val><<<grid_for_warps(n, num_sms_), kThreads, 0, s>>>(
+      ctx_, (const Key*)(st.dev + o_keys), n, (const Val*)(st.dev + o_vals), uniform ? nullptr : (const int64_t*)(st.dev + o_offs),
+      L.cls[0].len, set ? 1 : 0, (unsigned long long*)(st.dev + o_res), todo ? (uint8_t*)(st.dev + o_todo) : nullptr));
   ADAPM_COUNT_LAUNCH();
   ADAPM_CUDA_CHECK(cudaGetLastError());
   ADAPM_CUDA_CHECK(cudaMemcpyAsync(st.host + o_res, st.dev + o_res, (o_todo - o_res) + (todo ? n : 0), cudaMemcpyDeviceToHost, s));
@@ -735,7 +759,8 @@ void CudaBackend::register_intents(const IntentRec* recs, size_t n, const RoundP
   TraceScope ts_(this, "register", sync_stream_);
   upload_round(rp, (uint32_t)n, 0);
   ADAPM_CUDA_CHECK(cudaMemcpyAsync(st.dev, st.host, n * sizeof(IntentRec), cudaMemcpyHostToDevice, sync_stream_));
-  register_kernel<<<(int)((n + 255) / 256), 256, 0, sync_stream_>>>(ctx_, (const IntentRec*)st.dev, round_dev_, (uint8_t*)(st.dev + o_st));
+  ADAPM_DISPATCH_VAL(int_rows_, ctx_.L.val_bytes, register_kernel<Val><<<(int)((n + 255) / 256), 256, 0, sync_stream_>>>(
+      ctx_, (const IntentRec*)st.dev, round_dev_, (uint8_t*)(st.dev + o_st)));
   ADAPM_COUNT_LAUNCH();
   ADAPM_CUDA_CHECK(cudaGetLastError());
   ADAPM_CUDA_CHECK(cudaMemcpyAsync(st.host + o_st, st.dev + o_st, n, cudaMemcpyDeviceToHost, sync_stream_));
@@ -760,14 +785,14 @@ void CudaBackend::launch_phase(int phase) {
   const int gs = num_sms_ * scan_blocks_per_sm_, gm = num_sms_ * meta_blocks_per_sm_, gw = num_sms_ * work_blocks_per_sm_;
   if (phase == 0) {
     { TraceScope t_(this, "A.scan", sync_stream_); phase_scan_kernel<0><<<gs, kThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, wc); }
-    { TraceScope t_(this, "A.resolve", sync_stream_); phase_meta_kernel<0, 0><<<gm, kThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, wc); }
-    { TraceScope t_(this, "A.row", sync_stream_); phase_row_kernel<<<gw, kWorkThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, wc); }
-    { TraceScope t_(this, "A.commit", sync_stream_); phase_meta_kernel<0, 1><<<gm, kThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, wc); }
+    { TraceScope t_(this, "A.resolve", sync_stream_); ADAPM_DISPATCH_VAL(int_rows_, ctx_.L.val_bytes, phase_meta_kernel<Val, 0, 0><<<gm, kThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, wc)); }
+    { TraceScope t_(this, "A.row", sync_stream_); ADAPM_DISPATCH_VAL(int_rows_, ctx_.L.val_bytes, phase_row_kernel<Val><<<gw, kWorkThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, wc)); }
+    { TraceScope t_(this, "A.commit", sync_stream_); ADAPM_DISPATCH_VAL(int_rows_, ctx_.L.val_bytes, phase_meta_kernel<Val, 0, 1><<<gm, kThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, wc)); }
   } else {
     { TraceScope t_(this, "C.scan", sync_stream_); phase_scan_kernel<1><<<gs, kThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, wc); }
-    { TraceScope t_(this, "C.resolve", sync_stream_); phase_meta_kernel<1, 0><<<gm, kThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, wc); }
-    { TraceScope t_(this, "C.row", sync_stream_); phase_row_kernel<<<gw, kWorkThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, wc); }
-    { TraceScope t_(this, "C.commit", sync_stream_); phase_meta_kernel<1, 1><<<gm, kThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, wc); }
+    { TraceScope t_(this, "C.resolve", sync_stream_); ADAPM_DISPATCH_VAL(int_rows_, ctx_.L.val_bytes, phase_meta_kernel<Val, 1, 0><<<gm, kThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, wc)); }
+    { TraceScope t_(this, "C.row", sync_stream_); ADAPM_DISPATCH_VAL(int_rows_, ctx_.L.val_bytes, phase_row_kernel<Val><<<gw, kWorkThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, wc)); }
+    { TraceScope t_(this, "C.commit", sync_stream_); ADAPM_DISPATCH_VAL(int_rows_, ctx_.L.val_bytes, phase_meta_kernel<Val, 1, 1><<<gm, kThreads, 0, sync_stream_>>>(ctx_, round_dev_, worklist_, wc)); }
   }
   for (int i = 0; i < 4; ++i) ADAPM_COUNT_LAUNCH();
   ADAPM_CUDA_CHECK(cudaGetLastError());
@@ -821,7 +846,7 @@ RoundOutcome CudaBackend::fused_round(const RoundRequest& rq) {
   xbar(1, 1);
   if (n) {
     TraceScope ts_(this, "register", s);
-    register_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(ctx_, recs_dev_, round_dev_, status_dev_);
+    ADAPM_DISPATCH_VAL(int_rows_, ctx_.L.val_bytes, register_kernel<Val><<<(int)((n + 255) / 256), 256, 0, s>>>(ctx_, recs_dev_, round_dev_, status_dev_));
     ADAPM_COUNT_LAUNCH();
   }
   launch_phase(0);

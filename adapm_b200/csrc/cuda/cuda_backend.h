@@ -38,7 +38,7 @@ class CudaBackend : public Backend {
 
   const Ctx& ctx() const override { return ctx_; }
   bool is_cuda() const override { return true; }
-  void init_store(const std::vector<uint8_t>& key_class) override;
+  void init_store(const std::vector<uint8_t>& key_class, const std::vector<uint32_t>& key_lens) override;
 
   uint64_t pull(int worker, const Key* keys, size_t n, void* vals, bool local_only, uint8_t* ok, OpResult* res,
                 const IoDesc& io) override;
@@ -97,6 +97,7 @@ class CudaBackend : public Backend {
 
   std::shared_ptr<Fabric> fabric_;
   Ctx ctx_;
+  bool int_rows_ = false;   // Options::dtype == int64 (8-byte rows are float64 otherwise)
   int device_ = 0;
   int num_sms_ = 148;
   // grid sizes of the sync-round kernels, in blocks per SM. The round runs on a high-priority stream next to the

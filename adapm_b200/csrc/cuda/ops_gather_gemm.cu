@@ -185,6 +185,7 @@ void launch_gather(CudaBackend& be, cudaStream_t stream, const void* Q, const Ke
                    int ldc, const float* true_score, const int* true_col, int* rank_out, unsigned long long* stats) {
   ADAPM_CHECK(K % 4 == 0, "gather_gemm: the embedding length must be a multiple of 4");
   ADAPM_CHECK(ldq % 8 == 0 && ldq >= K, "gather_gemm: Q must be bf16 with a row pitch that is a multiple of 8 elements");
+  ADAPM_CHECK(be.ctx().L.val_bytes == 4, "the fused ops need float32 rows (Options::dtype)");
   be.track_stream(stream);
   CUtensorMap mq = make_map(Q, M, ldq, BM, KIND_BF16);
   const size_t smem = sizeof(SmemLayout) + 1024;

@@ -379,6 +379,7 @@ void kge_complex_step(CudaBackend& be, cudaStream_t stream, const Key* subj, con
   if (n_calls == 0) return;
   const Dropout de = make_dropout(dropout_e, seed, 0x11u), dr = make_dropout(dropout_r, seed, 0x22u);
   ADAPM_CHECK(nh % 2 == 0, "ComplEx needs an even embedding size");
+  ADAPM_CHECK(be.ctx().L.val_bytes == 4, "the fused ops need float32 rows (Options::dtype)");
   be.track_stream(stream);
   const Ctx& c = be.ctx();
   const int warps_per_block = kThreads / 32;
@@ -420,6 +421,7 @@ void kge_rescal_step(CudaBackend& be, cudaStream_t stream, const Key* subj, cons
                      unsigned long long* stats, float dropout_e, float dropout_r, uint64_t seed) {
   if (n_calls == 0) return;
   ADAPM_CHECK(D % 4 == 0 && D >= 4 && D <= 128, "kge_rescal_step: embedding size must be a multiple of 4 in [4, 128]");
+  ADAPM_CHECK(be.ctx().L.val_bytes == 4, "the fused ops need float32 rows (Options::dtype)");
   be.track_stream(stream);
   const Ctx& c = be.ctx();
   const Dropout de = make_dropout(dropout_e, seed, 0x11u), dr = make_dropout(dropout_r, seed, 0x22u);

@@ -139,6 +139,7 @@ void mf_step(CudaBackend& be, cudaStream_t stream, const Key* row_keys, const Ke
              const int* row_nnz, const int* col_nnz, int n, int rank, float eps, float lambda, float* loss_out,
              unsigned long long* stats) {
   if (n == 0) return;
+  ADAPM_CHECK(be.ctx().L.val_bytes == 4, "the fused ops need float32 rows (Options::dtype)");
   be.track_stream(stream);
   const Ctx& c = be.ctx();
   const int warps_per_block = kThreads / 32;

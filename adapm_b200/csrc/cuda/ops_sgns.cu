@@ -306,6 +306,7 @@ void sgns_step(CudaBackend& be, cudaStream_t stream, const Key* centers, const K
   ADAPM_CHECK(d % 4 == 0 && d <= 512, "sgns_step: embed_dim must be a multiple of 4 and <= 512");
   ADAPM_CHECK(neg >= 0, "sgns_step: negative must be >= 0");
   if (n_pairs == 0) return;
+  ADAPM_CHECK(be.ctx().L.val_bytes == 4, "the fused ops need float32 rows (Options::dtype)");
   be.track_stream(stream);
   static const int env_impl = [] { const char* e = getenv("ADAPM_SGNS_IMPL"); return e ? (e[0] == 't' ? 2 : 1) : 0; }();
   if (impl == 0) impl = env_impl ? env_impl : 2;

@@ -85,3 +85,60 @@ def test_locality_api(mode):
     res = run_cluster(_worker, world=3, workers=NUM_LOCAL, mode=mode, value_lengths=1, num_keys=12, dtype="int64")
     errs = [e for r in res.values() for k, v in r.items() if k != "counters" for e in v]
     assert not errs, "\n".join(errs)
+
+
+# ---- many distinct value lengths (reference: any value_lengths vector, coloc_kv_server_handle.h:162-170,996-999):
+# more distinct lengths than size classes -> keys of different lengths share a slab class and carry their own length
+def _many_lengths_worker(kv, server, wid):
+    import torch
+
+    nk = server.num_keys()
+    lens = torch.tensor([(k * 7) % 97 + 1 for k in range(nk)], dtype=torch.int64)
+    errors = []
+    keys = torch.arange(nk, dtype=torch.int64)
+    total = int(lens.sum())
+    kv.barrier()
+    if wid == 0:
+        vals = torch.cat([torch.full((int(lens[k]),), float(k + 1), dtype=server.dtype) for k in range(nk)])
+        kv.wait(kv.set(keys, vals))
+    kv.barrier()
+    # everybody intends a different third of the keys: relocations and replicas of rows of many lengths
+    mine = keys[(keys % 3) == (wid % 3)]
+    kv.intent(mine, kv.current_clock(), kv.current_clock() + 4)
+    kv.wait_sync(); kv.barrier(); kv.wait_sync(); kv.barrier()
+    for rep in range(3):
+        out = torch.zeros(int(lens[mine].sum()), dtype=server.dtype)
+        kv.wait(kv.pull(mine, out))
+        exp = torch.cat([torch.full((int(lens[k]),), float(k + 1) + rep * server.num_servers() * 2, dtype=server.dtype)
+                         for k in mine.tolist()])
+        if not torch.equal(out, exp) and rep == 0:
+            errors.append(f"worker {wid}: pull of mixed-length rows wrong: {out[:8].tolist()} vs {exp[:8].tolist()}")
+        kv.wait(kv.push(keys, torch.ones(total, dtype=server.dtype)))
+        kv.advance_clock()
+        kv.wait_sync(); kv.barrier(); kv.wait_sync(); kv.barrier()
+    for _ in range(6):
+        kv.advance_clock()
+    kv.wait_sync(); kv.barrier(); kv.wait_sync(); kv.barrier()
+    out = torch.zeros(total, dtype=server.dtype)
+    kv.wait(kv.pull(keys, out))
+    n_workers = server.num_servers() * 2
+    exp = torch.cat([torch.full((int(lens[k]),), float(k + 1) + 3 * n_workers, dtype=server.dtype) for k in range(nk)])
+    if not torch.equal(out, exp):
+        bad = (out != exp).nonzero()[:4].view(-1).tolist()
+        errors.append(f"worker {wid}: final values wrong at {bad}: {out[bad].tolist()} vs {exp[bad].tolist()}")
+    kv.barrier()
+    kv.finalize()
+    return errors
+
+
+def test_many_distinct_value_lengths():
+    import torch
+
+    nk = 150
+    lens = torch.tensor([(k * 7) % 97 + 1 for k in range(nk)], dtype=torch.int64)
+    assert lens.unique().numel() > 32     # more distinct lengths than size classes
+    res = run_cluster(_many_lengths_worker, world=3, workers=2, mode="threads", value_lengths=lens, num_keys=nk,
+                      dtype="float32")
+    errs = [e for r in res.values() for k, v in r.items() if k != "counters" for e in v]
+    assert not errs, "\n".join(errs)
+    assert all(r["counters"]["protocol_errors"] == 0 for r in res.values())

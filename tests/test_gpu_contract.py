@@ -65,3 +65,31 @@ def test_host_sequenced_round_cuda(monkeypatch):
     res = run_cluster(mk._worker, world=3, workers=2, mode="threads", value_lengths=mk.VPK, num_keys=mk.NUM_KEYS,
                       dtype="float32", backend="cuda")
     assert not _errs(res), "\n".join(_errs(res))
+
+
+def test_many_distinct_value_lengths_cuda():
+    """More distinct value lengths than size classes: keys of different lengths share a slab class (per-key length table)."""
+    import torch
+
+    nk = 150
+    lens = torch.tensor([(k * 7) % 97 + 1 for k in range(nk)], dtype=torch.int64)
+    res = run_cluster(loc._many_lengths_worker, world=3, workers=2, mode="threads", value_lengths=lens, num_keys=nk,
+                      dtype="float32", backend="cuda")
+    assert not _errs(res), "\n".join(_errs(res))
+    assert all(r["counters"]["protocol_errors"] == 0 for r in res.values())
+
+
+@pytest.mark.parametrize("dtype", ["int64", "float64"])
+def test_exact_value_types_cuda(dtype):
+    """The reference's contract tests use `long` values so that sums are exact (tests/test_many_key_operations.cc:11) and
+    its applications `double`: both run on the CUDA backend through the generic Pull/Push/Set kernels and the sync
+    round (element-wise protocol path; the fused application kernels are float32)."""
+    res = run_cluster(mk._worker, world=3, workers=2, mode="threads", value_lengths=mk.VPK, num_keys=mk.NUM_KEYS,
+                      dtype=dtype, backend="cuda")
+    assert not _errs(res), "\n".join(_errs(res))
+    assert all(r["counters"]["protocol_errors"] == 0 for r in res.values())
+    world, workers = 3, 2
+    res = run_cluster(dyn._dyn_worker, world=world, workers=workers, mode="threads", value_lengths=2, num_keys=20,
+                      dtype=dtype, backend="cuda")
+    total = world * workers * dyn.RUNS
+    assert res[0][0] == [total, 2 * total], f"lost or duplicated updates: {res[0][0]}"
