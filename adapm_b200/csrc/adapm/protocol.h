@@ -881,12 +881,14 @@ ADAPM_HD void finalize_row(const Ctx& c, const G& g, SlotWork& w) {
   const uint32_t s = w.slot;
   uint32_t* mp = meta_of(c, me) + s;
   const uint32_t m1 = meta_next(w.m, S_FINALIZING, (uint32_t)w.peer);
-  if (g.lane() == 0) mem::st_release(mp, m1);   // readers of row - base + source row re-validate this word
-  mem::fence(); g.sync();
+  if (g.lane() == 0) mem::st_release_local(mp, m1);   // readers of row - base + source row re-validate this word
+  // (everything this sequence WRITES is local memory - state word, row, base - so device-scope fences order it for
+  //  local and, through this GPU's L2, for remote readers)
+  mem::fence_local(); g.sync();
   bool rnz = false;
   row_fold<Val>(g, reinterpret_cast<Val*>(w.dst), reinterpret_cast<Val*>(w.ref), reinterpret_cast<const Val*>(w.src), w.len,
                 false, &rnz);
-  mem::fence(); g.sync();
+  mem::fence_local(); g.sync();
   if (g.lane() == 0) {
     // invariant used by the in-kernel read of in-flight rows (pm_kernels.cuh: value = local row + source row): a
     // placeholder that became the relocation target (INCOMING, not INCOMING_REPLICA) has an all-zero base
@@ -896,7 +898,7 @@ ADAPM_HD void finalize_row(const Ctx& c, const G& g, SlotWork& w) {
     mem::st_relaxed(ver_seen_of(c, me) + s, 0xffffffffu);
     mem::st_relaxed(flags_of(c, me) + s, (uint8_t)0);
     mem::st_relaxed(want_owner_of(c, me) + s, (uint8_t)0xff);
-    mem::st_release(mp, meta_next(m1, S_OWNED, 0));
+    mem::st_release_local(mp, meta_next(m1, S_OWNED, 0));
   }
 }
 

@@ -171,6 +171,7 @@ PYBIND11_MODULE(_C, m) {
       .def("intent_fast", [](Worker& w, uintptr_t keys, size_t n, Clock start, Clock end) {
              return w.IntentFast(ptr<const Key>(keys), n, start, end);
            }, py::call_guard<py::gil_scoped_release>())
+      .def("handle", [](Worker& w) { return (uintptr_t)&w; })   // for native step drivers (ops.SgnsLoop)
       .def("advance_clock", &Worker::advanceClock)
       .def("current_clock", &Worker::currentClock)
       .def("prepare_sample", &Worker::PrepareSample, py::call_guard<py::gil_scoped_release>())

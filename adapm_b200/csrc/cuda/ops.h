@@ -2,7 +2,10 @@
 // Python in ops_bind.cc).
 #pragma once
 #include <cstdint>
+#include <vector>
 #include "cuda_backend.h"
+
+namespace adapm { class Worker; }
 
 namespace adapm {
 namespace cudaops {
@@ -51,6 +54,38 @@ void gather_gemm(CudaBackend& be, cudaStream_t stream, const void* Q, const Key*
                  int ldc, unsigned long long* stats);
 void gather_gemm_rank_count(CudaBackend& be, cudaStream_t stream, const void* Q, const Key* keys, int M, int N, int K, int ldq,
                             const float* true_score, const int* true_col, int* rank_out, unsigned long long* stats);
+
+// Native step driver of the word2vec SGNS loop (ops_train_loop.cu)
+struct SgnsLoopConfig {
+  int batch_pairs = 0, negative = 0, embed_dim = 0, read_ahead = 0, max_inflight = 3, rank = 0;
+  bool signal_intent = true, local_only = false;
+  int64_t model_seed = 0;
+  int sampler_kind = 0;
+  const float* prob = nullptr;
+  const int32_t* alias = nullptr;
+  int64_t n_table = 0;
+  Key first_key = 0, key_stride = 1;
+  unsigned long long* sampler_stats = nullptr;
+};
+class SgnsLoop {
+ public:
+  SgnsLoop(Worker* worker, CudaBackend* be, const SgnsLoopConfig& cfg);
+  ~SgnsLoop();
+  void run(cudaStream_t stream, int64_t first, int64_t n, bool resident, const std::vector<uintptr_t>& batches,
+           const std::vector<uintptr_t>& intent_keys, const std::vector<int64_t>& intent_counts, float* loss_dev,
+           float* loss_host, unsigned long long* stats, int64_t step_no0, float alpha);
+
+ private:
+  Worker* w_;
+  CudaBackend* be_;
+  SgnsLoopConfig c_;
+  int depth_ = 0;
+  std::vector<Key*> key_bufs_;
+  std::vector<cudaEvent_t> copied_, done_;
+  std::vector<bool> done_valid_;
+  Key* neg_ = nullptr;
+  cudaStream_t copy_stream_ = nullptr;
+};
 
 }  // namespace cudaops
 }  // namespace adapm

@@ -77,6 +77,25 @@ void bind(py::module_& m) {
     gather_gemm_rank_count(backend_of(be), (cudaStream_t)stream, ptr<const void>(Q), ptr<const Key>(keys), M, N, K, ldq,
                            ptr<const float>(ts), ptr<const int>(tc), ptr<int>(rank), ptr<unsigned long long>(stats));
   });
+  py::class_<SgnsLoop>(m, "SgnsLoop")
+      .def(py::init([](uintptr_t worker, uintptr_t be, int batch_pairs, int negative, int embed_dim, int read_ahead,
+                       int max_inflight, int rank, bool signal_intent, bool local_only, int64_t model_seed, int sampler_kind,
+                       uintptr_t prob, uintptr_t alias, int64_t n_table, Key first_key, Key key_stride, uintptr_t sampler_stats) {
+        SgnsLoopConfig c;
+        c.batch_pairs = batch_pairs; c.negative = negative; c.embed_dim = embed_dim; c.read_ahead = read_ahead;
+        c.max_inflight = max_inflight; c.rank = rank; c.signal_intent = signal_intent; c.local_only = local_only;
+        c.model_seed = model_seed; c.sampler_kind = sampler_kind; c.prob = ptr<const float>(prob);
+        c.alias = ptr<const int32_t>(alias); c.n_table = n_table; c.first_key = first_key; c.key_stride = key_stride;
+        c.sampler_stats = ptr<unsigned long long>(sampler_stats);
+        return new SgnsLoop(reinterpret_cast<Worker*>(worker), &backend_of(be), c);
+      }))
+      .def("run", [](SgnsLoop& l, uintptr_t stream, int64_t first, int64_t n, bool resident, std::vector<uintptr_t> batches,
+                     std::vector<uintptr_t> intent_keys, std::vector<int64_t> intent_counts, uintptr_t loss_dev,
+                     uintptr_t loss_host, uintptr_t stats, int64_t step_no0, float alpha) {
+        py::gil_scoped_release rel;
+        l.run((cudaStream_t)stream, first, n, resident, batches, intent_keys, intent_counts, ptr<float>(loss_dev),
+              ptr<float>(loss_host), ptr<unsigned long long>(stats), step_no0, alpha);
+      });
   m.def("kernel_launches", [] { return kernel_launch_counter().load(); });
   m.def("track_stream", [](uintptr_t be, uintptr_t stream) { backend_of(be).track_stream((cudaStream_t)stream); });
 }

@@ -236,6 +236,47 @@ class Word2Vec:
         self.step_no += 1
         return self.loss
 
+    # ------------------------------------------------------------------ native step driver
+    def run_steps(self, batches, first: int, n: int, resident: bool = False, loss_host: Optional[torch.Tensor] = None,
+                  intent_batches=None) -> None:
+        """Runs steps ``first .. first+n-1`` from C++ (``ops.SgnsLoop``: Intent for batch ``s + read_ahead``, bounded
+        run-ahead, prefetched H2D of the step's keys, sampler + fused SGNS kernel, D2H of the loss into
+        ``loss_host[s]``, clock tick) - the same work per step as ``signal_intent`` + ``step`` + ``advance_clock`` in a
+        Python loop, without Python in it. ``batches``: sequence of [2, B] int64 key batches - pinned host tensors, or
+        device tensors with ``resident=True`` (entries of steps that are not run may be None); the keys for Intent come
+        from ``intent_batches`` (default: ``batches``): host tensors that may carry ``unique_keys`` (their distinct keys)."""
+        from .. import _C
+
+        assert self.cuda, "run_steps needs the cuda backend"
+        cfg = self.cfg
+        if getattr(self, "_loop", None) is None:
+            local_only = cfg.sampling_scheme == "local" and self.server.num_servers() > 1
+            sp = self.sampler
+            self._loop = _C.SgnsLoop(self.worker._impl.handle(), self.server._impl.backend_handle(), cfg.batch_pairs,
+                                     cfg.negative, cfg.embed_dim, cfg.read_ahead, max(1, cfg.max_inflight),
+                                     self.server.my_rank(), bool(cfg.signal_intent and self.server.num_servers() > 1),
+                                     local_only, cfg.model_seed, sp.kind, sp.prob.data_ptr(), sp.alias.data_ptr(), sp.n,
+                                     sp.first_key, sp.key_stride, sp.stats.data_ptr())
+            self._loop_cache = {}
+        ib = intent_batches if intent_batches is not None else batches
+        key = (id(batches), id(ib), resident)
+        tabs = self._loop_cache.get(key)
+        if tabs is None or tabs[3] != len(batches):
+            ptrs = [b.data_ptr() if b is not None else 0 for b in batches]
+            ik, ic, keep = [], [], []
+            for b in ib:
+                u = getattr(b, "unique_keys", None)
+                if u is None:
+                    u = b.view(-1) if not b.is_cuda else b.view(-1).cpu()
+                    keep.append(u)
+                ik.append(u.data_ptr()); ic.append(u.numel())
+            tabs = (ptrs, ik, ic, len(batches), keep, batches, ib)   # (the tensors are kept alive with the table)
+            self._loop_cache[key] = tabs
+        self._loop.run(torch.cuda.current_stream().cuda_stream, int(first), int(n), bool(resident), tabs[0], tabs[1], tabs[2],
+                       self.loss.data_ptr(), loss_host.data_ptr() if loss_host is not None else 0, self.stats.data_ptr(),
+                       self.step_no, float(self.alpha))
+        self.step_no += int(n)
+
     # reference-semantics step through the public Pull/Push API (CPU backend; also the numerics oracle)
     def _step_cpu(self, keys_host: torch.Tensor) -> torch.Tensor:
         cfg, kv, d = self.cfg, self.worker, self.cfg.embed_dim

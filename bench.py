@@ -51,6 +51,9 @@ def parse_args():
     ap.add_argument("--techniques", default="all")
     ap.add_argument("--no-intent", action="store_true")
     ap.add_argument("--sync-per-sec", type=float, default=1000)
+    ap.add_argument("--loop", default="native", choices=["native", "python"],
+                    help="who issues the steps of the timed loops: the C++ step driver (ops.SgnsLoop, GIL released) or a Python "
+                         "loop over the same public calls")
     ap.add_argument("--profile", action="store_true", help="also report per-kernel device times")
     ap.add_argument("--intent-prepass", action="store_true",
                     help="experimental: device-side Intent for keys that are already local (ops.IntentPrepass)")
@@ -225,11 +228,23 @@ def main():
             model.prefetch(batches[s + 1])                               # H2D of the next step's keys (copy stream)
         worker.advance_clock()
 
+    native = args.loop == "native"
+    host_list = [batches[i] for i in range(len(batches))]
+    dev_list = [dev_ring.get(i) for i in range(len(batches))]
+
+    def run_range(first, n, resident):
+        """Steps first .. first+n-1: one call into the C++ step driver, or the Python loop over the same public calls."""
+        if native:
+            model.run_steps(dev_list if resident else host_list, first, n, resident=resident,
+                            loss_host=None if resident else loss_host, intent_batches=host_list)
+        else:
+            for s_ in range(first, first + n):
+                train_step(s_, resident)
+
     # ---------------- placement steps + warm-up: the same loop as the timed one
     for s in range(min(RA, len(batches))):
         model.signal_intent(batches[s], worker.current_clock() + s)     # the first RA steps have no earlier step to signal them
-    for s in range(P + W):
-        train_step(s, False)
+    run_range(0, P + W, False)
     barrier()
     counters0 = server.counters()
     stats0 = model.stats.tolist()
@@ -244,8 +259,7 @@ def main():
     barrier()
     ev0.record(stream)
     t_host0 = time.perf_counter()
-    for s in range(P + W, P + W + K):
-        train_step(s, False)
+    run_range(P + W, K, False)
     host_ms = (time.perf_counter() - t_host0) * 1e3 / K
     ev1.record(stream)
     barrier()
@@ -253,15 +267,13 @@ def main():
     launches_e2e = _C.kernel_launches() - launches0
 
     # ---------------- device-resident timed region (same loop, inputs already on the device)
-    for s in range(P + W + K, P + W + K + 3):
-        train_step(s, True)
+    run_range(P + W + K, 3, True)
     barrier()
     launches1 = _C.kernel_launches()
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev2.record(stream)
-    for s in range(P + W + K + 3, P + W + 2 * K + 3):
-        train_step(s, True)
+    run_range(P + W + K + 3, K, True)
     ev3.record(stream)
     barrier()
     dev_ms = ev2.elapsed_time(ev3)
@@ -420,6 +432,7 @@ def main():
                        "seq_len": None, "updates_per_pair": cfg.updates_per_pair,
                        "parallelism": f"pm{world} (key-sharded store, intent-driven relocation/replication)",
                        "sampling": cfg.sampling_scheme, "intent_read_ahead": RA,
+                       "step_loop": "C++ step driver (ops.SgnsLoop, GIL released)" if native else "Python loop",
                        "placement_steps": P,
                        "placement_note": "P untimed training steps (same loop) run before the W warm-up steps so that the "
                                          "adaptive placement is in steady state; nothing is localised outside the loop",

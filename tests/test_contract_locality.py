@@ -113,6 +113,7 @@ def _many_lengths_worker(kv, server, wid):
                          for k in mine.tolist()])
         if not torch.equal(out, exp) and rep == 0:
             errors.append(f"worker {wid}: pull of mixed-length rows wrong: {out[:8].tolist()} vs {exp[:8].tolist()}")
+        kv.barrier()          # nobody pushes before everybody has read
         kv.wait(kv.push(keys, torch.ones(total, dtype=server.dtype)))
         kv.advance_clock()
         kv.wait_sync(); kv.barrier(); kv.wait_sync(); kv.barrier()

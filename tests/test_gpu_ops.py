@@ -177,6 +177,51 @@ def test_word2vec_training_reduces_loss(cluster1):
     assert losses[-1] < 0.9 * losses[0]
 
 
+def test_native_step_driver_matches_python_loop(cluster1):
+    """ops.SgnsLoop (C++ step driver: prefetched H2D, sampler, fused step, D2H of the loss, clock) does per step
+    exactly what the Python loop over step() does: same seeds -> same negatives -> same losses and update counts."""
+    from adapm_b200.models.word2vec import SyntheticPairs, Word2Vec, Word2VecConfig, zipf_counts
+
+    cfg = Word2VecConfig(vocab_size=4000, embed_dim=64, negative=5, batch_pairs=1024)
+    counts = zipf_counts(cfg.vocab_size)
+    data = SyntheticPairs(cfg, counts, 0)
+    n = 12
+    batches = [data.batch(s).pin_memory() for s in range(n)]
+    out = []
+    for native in (False, True):
+        server, kv = cluster1(cfg.row_len, cfg.num_keys)
+        model = Word2Vec(server, kv, cfg, counts)
+        model.init_model()
+        loss_host = torch.zeros(n).pin_memory()
+        if native:
+            model.run_steps(batches, 0, n, resident=False, loss_host=loss_host)
+            torch.cuda.synchronize()
+            losses = loss_host.tolist()
+        else:
+            losses = []
+            for s in range(n):
+                model.loss.zero_()
+                model.step(batches[s])
+                losses.append(model.loss.item())
+                kv.advance_clock()
+        torch.cuda.synchronize()
+        out.append((losses, model.stats.tolist()[3], kv.current_clock(), model.step_no))
+        kv.finalize(); server.shutdown()
+    (lp, up, cp, sp), (ln, un, cn, sn) = out
+    assert up == un and cp == cn == n and sp == sn == n
+    assert ln[-1] < ln[0]
+    # asynchronous float reductions: the same updates in a different order
+    assert all(abs(a - b) <= 2e-3 * abs(a) + 1e-2 for a, b in zip(lp, ln)), (lp, ln)
+    # device-resident variant
+    server, kv = cluster1(cfg.row_len, cfg.num_keys)
+    model = Word2Vec(server, kv, cfg, counts)
+    model.init_model()
+    dev_batches = [b.to(server.device) for b in batches]
+    model.run_steps(dev_batches, 2, 6, resident=True, intent_batches=batches)
+    torch.cuda.synchronize()
+    assert model.stats.tolist()[3] > 0 and kv.current_clock() == 6
+
+
 @pytest.mark.parametrize("nh", [512, 128, 20])
 def test_kge_complex_step_matches_pytorch_reference(cluster1, nh):
     """Distinct keys per call -> the fused kernel must equal the reference formula evaluated in PyTorch
