@@ -54,7 +54,7 @@ def _ninja_file() -> str:
     incs = f"-I{CSRC} -I{pybind11.get_include()} -I{py_inc} -I{CUDA_HOME}/include"
     cxxflags = f"-O3 -g1 -std=c++17 -fPIC -fvisibility=hidden -Wall -Wno-unused-function -pthread {incs}"
     nvflags = (
-        "-O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a "
+        "-O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=[sm_100a,compute_100a] "
         "--expt-relaxed-constexpr -Xcompiler -fPIC,-fvisibility=hidden,-pthread "
         f"-Xptxas -v {incs}"
     )

@@ -69,7 +69,9 @@ struct SyncArea {
   uint32_t active[2];
   uint32_t pad0[29];
   uint32_t bar_arrive[MAX_RANKS];
-  uint32_t flag_word[2][MAX_RANKS];   // [round parity][rank]
+  uint32_t flag_word[2][MAX_RANKS];   // [round parity][rank]            (unicast exchange)
+  uint32_t my_flag[2];                // [round parity] this rank's word (multicast: reduced in the switch by the readers)
+  uint32_t pad1[30];
 };
 
 struct IntentRec {
@@ -85,10 +87,16 @@ struct Ctx {
   int32_t rank;
   int32_t technique;    // MgmtTechniques
   char* heap[MAX_RANKS];
+  // NVLS multicast mapping of the heaps (cuda, NVSwitch, one process per GPU; nullptr otherwise): a multimem store /
+  // reduction to mc_heap + off reaches offset `off` of EVERY rank's heap with one NVLink transaction
+  char* mc_heap;
 };
 
 template <class T> ADAPM_HD T* at(const Ctx& c, int r, uint64_t off) {
   return reinterpret_cast<T*>(c.heap[r] + off);
+}
+template <class T> ADAPM_HD T* at_all(const Ctx& c, uint64_t off) {   // the multicast alias of `off` (mc_heap != nullptr)
+  return reinterpret_cast<T*>(c.mc_heap + off);
 }
 ADAPM_HD uint8_t* dir_of(const Ctx& c, int r) { return at<uint8_t>(c, r, c.L.off_dir); }
 ADAPM_HD int32_t* slot_of(const Ctx& c, int r) { return at<int32_t>(c, r, c.L.off_slot_of); }

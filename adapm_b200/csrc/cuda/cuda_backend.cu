@@ -318,9 +318,20 @@ __global__ void __launch_bounds__(64) xbar_kernel(const __grid_constant__ Ctx c,
   __syncthreads();
   if (r < c.L.world) {
     __threadfence_system();          // everything the earlier kernels of this round wrote (anywhere) is performed
-    SyncArea* theirs = sync_area_of(c, r);
-    if (gather) mem::st_relaxed(&theirs->flag_word[parity][me], rd->my_flags);
-    mem::st_release(&theirs->bar_arrive[me], seq);
+    if (c.mc_heap) {
+      // NVSwitch multicast: ONE multimem store per word reaches the sync area of every rank (incl. this one)
+      if (r == 0) {
+        const uint64_t area = c.L.off_sync;
+        // my request word stays in MY heap; after the barrier every rank reduces the words of all ranks in the switch
+        if (gather) mem::st_relaxed(&sync_area_of(c, me)->my_flag[parity], rd->my_flags);
+        __threadfence_system();
+        dev::multimem_st_release_u32(at_all<char>(c, area + offsetof(SyncArea, bar_arrive) + me * 4u), seq);
+      }
+    } else {
+      SyncArea* theirs = sync_area_of(c, r);
+      if (gather) mem::st_relaxed(&theirs->flag_word[parity][me], rd->my_flags);
+      mem::st_release(&theirs->bar_arrive[me], seq);
+    }
     const uint32_t* mine = &sync_area_of(c, me)->bar_arrive[r];
     const unsigned long long t0 = global_ns();
     unsigned spins = 0;
@@ -333,12 +344,18 @@ __global__ void __launch_bounds__(64) xbar_kernel(const __grid_constant__ Ctx c,
   if (r == 0) {
     if (failed) rd->error = 1;
     if (gather) {
-      const uint32_t* w = sync_area_of(c, me)->flag_word[parity];
       uint32_t all_stop = 1, any_sweep = 0;
-      for (int k = 0; k < c.L.world; ++k) {
-        const uint32_t f = mem::ld_relaxed(w + k);
-        all_stop &= f & 1u;
-        any_sweep |= (f >> 1) & 1u;
+      if (c.mc_heap) {   // stop = AND, sweep = OR over the ranks' words: two multimem.ld_reduce (in-switch reductions)
+        const void* mcw = at_all<char>(c, c.L.off_sync + offsetof(SyncArea, my_flag) + parity * 4u);
+        all_stop = dev::multimem_ld_and_u32(mcw) & 1u;
+        any_sweep = (dev::multimem_ld_or_u32(mcw) >> 1) & 1u;
+      } else {
+        const uint32_t* w = sync_area_of(c, me)->flag_word[parity];
+        for (int k = 0; k < c.L.world; ++k) {
+          const uint32_t f = mem::ld_relaxed(w + k);
+          all_stop &= f & 1u;
+          any_sweep |= (f >> 1) & 1u;
+        }
       }
       rd->stop = (all_stop && !failed) ? 1u : 0u;
       rd->any_sweep = any_sweep;
@@ -394,6 +411,8 @@ CudaBackend::CudaBackend(const Options& opt, const Layout& L, std::shared_ptr<Fa
   device_ = fabric_->device();
   use_device();
   for (int r = 0; r < L.world; ++r) ctx_.heap[r] = fabric_->heap(r);
+  ctx_.mc_heap = fabric_->mc_heap();
+  if (const char* e = getenv("ADAPM_MULTICAST_BARRIER")) { if (atoi(e) == 0) ctx_.mc_heap = nullptr; }
   cudaDeviceProp prop;
   ADAPM_CUDA_CHECK(cudaGetDeviceProperties(&prop, device_));
   num_sms_ = prop.multiProcessorCount;

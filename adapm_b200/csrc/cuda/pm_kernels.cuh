@@ -20,6 +20,30 @@ __device__ __forceinline__ float4 ld_row4(const float* p) {
 __device__ __forceinline__ float4 ld_row4_weak(const float* p) {
   return __ldcg(reinterpret_cast<const float4*>(p));
 }
+// NVLS multicast stores (the address is the multicast alias of a heap offset: the switch replicates the store into
+// every rank's heap)
+__device__ __forceinline__ void multimem_st_u32(void* mc, uint32_t v) {
+  asm volatile("multimem.st.relaxed.sys.global.u32 [%0], %1;" ::"l"(mc), "r"(v) : "memory");
+}
+__device__ __forceinline__ void multimem_st_release_u32(void* mc, uint32_t v) {
+  asm volatile("multimem.st.release.sys.global.u32 [%0], %1;" ::"l"(mc), "r"(v) : "memory");
+}
+// in-switch reductions over the same heap offset of all ranks (multimem.ld_reduce -> SASS LDGMC)
+__device__ __forceinline__ uint32_t multimem_ld_or_u32(const void* mc) {
+  uint32_t v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.or.b32 %0, [%1];" : "=r"(v) : "l"(mc) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t multimem_ld_and_u32(const void* mc) {
+  uint32_t v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.and.b32 %0, [%1];" : "=r"(v) : "l"(mc) : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st_f32x4(float* mc, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
 __device__ __forceinline__ void red_row4(float* p, float4 v) {
   asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y),
                "f"(v.z), "f"(v.w)

@@ -210,8 +210,10 @@ def test_native_step_driver_matches_python_loop(cluster1):
     (lp, up, cp, sp), (ln, un, cn, sn) = out
     assert up == un and cp == cn == n and sp == sn == n
     assert ln[-1] < ln[0]
-    # asynchronous float reductions: the same updates in a different order
-    assert all(abs(a - b) <= 2e-3 * abs(a) + 1e-2 for a, b in zip(lp, ln)), (lp, ln)
+    # same seeds -> same negatives; the first step starts from identical tables (only the float reduction order differs),
+    # later steps inherit the Hogwild races inside a step (pairs of one batch update shared rows concurrently)
+    assert abs(lp[0] - ln[0]) <= 1e-4 * abs(lp[0]) + 1e-2, (lp[0], ln[0])
+    assert all(abs(a - b) <= 3e-2 * abs(a) for a, b in zip(lp, ln)), (lp, ln)
     # device-resident variant
     server, kv = cluster1(cfg.row_len, cfg.num_keys)
     model = Word2Vec(server, kv, cfg, counts)
