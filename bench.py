@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--read-ahead", type=int, default=32, help="intent look-ahead in steps (the reference reads 1000 sentences ahead)")
     ap.add_argument("--placement-steps", type=int, default=-1,
                     help="untimed training steps before the W warm-up steps that let the adaptive placement reach its steady "
-                         "state (N > 1 only; default: 3 x read-ahead, 0 for N = 1)")
+                         "state (N > 1 only; default: 8 x read-ahead, 0 for N = 1)")
     ap.add_argument("--max-inflight", type=int, default=3, help="steps the host may run ahead of the GPU")
     ap.add_argument("--sampling", default="local", choices=["local", "naive"])
     ap.add_argument("--techniques", default="all")
@@ -179,7 +179,7 @@ def main():
     # a cold placement (every non-home row has to be requested once). P untimed training steps - same loop, same API -
     # precede the W warm-up steps; nothing is pre-localised outside the loop and timing starts more than RA steps after
     # the first intent, i.e. every timed step works on rows whose intent was signalled RA steps earlier INSIDE the loop.
-    P = args.placement_steps if args.placement_steps >= 0 else (3 * RA if world > 1 else 0)
+    P = args.placement_steps if args.placement_steps >= 0 else (8 * RA if world > 1 else 0)
     n_prof = 640 if args.profile else 0
     total_steps = P + W + K + 3 + K + n_prof   # placement + warm-up + e2e loop + device-resident loop (+ profiling)
     # data loader: batches are read ahead into pinned host memory (the reference reads sentences ahead too). Every step
