@@ -473,7 +473,11 @@ void launch(cudaStream_t stream, const void* A, const void* B, int M, int N, int
   static const int impl = [] { const char* e = getenv("ADAPM_GEMM_IMPL"); return e ? (e[0] == 'p' ? 2 : 1) : 0; }();
   const long tiles_p = (long)((M + BM - 1) / BM) * ((N + PBN - 1) / PBN);
   // CTA pairs (cta_group::2, 256 x 256 tiles): ADAPM_GEMM_IMPL=c
-  static const bool pair_impl = [] { const char* e = getenv("ADAPM_GEMM_IMPL"); return e && e[0] == 'c'; }();
+  // (default for big problems: >= one 256 x 256 tile per SM pair and a K extent that amortises the pair set-up;
+  //  measured 8192^3: 1417 vs 1313 TFLOP/s, 4096^3: 1315 vs 1167 - profiles/gemm_bench_v4.jsonl)
+  static const int pair_env = [] { const char* e = getenv("ADAPM_GEMM_IMPL"); return e ? (e[0] == 'c' ? 1 : -1) : 0; }();
+  const long tiles_pair = (long)((M + 2 * BM - 1) / (2 * BM)) * ((N + CBN - 1) / CBN);
+  const bool pair_impl = pair_env == 1 || (pair_env == 0 && tiles_pair >= 64 && K >= 1024);
   if (pair_impl) {
     CUtensorMap mbh = make_map(B, N, K, CBN / 2, KIND);
     const size_t csmem = sizeof(CSmemLayout) + 1024;
