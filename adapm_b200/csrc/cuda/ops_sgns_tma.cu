@@ -57,6 +57,19 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// Bulk reduction shared -> global through the TMA engine (cp.reduce.async.bulk ... add.f32): ONE instruction adds a whole
+// staged row (element-wise atomic at the row's home L2, local HBM or NVLink peer) instead of row_bytes / 16 RED.128
+// issued by the warp. Completion is tracked with bulk async-groups of the issuing thread.
+__device__ __forceinline__ void bulk_red_s2g(float* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+               ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() {   // all but the N youngest groups have read their source
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 struct WarpSmem {
   unsigned long long bar[RING];
 };
@@ -97,7 +110,10 @@ __device__ __noinline__ float slow_target_tma(const Ctx& c, Key tkey, float labe
 // sync-round kernels (40 registers x 256 threads) can be co-resident instead of waiting for a step block to retire.
 // INFLIGHT (experimental, ADAPM_SGNS_INFLIGHT=1): targets whose relocation to this rank is in flight are summed from
 // the local and the source row inside the kernel instead of taking the out-of-line generic path.
-template <int VPL, int MAXREG, bool INFLIGHT>
+// BULK (ADAPM_SGNS_BULKRED=1): the updates of a target leave as ONE TMA bulk reduction per row: the warp overwrites the
+// consumed ring slot with [embedding update | AdaGrad update] and lane 0 issues cp.reduce.async.bulk from it; the slot is
+// reloaded one target later, after the reduction has read it (prefetch distance RING - 1).
+template <int VPL, int MAXREG, bool INFLIGHT, bool BULK>
 __global__ void __maxnreg__(MAXREG)
 sgns_step_tma_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ centers, const Key* __restrict__ contexts,
                      const Key* __restrict__ negatives, int n_pairs, int neg, int d, float alpha,
@@ -159,6 +175,7 @@ sgns_step_tma_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ cent
       if (skip) {
         if (lane == 0) mbar_arrive(&bars[b]);            // nothing to load: complete the phase
       } else if (inflight) {
+        if (BULK) { if (lane == 0) bulk_wait_read<1>(); __syncwarp(); }
         // value = local row (adds that already arrived here) + source row (old owner, NVLink); 16-byte loads
         const float* src = (const float*)__shfl_sync(0xffffffffu, (unsigned long long)my_t.flag, t + 1);
         const uint32_t* tv = (const uint32_t*)__shfl_sync(0xffffffffu, (unsigned long long)my_t.version, t + 1);
@@ -173,12 +190,14 @@ sgns_step_tma_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ cent
       } else if (!remote || tma_remote) {
         // local HBM row - or a peer's row: the TMA engine reads NVLink-mapped addresses as well
         if (lane == 0) {
+          if (BULK) bulk_wait_read<1>();   // the reduction that used this slot (issued one target ago) has read it
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // order earlier LDS of this slot before the TMA write
           mbar_expect_tx(&bars[b], row_bytes);
           bulk_g2s(buf, row, row_bytes, &bars[b]);
         }
       } else {
         // NVLink peer row staged with 16-byte loads (ADAPM_TMA_REMOTE=0)
+        if (BULK) { if (lane == 0) bulk_wait_read<1>(); __syncwarp(); }
         for (int j = lane; j < 2 * nvec; j += 32) reinterpret_cast<float4*>(buf)[j] = dev::ld_row4(row + 4 * j);
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[b]);
@@ -190,8 +209,10 @@ sgns_step_tma_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ cent
     float* c_row = (float*)__shfl_sync(0xffffffffu, (unsigned long long)my_t.row, 0);
     const bool c_slow = (c_row == nullptr);
     float4 e0[VPL], g0[VPL];
-    // prefetch the first RING targets before touching the center row
-    const int pre = n_targets < RING ? n_targets : RING;
+    // prefetch the first RING (BULK: RING - 1) targets before touching the center row
+    constexpr int DIST = BULK ? RING - 1 : RING;
+    if (BULK) { if (lane == 0) bulk_wait_read<0>(); __syncwarp(); }   // the previous pair's reductions have read ring + scratch
+    const int pre = n_targets < DIST ? n_targets : DIST;
     for (int t = 0; t < pre; ++t) issue(t);
     if (c_slow) {
       ++n_slow;
@@ -199,6 +220,7 @@ sgns_step_tma_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ cent
         // drain the ring so that the barrier phases stay in step, then skip the pair
         for (int t = 0; t < pre; ++t) { mbar_wait(&bars[consumed % RING], (consumed / RING) & 1u); ++consumed; }
         for (int t = pre; t < n_targets; ++t) { issue(t); mbar_wait(&bars[consumed % RING], (consumed / RING) & 1u); ++consumed; }
+        (void)DIST;
         continue;
       }
 #pragma unroll
@@ -278,15 +300,30 @@ sgns_step_tma_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ cent
             ue.y = alpha * gr.y * rsqrtf(a1.y + ua.y);
             ue.z = alpha * gr.z * rsqrtf(a1.z + ua.z);
             ue.w = alpha * gr.w * rsqrtf(a1.w + ua.w);
-            dev::red_row4(t_row + 4 * j, ue);
-            dev::red_row4(t_row + d + 4 * j, ua);
+            if (BULK) {                   // stage the update in place of the consumed row
+              reinterpret_cast<float4*>(buf)[j] = ue;
+              reinterpret_cast<float4*>(buf + d)[j] = ua;
+            } else {
+              dev::red_row4(t_row + 4 * j, ue);
+              dev::red_row4(t_row + d + 4 * j, ua);
+            }
+          }
+        }
+        if (BULK) {
+          __syncwarp();
+          if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the staged update is visible to the TMA engine
+            bulk_red_s2g(t_row, buf, row_bytes);
           }
         }
         if (lane == t + 1) dev::mark_pushed(my_t);
         ++n_upd;
       }
+      // exactly one bulk group per target (empty for skipped / generic-path targets): "all but the youngest group"
+      // below always means "the reduction that used the slot of the previous target"
+      if (BULK && lane == 0) bulk_commit();
       __syncwarp();                       // all lanes are done reading ring slot b
-      if (t + RING < n_targets) issue(t + RING);
+      if (t + DIST < n_targets) issue(t + DIST);
     }
 
     // ---- center update
@@ -335,8 +372,21 @@ sgns_step_tma_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ cent
           ue.y = alpha * g0[v].y * rsqrtf(a0.y + ua.y);
           ue.z = alpha * g0[v].z * rsqrtf(a0.z + ua.z);
           ue.w = alpha * g0[v].w * rsqrtf(a0.w + ua.w);
-          dev::red_row4(c_row + 4 * j, ue);
-          dev::red_row4(c_row + d + 4 * j, ua);
+          if (BULK) {
+            reinterpret_cast<float4*>(scratch)[j] = ue;
+            reinterpret_cast<float4*>(scratch + d)[j] = ua;
+          } else {
+            dev::red_row4(c_row + 4 * j, ue);
+            dev::red_row4(c_row + d + 4 * j, ua);
+          }
+        }
+      }
+      if (BULK) {
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          bulk_red_s2g(c_row, scratch, row_bytes);
+          bulk_commit();
         }
       }
       if (lane == 0) dev::mark_pushed(my_t);
@@ -344,6 +394,7 @@ sgns_step_tma_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ cent
     }
     __syncwarp();
   }
+  if (BULK) { if (lane == 0) bulk_wait_all(); __syncwarp(); }   // every bulk reduction has been performed before the CTA leaves
 
   __syncwarp();
   if (lane == 0 && loss_out) atomicAdd(loss_out, loss_acc);
@@ -379,22 +430,25 @@ bool sgns_step_tma(CudaBackend& be, cudaStream_t stream, const Key* centers, con
   static const int regs_env = [] { const char* e = getenv("ADAPM_SGNS_REGS"); return e ? atoi(e) : 0; }();
   const bool lean = regs_env ? (regs_env < 128) : (c.L.world > 1);
   static const bool inflight = [] { const char* e = getenv("ADAPM_SGNS_INFLIGHT"); return e && atoi(e) != 0; }();
-#define ADAPM_LAUNCH_TMA3(V, T, F)                                                                              \
+  static const bool bulk = [] { const char* e = getenv("ADAPM_SGNS_BULKRED"); return e && atoi(e) != 0; }();
+#define ADAPM_LAUNCH_TMA3(V, T, F, B)                                                                           \
   do {                                                                                                          \
     static bool attr_set = false;                                                                               \
     if (!attr_set) {                                                                                            \
-      cudaFuncSetAttribute(sgns_step_tma_kernel<V, T, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024); \
+      cudaFuncSetAttribute(sgns_step_tma_kernel<V, T, F, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024); \
       attr_set = true;                                                                                          \
     }                                                                                                           \
-    sgns_step_tma_kernel<V, T, F><<<blocks, kThreads, smem, stream>>>(c, centers, contexts, negatives, n_pairs, neg, \
-                                                                     d, alpha, loss_out, stats, tma_remote);   \
+    sgns_step_tma_kernel<V, T, F, B><<<blocks, kThreads, smem, stream>>>(c, centers, contexts, negatives, n_pairs, neg, \
+                                                                        d, alpha, loss_out, stats, tma_remote);   \
   } while (0)
-#define ADAPM_LAUNCH_TMA(V)                                   \
-  do {                                                        \
-    if (inflight && lean) ADAPM_LAUNCH_TMA3(V, 104, true);    \
-    else if (inflight) ADAPM_LAUNCH_TMA3(V, 128, true);       \
-    else if (lean) ADAPM_LAUNCH_TMA3(V, 104, false);          \
-    else ADAPM_LAUNCH_TMA3(V, 128, false);                    \
+#define ADAPM_LAUNCH_TMA(V)                                              \
+  do {                                                                   \
+    if (bulk && lean) ADAPM_LAUNCH_TMA3(V, 104, false, true);            \
+    else if (bulk) ADAPM_LAUNCH_TMA3(V, 128, false, true);               \
+    else if (inflight && lean) ADAPM_LAUNCH_TMA3(V, 104, true, false);   \
+    else if (inflight) ADAPM_LAUNCH_TMA3(V, 128, true, false);           \
+    else if (lean) ADAPM_LAUNCH_TMA3(V, 104, false, false);              \
+    else ADAPM_LAUNCH_TMA3(V, 128, false, false);                        \
   } while (0)
   switch (vpl) {
     case 1: ADAPM_LAUNCH_TMA(1); break;
