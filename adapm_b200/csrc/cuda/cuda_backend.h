@@ -126,6 +126,7 @@ class CudaBackend : public Backend {
   // device-resident round (default for world > 1; ADAPM_HOST_ROUND=1 selects the host-sequenced round)
   void upload_round(const RoundParams& rp, uint32_t n_recs, uint32_t flags);
   void launch_phase(int phase);   // 0 = A, 1 = B, 2 = C
+  void launch_row_pass(unsigned int* work_count);
   bool fused_round_ = false;
   RoundDev* round_dev_ = nullptr;      // device
   RoundDev* round_host_ = nullptr;     // pinned: [0] = upload staging, [1] = results

@@ -33,6 +33,11 @@ class Ctx:
         return t.tolist()
 
 
+def _pm_counters(server):
+    keep = ("relocations", "replica_setups", "refreshes", "protocol_errors")
+    return {k: v for k, v in server.counters().items() if k in keep}
+
+
 def timed_loops(ctx: Ctx, step_e2e, step_resident, K: int, W: int, P: int):
     """step_*(s) run step number s. Returns dict(e2e_ms, dev_ms, launches_e2e, launches_dev, clocks, host_ms)."""
     from adapm_b200 import _C
@@ -150,7 +155,7 @@ def run_kge(ctx: Ctx):
                      "updates_per_triple": cfg.updates_per_triple, "intent_read_ahead": RA, "placement_steps": P},
                     upd, t, K, W, cfg.batch_triples * 3 * 8, 4,
                     {"locality": {"rows_local": st[0], "rows_remote": st[1], "rows_slow_path": st[2]},
-                     "pm": {k: v for k, v in server.counters().items() if k in ("relocations", "replica_setups", "refreshes", "protocol_errors")}})
+                     "pm": _pm_counters(server)})
     kv.finalize(); server.shutdown()
     return out
 
@@ -244,7 +249,7 @@ def run_mf(ctx: Ctx):
                      "placement_steps": P},
                     world * 2 * n, t, K, W, n * 20, 4,
                     {"locality": {"rows_local": st[0], "rows_remote": st[1], "rows_slow_path": st[2]},
-                     "pm": {k: v for k, v in server.counters().items() if k in ("relocations", "replica_setups", "refreshes", "protocol_errors")}})
+                     "pm": _pm_counters(server)})
     kv.finalize(); server.shutdown()
     return out
 
@@ -296,7 +301,7 @@ def run_ctr(ctx: Ctx):
                      "placement_steps": P, "examples_per_s": ctx.world * cfg.batch_size * K / (t["dev_ms"] * 1e-3),
                      "updates_per_step": "distinct feature rows of the batch (mean over the run)"},
                     upd_step, t, K, W, cfg.batch_size * (26 * 8 + 4), 4,
-                    {"pm": {k: v for k, v in server.counters().items() if k in ("relocations", "replica_setups", "refreshes", "protocol_errors")}})
+                    {"pm": _pm_counters(server)})
     kv.finalize(); server.shutdown()
     return out
 

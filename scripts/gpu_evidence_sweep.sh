@@ -29,16 +29,19 @@ ADAPM_SGNS_REGS=104 capture sgns_tma_lean_1m sgns_step_tma_kernel 12 python benc
 # sync-round kernels: three logical ranks on one GPU (host-sequenced round, so ncu's kernel serialisation is harmless)
 capture round_row        phase_row_kernel 40 python -m pytest tests/test_gpu_contract.py -q -m gpu -k "many_key_operations_cuda and all"
 capture round_resolve    "phase_meta_kernel.*1E.*0E" 40 python -m pytest tests/test_gpu_contract.py -q -m gpu -k "many_key_operations_cuda and all"
+capture gemm_pair        gemm_nt_tcgen05_pair_kernel 12 python benchmarks/gemm_bench.py
+if [ "${ADAPM_SWEEP_ALL:-0}" = "1" ]; then
 capture round_scan       phase_scan_kernel 40 python -m pytest tests/test_gpu_contract.py -q -m gpu -k "many_key_operations_cuda and all"
 capture round_b          phase_b_kernel 40 python -m pytest tests/test_gpu_contract.py -q -m gpu -k "many_key_operations_cuda and all"
 capture kge_step         kge_step_kernel 5 python benchmarks/app_bench.py
 capture mf_step          mf_step_kernel 5 python benchmarks/app_bench.py
 capture gemm_persistent  gemm_nt_tcgen05_persistent_kernel 30 python benchmarks/gemm_bench.py
+fi
 capture gather_gemm      gather_gemm_kernel 2 python -m pytest tests/test_gpu_gemm.py -q -m gpu -k gather
 capture rescal           kge_rescal_kernel 0 python -m pytest tests/test_gpu_ops.py -q -m gpu -k "rescal_and_dropout and RESCAL-64"
 
 echo "== compute-sanitizer (multi-rank protocol on one GPU + the fused ops)"
-for tool in memcheck racecheck synccheck; do
+for tool in memcheck racecheck ${ADAPM_SWEEP_SYNCCHECK:+synccheck}; do
   timeout 900 compute-sanitizer --tool $tool --target-processes all --print-limit 20 \
       python -m pytest tests/test_gpu_contract.py tests/test_gpu_ops.py -q -m gpu -x \
       -k "locality_api_cuda or set_operation_cuda or set_under_relocation_cuda or sgns_step_matches or kge_complex or rescal_and_dropout or mf_step" \

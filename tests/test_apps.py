@@ -61,7 +61,7 @@ def test_kge_reference_flags(tmp_path):
                        "--eval_truncate_va", "50", "--max_N", "400", "--init_parameters", "uniform{-0.1/0.1}",
                        "--enforce_random_keys", "1", "--write_embeddings", out_dir, "--async_push", "0"])
     assert rc == 0, out[-2000:]
-    assert "[kge] initial valid: {'mrr'" in out and "'n': 50" in out, out[-2000:]
+    assert "[kge] initial valid: {'mrr_s'" in out and "'mrr':" in out and "'n': 50" in out, out[-2000:]
     assert os.path.exists(os.path.join(out_dir, "export.epoch.2.entities.bin"))
     rc, out = _launch(["-m", "adapm_b200.apps.kge", "--", "--dataset", os.path.join(D, "kge") + "/", "--num_entities", "280",
                        "--num_relations", "112", "--embed_dim", "8", "--num_epochs", "1", "--read_partitioned_dataset", "1",

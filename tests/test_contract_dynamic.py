@@ -130,6 +130,8 @@ def _set_under_relocation_worker(kv, server, wid):
         for it in range(300):
             if (it % 2) == rank:
                 kv.intent(keys, kv.current_clock(), kv.current_clock() + 3)
+                if it % 16 < 2:
+                    kv.wait_sync()   # a starved sync thread (loaded CI box) must not turn this into a test without relocations
             for _ in range(3):
                 kv.advance_clock()
             kv.wait(kv.pull(keys[:4], torch.zeros(4 * 2, dtype=server.dtype)))
