@@ -93,3 +93,63 @@ def test_exact_value_types_cuda(dtype):
                       dtype=dtype, backend="cuda")
     total = world * workers * dyn.RUNS
     assert res[0][0] == [total, 2 * total], f"lost or duplicated updates: {res[0][0]}"
+
+
+PP_KEYS = 96
+
+
+def _prepass_worker(kv, server, wid):
+    """Device-side Intent pre-pass (ops_intent.cu): keys with a usable local slot only get their end clock extended on the
+    device, the others come back in a compacted list and go through Worker.intent."""
+    import torch
+
+    from adapm_b200.ops import IntentPrepass
+
+    rank, world = server.my_rank(), server.num_servers()
+    errors = []
+    keys = torch.arange(PP_KEYS, dtype=torch.int64)
+    kv.wait(kv.push(keys, torch.ones(PP_KEYS * 2, dtype=server.dtype)))
+    kv.barrier()
+    pp = IntentPrepass(server, kv, max_keys=PP_KEYS + 2)
+    local0 = sum(1 for k in range(PP_KEYS) if server.is_local(k))
+    # 1) first submission: exactly the keys that are not local yet go to the host path
+    pp.submit(keys.to(server.device), kv.current_clock(), kv.current_clock() + 1000)
+    pp.harvest(block=True)
+    if pp.keys_to_host != PP_KEYS - local0:
+        errors.append(f"rank {rank}: {pp.keys_to_host} keys went to the host, {PP_KEYS - local0} are not local")
+    kv.wait_sync(); kv.barrier()
+    kv.wait_sync(); kv.barrier()
+    # 2) every key is local now (replica or relocated): the second submission stays on the device
+    before = pp.keys_to_host
+    pp.submit(keys.to(server.device), kv.current_clock(), kv.current_clock() + 2000)
+    pp.harvest(block=True)
+    if pp.keys_to_host != before:
+        errors.append(f"rank {rank}: {pp.keys_to_host - before} keys of an all-local batch went to the host path")
+    # 3) the extension is honoured: far beyond the first intent's end the keys are still local
+    for _ in range(1500):
+        kv.advance_clock()
+    kv.wait_sync(); kv.barrier()
+    kv.wait_sync(); kv.barrier()
+    out = torch.zeros(PP_KEYS * 2, dtype=server.dtype)
+    kv.wait(kv.pull(keys, out))
+    if not torch.equal(out, torch.full_like(out, float(world))):
+        errors.append(f"rank {rank}: pulled {out[:6].tolist()}, expected {float(world)}")
+    if not kv.pull_if_local(3, torch.zeros(2, dtype=server.dtype)):
+        errors.append(f"rank {rank}: key 3 is not local at clock {kv.current_clock()} although the pre-pass extended its intent")
+    # 4) an out-of-range key is handed to the host path, which raises like Worker.intent does
+    try:
+        pp.submit(torch.tensor([1, PP_KEYS + 100], dtype=torch.int64), kv.current_clock(), kv.current_clock() + 1)
+        pp.harvest(block=True)
+        errors.append("out-of-range key was accepted")
+    except Exception:  # noqa
+        pass
+    kv.barrier()
+    kv.finalize()
+    return errors
+
+
+def test_intent_prepass_cuda():
+    res = run_cluster(_prepass_worker, world=3, workers=1, mode="threads", value_lengths=2, num_keys=PP_KEYS + 8,
+                      dtype="float32", backend="cuda")
+    assert not _errs(res), "\n".join(_errs(res))
+    assert all(r["counters"]["protocol_errors"] == 0 for r in res.values())
