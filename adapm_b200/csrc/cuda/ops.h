@@ -17,6 +17,12 @@ void sgns_step(CudaBackend& be, cudaStream_t stream, const Key* centers, const K
 bool sgns_step_tma(CudaBackend& be, cudaStream_t stream, const Key* centers, const Key* contexts, const Key* negatives,
                    int n_pairs, int neg, int d, float alpha, float* loss_out, unsigned long long* stats);
 
+// word2vec SGNS with shared negatives on the tensor cores (ops_sgns_shared.cu): three tcgen05 GEMMs + three elementwise
+// kernels between ONE Pull and ONE Push of the rows [centers | contexts | shared negatives].
+size_t sgns_shared_workspace_bytes(int B, int Nn, int d);
+void sgns_shared_core(cudaStream_t stream, const float* R, const Key* contexts, const Key* negs, int B, int Nn, int d,
+                      float alpha, void* workspace, float* U, float* loss);
+
 // key sampling (ops_sampler.cu). kind: 0 alias table, 1 uniform, 2 log-uniform
 void sample_keys(CudaBackend& be, cudaStream_t stream, int kind, const float* prob, const int32_t* alias,
                  int64_t n_table, Key first, Key stride, Key* out, int64_t n, uint64_t seed, bool local_only,

@@ -56,6 +56,12 @@ void bind(py::module_& m) {
             ptr<const int>(rn), ptr<const int>(cn), n, rank, eps, lambda, ptr<float>(loss),
             ptr<unsigned long long>(stats));
   });
+  m.def("sgns_shared_workspace_bytes", [](int B, int Nn, int d) { return sgns_shared_workspace_bytes(B, Nn, d); });
+  m.def("sgns_shared_core", [](uintptr_t stream, uintptr_t R, uintptr_t contexts, uintptr_t negs, int B, int Nn, int d, float alpha,
+                               uintptr_t ws, uintptr_t U, uintptr_t loss) {
+    sgns_shared_core((cudaStream_t)stream, ptr<const float>(R), ptr<const Key>(contexts), ptr<const Key>(negs), B, Nn, d, alpha,
+                     ptr<void>(ws), ptr<float>(U), ptr<float>(loss));
+  });
   m.def("gemm_nt_bf16", [](uintptr_t stream, uintptr_t A, uintptr_t B, int M, int N, int K, uintptr_t C, int ldc) {
     gemm_nt_bf16((cudaStream_t)stream, ptr<const void>(A), ptr<const void>(B), M, N, K, ptr<float>(C), ldc);
   });

@@ -45,6 +45,8 @@ class Word2VecConfig:
     zipf_exponent: float = 1.0       # synthetic corpus skew
     max_inflight: int = 3            # steps the host may run ahead of the GPU (bounds the sync grace period)
     intent_prepass: bool = False     # experimental: device-side Intent for keys that are already local (ops.IntentPrepass)
+    shared_negatives: int = 0        # > 0: ONE set of this many negatives per batch, contractions on the tensor cores
+                                     # (ops.SgnsSharedStep); 0: `negative` private negatives per pair (the reference)
 
     @property
     def row_len(self) -> int:
@@ -178,8 +180,6 @@ class Word2Vec:
         Returns the device tensor that accumulates the summed loss (read it with ``.item()``/copy)."""
         cfg = self.cfg
         if self.cuda:
-            from ..ops import sgns_step
-
             slot = self.step_no % len(self._keys_dev)
             if self._events[slot] is not None:
                 self._events[slot].synchronize()   # bounded run-ahead: at most max_inflight steps queued
@@ -191,7 +191,7 @@ class Word2Vec:
                 kd = self._keys_dev[slot]
                 kd.copy_(keys_host, non_blocking=True)               # H2D of this step's inputs
             self.sample_negatives()
-            sgns_step(self.server, kd[0], kd[1], self._neg, cfg.embed_dim, self.alpha, self.loss, self.stats)
+            self._device_step(kd[0], kd[1])
             ev = self._events[slot] or torch.cuda.Event()
             ev.record()
             self._events[slot] = ev
@@ -220,16 +220,24 @@ class Word2Vec:
         seed = (cfg.model_seed * 1000003 + self.server.my_rank() * 7919 + self.step_no) & 0xFFFFFFFFFFFF
         return self.sampler.sample(self._neg.numel(), seed, local_only=local_only, out=self._neg)
 
-    def step_resident(self, keys_dev: torch.Tensor) -> torch.Tensor:
-        """Same as step() for a key batch that already lives on the device."""
-        from ..ops import sgns_step
+    def _device_step(self, centers: torch.Tensor, contexts: torch.Tensor) -> None:
+        from ..ops import SgnsSharedStep, sgns_step
 
         cfg = self.cfg
+        if cfg.shared_negatives > 0:
+            if getattr(self, "_shared", None) is None:
+                self._shared = SgnsSharedStep(self.server, self.worker, cfg.batch_pairs, cfg.shared_negatives, cfg.embed_dim)
+            self._shared(centers, contexts, self._neg[:cfg.shared_negatives], self.alpha, self.loss)
+        else:
+            sgns_step(self.server, centers, contexts, self._neg, cfg.embed_dim, self.alpha, self.loss, self.stats)
+
+    def step_resident(self, keys_dev: torch.Tensor) -> torch.Tensor:
+        """Same as step() for a key batch that already lives on the device."""
         slot = self.step_no % len(self._events)
         if self._events[slot] is not None:
             self._events[slot].synchronize()
         self.sample_negatives()
-        sgns_step(self.server, keys_dev[0], keys_dev[1], self._neg, cfg.embed_dim, self.alpha, self.loss, self.stats)
+        self._device_step(keys_dev[0], keys_dev[1])
         ev = self._events[slot] or torch.cuda.Event()
         ev.record()
         self._events[slot] = ev

@@ -46,6 +46,76 @@ def sgns_step(server, centers: torch.Tensor, contexts: torch.Tensor, negatives: 
                  stats.data_ptr() if stats is not None else 0, {"auto": 0, "ldg": 1, "tma": 2}[impl])
 
 
+class SgnsSharedStep:
+    """word2vec SGNS with one set of negatives shared by all pairs of a batch, on the tensor cores
+    (csrc/cuda/ops_sgns_shared.cu; SURVEY K7's GEMM formulation, an option next to the reference-faithful fused step).
+
+    Per step: ONE Pull of the rows ``[centers | contexts | shared negatives]`` through the store (any protocol state,
+    local HBM or NVLink), three tcgen05 GEMMs (scores, center gradient, negative gradient; bf16 operands, fp32
+    accumulation) with three elementwise kernels around them, ONE Push of the additive ``[embedding | AdaGrad]`` updates.
+    ``B`` pairs x ``Nn`` negatives = B * Nn sample pairs for 2 B + Nn rows of traffic.
+    """
+
+    def __init__(self, server, worker, batch_pairs: int, shared_negatives: int, embed_dim: int):
+        if batch_pairs % 32 or shared_negatives % 32:
+            raise ValueError("batch_pairs and shared_negatives must be multiples of 32")
+        self.server, self.worker = server, worker
+        self.B, self.Nn, self.d = int(batch_pairs), int(shared_negatives), int(embed_dim)
+        dev = server.device
+        rows = 2 * self.B + self.Nn
+        self.keys = torch.empty(rows, dtype=torch.int64, device=dev)
+        self.R = torch.empty(rows * 2 * self.d, dtype=torch.float32, device=dev)
+        self.U = torch.empty(rows * 2 * self.d, dtype=torch.float32, device=dev)
+        self.ws = torch.empty(_C.sgns_shared_workspace_bytes(self.B, self.Nn, self.d), dtype=torch.uint8, device=dev)
+
+    def __call__(self, centers: torch.Tensor, contexts: torch.Tensor, negatives: torch.Tensor, alpha: float,
+                 loss: torch.Tensor) -> None:
+        """``centers`` / ``contexts``: [B] syn0 / syn1 keys, ``negatives``: [Nn] syn1 keys (CUDA int64);
+        ``loss``: CUDA float32[1], accumulated (+=) with the summed logistic loss of the B * (1 + Nn) sample pairs."""
+        B, Nn = self.B, self.Nn
+        if centers.numel() != B or contexts.numel() != B or negatives.numel() != Nn:
+            raise ValueError(f"expected {B} centers / contexts and {Nn} shared negatives")
+        if not (loss.is_cuda and loss.dtype == torch.float32):
+            raise TypeError("loss must be a CUDA float32 tensor")
+        k = self.keys
+        k[:B].copy_(centers.view(-1)); k[B:2 * B].copy_(contexts.view(-1)); k[2 * B:].copy_(negatives.view(-1))
+        self.worker.wait(self.worker.pull(k, self.R, True))
+        _C.sgns_shared_core(_stream(k), self.R.data_ptr(), k[B:2 * B].data_ptr(), k[2 * B:].data_ptr(), B, Nn, self.d,
+                            float(alpha), self.ws.data_ptr(), self.U.data_ptr(), loss.data_ptr())
+        self.worker.push(k, self.U, True)
+
+
+def sgns_shared_reference_step(table: torch.Tensor, centers: torch.Tensor, contexts: torch.Tensor, negatives: torch.Tensor,
+                               d: int, alpha: float):
+    """Plain fp32 PyTorch reference of :class:`SgnsSharedStep` on a dense ``[keys, 2 d]`` table (tests): returns
+    ``(new_table, loss)``. Same rule as the kernels: all gradients from the values before the step, AdaGrad accumulator
+    read before the update, duplicates add up."""
+    t = table.to(torch.float32)
+    e0, a0 = t[centers, :d], t[centers, d:]
+    ec, ac = t[contexts, :d], t[contexts, d:]
+    en, an = t[negatives, :d], t[negatives, d:]
+
+    def grad(f, label):
+        g = label - torch.sigmoid(f)
+        g = torch.where(f > 6, torch.full_like(f, label - 1.0), g)
+        return torch.where(f < -6, torch.full_like(f, label), g)
+
+    fp = (e0 * ec).sum(-1)
+    gp = grad(fp, 1.0)
+    S = e0 @ en.t()
+    mask = contexts.view(-1, 1) != negatives.view(1, -1)
+    G = grad(S, 0.0) * mask
+    loss = torch.log1p(torch.exp(-fp.clamp(-6, 6))).sum() + (torch.log1p(torch.exp(S.clamp(-6, 6))) * mask).sum()
+    g0 = G @ en + gp.unsqueeze(1) * ec
+    gc = gp.unsqueeze(1) * e0
+    gn = G.t() @ e0
+    out = t.clone()
+    for keys, g, a in ((centers, g0, a0), (contexts, gc, ac), (negatives, gn, an)):
+        ua = g * g
+        out.index_add_(0, keys, torch.cat([alpha * g * torch.rsqrt(a + ua), ua], 1))
+    return out, loss
+
+
 class DeviceSampler:
     """Key sampler on the GPU: alias table (any weights, e.g. unigram^0.75), uniform or log-uniform.
 

@@ -355,3 +355,44 @@ def test_mf_step_matches_pytorch_reference(cluster1, rank):
     torch.testing.assert_close(got, ref, rtol=3e-4, atol=3e-5)
     torch.testing.assert_close(loss.cpu()[0], torch.tensor(ref_loss), rtol=1e-3, atol=1e-3)
     assert stats.tolist()[3] == 2 * n
+
+
+@pytest.mark.parametrize("d,B,Nn", [(300, 256, 128), (128, 512, 256), (64, 64, 32)])
+def test_sgns_shared_negatives_tensor_core_step(cluster1, d, B, Nn):
+    """Shared-negative SGNS on the tcgen05 GEMMs (ops_sgns_shared.cu) against the fp32 PyTorch reference of the same
+    op: the contractions run with bf16 operands (fp32 accumulation), so gradients agree to bf16 rounding; the AdaGrad
+    accumulator update g^2 and the embedding update are compared on the rows after ONE step."""
+    from adapm_b200.ops import SgnsSharedStep, sgns_shared_reference_step
+
+    n_keys = 2 * (B + Nn + 16)
+    server, kv = cluster1(2 * d, n_keys)
+    dev = server.device
+    g = torch.Generator().manual_seed(17 * d + B)
+    rows = torch.empty(n_keys, 2 * d)
+    rows[:, :d] = torch.randn(n_keys, d, generator=g) * 0.3
+    rows[:, d:] = torch.rand(n_keys, d, generator=g) + 1e-2
+    allk = torch.arange(n_keys)
+    kv.set(allk, rows.clone().view(-1))
+    words = torch.randperm(n_keys // 2, generator=g)
+    centers = 2 * words[torch.randint(0, B // 2, (B,), generator=g)]            # duplicates among the centers
+    contexts = 2 * words[torch.randint(0, words.numel(), (B,), generator=g)] + 1   # ... and contexts that are negatives too
+    negatives = 2 * words[:Nn] + 1
+    contexts[0] = negatives[3]      # a shared negative that is the positive target of pair 0: masked for that pair
+    alpha = 0.05
+    step = SgnsSharedStep(server, kv, B, Nn, d)
+    loss = torch.zeros(1, device=dev)
+    step(centers.to(dev), contexts.to(dev), negatives.to(dev), alpha, loss)
+    torch.cuda.synchronize()
+    got = torch.empty(n_keys * 2 * d)
+    kv.pull(allk, got)
+    got = got.view(n_keys, 2 * d)
+    ref, ref_loss = sgns_shared_reference_step(rows, centers, contexts, negatives, d, alpha)
+    # untouched rows are bit-identical, touched rows agree to bf16 rounding of the GEMM operands
+    touched = torch.zeros(n_keys, dtype=torch.bool)
+    touched[centers] = True; touched[contexts] = True; touched[negatives] = True
+    assert torch.equal(got[~touched], rows[~touched])
+    d_emb = (got[:, :d] - ref[:, :d]).abs().max().item()
+    scale = (ref[:, :d] - rows[:, :d]).abs().max().item()
+    assert d_emb <= 0.03 * scale + 1e-6, (d_emb, scale)
+    torch.testing.assert_close(got[:, d:], ref[:, d:], rtol=6e-2, atol=2e-3 * (ref[:, d:] - rows[:, d:]).abs().max().item())
+    assert abs(loss.item() - ref_loss.item()) <= 2e-3 * abs(ref_loss.item())

@@ -146,3 +146,35 @@ def test_mf_cpu(tmp_path, algo, world):
         assert min(r[0][-3:]) < 0.9 * r[0][0], r[0]
     lines = open(tmp_path / "W.mma").read().splitlines()
     assert lines[0].startswith("%%MatrixMarket matrix array") and lines[1] == "80 8" and len(lines) == 2 + 80 * 8
+
+
+def test_sgns_shared_reference_matches_autograd():
+    """The fp32 reference of the shared-negative SGNS step (the yardstick of the tensor-core kernels' GPU test) against
+    autograd of the same objective: accumulated g^2 of every row that is touched exactly once."""
+    import collections
+
+    import torch
+
+    from adapm_b200.ops import sgns_shared_reference_step
+
+    torch.manual_seed(0)
+    d, B, Nn, n = 8, 6, 4, 40
+    t = torch.randn(n, 2 * d) * 0.5
+    t[:, d:] = torch.rand(n, d) + 0.1
+    c = torch.randint(0, n, (B,)); x = torch.randint(0, n, (B,)); ng = torch.randperm(n)[:Nn]
+    x[0] = ng[1]
+    out, loss = sgns_shared_reference_step(t, c, x, ng, d, 0.1)
+    E = t[:, :d].clone().requires_grad_(True)
+    fp = (E[c] * E[x]).sum(-1)
+    S = E[c] @ E[ng].t()
+    mask = x.view(-1, 1) != ng.view(1, -1)
+    L = torch.nn.functional.softplus(-fp).sum() + (torch.nn.functional.softplus(S) * mask).sum()
+    L.backward()
+    assert abs(loss.item() - L.item()) < 1e-4
+    cnt = collections.Counter(c.tolist() + x.tolist() + ng.tolist())
+    once = [k for k, v in cnt.items() if v == 1]
+    assert once
+    for k in once:
+        g = -E.grad[k]
+        torch.testing.assert_close(out[k, d:] - t[k, d:], g * g, atol=1e-5, rtol=1e-4)
+        torch.testing.assert_close(out[k, :d] - t[k, :d], 0.1 * g * torch.rsqrt(t[k, d:] + g * g), atol=1e-5, rtol=1e-4)
