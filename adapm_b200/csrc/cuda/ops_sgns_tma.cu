@@ -117,8 +117,7 @@ template <int VPL, int MAXREG, bool INFLIGHT, bool BULK>
 __global__ void __maxnreg__(MAXREG)
 sgns_step_tma_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ centers, const Key* __restrict__ contexts,
                      const Key* __restrict__ negatives, int n_pairs, int neg, int d, float alpha,
-                     float* __restrict__ loss_out, unsigned long long* __restrict__ stats, int flags) {
-  const int tma_remote = flags & 1;   // bit 1: L2 prefetch of the next pair's keys | bit 2: of the center's AdaGrad half
+                     float* __restrict__ loss_out, unsigned long long* __restrict__ stats, int tma_remote) {
   // per warp: RING row buffers of 2*d floats (16-byte aligned) | generic-path scratch is carved from the ring
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ WarpSmem wsm[kWarps];
@@ -154,13 +153,6 @@ sgns_step_tma_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ cent
     int my_remote = 0;
     if (lane == 0) my_key = ckey;
     else if (lane - 1 < n_targets) my_key = (lane == 1) ? pos_key : negatives[(size_t)p * neg + (lane - 2)];
-    if ((flags & 2) && p + nwarps < n_pairs && lane - 1 < n_targets) {
-      // the keys of this warp's next pair are streamed data (one use, DRAM): start them towards L2 now, the first link
-      // of the next pair's resolve chain (key -> slot -> meta word) then costs an L2 hit
-      const Key* nk = lane == 0 ? centers + (p + nwarps)
-                                : (lane == 1 ? contexts + (p + nwarps) : negatives + (size_t)(p + nwarps) * neg + (lane - 2));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(nk));
-    }
     if (my_key >= 0) {
       unsigned r0 = n_remote;
       my_t = INFLIGHT ? dev::resolve_fast_inflight(c, my_key, 0, &n_local, &n_remote)
@@ -243,8 +235,6 @@ sgns_step_tma_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ cent
         int j = lane + v * 32;
         e0[v] = j < nvec ? dev::ld_row4(c_row + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      // the AdaGrad half of the center row is read once, at the end of the pair: one 128-byte line per lane towards L2
-      if ((flags & 4) && lane * 32 < d + 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(c_row + d + lane * 32));
     }
 #pragma unroll
     for (int v = 0; v < VPL; ++v) g0[v] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -432,24 +422,20 @@ bool sgns_step_tma(CudaBackend& be, cudaStream_t stream, const Key* centers, con
   const Ctx& c = be.ctx();
   const int vpl = (d / 4 + 31) / 32;
   const size_t buf_floats = ((size_t)2 * d + 31) & ~(size_t)31;
-  // block shape: warps are independent (no block-level barrier), so the block size only decides how many warps fit next
-  // to each other: 256 threads x 2 blocks = 16 warps per SM (128 or 104 registers), 192 threads x 3 blocks = 18 warps
-  // (<= 112 registers). ADAPM_SGNS_THREADS overrides.
-  static const int threads_env = [] { const char* e = getenv("ADAPM_SGNS_THREADS"); return e ? atoi(e) : 0; }();
-  const int threads = (threads_env >= 32 && threads_env <= kThreads && threads_env % 32 == 0) ? threads_env : kThreads;
+  // Block shape: 256 threads x 2 blocks = 16 warps per SM. Measured alternatives at the headline config (1 GPU,
+  // profiles/README.md): 192 threads x 3 blocks = 18 warps per SM at 112 / 104 registers: -7 % / -8 % (the registers
+  // cost more than the warps bring); L2 prefetch of the next pair's keys and of the center's AdaGrad half: +-0.2 %.
+  // ncu at this config: DRAM 4.54 TB/s = 69 % of the measured copy bandwidth with random 2400-byte rows - the
+  // kernel is at the memory system, not at an issue or occupancy limit.
+  const int threads = kThreads;
   const int warps = threads / 32;
   const size_t smem = (size_t)warps * (RING + 1) * buf_floats * sizeof(float) + 128;
   if (smem > 110 * 1024) return false;  // keep 2 blocks per SM
   int blocks = std::min((n_pairs + warps - 1) / warps, be.num_sms() * 12);
-  static const int tma_remote = [] {
-    const char* e = getenv("ADAPM_TMA_REMOTE");
-    const char* pf = getenv("ADAPM_SGNS_PREFETCH");   // bit 0: next pair's keys, bit 1: center AdaGrad half
-    return ((e ? atoi(e) : 1) & 1) | ((pf ? atoi(pf) : 0) & 3) << 1;
-  }();
+  static const int tma_remote = [] { const char* e = getenv("ADAPM_TMA_REMOTE"); return e ? atoi(e) : 1; }();
   // register budget: 128 (single GPU: nothing to share the SMs with) or 104 (multi GPU); ADAPM_SGNS_REGS overrides
   static const int regs_env = [] { const char* e = getenv("ADAPM_SGNS_REGS"); return e ? atoi(e) : 0; }();
-  const bool lean = regs_env ? (regs_env < 112) : (c.L.world > 1);
-  const bool mid = regs_env >= 112 && regs_env < 128;   // 112 registers: three 192-thread blocks per SM
+  const bool lean = regs_env ? (regs_env < 128) : (c.L.world > 1);
   static const bool inflight = [] { const char* e = getenv("ADAPM_SGNS_INFLIGHT"); return e && atoi(e) != 0; }();
   // TMA bulk reductions are the default (measured +2.6 % on one GPU, and the warp's LSU slots stay free for the sync
   // round's kernels); ADAPM_SGNS_BULKRED=0 selects the RED.128 variants. (A software-pipelined target loop - score of
@@ -471,7 +457,6 @@ bool sgns_step_tma(CudaBackend& be, cudaStream_t stream, const Key* centers, con
     if (inflight && lean) ADAPM_LAUNCH_TMA3(V, 104, true, false);        \
     else if (inflight) ADAPM_LAUNCH_TMA3(V, 128, true, false);           \
     else if (bulk && lean) ADAPM_LAUNCH_TMA3(V, 104, false, true);       \
-    else if (bulk && mid) ADAPM_LAUNCH_TMA3(V, 112, false, true);        \
     else if (bulk) ADAPM_LAUNCH_TMA3(V, 128, false, true);               \
     else if (lean) ADAPM_LAUNCH_TMA3(V, 104, false, false);              \
     else ADAPM_LAUNCH_TMA3(V, 128, false, false);                        \

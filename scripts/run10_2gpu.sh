@@ -10,6 +10,7 @@ runp reg ADAPM_ROW_TMA=0
 run tma_k20 "--steps 20 --warmup 5" X=1
 run reg_k20 "--steps 20 --warmup 5" ADAPM_ROW_TMA=0
 run tma_k200 "--steps 200 --warmup 10" X=1
-run tma_wb2 "--steps 200 --warmup 10" ADAPM_SYNC_WORK_BLOCKS=2
+CUDA_VISIBLE_DEVICES=0 timeout 300 python benchmarks/sgns_shared_bench.py > $O/sgns_shared_bench.log 2>&1
 python scripts/summarize_bench_logs.py $O | grep -v "^    \[rank"
+tail -4 $O/pytest_gpu.log | cut -c1-300; tail -2 $O/sgns_shared_bench.log | cut -c1-1500
 for n in tma reg; do echo "== $n"; head -24 $O/$n.trace.txt | cut -c1-150 | grep -v "commit\|resolve"; done
