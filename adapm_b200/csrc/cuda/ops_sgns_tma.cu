@@ -108,12 +108,13 @@ __device__ __noinline__ float slow_target_tma(const Ctx& c, Key tkey, float labe
 // VPL = float4 per lane over d floats. MAXREG is the register budget: the kernel runs 2 blocks of 256 threads per SM;
 // 128 registers use the whole register file, 104 leave 12 K registers per SM free so that one block of the
 // sync-round kernels (40 registers x 256 threads) can be co-resident instead of waiting for a step block to retire.
-// INFLIGHT (experimental, ADAPM_SGNS_INFLIGHT=1): targets whose relocation to this rank is in flight are summed from
-// the local and the source row inside the kernel instead of taking the out-of-line generic path.
+// (A variant that summed rows whose relocation to this rank is in flight inside the kernel - local row + source row -
+// instead of taking the out-of-line generic path for them was measured on 2 GPUs and removed: no gain, 2 x the
+// instantiations.)
 // BULK (ADAPM_SGNS_BULKRED=1): the updates of a target leave as ONE TMA bulk reduction per row: the warp overwrites the
 // consumed ring slot with [embedding update | AdaGrad update] and lane 0 issues cp.reduce.async.bulk from it; the slot is
 // reloaded one target later, after the reduction has read it (prefetch distance RING - 1).
-template <int VPL, int MAXREG, bool INFLIGHT, bool BULK>
+template <int VPL, int MAXREG, bool BULK>
 __global__ void __maxnreg__(MAXREG)
 sgns_step_tma_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ centers, const Key* __restrict__ contexts,
                      const Key* __restrict__ negatives, int n_pairs, int neg, int d, float alpha,
@@ -155,14 +156,9 @@ sgns_step_tma_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ cent
     else if (lane - 1 < n_targets) my_key = (lane == 1) ? pos_key : negatives[(size_t)p * neg + (lane - 2)];
     if (my_key >= 0) {
       unsigned r0 = n_remote;
-      my_t = INFLIGHT ? dev::resolve_fast_inflight(c, my_key, 0, &n_local, &n_remote)
-                      : dev::resolve_fast(c, my_key, 0, &n_local, &n_remote);
+      my_t = dev::resolve_fast(c, my_key, 0, &n_local, &n_remote);
       my_remote = (n_remote != r0) ? 1 : 0;
-      if (INFLIGHT && lane == 0 && dev::target_inflight(my_t)) {   // in-flight center: generic path
-        my_t.row = nullptr; my_t.version = nullptr; my_t.flag = nullptr;
-      }
     }
-    unsigned stale_mask = 0;   // INFLIGHT: targets whose in-kernel sum raced with the finalize step
     // target t (0-based) -> lane t+1 (only pairs with <= 31 targets use this kernel)
     auto issue = [&](int t) {
       const int b = issued % RING;
@@ -171,22 +167,8 @@ sgns_step_tma_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ cent
       float* row = (float*)__shfl_sync(0xffffffffu, (unsigned long long)my_t.row, t + 1);
       const int remote = __shfl_sync(0xffffffffu, my_remote, t + 1);
       const bool skip = (t > 0 && tkey == pos_key) || row == nullptr;
-      const bool inflight = INFLIGHT && __shfl_sync(0xffffffffu, dev::target_inflight(my_t) ? 1 : 0, t + 1) != 0;
       if (skip) {
         if (lane == 0) mbar_arrive(&bars[b]);            // nothing to load: complete the phase
-      } else if (inflight) {
-        if (BULK) { if (lane == 0) bulk_wait_read<1>(); __syncwarp(); }
-        // value = local row (adds that already arrived here) + source row (old owner, NVLink); 16-byte loads
-        const float* src = (const float*)__shfl_sync(0xffffffffu, (unsigned long long)my_t.flag, t + 1);
-        const uint32_t* tv = (const uint32_t*)__shfl_sync(0xffffffffu, (unsigned long long)my_t.version, t + 1);
-        for (int j = lane; j < 2 * nvec; j += 32) {
-          const float4 a = dev::ld_row4(row + 4 * j), q = dev::ld_row4(src + 4 * j);
-          reinterpret_cast<float4*>(buf)[j] = make_float4(a.x + q.x, a.y + q.y, a.z + q.z, a.w + q.w);
-        }
-        __syncwarp();
-        const int still = __shfl_sync(0xffffffffu, lane == 0 ? (dev::inflight_still_valid(c, tv) ? 1 : 0) : 0, 0);
-        if (!still) stale_mask |= 1u << t;
-        if (lane == 0) mbar_arrive(&bars[b]);
       } else if (!remote || tma_remote) {
         // local HBM row - or a peer's row: the TMA engine reads NVLink-mapped addresses as well
         if (lane == 0) {
@@ -250,7 +232,7 @@ sgns_step_tma_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ cent
       ++consumed;
       const float label = (t == 0) ? 1.f : 0.f;
       const bool dup = (t > 0 && tkey == pos_key);  // reference: negative == positive target is skipped
-      if (!dup && (t_row == nullptr || (INFLIGHT && ((stale_mask >> t) & 1u)))) {
+      if (!dup && t_row == nullptr) {
         ++n_slow;
         float* e0s = scratch; float* g0s = scratch + d;
         if (!have_slow) {
@@ -436,30 +418,27 @@ bool sgns_step_tma(CudaBackend& be, cudaStream_t stream, const Key* centers, con
   // register budget: 128 (single GPU: nothing to share the SMs with) or 104 (multi GPU); ADAPM_SGNS_REGS overrides
   static const int regs_env = [] { const char* e = getenv("ADAPM_SGNS_REGS"); return e ? atoi(e) : 0; }();
   const bool lean = regs_env ? (regs_env < 128) : (c.L.world > 1);
-  static const bool inflight = [] { const char* e = getenv("ADAPM_SGNS_INFLIGHT"); return e && atoi(e) != 0; }();
   // TMA bulk reductions are the default (measured +2.6 % on one GPU, and the warp's LSU slots stay free for the sync
   // round's kernels); ADAPM_SGNS_BULKRED=0 selects the RED.128 variants. (A software-pipelined target loop - score of
   // target t+1 during the update of target t - was measured too: no gain at 128 registers, -5 % at 104: the kernel is
   // not bound by the per-warp dependency chain.)
   static const bool bulk = [] { const char* e = getenv("ADAPM_SGNS_BULKRED"); return !e || atoi(e) != 0; }();
-#define ADAPM_LAUNCH_TMA3(V, T, F, B)                                                                           \
+#define ADAPM_LAUNCH_TMA3(V, T, B)                                                                              \
   do {                                                                                                          \
     static bool attr_set = false;                                                                               \
     if (!attr_set) {                                                                                            \
-      cudaFuncSetAttribute(sgns_step_tma_kernel<V, T, F, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024); \
+      cudaFuncSetAttribute(sgns_step_tma_kernel<V, T, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024); \
       attr_set = true;                                                                                          \
     }                                                                                                           \
-    sgns_step_tma_kernel<V, T, F, B><<<blocks, threads, smem, stream>>>(c, centers, contexts, negatives, n_pairs, neg, \
+    sgns_step_tma_kernel<V, T, B><<<blocks, threads, smem, stream>>>(c, centers, contexts, negatives, n_pairs, neg, \
                                                                         d, alpha, loss_out, stats, tma_remote);   \
   } while (0)
 #define ADAPM_LAUNCH_TMA(V)                                              \
   do {                                                                   \
-    if (inflight && lean) ADAPM_LAUNCH_TMA3(V, 104, true, false);        \
-    else if (inflight) ADAPM_LAUNCH_TMA3(V, 128, true, false);           \
-    else if (bulk && lean) ADAPM_LAUNCH_TMA3(V, 104, false, true);       \
-    else if (bulk) ADAPM_LAUNCH_TMA3(V, 128, false, true);               \
-    else if (lean) ADAPM_LAUNCH_TMA3(V, 104, false, false);              \
-    else ADAPM_LAUNCH_TMA3(V, 128, false, false);                        \
+    if (bulk && lean) ADAPM_LAUNCH_TMA3(V, 104, true);                   \
+    else if (bulk) ADAPM_LAUNCH_TMA3(V, 128, true);                      \
+    else if (lean) ADAPM_LAUNCH_TMA3(V, 104, false);                     \
+    else ADAPM_LAUNCH_TMA3(V, 128, false);                               \
   } while (0)
   switch (vpl) {
     case 1: ADAPM_LAUNCH_TMA(1); break;

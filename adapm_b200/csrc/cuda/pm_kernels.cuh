@@ -155,48 +155,8 @@ __device__ __forceinline__ Target resolve_fast(const Ctx& c, Key key, int cls, u
   return t;
 }
 
-// Variant that can also use a key whose relocation TO this rank is in flight (local slot INCOMING; experimental,
-// ADAPM_SGNS_INFLIGHT=1). Pushes go to the local row like for an owned key. The value is local.row + source.row (the
-// placeholder's base is all-zero); the source row pointer travels in `flag` and the low bit of `version` tags the
-// target, so that Target does not grow (the fused kernels sit exactly at their register budget). After reading both
-// rows the caller checks inflight_still_valid(): if the transfer was finalized meanwhile (the source row has been
-// folded into the local one) the sum is not valid and the generic path must be used.
-constexpr uintptr_t kInflightTag = 1;
-__device__ __forceinline__ bool target_inflight(const Target& t) { return ((uintptr_t)t.version & kInflightTag) != 0; }
-__device__ __forceinline__ Target resolve_fast_inflight(const Ctx& c, Key key, int cls, unsigned* n_local, unsigned* n_remote) {
-  const int me = c.rank;
-  int32_t s = __ldcg(slot_of(c, me) + key);
-  if (s >= 0) {
-    const uint32_t m = __ldcg(meta_of(c, me) + s);
-    if (meta_state(m) == S_INCOMING) {
-      Target t;
-      t.row = nullptr; t.version = nullptr; t.flag = nullptr;
-      const int src = (int)meta_peer(m);
-      const int32_t ss = (int32_t)mem::ld_relaxed(ver_seen_of(c, me) + s);   // source slot id while INCOMING
-      if (ss < 0) return t;
-      t.row = row_ptr<float>(c, me, cls, (uint32_t)s);
-      t.version = reinterpret_cast<uint32_t*>(reinterpret_cast<uintptr_t>(version_of(c, me) + s) | kInflightTag);
-      t.flag = reinterpret_cast<uint8_t*>(row_ptr<float>(c, src, cls, (uint32_t)ss));
-      ++*n_remote;
-      return t;
-    }
-  }
-  return resolve_fast(c, key, cls, n_local, n_remote);
-}
-__device__ __forceinline__ const float* inflight_source_row(const Target& t) { return reinterpret_cast<const float*>(t.flag); }
-// one lane: is the tagged target's local slot still INCOMING (nothing was folded while we were reading)?
-__device__ __forceinline__ bool inflight_still_valid(const Ctx& c, const uint32_t* tagged_version) {
-  const uint32_t* v = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(tagged_version) & ~kInflightTag);
-  const size_t s = (size_t)(v - version_of(c, c.rank));
-  return meta_state(mem::ld_acquire(meta_of(c, c.rank) + s)) == S_INCOMING;
-}
-
 // lane 0 marks a completed fast-path push
 __device__ __forceinline__ void mark_pushed(const Target& t) {
-  if (target_inflight(t)) {   // in-flight key: the local row is the accumulator of the incoming owner
-    mem::red_add(reinterpret_cast<uint32_t*>(reinterpret_cast<uintptr_t>(t.version) & ~kInflightTag), 1u);
-    return;
-  }
   if (t.version) mem::red_add(t.version, 1u);
   if (t.flag) *t.flag = (uint8_t)1;
 }

@@ -37,14 +37,14 @@ def test_hot_kernels_stay_within_their_register_budget():
     if not k:
         pytest.skip("no ptxas logs (extension was not built in-tree)")
     # full-register variants of the fused steps: 2 blocks x 256 threads x 128 registers = the register file, no spills
-    # (sgns_step_tma_kernel<VPL, MAXREG, INFLIGHT, BULK>: the bulk-reduction variant is the default)
-    for name in ("sgns_step_tma_kernel<3, 128, false, true>", "sgns_step_tma_kernel<2, 128, false, true>",
-                 "sgns_step_tma_kernel<1, 128, false, true>",
+    # (sgns_step_tma_kernel<VPL, MAXREG, BULK>: the bulk-reduction variant is the default)
+    for name in ("sgns_step_tma_kernel<3, 128, true>", "sgns_step_tma_kernel<2, 128, true>",
+                 "sgns_step_tma_kernel<1, 128, true>",
                  "sgns_step_kernel<3, 2>", "kge_step_kernel<2, 128>", "kge_step_kernel<2, 104>", "mf_step_kernel<1>"):
         assert name in k, sorted(k)
         assert k[name]["regs"] <= 128 and k[name]["spill"] == 0, (name, k[name])
     # lean multi-GPU variant: 104 registers leave 12 K registers per SM for one block of the round kernels
-    lean = k["sgns_step_tma_kernel<3, 104, false, true>"]
+    lean = k["sgns_step_tma_kernel<3, 104, true>"]
     assert lean["regs"] <= 104 and lean["spill"] <= 256, lean
     # the round's kernels must fit NEXT to two lean training blocks: meta passes (128-thread blocks, no spills) and
     # the row passes (register variant: 128 threads, TMA-engine variant: 64 threads)
