@@ -224,14 +224,16 @@ __global__ void __launch_bounds__(kThreads) phase_scan_kernel(const __grid_const
   }
 }
 
-// ---- row pass on the TMA engine (float32 rows): the rows of an operation travel as bulk copies
+// ---- row pass on the TMA engine (float32 rows; opt-in: ADAPM_ROW_TMA=1): the rows of an operation travel as bulk copies
 //   global (local HBM or NVLink peer) --cp.async.bulk--> shared memory --(warp: LDS, subtract, STS)-->
 //   --cp.reduce.async.bulk.add.f32 / cp.async.bulk--> global
-// and every warp keeps kRowStages operations in flight in a ring of shared-memory stages. The register variant
-// (phase_row_kernel) keeps ONE operation per warp in flight and pays its two or three dependent round trips per
-// operation with the warp's load/store slots - next to a training kernel that saturates them: ~12 us per operation.
-// Here a warp issues two bulk loads per operation and is done until the bytes have landed; 64 threads per SM keep six
-// operations in flight without occupying registers or LSU slots the training kernels need.
+// and every warp keeps kRowStages operations in flight in a ring of shared-memory stages, without occupying the
+// load / store slots of the SM. MEASURED (2 GPUs, next to the SGNS step, profiles/README.md): the pass takes 3 x LONGER
+// than the register variant (C.row 11.3 vs 3.3 ms, A.row 2.5 vs 0.9 ms per round) - the training kernel keeps the SM's
+// TMA unit busy (27 bulk loads + 27 bulk reductions per pair), so the round's bulk operations queue behind it, while
+// the LSU path it leaves alone is comparatively idle. Steps that overlap the pass are slightly faster (0.996 vs
+// 1.072 ms) and the end-to-end rate is the same within noise (2.00 vs 1.97 G updates/s), but rounds that take three
+// times as long mean staler replicas, so the register variant stays the default.
 constexpr int kRowWarps = 2;        // warps per block
 constexpr int kRowStages = 3;       // operations in flight per warp
 __device__ __forceinline__ uint32_t rsm_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -932,15 +934,15 @@ void CudaBackend::register_intents(const IntentRec* recs, size_t n, const RoundP
   memcpy(status, st.host + o_st, n);
 }
 
-// The row pass of phase A / C: TMA-engine variant for float32 rows whose staging fits into shared memory
-// (ADAPM_ROW_TMA=0 selects the register variant), register variant otherwise.
+// The row pass of phase A / C: register variant by default; ADAPM_ROW_TMA=1 selects the TMA-engine variant for float32
+// rows whose staging fits into shared memory (measured slower next to the SGNS step, see phase_row_tma_kernel).
 void CudaBackend::launch_row_pass(unsigned int* wc) {
   const Layout& L = ctx_.L;
   uint32_t max_len = 0;
   for (int k = 0; k < L.num_classes; ++k) max_len = std::max(max_len, L.cls[k].len);
   const uint32_t stage_floats = (max_len + 31u) & ~31u;
   const size_t smem = (size_t)kRowWarps * kRowStages * 2 * stage_floats * sizeof(float);
-  static const bool tma_env = [] { const char* e = getenv("ADAPM_ROW_TMA"); return !e || atoi(e) != 0; }();
+  static const bool tma_env = [] { const char* e = getenv("ADAPM_ROW_TMA"); return e && atoi(e) != 0; }();
   if (tma_env && L.val_bytes == 4 && !int_rows_ && smem <= 30 * 1024) {
     phase_row_tma_kernel<<<num_sms_ * work_blocks_per_sm_, kRowWarps * 32, smem, sync_stream_>>>(ctx_, round_dev_, worklist_, wc,
                                                                                                stage_floats);

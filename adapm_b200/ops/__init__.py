@@ -86,10 +86,11 @@ class SgnsSharedStep:
 
 
 def sgns_shared_reference_step(table: torch.Tensor, centers: torch.Tensor, contexts: torch.Tensor, negatives: torch.Tensor,
-                               d: int, alpha: float):
+                               d: int, alpha: float, emulate_bf16: bool = False):
     """Plain fp32 PyTorch reference of :class:`SgnsSharedStep` on a dense ``[keys, 2 d]`` table (tests): returns
     ``(new_table, loss)``. Same rule as the kernels: all gradients from the values before the step, AdaGrad accumulator
-    read before the update, duplicates add up."""
+    read before the update, duplicates add up. ``emulate_bf16`` rounds the operands of the three contractions to bf16
+    like the tensor-core path does (fp32 accumulation, everything else fp32)."""
     t = table.to(torch.float32)
     e0, a0 = t[centers, :d], t[centers, d:]
     ec, ac = t[contexts, :d], t[contexts, d:]
@@ -100,15 +101,20 @@ def sgns_shared_reference_step(table: torch.Tensor, centers: torch.Tensor, conte
         g = torch.where(f > 6, torch.full_like(f, label - 1.0), g)
         return torch.where(f < -6, torch.full_like(f, label), g)
 
+    def rnd(x):
+        return x.to(torch.bfloat16).to(torch.float32) if emulate_bf16 else x
+
     fp = (e0 * ec).sum(-1)
     gp = grad(fp, 1.0)
-    S = e0 @ en.t()
+    e0m, enm = rnd(e0), rnd(en)
+    S = e0m @ enm.t()
     mask = contexts.view(-1, 1) != negatives.view(1, -1)
     G = grad(S, 0.0) * mask
     loss = torch.log1p(torch.exp(-fp.clamp(-6, 6))).sum() + (torch.log1p(torch.exp(S.clamp(-6, 6))) * mask).sum()
-    g0 = G @ en + gp.unsqueeze(1) * ec
+    Gm = rnd(G)
+    g0 = Gm @ enm + gp.unsqueeze(1) * ec
     gc = gp.unsqueeze(1) * e0
-    gn = G.t() @ e0
+    gn = Gm.t() @ e0m
     out = t.clone()
     for keys, g, a in ((centers, g0, a0), (contexts, gc, ac), (negatives, gn, an)):
         ua = g * g

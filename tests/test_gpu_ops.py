@@ -387,12 +387,18 @@ def test_sgns_shared_negatives_tensor_core_step(cluster1, d, B, Nn):
     kv.pull(allk, got)
     got = got.view(n_keys, 2 * d)
     ref, ref_loss = sgns_shared_reference_step(rows, centers, contexts, negatives, d, alpha)
-    # untouched rows are bit-identical, touched rows agree to bf16 rounding of the GEMM operands
+    emu, emu_loss = sgns_shared_reference_step(rows, centers, contexts, negatives, d, alpha, emulate_bf16=True)
+    # untouched rows are bit-identical
     touched = torch.zeros(n_keys, dtype=torch.bool)
     touched[centers] = True; touched[contexts] = True; touched[negatives] = True
     assert torch.equal(got[~touched], rows[~touched])
-    d_emb = (got[:, :d] - ref[:, :d]).abs().max().item()
-    scale = (ref[:, :d] - rows[:, :d]).abs().max().item()
-    assert d_emb <= 0.03 * scale + 1e-6, (d_emb, scale)
-    torch.testing.assert_close(got[:, d:], ref[:, d:], rtol=6e-2, atol=2e-3 * (ref[:, d:] - rows[:, d:]).abs().max().item())
-    assert abs(loss.item() - ref_loss.item()) <= 2e-3 * abs(ref_loss.item())
+    # tight: against the reference with the GEMM operands rounded to bf16 like the tensor-core path (differences left:
+    # accumulation order, __expf); loose: against plain fp32 (bf16 rounding of the operands, a few per cent of the step)
+    for half, name in ((slice(0, d), "embedding"), (slice(d, 2 * d), "adagrad")):
+        scale = (ref[:, half] - rows[:, half]).abs().max().item()
+        err_emu = (got[:, half] - emu[:, half]).abs().max().item()
+        err_f32 = (got[:, half] - ref[:, half]).abs().max().item()
+        assert err_emu <= 1.5e-2 * scale, (name, err_emu, scale)
+        assert err_f32 <= 0.12 * scale, (name, err_f32, scale)
+    assert abs(loss.item() - emu_loss.item()) <= 1e-3 * abs(emu_loss.item())
+    assert abs(loss.item() - ref_loss.item()) <= 1e-2 * abs(ref_loss.item())
