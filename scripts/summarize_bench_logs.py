@@ -14,6 +14,9 @@ for f in sorted(glob.glob(os.path.join(d, "*.log"))):
         print(name, "| NO JSON:", " / ".join(tail)[:400])
         continue
     j = json.loads(js[-1])
+    if "value" not in j:
+        print(name, "|", js[-1].strip()[:600])
+        continue
     k = j.get("steps", 1)
     pm = j.get("pm") or {}
     nst = 2 * k + 3
