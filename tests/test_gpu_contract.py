@@ -153,3 +153,35 @@ def test_intent_prepass_cuda():
                       dtype="float32", backend="cuda")
     assert not _errs(res), "\n".join(_errs(res))
     assert all(r["counters"]["protocol_errors"] == 0 for r in res.values())
+
+
+def test_random_programs_are_exact_cuda():
+    """The hypothesis property test of the protocol (tests/test_protocol_property.py: random Intent / device pre-pass /
+    Push / Pull / clock / WaitSync programs on 3 ranks stay exact and give read-your-writes) on the CUDA backend with
+    int64 rows; derandomized so that every box runs the same programs."""
+    import functools
+
+    from hypothesis import HealthCheck, given, settings
+    from hypothesis import strategies as st
+
+    import test_protocol_property as prop
+
+    @settings(max_examples=8, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True, database=None)
+    @given(programs=st.lists(prop.program, min_size=3, max_size=3),
+           technique=st.sampled_from(["all", "replication_only", "relocation_only"]),
+           idle_period=st.integers(1, 5), sweep_period=st.integers(0, 4))
+    def check(programs, technique, idle_period, sweep_period):
+        res = run_cluster(functools.partial(prop._run, programs=programs), world=3, workers=1, mode="threads",
+                          value_lengths=prop.VPK, num_keys=prop.NUM_KEYS, dtype="int64", backend="cuda",
+                          options={"sys.techniques": technique, "sys.sync.idle_period": idle_period,
+                                   "sys.sync.sweep_period": sweep_period})
+        total = [0] * prop.NUM_KEYS
+        for r in res.values():
+            errs, final, mine = r[0]
+            assert not errs, errs
+            total = [a + b for a, b in zip(total, mine)]
+        for r in res.values():
+            assert r[0][1] == total, (r[0][1], total)
+            assert r["counters"]["protocol_errors"] == 0
+
+    check()

@@ -29,12 +29,22 @@ def _run(kv, server, wid, programs=None):
     rounds = max(len(p) for p in programs)
     mine = torch.zeros(NUM_KEYS, dtype=torch.int64)          # what this worker pushed so far, per key
     errs = []
+    prepass = None
     for r in range(rounds):
         for o in (prog[r] if r < len(prog) else []):
             if o[0] == "intent":
                 kv.intent(torch.tensor(o[1]), kv.current_clock() + o[2], kv.current_clock() + o[2] + o[3])
             elif o[0] == "intent_fast":
-                kv.intent_fast(torch.tensor(o[1]), kv.current_clock() + o[2], kv.current_clock() + o[2] + o[3])
+                c0 = kv.current_clock()
+                if server.device.type == "cuda":     # the pre-pass runs on the device there (ops_intent.cu)
+                    if prepass is None:
+                        from adapm_b200.ops import IntentPrepass
+
+                        prepass = IntentPrepass(server, kv, max_keys=8)
+                    prepass.submit(torch.tensor(o[1]), c0 + o[2], c0 + o[2] + o[3])
+                    prepass.harvest(block=True)
+                else:
+                    kv.intent_fast(torch.tensor(o[1]), c0 + o[2], c0 + o[2] + o[3])
             elif o[0] == "push":
                 k = torch.tensor(o[1])
                 kv.wait(kv.push(k, torch.ones(len(o[1]) * VPK, dtype=torch.int64)))
