@@ -21,6 +21,7 @@
 
 #include "ops.h"
 #include "pm_kernels.cuh"
+#include "sgns_common.cuh"
 
 namespace adapm {
 namespace cudaops {
@@ -28,7 +29,7 @@ namespace cudaops {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr float kMaxExp = 6.0f;
+using sgns::kMaxExp;
 
 using dev::Target;
 using dev::warp_sum;
@@ -37,38 +38,7 @@ __device__ __forceinline__ Target resolve_fast(const Ctx& c, Key key, unsigned* 
   return dev::resolve_fast(c, key, 0, n_local, n_remote);
 }
 
-// ---- slow path (key in a transitional protocol state: INCOMING, FINALIZING, ...). Rare, so it is
-// kept out of line and works through shared memory with the generic protocol functions.
-//   stage: 2*d floats scratch; e0s: center embedding (d); g0s: center gradient accumulator (d)
-__device__ __noinline__ float slow_target(const Ctx& c, Key tkey, float label, float alpha, int d, float* stage,
-                                          const float* e0s, float* g0s, bool* applied) {
-  WarpGroup g;
-  const int lane = threadIdx.x & 31;
-  *applied = false;
-  if (!pull_key<float>(c, g, tkey, stage, false, nullptr)) return 0.f;
-  __syncwarp();
-  float f = 0.f;
-  for (int j = lane; j < d; j += 32) f += e0s[j] * stage[j];
-  f = warp_sum(f);
-  float gs;
-  if (f > kMaxExp) gs = label - 1.f;
-  else if (f < -kMaxExp) gs = label;
-  else gs = label - 1.f / (1.f + __expf(-f));
-  for (int j = lane; j < d; j += 32) {
-    float e1 = stage[j], a1 = stage[d + j];
-    g0s[j] += gs * e1;
-    float gr = gs * e0s[j];
-    float ua = gr * gr;
-    stage[j] = alpha * gr * rsqrtf(a1 + ua);
-    stage[d + j] = ua;
-  }
-  __syncwarp();
-  *applied = push_key<float>(c, g, tkey, stage, nullptr);
-  __syncwarp();
-  float z = label > 0.5f ? f : -f;
-  z = fminf(fmaxf(z, -kMaxExp), kMaxExp);
-  return __logf(1.f + __expf(-z));
-}
+using sgns::slow_target;
 
 using dev::slow_pull;
 using dev::slow_push;

@@ -16,6 +16,7 @@
 
 #include "ops.h"
 #include "pm_kernels.cuh"
+#include "sgns_common.cuh"
 
 namespace adapm {
 namespace cudaops {
@@ -25,7 +26,7 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int RING = 4;
-constexpr float kMaxExp = 6.0f;
+using sgns::kMaxExp;
 
 using dev::Target;
 using dev::warp_sum;
@@ -73,37 +74,6 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 struct WarpSmem {
   unsigned long long bar[RING];
 };
-
-// out-of-line generic target (transitional protocol states), same as in ops_sgns.cu
-__device__ __noinline__ float slow_target_tma(const Ctx& c, Key tkey, float label, float alpha, int d, float* stage,
-                                              const float* e0s, float* g0s, bool* applied) {
-  WarpGroup g;
-  const int lane = threadIdx.x & 31;
-  *applied = false;
-  if (!pull_key<float>(c, g, tkey, stage, false, nullptr)) return 0.f;
-  __syncwarp();
-  float f = 0.f;
-  for (int j = lane; j < d; j += 32) f += e0s[j] * stage[j];
-  f = warp_sum(f);
-  float gs;
-  if (f > kMaxExp) gs = label - 1.f;
-  else if (f < -kMaxExp) gs = label;
-  else gs = label - 1.f / (1.f + __expf(-f));
-  for (int j = lane; j < d; j += 32) {
-    float e1 = stage[j], a1 = stage[d + j];
-    g0s[j] += gs * e1;
-    float gr = gs * e0s[j];
-    float ua = gr * gr;
-    stage[j] = alpha * gr * rsqrtf(a1 + ua);
-    stage[d + j] = ua;
-  }
-  __syncwarp();
-  *applied = push_key<float>(c, g, tkey, stage, nullptr);
-  __syncwarp();
-  float z = label > 0.5f ? f : -f;
-  z = fminf(fmaxf(z, -kMaxExp), kMaxExp);
-  return __logf(1.f + __expf(-z));
-}
 
 // VPL = float4 per lane over d floats. MAXREG is the register budget: the kernel runs 2 blocks of 256 threads per SM;
 // 128 registers use the whole register file, 104 leave 12 K registers per SM free so that one block of the
@@ -248,7 +218,7 @@ sgns_step_tma_kernel(const __grid_constant__ Ctx c, const Key* __restrict__ cent
           have_slow = true;
         }
         bool applied;
-        loss_acc += slow_target_tma(c, tkey, label, alpha, d, buf, e0s, g0s, &applied);  // ring slot b is free: use it as stage
+        loss_acc += sgns::slow_target(c, tkey, label, alpha, d, buf, e0s, g0s, &applied);  // ring slot b is free: use it as stage
         if (applied) ++n_upd;
       } else if (!dup) {
         float4 e1[VPL];
