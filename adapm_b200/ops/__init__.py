@@ -67,6 +67,7 @@ class SgnsSharedStep:
         self.R = torch.empty(rows * 2 * self.d, dtype=torch.float32, device=dev)
         self.U = torch.empty(rows * 2 * self.d, dtype=torch.float32, device=dev)
         self.ws = torch.empty(_C.sgns_shared_workspace_bytes(self.B, self.Nn, self.d), dtype=torch.uint8, device=dev)
+        self._push_ts = None
 
     def __call__(self, centers: torch.Tensor, contexts: torch.Tensor, negatives: torch.Tensor, alpha: float,
                  loss: torch.Tensor) -> None:
@@ -77,12 +78,14 @@ class SgnsSharedStep:
             raise ValueError(f"expected {B} centers / contexts and {Nn} shared negatives")
         if not (loss.is_cuda and loss.dtype == torch.float32):
             raise TypeError("loss must be a CUDA float32 tensor")
+        if self._push_ts is not None:      # the previous step's Push: done long ago (same stream), retire its ticket
+            self.worker.wait(self._push_ts)
         k = self.keys
         k[:B].copy_(centers.view(-1)); k[B:2 * B].copy_(contexts.view(-1)); k[2 * B:].copy_(negatives.view(-1))
         self.worker.wait(self.worker.pull(k, self.R, True))
         _C.sgns_shared_core(_stream(k), self.R.data_ptr(), k[B:2 * B].data_ptr(), k[2 * B:].data_ptr(), B, Nn, self.d,
                             float(alpha), self.ws.data_ptr(), self.U.data_ptr(), loss.data_ptr())
-        self.worker.push(k, self.U, True)
+        self._push_ts = self.worker.push(k, self.U, True)
 
 
 def sgns_shared_reference_step(table: torch.Tensor, centers: torch.Tensor, contexts: torch.Tensor, negatives: torch.Tensor,
