@@ -46,7 +46,13 @@ gemm_nt_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int tile_n = blockIdx.x, tile_m = blockIdx.y;
-  const int num_kb = (K + BK - 1) / BK;
+  // split-K (gridDim.z > 1, EPI_STORE only): this CTA accumulates k-blocks [kb0, kb0 + num_kb) and ADDS its partial tile
+  // to C, which the host zeroed - for problems with few output tiles and a long K extent
+  const int total_kb = (K + BK - 1) / BK;
+  const int kb_per = (total_kb + (int)gridDim.z - 1) / (int)gridDim.z;
+  const int kb0 = (int)blockIdx.z * kb_per;
+  const int num_kb = min(kb_per, total_kb - kb0);
+  if (num_kb <= 0) return;          // (uniform for the CTA: nothing was allocated yet)
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&sm.full_bar[s], 1); mbar_init(&sm.empty_bar[s], 1); }
@@ -75,8 +81,8 @@ gemm_nt_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
         mbar_wait(&sm.empty_bar[s], ph ^ 1u);  // first pass over the ring passes immediately
         mbar_expect_tx(&sm.full_bar[s], A_BYTES + B_BYTES);
-        tma_load_2d(sm.a[s], &tmap_a, &sm.full_bar[s], kb * BK, tile_m * BM);
-        tma_load_2d(sm.b[s], &tmap_b, &sm.full_bar[s], kb * BK, tile_n * BN);
+        tma_load_2d(sm.a[s], &tmap_a, &sm.full_bar[s], (kb0 + kb) * BK, tile_m * BM);
+        tma_load_2d(sm.b[s], &tmap_b, &sm.full_bar[s], (kb0 + kb) * BK, tile_n * BN);
       }
     }
   } else if (warp == 1) {
@@ -116,7 +122,8 @@ gemm_nt_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
       const int col0 = tile_n * BN + c0;
       if (EPI == EPI_STORE) {
-        store_chunk_coalesced(r, sm.epi[q], alpha, C, ldc, tile_m * BM + q * 32, col0, M, N, lane);
+        if (gridDim.z > 1) add_chunk_coalesced(r, sm.epi[q], alpha, C, ldc, tile_m * BM + q * 32, col0, M, N, lane);
+        else store_chunk_coalesced(r, sm.epi[q], alpha, C, ldc, tile_m * BM + q * 32, col0, M, N, lane);
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -525,6 +532,31 @@ void launch(cudaStream_t stream, const void* A, const void* B, int M, int N, int
     attr_set = true;
   }
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+  // split-K: few output tiles and a long K extent (e.g. the G^T E0 gradient GEMM of the shared-negative SGNS step:
+  // 1024 x 304 x 32768 = 24 tiles) - spread the k-blocks of a tile over gridDim.z CTAs that add their partial tiles
+  // into the zeroed C. ADAPM_GEMM_SPLITK=<n> forces n splits (1 = off).
+  if (EPI == EPI_STORE) {
+    static const int split_env = [] { const char* e = getenv("ADAPM_GEMM_SPLITK"); return e ? atoi(e) : 0; }();
+    static int num_sms_t = 0;
+    if (!num_sms_t) {
+      int dev = 0;
+      ADAPM_CUDA_CHECK(cudaGetDevice(&dev));
+      ADAPM_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms_t, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int BKh = KIND == KIND_BF16 ? 64 : 128;
+    const int total_kb = (K + BKh - 1) / BKh;
+    const long tiles = (long)grid.x * grid.y;
+    int splits = 1;
+    if (split_env > 0) splits = split_env;
+    else if (tiles * 2 <= num_sms_t && total_kb >= 32) splits = (int)std::min<long>(num_sms_t / tiles, total_kb / 8);
+    splits = std::max(1, std::min(splits, std::min(total_kb, 64)));
+    if (splits > 1) {
+      const int kb_per = (total_kb + splits - 1) / splits;
+      splits = (total_kb + kb_per - 1) / kb_per;          // no empty split
+      ADAPM_CUDA_CHECK(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, stream));
+      grid.z = (unsigned)splits;
+    }
+  }
   gemm_nt_tcgen05_kernel<EPI, KIND><<<grid, kGemmThreads, smem, stream>>>(ma, mb, M, N, K, C, ldc, alpha, true_score,
                                                                           true_col, rank_out);
   ADAPM_COUNT_LAUNCH();

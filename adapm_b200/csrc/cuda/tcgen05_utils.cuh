@@ -48,6 +48,22 @@ __device__ __forceinline__ void store_chunk_coalesced(const uint32_t (&r)[32], f
   __syncwarp();
 }
 
+// Split-K variant: the partial tile is ADDED to C (which the host zeroed), one `red.global.add.f32` per element, same
+// coalesced shape.
+__device__ __forceinline__ void add_chunk_coalesced(const uint32_t (&r)[32], float* tile, float alpha, float* C, int ldc,
+                                                    int row0, int col0, int M, int N, int lane) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = alpha * __uint_as_float(r[j]);
+  __syncwarp();
+  const int col = col0 + lane;
+#pragma unroll 4
+  for (int rr = 0; rr < 32; ++rr) {
+    const int row = row0 + rr;
+    if (row < M && col < N) atomicAdd(C + (size_t)row * ldc + col, tile[rr * 33 + lane]);
+  }
+  __syncwarp();
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {

@@ -19,6 +19,23 @@ def test_gemm_nt_bf16_matches_torch(M, N, K):
     torch.testing.assert_close(c, ref, rtol=1e-3, atol=1e-2 * (K ** 0.5) / 8)
 
 
+@pytest.mark.parametrize("M,N,K", [(1024, 304, 32768), (200, 130, 4100), (128, 128, 2048)])
+def test_gemm_split_k_matches_torch(M, N, K):
+    """Few output tiles + long K: the tile kernel spreads the k-blocks of a tile over gridDim.z CTAs that add their
+    partial tiles into the zeroed result (the G^T E0 gradient GEMM of the shared-negative SGNS step is the first shape)."""
+    from adapm_b200.ops import gemm_nt_bf16
+
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda", generator=g)
+    b = torch.randn(N, K, device="cuda", generator=g)
+    c = gemm_nt_bf16(a, b)
+    c2 = gemm_nt_bf16(a, b)            # a second call: the result buffer is zeroed by the call itself
+    torch.cuda.synchronize()
+    ref = a.to(torch.bfloat16).float() @ b.to(torch.bfloat16).float().t()
+    torch.testing.assert_close(c, ref, rtol=1e-3, atol=1e-2 * (K ** 0.5) / 8)
+    torch.testing.assert_close(c2, ref, rtol=1e-3, atol=1e-2 * (K ** 0.5) / 8)
+
+
 def test_gemm_rank_count_epilogue():
     from adapm_b200.ops import gemm_nt_rank_count
 
