@@ -459,6 +459,10 @@ def main():
             "pm": {k: dcnt.get(k, 0) for k in ("relocations", "replica_setups", "replica_drops", "refreshes",
                                                 "deltas_shipped", "sync_rounds", "protocol_errors")},
             "profile": prof, "host_loop_ms_per_step": host_ms,
+            "host_loop_note": ("wall time of the e2e loop per step as seen by the calling thread. With --loop native it is "
+                               "NOT host work: the C++ step driver blocks on its bounded run-ahead (max_inflight steps), "
+                               "so it tracks the GPU step time; no Python runs inside the loop"
+                               if args.loop == "native" else "Python loop: host work + waits of the bounded run-ahead"),
             "sync_report": server._impl.sync_report() if world > 1 else None,
             "loss_last": float(loss_host[P + W + K - 1]) / max(1, cfg.batch_pairs * (cfg.negative + 1)),
         }
