@@ -29,7 +29,6 @@ PY
 }
 run default
 ADAPM_SGNS_REGS=128 run regs128
-ADAPM_SGNS_INFLIGHT=1 run inflight
 run prepass --intent-prepass
 ADAPM_SYNC_WORK_BLOCKS=1 run work1
 ADAPM_SYNC_WORK_BLOCKS=4 run work4
