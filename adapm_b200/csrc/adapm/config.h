@@ -40,6 +40,10 @@ struct Options {
   bool locality_stats = false;               // sys.stats.locality (reference: compile-time PS_LOCALITY_STATS)
   double sync_max_per_sec = 1000;            // sys.sync.max_per_sec
   int sync_pause_ms = 0;                     // sys.sync.pause
+  int sync_min_clocks = 8;                   // sys.sync.min_clocks (new; device-resident round): a new round starts only
+                                             // after the workers advanced this many clocks since the previous round started
+                                             // (or after sync_min_clocks_wait_ms, or at once for WaitSync / shutdown); 0 = off
+  int sync_min_clocks_wait_ms = 10;          // sys.sync.min_clocks_wait_ms
   double sync_threshold = 0;                 // sys.sync.threshold (-1 all, 0 non-zero, >0 L2, inf off)
   int sweep_period = 64;                     // rolling sweep: every slot ignores dirty hints/versions once per n rounds (new)
   int idle_period = 4;                       // idle replicas check the owner's version every n-th round (new; 1 = every round)
@@ -97,6 +101,8 @@ struct Options {
     else if (name == "sys.stats.locality") locality_stats = b(v);
     else if (name == "sys.sync.max_per_sec") { sync_max_per_sec = std::stod(v); }
     else if (name == "sys.sync.pause") { sync_pause_ms = std::stoi(v); if (sync_pause_ms > 0) sync_max_per_sec = 0; }
+    else if (name == "sys.sync.min_clocks") sync_min_clocks = std::stoi(v);
+    else if (name == "sys.sync.min_clocks_wait_ms") sync_min_clocks_wait_ms = std::stoi(v);
     else if (name == "sys.sync.threshold") sync_threshold = (v == "inf") ? std::numeric_limits<double>::infinity() : std::stod(v);
     else if (name == "sys.sync.sweep_period") sweep_period = std::stoi(v);
     else if (name == "sys.sync.idle_period") idle_period = std::stoi(v);

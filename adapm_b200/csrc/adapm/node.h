@@ -81,6 +81,7 @@ class SyncEngine {
   std::vector<uint8_t> status_;
   std::atomic<uint64_t> round_no_{0};   // written by the sync thread, read by report()
   std::chrono::steady_clock::time_point last_run_;
+  Clock last_round_clock_ = 0;          // fastest worker clock when the previous round started (loop_fused pacing)
   Stopwatch sw_total_, sw_pausing_, sw_register_, sw_collect_, sw_phase_a_, sw_phase_b_, sw_grace_, sw_phase_c_, sw_barriers_;
   std::atomic<uint64_t> intents_seen_{0}, recs_registered_{0};
 };
