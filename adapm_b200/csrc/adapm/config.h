@@ -40,9 +40,10 @@ struct Options {
   bool locality_stats = false;               // sys.stats.locality (reference: compile-time PS_LOCALITY_STATS)
   double sync_max_per_sec = 1000;            // sys.sync.max_per_sec
   int sync_pause_ms = 0;                     // sys.sync.pause
-  int sync_min_clocks = 8;                   // sys.sync.min_clocks (new; device-resident round): a new round starts only
-                                             // after the workers advanced this many clocks since the previous round started
-                                             // (or after sync_min_clocks_wait_ms, or at once for WaitSync / shutdown); 0 = off
+  int sync_min_clocks = -1;                  // sys.sync.min_clocks (new): a new round starts only after the workers advanced
+                                             // this many clocks since the previous round started (or after
+                                             // sync_min_clocks_wait_ms, or at once for WaitSync / shutdown); 0 = off,
+                                             // -1 = auto: 8 for the device-resident round, off for host-sequenced rounds
   int sync_min_clocks_wait_ms = 10;          // sys.sync.min_clocks_wait_ms
   double sync_threshold = 0;                 // sys.sync.threshold (-1 all, 0 non-zero, >0 L2, inf off)
   int sweep_period = 64;                     // rolling sweep: every slot ignores dirty hints/versions once per n rounds (new)

@@ -59,6 +59,7 @@ class SyncEngine {
  private:
   void loop();
   void loop_fused();
+  void pace(bool device_round);
   void round(bool sweep);
   bool fused_ = false;
   void collect_intents(const std::vector<Clock>& clocks, const std::vector<Clock>& windows);

@@ -263,6 +263,47 @@ void SyncEngine::round(bool sweep) {
   if (server_->tracing()) server_->observe_traced_keys();
 }
 
+// Pacing of the rounds (reference wait_none / wait_period / wait_interval, sync_manager.h:385-411) plus a cadence floor
+// in worker clocks.
+//
+// The work of a round is "every replica that changed since the previous round"; with many ranks the hot replicas change
+// within a step or two, so that set saturates and a round costs the same whether it comes after 2 steps or after 20.
+// Under load the rounds pace themselves (a round takes longer than min_clocks steps), but after any gap in the step
+// stream (barrier, checkpoint, loader stall) the engine would otherwise restart with a burst of short-interval rounds,
+// each refreshing the whole hot set again - measured at 8 GPUs: 2 x the refresh traffic per step and 20 % slower steps in
+// the 20 steps after a barrier (profiles/README.md). Requests that wait for rounds (WaitSync, shutdown) are served at
+// once, and without clock progress a round starts every min_clocks_wait_ms so that intents and evictions never starve.
+void SyncEngine::pace(bool device_round) {
+  const Options& opt = server_->options();
+  RankControl& rc = server_->my_control();
+  sw_pausing_.resume();
+  auto fastest_clock = [&] {
+    Clock m = 0;
+    for (Clock c : server_->worker_clocks()) if (c != WORKER_FINISHED && c > m) m = c;
+    return m;
+  };
+  auto urgent = [&] { return rc.sweep_requested.load() > 0 || rc.stop_requested.load() > 0; };
+  if (round_no_ > 0 && !urgent()) {
+    if (opt.sync_pause_ms > 0) {
+      std::this_thread::sleep_for(std::chrono::milliseconds(opt.sync_pause_ms));
+    } else if (opt.sync_max_per_sec > 0) {
+      auto target = last_run_ + std::chrono::nanoseconds((int64_t)(1e9 / opt.sync_max_per_sec));
+      if (std::chrono::steady_clock::now() < target) std::this_thread::sleep_until(target);
+    }
+    const int min_clocks = opt.sync_min_clocks >= 0 ? opt.sync_min_clocks : (device_round ? 8 : 0);
+    if (min_clocks > 0) {
+      const auto deadline = last_run_ + std::chrono::milliseconds(std::max(1, opt.sync_min_clocks_wait_ms));
+      while (std::chrono::steady_clock::now() < deadline) {
+        if (fastest_clock() - last_round_clock_ >= (Clock)min_clocks || urgent()) break;
+        std::this_thread::sleep_for(std::chrono::microseconds(100));
+      }
+    }
+  }
+  last_run_ = std::chrono::steady_clock::now();
+  last_round_clock_ = fastest_clock();
+  sw_pausing_.stop();
+}
+
 // The same loop for backends that run a whole round by themselves (cuda: device-side barriers, grace period and
 // stop/sweep agreement - the round is one enqueue): this thread only feeds intents and reads the outcome back.
 void SyncEngine::loop_fused() {
@@ -271,40 +312,7 @@ void SyncEngine::loop_fused() {
   RankControl& rc = server_->my_control();
   sw_total_.start();
   for (;;) {
-    sw_pausing_.resume();
-    auto fastest_clock = [&] {
-      Clock m = 0;
-      for (Clock c : server_->worker_clocks()) if (c != WORKER_FINISHED && c > m) m = c;
-      return m;
-    };
-    const bool urgent = rc.sweep_requested.load() > 0 || rc.stop_requested.load() > 0;
-    if (round_no_ > 0 && !urgent) {
-      if (opt.sync_pause_ms > 0) {
-        std::this_thread::sleep_for(std::chrono::milliseconds(opt.sync_pause_ms));
-      } else if (opt.sync_max_per_sec > 0) {
-        auto target = last_run_ + std::chrono::nanoseconds((int64_t)(1e9 / opt.sync_max_per_sec));
-        if (std::chrono::steady_clock::now() < target) std::this_thread::sleep_until(target);
-      }
-      // Cadence in worker clocks. The work of a round is "every replica that changed since the previous round"; with
-      // many ranks the hot replicas change within a step or two, so that set saturates and a round costs the same
-      // whether it comes after 2 steps or after 20. Under load the rounds pace themselves (a round takes longer than
-      // min_clocks steps), but after any gap in the step stream (barrier, checkpoint, loader stall) the engine would
-      // otherwise restart with a burst of short-interval rounds, each refreshing the whole hot set again - measured at
-      // 8 GPUs: 2 x the refresh traffic per step and 20 % slower steps in the 20 steps after a barrier. Requests that
-      // wait for rounds (WaitSync, shutdown) are served at once, and without clock progress a round starts every
-      // min_clocks_wait_ms so that intents and evictions never starve.
-      if (opt.sync_min_clocks > 0) {
-        const auto deadline = last_run_ + std::chrono::milliseconds(std::max(1, opt.sync_min_clocks_wait_ms));
-        while (std::chrono::steady_clock::now() < deadline) {
-          if (fastest_clock() - last_round_clock_ >= (Clock)opt.sync_min_clocks) break;
-          if (rc.sweep_requested.load() > 0 || rc.stop_requested.load() > 0) break;
-          std::this_thread::sleep_for(std::chrono::microseconds(100));
-        }
-      }
-    }
-    last_run_ = std::chrono::steady_clock::now();
-    last_round_clock_ = fastest_clock();
-    sw_pausing_.stop();
+    pace(/*device_round=*/true);
 
     RoundRequest rq;
     rq.want_stop = rc.stop_requested.load(std::memory_order_acquire) != 0;
@@ -359,18 +367,7 @@ void SyncEngine::loop() {
   sw_total_.start();
   for (;;) {
     // ---- pacing (reference wait_none / wait_period / wait_interval, sync_manager.h:385-411)
-    sw_pausing_.resume();
-    const bool urgent = rc.sweep_requested.load() > 0 || rc.stop_requested.load() > 0;
-    if (round_no_ > 0 && !urgent) {
-      if (opt.sync_pause_ms > 0) {
-        std::this_thread::sleep_for(std::chrono::milliseconds(opt.sync_pause_ms));
-      } else if (opt.sync_max_per_sec > 0) {
-        auto target = last_run_ + std::chrono::nanoseconds((int64_t)(1e9 / opt.sync_max_per_sec));
-        if (std::chrono::steady_clock::now() < target) std::this_thread::sleep_until(target);
-      }
-    }
-    last_run_ = std::chrono::steady_clock::now();
-    sw_pausing_.stop();
+    pace(/*device_round=*/false);
 
     // ---- agree on stop / sweep
     rc.snap_stop.store(rc.stop_requested.load(std::memory_order_acquire));
