@@ -12,7 +12,8 @@ SYS_FLAGS = ["sys.zmq_threads", "sys.techniques", "sys.time_intent_actions", "sy
              "sys.timing.buffer_quantile", "sampling.scheme", "sampling.pool_size", "sampling.reuse",
              "sampling.batch_size", "sampling.with_replacement",
              # additions of this implementation
-             "sys.sync.sweep_period", "sys.sync.idle_period", "sys.stats.locality", "pool_factor", "pool_bytes", "wait_timeout_s"]
+             "sys.sync.sweep_period", "sys.sync.idle_period", "sys.sync.min_clocks", "sys.sync.min_clocks_wait_ms",
+             "sys.stats.locality", "pool_factor", "pool_bytes", "wait_timeout_s"]
 
 
 def add_system_options(ap: argparse.ArgumentParser) -> None:
@@ -20,6 +21,9 @@ def add_system_options(ap: argparse.ArgumentParser) -> None:
     for f in SYS_FLAGS:
         g.add_argument("--" + f, dest=f, default=None)
     g.add_argument("--backend", default=None, choices=["cpu", "cuda"])
+    g.add_argument("--value_type", default="float", choices=["float", "double"],
+                   help="type of the parameter values: float (fused sm_100a kernels) or double (the reference's ValT for kge "
+                        "and mf; trains through Pull / Push with the same update rule on either backend)")
 
 
 def add_ablation_options(ap: argparse.ArgumentParser) -> None:

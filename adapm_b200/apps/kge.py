@@ -91,7 +91,8 @@ def main(argv=None) -> int:
     if args.eval_truncate_va:
         va = va[: args.eval_truncate_va]
     ad.setup(cfg.num_keys, 1)   # one worker per rank: the per-thread loops of the reference are batched kernels here
-    server = ad.Server(cfg.value_lengths(), backend=args.backend, options=system_options(args))
+    server = ad.Server(cfg.value_lengths(), backend=args.backend, options=system_options(args),
+                       dtype={"float": "float32", "double": "float64"}[args.value_type])
     kv = ad.Worker(0, server)
     model = KGE(server, kv, cfg)
     model.init_model(init=args.init_parameters)

@@ -77,7 +77,8 @@ def main(argv=None) -> int:
                    signal_intent_rows=bool(args.signal_intent_rows), wor_blocks=bool(args.wor_blocks),
                    wor_points=bool(args.wor_points), early_stop=args.early_stop)
     ad.setup(cfg.num_keys(world), 1)   # one worker per rank: the per-thread loops of the reference are batched kernels here
-    server = ad.Server(cfg.row_len, backend=args.backend, options=system_options(args))
+    server = ad.Server(cfg.row_len, backend=args.backend, options=system_options(args),
+                       dtype={"float": "float32", "double": "float64"}[args.value_type])
     kv = ad.Worker(0, server)
     model = MatrixFactorization(server, kv, cfg, data)
     if args.init_parameters == 2:

@@ -116,7 +116,10 @@ def load_triples(path: str) -> torch.Tensor:
 class KGE:
     def __init__(self, server, worker, cfg: KGEConfig):
         self.server, self.worker, self.cfg = server, worker, cfg
-        self.cuda = server.backend == "cuda"
+        # the fused kernels are float32; float64 rows (the reference's ValT = double, kge.cc:33) train through the
+        # Pull / Push API with the same update rule (kge_reference_step) on either backend
+        self.cuda = server.backend == "cuda" and server.dtype == torch.float32
+        self.dtype = server.dtype
         self.step_no = 0
         dev = server.device
         self._gen = torch.Generator().manual_seed(cfg.model_seed + 31 * server.my_rank())
@@ -163,11 +166,11 @@ class KGE:
             per = max(1, min(chunk, (64 << 20) // (4 * ln)))
             for i in range(0, keys.numel(), per):
                 k = keys[i:i + per]
-                rows = torch.empty(k.numel(), ln)
+                rows = torch.empty(k.numel(), ln, dtype=self.dtype)
                 if kind == "normal":
-                    rows[:, : ln // 2] = torch.randn(k.numel(), ln // 2, generator=gen) * p2 + p1
+                    rows[:, : ln // 2] = (torch.randn(k.numel(), ln // 2, generator=gen) * p2 + p1).to(self.dtype)
                 else:
-                    rows[:, : ln // 2] = torch.rand(k.numel(), ln // 2, generator=gen) * (p2 - p1) + p1
+                    rows[:, : ln // 2] = (torch.rand(k.numel(), ln // 2, generator=gen) * (p2 - p1) + p1).to(self.dtype)
                 rows[:, ln // 2:] = 1e-6
                 self.worker.set(k, rows.view(-1))
         self.worker.waitall()
@@ -226,10 +229,10 @@ class KGE:
         """Returns (E [ne, d], Eg [ne, d], R [nr, rel_dim], Rg) by pulling the whole model through the API."""
         cfg, kv = self.cfg, self.worker
         ek = torch.arange(cfg.num_entities)
-        ev = torch.empty(cfg.num_entities * cfg.entity_len, dtype=torch.float32)
+        ev = torch.empty(cfg.num_entities * cfg.entity_len, dtype=self.dtype)
         kv.wait(kv.pull(ek, ev))
         rk = torch.arange(cfg.num_entities, cfg.num_entities + cfg.num_relations)
-        rv = torch.empty(cfg.num_relations * cfg.relation_len, dtype=torch.float32)
+        rv = torch.empty(cfg.num_relations * cfg.relation_len, dtype=self.dtype)
         kv.wait(kv.pull(rk, rv))
         ev = ev.view(cfg.num_entities, cfg.entity_len)
         rv = rv.view(cfg.num_relations, cfg.relation_len)
@@ -414,9 +417,11 @@ def kge_reference_step(kv, S, R, O, L, cfg: KGEConfig, masks=None) -> float:
     dropout scale masks [n, len] (``ops.kge_dropout_mask``) instead of fresh random ones."""
     d = cfg.embed_dim
     n = S.numel()
+    dt = kv.server.dtype      # float32, or float64 like the reference's ValT
+    L = L.to(dt)
 
     def pull(keys, ln):
-        v = torch.empty(n * ln, dtype=torch.float32)
+        v = torch.empty(n * ln, dtype=dt)
         kv.wait(kv.pull(keys.contiguous(), v))
         return v.view(n, ln)
 
@@ -448,7 +453,7 @@ def kge_reference_step(kv, S, R, O, L, cfg: KGEConfig, masks=None) -> float:
         do = torch.einsum("bi,bij->bj", Es, Rm)
         dr = torch.einsum("bi,bj->bij", Es, Eo).reshape(n, d * d)
     dl = (torch.sigmoid(sc) - L).view(-1, 1)
-    pos = (L > 0.5).view(-1, 1).float()
+    pos = (L > 0.5).view(-1, 1).to(dt)
     gs = dl * ds + pos * cfg.gamma_entity * Es
     gr = dl * dr + pos * cfg.gamma_relation * Er
     go = dl * do + pos * cfg.gamma_entity * Eo

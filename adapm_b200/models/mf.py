@@ -99,7 +99,10 @@ def wor_block_schedule(world: int, epoch: int, seed: int = 0) -> np.ndarray:
 class MatrixFactorization:
     def __init__(self, server, worker, cfg: MFConfig, data: SparseMatrix):
         self.server, self.worker, self.cfg, self.data = server, worker, cfg, data
-        self.cuda = server.backend == "cuda"
+        # the fused kernel is float32; float64 rows (the reference's ValT = double) train through Pull / Push with the same
+        # update rule (mf_reference_step) on either backend
+        self.cuda = server.backend == "cuda" and server.dtype == torch.float32
+        self.dtype = server.dtype
         self.world = server.num_servers()
         self.fck = cfg.first_col_key(self.world)
         self.eps = cfg.eps
@@ -124,8 +127,8 @@ class MatrixFactorization:
         keys = keys[(keys < cfg.num_rows) | (keys >= self.fck)]
         for s in range(0, keys.numel(), chunk):
             k = keys[s:s + chunk]
-            rows = torch.empty(k.numel(), 2 * cfg.rank)
-            rows[:, :cfg.rank] = torch.rand(k.numel(), cfg.rank, generator=gen) / np.sqrt(cfg.rank)
+            rows = torch.empty(k.numel(), 2 * cfg.rank, dtype=self.dtype)
+            rows[:, :cfg.rank] = (torch.rand(k.numel(), cfg.rank, generator=gen) / np.sqrt(cfg.rank)).to(self.dtype)
             rows[:, cfg.rank:] = 0.0
             if self.cuda:
                 self.worker.set(k.to(self.server.device), rows.to(self.server.device).view(-1))
@@ -218,8 +221,8 @@ class MatrixFactorization:
         from ..utils.mmio import read_matrix_market_array
 
         cfg, world, rank = self.cfg, self.world, self.server.my_rank()
-        Wm = torch.from_numpy(read_matrix_market_array(w_path)).float()
-        Hm = torch.from_numpy(read_matrix_market_array(h_path)).float().t().contiguous()
+        Wm = torch.from_numpy(read_matrix_market_array(w_path)).to(self.dtype)
+        Hm = torch.from_numpy(read_matrix_market_array(h_path)).to(self.dtype).t().contiguous()
         assert Wm.shape == (cfg.num_rows, cfg.rank) and Hm.shape == (cfg.num_cols, cfg.rank), (Wm.shape, Hm.shape)
         self.worker.begin_setup()
         for first, M in ((0, Wm), (self.fck, Hm)):
@@ -227,7 +230,7 @@ class MatrixFactorization:
             sel = (keys % world) == rank
             keys, vals = keys[sel], M[sel]
             for s in range(0, keys.numel(), chunk):
-                rows = torch.zeros(min(chunk, keys.numel() - s), 2 * cfg.rank)
+                rows = torch.zeros(min(chunk, keys.numel() - s), 2 * cfg.rank, dtype=self.dtype)
                 rows[:, :cfg.rank] = vals[s:s + chunk]
                 self.worker.wait(self.worker.set(keys[s:s + chunk], rows.view(-1)))
         self.worker.waitall()
@@ -240,12 +243,12 @@ class MatrixFactorization:
         for s in range(0, len(x), 1 << 16):
             ri = torch.from_numpy(np.ascontiguousarray(i[s:s + (1 << 16)])).long()
             cj = torch.from_numpy(np.ascontiguousarray(j[s:s + (1 << 16)])).long()
-            wv = torch.empty(ri.numel() * 2 * cfg.rank)
+            wv = torch.empty(ri.numel() * 2 * cfg.rank, dtype=self.dtype)
             kv.wait(kv.pull(self.row_key(ri), wv))
-            hv = torch.empty(cj.numel() * 2 * cfg.rank)
+            hv = torch.empty(cj.numel() * 2 * cfg.rank, dtype=self.dtype)
             kv.wait(kv.pull(self.col_key(cj), hv))
             pred = (wv.view(-1, 2 * cfg.rank)[:, :cfg.rank] * hv.view(-1, 2 * cfg.rank)[:, :cfg.rank]).sum(1)
-            total += float(((torch.from_numpy(np.ascontiguousarray(x[s:s + (1 << 16)])).float() - pred) ** 2).sum())
+            total += float(((torch.from_numpy(np.ascontiguousarray(x[s:s + (1 << 16)])).to(self.dtype) - pred) ** 2).sum())
         return total
 
     def bold_driver(self, loss: float, prev_loss: Optional[float]) -> None:
@@ -255,9 +258,9 @@ class MatrixFactorization:
 
     def pull_factors(self):
         cfg, kv = self.cfg, self.worker
-        wv = torch.empty(cfg.num_rows * 2 * cfg.rank)
+        wv = torch.empty(cfg.num_rows * 2 * cfg.rank, dtype=self.dtype)
         kv.wait(kv.pull(torch.arange(cfg.num_rows), wv))
-        hv = torch.empty(cfg.num_cols * 2 * cfg.rank)
+        hv = torch.empty(cfg.num_cols * 2 * cfg.rank, dtype=self.dtype)
         kv.wait(kv.pull(torch.arange(cfg.num_cols) + self.fck, hv))
         return wv.view(-1, 2 * cfg.rank)[:, :cfg.rank], hv.view(-1, 2 * cfg.rank)[:, :cfg.rank]
 
@@ -276,13 +279,14 @@ class MatrixFactorization:
 
 def mf_reference_step(kv, rk, ck, x, rn, cn, rank: int, eps: float, lam: float) -> float:
     n = rk.numel()
-    wv = torch.empty(n * 2 * rank)
-    hv = torch.empty(n * 2 * rank)
+    dt = kv.server.dtype          # float32, or float64 like the reference's ValT
+    wv = torch.empty(n * 2 * rank, dtype=dt)
+    hv = torch.empty(n * 2 * rank, dtype=dt)
     kv.wait(kv.pull(rk.contiguous(), wv))
     kv.wait(kv.pull(ck.contiguous(), hv))
     wv, hv = wv.view(n, 2 * rank), hv.view(n, 2 * rank)
     w, aw, h, ah = wv[:, :rank], wv[:, rank:], hv[:, :rank], hv[:, rank:]
-    e = x.float() - (w * h).sum(1)
+    e = x.to(dt) - (w * h).sum(1)
     f1 = (-2 * e).view(-1, 1)
     f2 = 2 * lam
     gw = -(f1 * h + f2 * w / rn.clamp(min=1).view(-1, 1))

@@ -84,3 +84,33 @@ def test_mf_reference_flags(tmp_path):
                        "--epochs", "2", "--algorithm", "plain", "--enforce_random_keys", "1", "--early_stop", "10",
                        "--wor_points", "0", "--enforce_full_replication", "1", "--max_runtime", "100", "--compute_loss", "1"])
     assert rc == 0 and "[mf] epoch 1" in out, out[-2000:]
+
+
+def test_kge_and_mf_with_double_values(tmp_path):
+    """--value_type double = the reference's ValT for kge and mf (kge.cc:33, mf.cc): float64 rows through Pull / Push with
+    the same update rule; the float32 and the float64 run of the same job agree to float32 rounding."""
+    def loss_of(out, pattern):
+        m = re.findall(pattern, out)
+        assert m, out[-2000:]
+        return float(m[-1])
+
+    kge = ["-m", "adapm_b200.apps.kge", "--", "--dataset", os.path.join(D, "kge") + "/", "--num_entities", "280",
+           "--num_relations", "112", "--embed_dim", "8", "--num_epochs", "2", "--write_embeddings", str(tmp_path / "d_"),
+           "--sys.techniques", "replication_only"]
+    rc, out64 = _launch(kge + ["--value_type", "double"], world=1)
+    assert rc == 0 and "protocol errors 0" in out64, out64[-2000:]
+    rc, out32 = _launch(kge, world=1)
+    assert rc == 0, out32[-2000:]
+    l64, l32 = (loss_of(o, r"\[kge\] epoch 2: bce loss ([\d.]+)") for o in (out64, out32))
+    assert abs(l64 - l32) <= 2e-3 * abs(l64), (l64, l32)
+    mf = ["-m", "adapm_b200.apps.mf", "--", "--dataset", os.path.join(D, "mf", "train.mmc"), "--rank", "2", "--epochs", "3",
+          "--init_parameters", "1", "--algorithm", "plain", "--wor_points", "0"]
+    rc, out64 = _launch(mf + ["--value_type", "double"], world=1)
+    assert rc == 0 and "protocol errors 0" in out64, out64[-2000:]
+    rc, out32 = _launch(mf, world=1)
+    assert rc == 0, out32[-2000:]
+    e64, e32 = (loss_of(o, r"\[mf\] epoch 2: local squared error ([\d.]+)") for o in (out64, out32))
+    assert abs(e64 - e32) <= 2e-3 * abs(e64) + 1e-6, (e64, e32)
+    # two ranks, double values: the whole protocol (relocation + replication) on float64 rows
+    rc, out = _launch(kge + ["--value_type", "double"], world=2)
+    assert rc == 0 and "[kge] epoch 2: bce loss" in out and "protocol errors 0" in out, out[-2000:]
