@@ -1,4 +1,5 @@
 #include "node.h"
+#include "nvtx.h"
 
 #include <fstream>
 #include <sstream>
@@ -267,6 +268,7 @@ int Worker::new_ts(uint64_t ticket) {
 }
 
 int Worker::Push(const Key* keys, size_t n, const void* vals, bool set, const IoDesc& io) {
+  ADAPM_NVTX("adapm::Push");
   ++num_push_ops;
   num_push_params += n;
   OpResult res;
@@ -301,6 +303,7 @@ int Worker::Push(const Key* keys, size_t n, const void* vals, bool set, const Io
 }
 
 int Worker::Pull(const Key* keys, size_t n, void* vals, const IoDesc& io) {
+  ADAPM_NVTX("adapm::Pull");
   ++num_pull_ops;
   num_pull_params += n;
   OpResult res;
@@ -322,6 +325,7 @@ bool Worker::PullIfLocal(Key key, void* vals) {
 }
 
 int Worker::Intent(const Key* keys, size_t n, Clock start, Clock end) {
+  ADAPM_NVTX("adapm::Intent");
   if (end == 0) end = start + 1;
   if (server_.num_servers() == 1 || n == 0) return LOCAL;  // single node: nothing to manage
   // Copy only: duplicates are removed by the sync thread (off the worker's critical path).
@@ -373,6 +377,7 @@ SampleID Worker::PrepareSample(size_t K, Clock start, Clock end) {
   return server_.sampling_->prepare_sample(K, id_, start, end);
 }
 int Worker::PullSample(SampleID id, Key* keys, size_t n, void* vals) {
+  ADAPM_NVTX("adapm::PullSample");
   ADAPM_CHECK(server_.sampling_, "sampling support is not enabled (call enable_sampling_support)");
   return server_.sampling_->pull_sample(id, keys, n, vals, *this);
 }
@@ -381,6 +386,7 @@ void Worker::FinishSample(SampleID id) {
 }
 
 void Worker::Wait(int ts) {
+  ADAPM_NVTX("adapm::Wait");
   if (ts == LOCAL) return;
   uint64_t t;
   {
@@ -403,16 +409,21 @@ bool Worker::IsFinished(int ts) {
   return false;
 }
 void Worker::WaitAll() {
+  ADAPM_NVTX("adapm::WaitAll");
   server_.backend_->wait_worker(id_);
   std::lock_guard<std::mutex> lk(ts_mu_);
   for (auto& t : tickets_) t = 0;
 }
 void Worker::WaitSync() {
+  ADAPM_NVTX("adapm::WaitSync");
   if (server_.num_servers() == 1) return;
   server_.backend_->wait_worker(id_);
   server_.sync_->wait_sync();
 }
-void Worker::Barrier() { server_.worker_barrier(); }
+void Worker::Barrier() {
+  ADAPM_NVTX("adapm::Barrier");
+  server_.worker_barrier();
+}
 void Worker::BeginSetup() { WaitSync(); Barrier(); }
 void Worker::EndSetup() { WaitSync(); WaitSync(); Barrier(); ResetStats(); }
 void Worker::ResetStats() {

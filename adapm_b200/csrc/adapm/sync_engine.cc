@@ -13,6 +13,7 @@
 // Reference equivalent: SyncManager::thread/startSync/ProcessSyncMessage
 // (sync_manager.h:291-382,452-520,544-799); message round trips became barriers.
 #include "node.h"
+#include "nvtx.h"
 
 #include <algorithm>
 #include <sstream>
@@ -240,25 +241,37 @@ void SyncEngine::round(bool sweep) {
   sw_register_.stop();
 
   sw_phase_a_.resume();
-  be.phase_a(rp);
-  be.round_fence();
+  {
+    ADAPM_NVTX("adapm::sync::phase_a");
+    be.phase_a(rp);
+    be.round_fence();
+  }
   sw_phase_a_.stop();
   sw_barriers_.resume(); ctl->sync_barrier.wait(world, to, "sync round: after phase A"); sw_barriers_.stop();
 
   sw_phase_b_.resume();
-  be.phase_b(rp);
-  be.round_fence();
+  {
+    ADAPM_NVTX("adapm::sync::phase_b");
+    be.phase_b(rp);
+    be.round_fence();
+  }
   sw_phase_b_.stop();
   sw_barriers_.resume(); ctl->sync_barrier.wait(world, to, "sync round: after phase B"); sw_barriers_.stop();
 
   sw_grace_.resume();
-  be.grace();
+  {
+    ADAPM_NVTX("adapm::sync::grace");
+    be.grace();
+  }
   sw_grace_.stop();
   sw_barriers_.resume(); ctl->sync_barrier.wait(world, to, "sync round: grace"); sw_barriers_.stop();
 
   sw_phase_c_.resume();
-  be.phase_c(rp);
-  be.round_fence();
+  {
+    ADAPM_NVTX("adapm::sync::phase_c");
+    be.phase_c(rp);
+    be.round_fence();
+  }
   sw_phase_c_.stop();
   if (server_->tracing()) server_->observe_traced_keys();
 }
@@ -274,6 +287,7 @@ void SyncEngine::round(bool sweep) {
 // the 20 steps after a barrier (profiles/README.md). Requests that wait for rounds (WaitSync, shutdown) are served at
 // once, and without clock progress a round starts every min_clocks_wait_ms so that intents and evictions never starve.
 void SyncEngine::pace(bool device_round) {
+  ADAPM_NVTX("adapm::sync::pace");
   const Options& opt = server_->options();
   RankControl& rc = server_->my_control();
   sw_pausing_.resume();
@@ -329,7 +343,10 @@ void SyncEngine::loop_fused() {
 
     sw_register_.resume();
     sw_collect_.resume();
-    collect_intents(clocks, windows);
+    {
+      ADAPM_NVTX("adapm::sync::collect_intents");
+      collect_intents(clocks, windows);
+    }
     sw_collect_.stop();
     sw_register_.stop();
     status_.assign(recs_.size(), 0);
@@ -338,7 +355,11 @@ void SyncEngine::loop_fused() {
     rq.status = status_.data();
 
     sw_phase_a_.resume();   // (the whole device round is accounted here)
-    RoundOutcome out = be.fused_round(rq);
+    RoundOutcome out;
+    {
+      ADAPM_NVTX("adapm::sync::device_round");
+      out = be.fused_round(rq);
+    }
     sw_phase_a_.stop();
     if (out.all_stop) break;
     for (size_t i = 0; i < recs_.size(); ++i) {

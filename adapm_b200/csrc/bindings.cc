@@ -11,6 +11,7 @@
 #include "adapm/corpus.h"
 #include "adapm/io.h"
 #include "adapm/node.h"
+#include "adapm/nvtx.h"
 
 namespace py = pybind11;
 using namespace adapm;
@@ -47,6 +48,7 @@ PYBIND11_MODULE(_C, m) {
   m.attr("MAX_RANKS") = (int)MAX_RANKS;
   m.def("cuda_available", [] { return cudamem::available(); });
   m.def("_fdpass_selftest", [] { return fabric_fdpass_selftest(); });
+  m.def("nvtx_compiled_in", [] { return nvtx_compiled_in(); });
   m.def("cuda_device_count", [] { return cudamem::available() ? cudamem::device_count() : 0; });
   m.def("poisson_quantile", &poisson_quantile);
 

@@ -253,16 +253,18 @@ def _cadence_worker(kv, server, wid):
     keys = torch.arange(8, dtype=torch.int64)
     kv.wait(kv.push(keys, torch.ones(8 * 2, dtype=server.dtype)))
     kv.barrier()
-    # 1) no clock progress: a round only every min_clocks_wait_ms (50 ms), not every millisecond
+    # 1) no clock progress: a round only every min_clocks_wait_ms (200 ms), not every millisecond
     r0 = server.counters()["sync_rounds"]
-    time.sleep(0.5)
+    t0 = time.perf_counter()
+    time.sleep(1.0)
     idle_rounds = server.counters()["sync_rounds"] - r0
-    if not (3 <= idle_rounds <= 25):
-        errors.append(f"{idle_rounds} rounds in 0.5 s without clock progress (expected about 10)")
-    # 2) requests that wait for rounds are served at once
+    el = time.perf_counter() - t0
+    if not (1 <= idle_rounds <= el / 0.2 + 3):
+        errors.append(f"{idle_rounds} rounds in {el:.2f} s without clock progress (one per 200 ms expected)")
+    # 2) requests that wait for rounds are served at once (two floor-delayed rounds would take >= 0.4 s)
     t0 = time.perf_counter()
     kv.wait_sync()
-    if time.perf_counter() - t0 > 0.04:
+    if time.perf_counter() - t0 > 0.3:
         errors.append(f"WaitSync took {time.perf_counter() - t0:.3f} s under the cadence floor")
     kv.barrier()
     # 3) clock progress releases rounds: 4 clocks per round
@@ -272,7 +274,7 @@ def _cadence_worker(kv, server, wid):
         kv.advance_clock()
         time.sleep(0.002)
     busy_rounds = server.counters()["sync_rounds"] - r1
-    if busy_rounds < 6:
+    if busy_rounds < 2:       # (a loaded CI box runs few rounds in 0.1 s; without clock progress it would be at most one)
         errors.append(f"only {busy_rounds} rounds while the clock advanced by 40 in {time.perf_counter() - t0:.2f} s")
     kv.barrier()
     kv.finalize()
@@ -283,6 +285,6 @@ def test_round_cadence_floor_in_worker_clocks():
     """sys.sync.min_clocks: a new round starts only after the workers advanced that many clocks (default for the
     device-resident round on GPUs; opt-in here), but never later than min_clocks_wait_ms, and at once for WaitSync."""
     res = run_cluster(_cadence_worker, world=2, workers=1, mode="threads", value_lengths=2, num_keys=16, dtype="float32",
-                      options={"sys.sync.min_clocks": 4, "sys.sync.min_clocks_wait_ms": 50})
+                      options={"sys.sync.min_clocks": 4, "sys.sync.min_clocks_wait_ms": 200})
     errs = [e for r in res.values() for k, v in r.items() if k != "counters" for e in v]
     assert not errs, "\n".join(errs)

@@ -64,7 +64,9 @@ def _kge_worker(kv, server, wid):
             tot += float(model.step(b))
             kv.advance_clock()
         losses.append(tot)
-    kv.barrier()
+    # propagation idiom: every replica delta has reached its owner before anybody evaluates (otherwise the local and the
+    # distributed evaluation below may see models that differ by the deltas still in flight)
+    kv.barrier(); kv.wait_sync(); kv.barrier(); kv.wait_sync(); kv.barrier()
     out = {"losses": losses}
     if wid == 0:
         out["eval"] = model.evaluate(tr[:100], tr)
