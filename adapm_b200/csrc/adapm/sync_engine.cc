@@ -296,7 +296,18 @@ void SyncEngine::pace(bool device_round) {
     for (Clock c : server_->worker_clocks()) if (c != WORKER_FINISHED && c > m) m = c;
     return m;
   };
-  auto urgent = [&] { return rc.sweep_requested.load() > 0 || rc.stop_requested.load() > 0; };
+  // somebody waits for rounds (WaitSync, shutdown) - on ANY rank: a round is collective, so a peer's request is as urgent
+  // as my own (the requests live in the shared control block)
+  ControlBlock* ctl = server_->control();
+  const int world = opt.world;
+  auto urgent = [&] {
+    if (rc.sweep_requested.load() > 0 || rc.stop_requested.load() > 0) return true;
+    for (int r = 0; r < world; ++r) {
+      if (ctl->ranks[r].sweep_requested.load(std::memory_order_relaxed) > 0 ||
+          ctl->ranks[r].stop_requested.load(std::memory_order_relaxed) > 0) return true;
+    }
+    return false;
+  };
   if (round_no_ > 0 && !urgent()) {
     if (opt.sync_pause_ms > 0) {
       std::this_thread::sleep_for(std::chrono::milliseconds(opt.sync_pause_ms));
