@@ -224,6 +224,23 @@ def test_examples_run(tmp_path):
     assert r.returncode == 0 and "all 1000 rows verified" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
 
 
+def test_torchrun_launch_with_gloo():
+    """One rank per process under `python -m torch.distributed.run` (how bench.py and the multi-GPU apps are launched):
+    rank / world / job come from the environment torchrun sets; gloo cross-checks the result with an all-reduce."""
+    import socket
+
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    env = dict(os.environ, PYTHONPATH=ROOT, OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "3", "--master-addr",
+                        "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "examples", "torchrun_example.py")],
+                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=300)
+    out = r.stdout + r.stderr
+    assert r.returncode == 0, out[-2500:]
+    assert out.count("PASSED") == 3 and "FAILED" not in out, out[-2500:]
+
+
 def _allreduce_sum_worker(kv, server, wid):
     out = server.allreduce_sum([float(wid + 1), 0.5, -2.0 * wid])
     out2 = server.allreduce_sum([1.0])           # reusable
