@@ -21,6 +21,8 @@ def main() -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("--backend", default="cpu", choices=["cpu", "cuda"])
     args = ap.parse_args()
+    if args.backend == "cuda":
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
     dist.init_process_group("gloo" if args.backend == "cpu" else "nccl")
     rank, world = dist.get_rank(), dist.get_world_size()
     num_keys, vpk = 64, 4
