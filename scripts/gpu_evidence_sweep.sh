@@ -37,11 +37,13 @@ capture kge_step         kge_step_kernel 5 python benchmarks/app_bench.py
 capture mf_step          mf_step_kernel 5 python benchmarks/app_bench.py
 capture gemm_persistent  gemm_nt_tcgen05_persistent_kernel 30 python benchmarks/gemm_bench.py
 fi
-capture gather_gemm      gather_gemm_kernel 2 python -m pytest tests/test_gpu_gemm.py -q -m gpu -k gather
+capture gather_gemm      gather_gemm_kernel 0 python -m pytest tests/test_gpu_gemm.py -q -m gpu -k gather
 capture rescal           kge_rescal_kernel 0 python -m pytest tests/test_gpu_ops.py -q -m gpu -k "rescal_and_dropout and RESCAL-64"
 
 echo "== compute-sanitizer (multi-rank protocol on one GPU + the fused ops)"
-for tool in memcheck racecheck ${ADAPM_SWEEP_SYNCCHECK:+synccheck}; do
+# (racecheck loses track of the launches of the multi-threaded multi-rank harness - profiles/sanitizer_racecheck.txt; it is
+#  opt-in here: ADAPM_SWEEP_RACECHECK=1)
+for tool in memcheck ${ADAPM_SWEEP_RACECHECK:+racecheck} ${ADAPM_SWEEP_SYNCCHECK:+synccheck}; do
   timeout 900 compute-sanitizer --tool $tool --target-processes all --print-limit 20 \
       python -m pytest tests/test_gpu_contract.py tests/test_gpu_ops.py -q -m gpu -x \
       -k "locality_api_cuda or set_operation_cuda or set_under_relocation_cuda or sgns_step_matches or kge_complex or rescal_and_dropout or mf_step" \
@@ -67,3 +69,7 @@ try:
 except Exception as e: print(sys.argv[1], "FAILED", e)
 PY
 done
+# gpurun merges only gpurun_out/ back: mirror the summaries written to profiles/ on the box
+mkdir -p $OUT/profiles
+cp profiles/prof_*_ncu_details.txt profiles/prof_*_ncu_raw.csv profiles/prof_*_ncu_source_head.csv profiles/sanitizer_*.txt \
+   profiles/*_latest.jsonl profiles/bench_*_1gpu.json profiles/nccl_arm_1gpu.json $OUT/profiles/ 2>/dev/null
