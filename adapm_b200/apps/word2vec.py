@@ -32,8 +32,8 @@ def main(argv=None) -> int:
     ap.add_argument("--embed_dim", "-v", type=int, default=200)
     ap.add_argument("--negative", type=int, default=25)
     ap.add_argument("--shared_negatives", type=int, default=0,
-                    help="cuda backend: > 0 = one set of this many negatives per batch, contractions on the tensor cores "
-                         "(a multiple of 32; 0 = the reference's private negatives per pair)")
+                    help="> 0 = one set of this many negatives per batch (cuda: contractions on the tensor cores, a multiple "
+                         "of 32, batch_pairs too; cpu: the same rule through Pull / Push); 0 = the reference's private negatives")
     ap.add_argument("--min_count", type=int, default=5)
     ap.add_argument("--neg_power", type=float, default=0.75)
     ap.add_argument("--starting_alpha", type=float, default=0.025)
@@ -95,7 +95,7 @@ def main(argv=None) -> int:
                          starting_alpha=args.starting_alpha, neg_power=args.neg_power, batch_pairs=args.batch_pairs,
                          read_ahead=args.read_sentences_ahead, signal_intent=bool(args.signal_intent),
                          sampling_scheme=getattr(args, "sampling.scheme") or "local", model_seed=args.model_seed,
-                         shared_negatives=args.shared_negatives if args.backend == "cuda" else 0)
+                         shared_negatives=args.shared_negatives)
     ad.setup(cfg.num_keys, 1)   # one worker per rank: the per-thread loops of the reference are batched kernels here
     server = ad.Server(cfg.row_len, backend=args.backend, options=system_options(args))
     kv = ad.Worker(0, server)

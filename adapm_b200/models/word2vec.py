@@ -290,6 +290,12 @@ class Word2Vec:
         cfg, kv, d = self.cfg, self.worker, self.cfg.embed_dim
         centers, contexts = keys_host[0], keys_host[1]
         B = centers.numel()
+        if cfg.shared_negatives > 0:      # one set of negatives for the batch (the GEMM formulation), through Pull / Push
+            u = torch.rand(cfg.shared_negatives, generator=self._gen, dtype=torch.float64)
+            negs = syn1_key(torch.searchsorted(self._neg_cdf, u).clamp_(max=cfg.vocab_size - 1))
+            loss = sgns_shared_pull_push_step(kv, centers, contexts, negs, d, self.alpha)
+            self.step_no += 1
+            return torch.tensor([loss], dtype=torch.float32)
         u = torch.rand(B * cfg.negative, generator=self._gen, dtype=torch.float64)
         negw = torch.searchsorted(self._neg_cdf, u).clamp_(max=cfg.vocab_size - 1)
         negs = syn1_key(negw).view(B, cfg.negative)
@@ -326,6 +332,22 @@ class Word2Vec:
         dump(path, syn0_key)
         if write_syn1:
             dump(path + ".syn1", syn1_key)
+
+
+def sgns_shared_pull_push_step(kv, centers, contexts, negatives, d: int, alpha: float) -> float:
+    """Shared-negative SGNS step through the public Pull / Push API (any backend): the same rule as the tensor-core
+    variant (``ops.SgnsSharedStep``), computed with ``ops.sgns_shared_reference_step`` on the pulled rows."""
+    from ..ops import sgns_shared_reference_step
+
+    keys = torch.cat([centers.view(-1), contexts.view(-1), negatives.view(-1)])
+    uk, inv = torch.unique(keys, return_inverse=True)
+    rows = torch.empty(uk.numel() * 2 * d, dtype=torch.float32)
+    kv.wait(kv.pull(uk, rows))
+    rows = rows.view(-1, 2 * d)
+    B, Nn = centers.numel(), negatives.numel()
+    new, loss = sgns_shared_reference_step(rows, inv[:B], inv[B:2 * B], inv[2 * B:], d, alpha)
+    kv.wait(kv.push(uk, (new - rows).contiguous().view(-1)))
+    return float(loss)
 
 
 def read_word2vec_binary(path: str):

@@ -180,3 +180,35 @@ def test_sgns_shared_reference_matches_autograd():
         g = -E.grad[k]
         torch.testing.assert_close(out[k, d:] - t[k, d:], g * g, atol=1e-5, rtol=1e-4)
         torch.testing.assert_close(out[k, :d] - t[k, :d], 0.1 * g * torch.rsqrt(t[k, d:] + g * g), atol=1e-5, rtol=1e-4)
+
+
+def _w2v_shared_worker(kv, server, wid):
+    from adapm_b200.models.word2vec import SyntheticPairs, Word2Vec, Word2VecConfig, zipf_counts
+
+    V = 2000
+    cfg = Word2VecConfig(vocab_size=V, embed_dim=16, negative=5, batch_pairs=256, shared_negatives=32, read_ahead=2)
+    cnt = zipf_counts(V, 1.0)
+    model = Word2Vec(server, kv, cfg, cnt)
+    model.init_model()
+    data = SyntheticPairs(cfg, cnt, server.my_rank(), seed=1)
+    losses = []
+    for it in range(80):
+        b = data.batch(it % 4)
+        model.signal_intent(data.batch((it + 2) % 4), kv.current_clock() + 2)
+        losses.append(float(model.step(b)) / (cfg.batch_pairs * (1 + cfg.shared_negatives)))
+        kv.advance_clock()
+    kv.barrier()
+    kv.finalize()
+    return losses
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_word2vec_shared_negatives_through_pull_push(world):
+    """--shared_negatives on the CPU backend: one set of negatives per batch, the same rule as the tensor-core variant
+    (ops.SgnsSharedStep) computed on pulled rows and pushed back as additive updates; the loss goes down, also with
+    relocation / replication between two ranks."""
+    res = run_cluster(_w2v_shared_worker, world=world, workers=1, mode="threads", value_lengths=32, num_keys=4000)
+    for r in res.values():
+        ls = r[0]
+        assert ls[-1] < 0.97 * ls[0], (ls[0], ls[-1])
+        assert r["counters"]["protocol_errors"] == 0
