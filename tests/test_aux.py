@@ -307,3 +307,34 @@ def test_round_cadence_floor_in_worker_clocks():
                       options={"sys.sync.min_clocks": 4, "sys.sync.min_clocks_wait_ms": 200})
     errs = [e for r in res.values() for k, v in r.items() if k != "counters" for e in v]
     assert not errs, "\n".join(errs)
+
+
+def _metrics_worker(kv, server, wid):
+    import urllib.request
+
+    from adapm_b200.utils.metrics import start_metrics_server
+
+    keys = torch.arange(10, dtype=torch.int64)
+    kv.wait(kv.push(keys, torch.ones(10 * 2, dtype=server.dtype)))
+    kv.intent(keys, kv.current_clock(), kv.current_clock() + 50)
+    kv.wait_sync(); kv.barrier()
+    _, port = start_metrics_server(server, workers=[kv])
+    body = urllib.request.urlopen(f"http://127.0.0.1:{port}/metrics", timeout=10).read().decode()
+    kv.barrier()
+    kv.finalize()
+    return body
+
+
+def test_prometheus_metrics_endpoint():
+    """utils/metrics.py: the node's counters and the workers' locality counters are scraped over HTTP while the job runs."""
+    pytest.importorskip("prometheus_client")
+    res = run_cluster(_metrics_worker, world=2, workers=1, mode="threads", value_lengths=2, num_keys=16, dtype="float32")
+    for rank, r in res.items():
+        body = r[0]
+        assert f'adapm_sync_rounds_total{{rank="{rank}"}}' in body, body[:600]
+        assert "adapm_protocol_errors_total" in body and "adapm_worker_push_params_total" in body
+        rounds = [float(l.split()[-1]) for l in body.splitlines() if l.startswith("adapm_sync_rounds_total")]
+        assert rounds and rounds[0] >= 2          # the WaitSync before the scrape ran at least two rounds
+    moved = sum(float(l.split()[-1]) for r in res.values() for l in r[0].splitlines()
+                if l.startswith(("adapm_relocations_total", "adapm_replica_setups_total")))
+    assert moved > 0                              # both ranks wanted all ten keys: relocated or replicated
