@@ -222,7 +222,8 @@ class Worker:
 
     def __init__(self, customer_id: int, server: Server) -> None:
         self.server = server
-        self._impl = _C.Worker(int(customer_id), server._impl)
+        self.customer_id = int(customer_id)
+        self._impl = _C.Worker(self.customer_id, server._impl)
         self._pending = {}
 
     # -- helpers ------------------------------------------------------------------
