@@ -201,11 +201,32 @@ class MatrixFactorization:
                 order = order[: cfg.early_stop]
                 n = order.shape[0]
             starts = list(range(0, n, cfg.batch_nnz))
+            col_plan = None
+            if cfg.algorithm == "columnwise" and W > 1:
+                # Ranged intents like the reference's column-wise schedule (mf.cc:477-482: one Intent per column for the
+                # clocks during which the column's data points are processed): the points are sorted by column, so a
+                # column occupies a contiguous run of batches [first, last]; it is signalled ONCE, read_ahead batches before
+                # its first one, for last - first + 1 clocks - not again in every batch it spans.
+                js = data.j[order]
+                cols, first_idx = np.unique(js, return_index=True)
+                last_idx = np.r_[first_idx[1:], n] - 1
+                first_b, last_b = first_idx // cfg.batch_nnz, last_idx // cfg.batch_nnz
+                ptr = np.searchsorted(first_b, np.arange(len(starts) + 1))     # columns whose first batch is b: ptr[b]:ptr[b+1]
+                col_plan = (cols, last_b - first_b + 1, ptr)
             for bi, s in enumerate(starts):
                 fut = bi + cfg.read_ahead
                 if W > 1 and fut < len(starts):
-                    p = order[starts[fut]:starts[fut] + cfg.batch_nnz]
-                    kv.intent(torch.from_numpy(np.unique(data.j[p])) + self.fck, kv.current_clock() + cfg.read_ahead)
+                    if col_plan is not None:
+                        cols, dur, ptr = col_plan
+                        lo, hi = int(ptr[fut]), int(ptr[fut + 1])
+                        if hi > lo:
+                            start = kv.current_clock() + cfg.read_ahead
+                            for dd in np.unique(dur[lo:hi]):               # (almost always a single duration: 1 batch)
+                                sel = cols[lo:hi][dur[lo:hi] == dd]
+                                kv.intent(torch.from_numpy(sel.astype(np.int64)) + self.fck, start, start + int(dd))
+                    else:
+                        p = order[starts[fut]:starts[fut] + cfg.batch_nnz]
+                        kv.intent(torch.from_numpy(np.unique(data.j[p])) + self.fck, kv.current_clock() + cfg.read_ahead)
                 p = order[s:s + cfg.batch_nnz]
                 out = self.step(data.i[p], data.j[p], data.x[p])
                 if not self.cuda:

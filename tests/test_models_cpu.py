@@ -212,3 +212,47 @@ def test_word2vec_shared_negatives_through_pull_push(world):
         ls = r[0]
         assert ls[-1] < 0.97 * ls[0], (ls[0], ls[-1])
         assert r["counters"]["protocol_errors"] == 0
+
+
+def _mf_ranged_worker(kv, server, wid):
+    from adapm_b200.models.mf import MatrixFactorization, SparseMatrix
+
+    cfg = server._cfg
+    data = SparseMatrix.synthetic(cfg.num_rows, cfg.num_cols, 4000, 4, server.num_servers(), server.my_rank(), seed=7)
+    model = MatrixFactorization(server, kv, cfg, data)
+    model.init_model()
+    kv.barrier()
+    calls = []
+    orig = kv.intent
+    kv.intent = lambda keys, start, end=0: (calls.append((keys.numel(), int(end) - int(start) if end else 1)), orig(keys, start, end))[1]
+    l0 = model.run_epoch(0)
+    n_batches = (data.i.shape[0] + cfg.batch_nnz - 1) // cfg.batch_nnz
+    kv.intent = orig
+    for ep in range(1, 6):
+        l = model.run_epoch(ep)
+    kv.barrier()
+    loc = kv.locality()
+    kv.finalize()
+    return {"l0": l0, "l": l, "calls": calls, "n_batches": n_batches, "loc": loc}
+
+
+def test_mf_columnwise_ranged_intents(tmp_path):
+    """Column-wise MF signals ONE intent per column for the clocks its data points span (reference mf.cc:477-482): with 6
+    columns spread over ~40 batches every column is signalled once per epoch, with a multi-clock window."""
+    from adapm_b200.models.mf import MFConfig
+
+    cfg = MFConfig(num_rows=200, num_cols=6, rank=4, algorithm="columnwise", eps=0.02, lam=0.01, batch_nnz=50, read_ahead=2)
+
+    def setup(server):
+        server._cfg, server._tmp = cfg, str(tmp_path)
+
+    res = run_cluster(_mf_ranged_worker, world=2, workers=1, mode="threads", setup_fn=setup, value_lengths=2 * cfg.rank,
+                      num_keys=cfg.num_keys(2))
+    for r in res.values():
+        out = r[0]
+        keys_signalled = sum(n for n, _ in out["calls"])
+        assert keys_signalled <= cfg.num_cols, out["calls"]              # once per column, not once per batch
+        assert out["n_batches"] > 3 * cfg.num_cols
+        assert max(d for _, d in out["calls"]) >= 3, out["calls"]           # windows cover the batches a column spans
+        assert out["l"] < out["l0"]
+        assert r["counters"]["protocol_errors"] == 0
