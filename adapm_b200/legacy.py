@@ -222,6 +222,22 @@ class KVWorker:
         kv = KVPairs(np.asarray(keys, np.int64))
         return self._send(False, kv, cmd, callback, (vals_out, lens_out))
 
+    # zero-copy variants of the reference (kv_app.h:182-210: SArray arguments instead of std::vector): numpy arrays are
+    # passed by reference here anyway, so they are the same calls
+    zpush = push
+    zpull = pull
+
+    def add_callback(self, ts: int, callback: Callable) -> None:
+        """Runs ``callback`` when request ``ts`` completes (reference ``AddCallback``, kv_app.h:250-258); at once if it
+        already has."""
+        with self._mu:
+            st = self._pending.get(ts)
+            if st is not None and not st.get("finished"):
+                prev = st["cb"]
+                st["cb"] = callback if prev is None else (lambda: (prev(), callback()))
+                return
+        callback()
+
     def wait(self, ts: int) -> None:
         with self._mu:
             st = self._pending.get(ts)
@@ -255,6 +271,8 @@ class KVWorker:
             if lens_out is not None:
                 lens = np.concatenate([p.lens for p in parts])
                 lens_out.reshape(-1)[:lens.size] = lens
-        if st["cb"] is not None:
-            st["cb"]()
+        with self._mu:                      # (add_callback either lands before this point or runs its callback itself)
+            cb, st["finished"] = st["cb"], True
+        if cb is not None:
+            cb()
         st["done"].set()

@@ -75,6 +75,15 @@ def _kv_app_worker(kv, server, wid):
     w.wait(w.pull(keys, out, lens))
     assert np.all(lens == vlen)
     np.testing.assert_allclose(out, vals * repeat * world, rtol=1e-5)
+    # ZPull + AddCallback (kv_app.h:182-258): the callback runs when the request completes, or at once if it already has
+    out2, late = np.zeros_like(vals), []
+    t2 = w.zpull(keys, out2)
+    w.add_callback(t2, lambda: late.append("cb"))
+    w.wait(t2)
+    assert late == ["cb"]
+    np.testing.assert_allclose(out2, out)
+    w.add_callback(t2, lambda: late.append("after"))
+    assert late == ["cb", "after"]
     # static range partition: this server only ever stored keys of its own range
     lo, hi = w.ranges[server.my_rank()]
     assert all(lo <= k < hi for k in handle.store)
