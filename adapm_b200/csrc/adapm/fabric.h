@@ -4,12 +4,15 @@
 //           on one GPU); heaps are plain allocations visible to everybody.
 //   shm     one process per rank on one host (the torchrun model). The control block is
 //           a POSIX shm segment. CPU heaps are shm segments mapped by every rank; CUDA
-//           heaps are cudaMalloc'ed and exported with CUDA IPC so that peers read and
-//           write them directly over NVLink/NVSwitch.
+//           heaps are VMM allocations (cuMemCreate) whose handles travel as POSIX file
+//           descriptors over a unix datagram socket (SCM_RIGHTS, once at start-up), are
+//           mapped by every peer and bound to an NVLS multicast object when the devices
+//           support it; cudaMalloc + CUDA IPC is the fallback. Peers read and write the
+//           heaps directly over NVLink/NVSwitch.
 //
 // This is the B200-native stand-in for ZMQVan + Van + Postoffice node management
-// (include/zmq_van.h:30-250, src/van.cc:267-357): there are no sockets and no message
-// (de)serialisation anywhere.
+// (include/zmq_van.h:30-250, src/van.cc:267-357): no data ever travels through a socket
+// and there is no message (de)serialisation anywhere.
 #pragma once
 #include <atomic>
 #include <memory>

@@ -1,6 +1,6 @@
 // CudaBackend: the B200 executor of the protocol. One instance per rank = per GPU.
-// Heaps are cudaMalloc'ed and peer-mapped (CUDA IPC across processes, peer access inside
-// one process); every kernel receives the Ctx by value and dereferences peer heaps
+// Heaps are peer-mapped device allocations (VMM handles + NVLS multicast or CUDA IPC across
+// processes - fabric.cc; peer access inside one process); every kernel receives the Ctx by value and dereferences peer heaps
 // directly, so Pull = NVLink loads, Push = NVLink reductions (REDG), directory updates =
 // NVLink stores - all issued from inside the kernels.
 #pragma once

@@ -1,6 +1,7 @@
-// Device memory helpers behind fabric.h's cudamem namespace: heap allocation, CUDA IPC
-// export/import (the NVLink/NVSwitch peer mapping between one-process-per-GPU ranks) and
-// peer access between devices of one process.
+// Device memory helpers behind fabric.h's cudamem namespace: heap allocation, the NVLink/NVSwitch
+// peer mapping between one-process-per-GPU ranks (VMM allocations exported as file descriptors,
+// NVLS multicast objects; CUDA IPC export/import as the fallback) and peer access between devices
+// of one process. The driver API is resolved at run time (cudaGetDriverEntryPoint): no libcuda link.
 #include <cuda_runtime.h>
 #include <cstring>
 #include <sstream>

@@ -8,7 +8,7 @@ DMLC_ROLE / DMLC_RANK / DMLC_PS_ROOT_URI / DMLC_PS_ROOT_PORT`` for scripts that 
 scheduler process: ranks rendezvous through a POSIX-shm control block. A rank that exits with
 code 254 is restarted (``keepalive`` of tracker/dmlc_local.py:15-26). ``torchrun`` and ``mpirun``
 work too - the package also reads ``OMPI_COMM_WORLD_*``, ``PMI_*`` and ``SLURM_*``.
-The fabric is single-node (shm + CUDA IPC over NVLink/NVSwitch): one 8xB200 box is the target.
+The fabric is single-node (shm control block + peer-mapped heaps over NVLink/NVSwitch): one 8xB200 box is the target.
 """
 from __future__ import annotations
 
@@ -76,7 +76,7 @@ def main(argv=None) -> int:
         hosts = [h.split()[0] for h in open(a.hostfile).read().splitlines() if h.strip() and not h.startswith("#")] \
             if a.hostfile else ["127.0.0.1"]
         if len(set(hosts)) != 1:
-            print("[launch] the fabric is single-node (shm + CUDA IPC over NVSwitch): the hostfile must name exactly "
+            print("[launch] the fabric is single-node (shm control block + peer-mapped heaps over NVSwitch): the hostfile must name exactly "
                   "one host; all ranks of a job share one box", file=sys.stderr)
             return 2
         ssh_host = hosts[0]
