@@ -76,7 +76,7 @@ def main(argv=None) -> int:
         hosts = [h.split()[0] for h in open(a.hostfile).read().splitlines() if h.strip() and not h.startswith("#")] \
             if a.hostfile else ["127.0.0.1"]
         if len(set(hosts)) != 1:
-            print("[launch] the fabric is single-node (shm control block + peer-mapped heaps over NVSwitch): the hostfile must name exactly "
+            print("[launch] the fabric is single-node (shm control block + peer-mapped heaps, NVSwitch): the hostfile must name exactly "
                   "one host; all ranks of a job share one box", file=sys.stderr)
             return 2
         ssh_host = hosts[0]
