@@ -23,10 +23,13 @@ def main(argv=None) -> int:
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--read_ahead", type=int, default=4)
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16", "fp8"])
+    ap.add_argument("--table_precision", default="fp32", choices=["fp32", "fp8_block"],
+                    help="fp8_block: train on the values a block-scaled e4m3 embedding table would deliver (fp32 master rows)")
     add_system_options(ap)
     args = ap.parse_args(strip_dashes(argv if argv is not None else sys.argv[1:]))
     cfg = DeepFMConfig(num_features=args.num_features, num_fields=args.num_fields, embed_dim=args.embed_dim,
-                       batch_size=args.batch_size, read_ahead=args.read_ahead, precision=args.precision)
+                       batch_size=args.batch_size, read_ahead=args.read_ahead, precision=args.precision,
+                       table_precision=args.table_precision)
     ad.setup(cfg.num_features, 1)
     server = ad.Server(cfg.row_len, backend=args.backend, options=system_options(args))
     kv = ad.Worker(0, server)

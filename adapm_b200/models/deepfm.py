@@ -34,6 +34,9 @@ class DeepFMConfig:
     batch_size: int = 8192
     read_ahead: int = 4
     precision: str = "bf16"             # bf16 | fp8 | fp32 (dense GEMMs)
+    table_precision: str = "fp32"       # fp32 | fp8_block: the model sees the embedding values a block-scaled e4m3 table
+                                        # (UE8M0 scale per 32 values, utils/blockscale.py) would deliver; the parameter
+                                        # manager keeps fp32 master rows (deltas and AdaGrad accumulate in fp32)
     model_seed: int = 1
 
     @property
@@ -132,7 +135,12 @@ class DeepFM:
         el = cfg.emb_len
         emb = rows[:, :el].detach().clone().requires_grad_(True)      # [U, el]  (w | v | pad)
         acc = rows[:, el:]
-        e = emb[inv].view(B, F, el)
+        if cfg.table_precision == "fp8_block":
+            from ..utils.blockscale import FakeQuantSTE
+
+            e = FakeQuantSTE.apply(emb)[inv].view(B, F, el)           # straight-through: gradients reach the fp32 masters
+        else:
+            e = emb[inv].view(B, F, el)
         w1, v = e[:, :, 0], e[:, :, 1:1 + k]
         fm = w1.sum(1) + 0.5 * ((v.sum(1) ** 2) - (v ** 2).sum(1)).sum(1)
         logit = fm + self.net(v.reshape(B, F * k))
