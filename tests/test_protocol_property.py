@@ -112,3 +112,72 @@ def test_random_programs_two_workers_per_rank(programs, technique):
         for cid in (0, 1):
             assert r[cid][1] == total, (r[cid][1], total)
         assert r["counters"]["protocol_errors"] == 0
+
+
+def _run_var(kv, server, wid, programs=None, lens=None):
+    """Like _run, on a store whose keys have different value lengths (size classes + per-key length table)."""
+    prog = programs[wid]
+    rounds = max(len(p) for p in programs)
+    lens_t = torch.tensor(lens, dtype=torch.int64)
+    mine = torch.zeros(NUM_KEYS, dtype=torch.int64)
+    errs = []
+    for r in range(rounds):
+        for o in (prog[r] if r < len(prog) else []):
+            if o[0] in ("intent", "intent_fast"):
+                c0 = kv.current_clock()
+                fn = kv.intent_fast if (o[0] == "intent_fast" and server.device.type != "cuda") else kv.intent
+                fn(torch.tensor(o[1]), c0 + o[2], c0 + o[2] + o[3])
+            elif o[0] == "push":
+                k = torch.tensor(sorted(o[1]))
+                kv.wait(kv.push(k, torch.ones(int(lens_t[k].sum()), dtype=torch.int64)))
+                mine[k] += 1
+            elif o[0] == "pull":
+                k = torch.tensor(sorted(o[1]))
+                v = torch.zeros(int(lens_t[k].sum()), dtype=torch.int64)
+                kv.wait(kv.pull(k, v))
+                off = 0
+                for key in k.tolist():
+                    seg = v[off:off + lens[key]]
+                    off += lens[key]
+                    if bool((seg < mine[key]).any()):
+                        errs.append(f"w{wid} round {r}: read-your-writes violated for key {key}: {seg.tolist()} < {int(mine[key])}")
+            elif o[0] == "clock":
+                kv.advance_clock()
+            elif o[0] == "sync":
+                kv.wait_sync()
+        kv.barrier()
+    kv.waitall(); kv.wait_sync(); kv.barrier(); kv.wait_sync(); kv.barrier()
+    out = torch.zeros(int(lens_t.sum()), dtype=torch.int64)
+    kv.wait(kv.pull(torch.arange(NUM_KEYS), out))
+    kv.barrier()
+    kv.finalize()
+    final, off = [], 0
+    for key in range(NUM_KEYS):
+        seg = out[off:off + lens[key]]
+        off += lens[key]
+        if not bool((seg == seg[0]).all()):
+            errs.append(f"key {key}: elements of one row differ: {seg.tolist()}")
+        final.append(int(seg[0]))
+    return errs, final, mine.tolist()
+
+
+@settings(max_examples=int(os.environ.get("ADAPM_HYP_EXAMPLES", "12")), deadline=None, suppress_health_check=list(HealthCheck))
+@given(programs=st.lists(program, min_size=3, max_size=3),
+       lens=st.lists(st.sampled_from([1, 2, 3, 5, 8, 13, 40]), min_size=NUM_KEYS, max_size=NUM_KEYS),
+       technique=st.sampled_from(["all", "replication_only", "relocation_only"]))
+def test_random_programs_with_mixed_value_lengths(programs, lens, technique):
+    """The same property on keys of different lengths: rows of up to 7 distinct lengths relocate / replicate between
+    per-class pools (reference coloc_kv_server_handle.h:162-170: any value_lengths vector)."""
+    import functools
+
+    res = run_cluster(functools.partial(_run_var, programs=programs, lens=lens), world=3, workers=1, mode="threads",
+                      value_lengths=torch.tensor(lens, dtype=torch.int64), num_keys=NUM_KEYS, dtype="int64",
+                      options={"sys.techniques": technique})
+    total = [0] * NUM_KEYS
+    for r in res.values():
+        errs, final, mine = r[0]
+        assert not errs, errs
+        total = [a + b for a, b in zip(total, mine)]
+    for r in res.values():
+        assert r[0][1] == total, (r[0][1], total)
+        assert r["counters"]["protocol_errors"] == 0
