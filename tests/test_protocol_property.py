@@ -75,14 +75,15 @@ def _run(kv, server, wid, programs=None):
 @given(programs=st.lists(program, min_size=3, max_size=3),
        technique=st.sampled_from(["all", "replication_only", "relocation_only"]),
        idle_period=st.integers(1, 5), sweep_period=st.integers(0, 4),
-       threshold=st.sampled_from(["-1", "0", "0.5", "3"]))
-def test_random_programs_are_exact(programs, technique, idle_period, sweep_period, threshold):
+       threshold=st.sampled_from(["-1", "0", "0.5", "3"]), min_clocks=st.sampled_from([0, 0, 2, 8]))
+def test_random_programs_are_exact(programs, technique, idle_period, sweep_period, threshold, min_clocks):
     import functools
 
     res = run_cluster(functools.partial(_run, programs=programs), world=3, workers=1, mode="threads", value_lengths=VPK,
                       num_keys=NUM_KEYS, dtype="int64",
                       options={"sys.techniques": technique, "sys.sync.idle_period": idle_period,
-                               "sys.sync.sweep_period": sweep_period, "sys.sync.threshold": threshold})
+                               "sys.sync.sweep_period": sweep_period, "sys.sync.threshold": threshold,
+                               "sys.sync.min_clocks": min_clocks, "sys.sync.min_clocks_wait_ms": 3})
     total = [0] * NUM_KEYS
     for r in res.values():
         errs, final, mine = r[0]
