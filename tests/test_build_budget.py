@@ -58,3 +58,46 @@ def test_hot_kernels_stay_within_their_register_budget():
     for name, v in k.items():
         if name.startswith(("gemm_nt_tcgen05", "gather_gemm_kernel")):
             assert v["spill"] == 0, (name, v)
+
+
+def test_blackwell_instructions_are_in_the_built_extension():
+    """SASS / PTX of the in-tree extension (cuobjdump, no GPU needed): the kernels that are documented to use the 5th-gen
+    tensor cores, TMA, clusters and NVLS multimem really contain those instructions - a refactoring that silently drops
+    one of them (e.g. a fallback path becoming the only path) fails here, not in a benchmark weeks later."""
+    import shutil
+
+    so = glob.glob(os.path.join(ROOT, "adapm_b200", "_C*.so"))
+    if not so or shutil.which("cuobjdump") is None:
+        pytest.skip("no built extension or no cuobjdump")
+    sass = subprocess.run(["cuobjdump", "-sass", so[0]], capture_output=True, text=True).stdout
+    per, cur = {}, None
+    for ln in sass.splitlines():
+        m = re.search(r"Function : (\S+)", ln)
+        if m:
+            cur = m.group(1)
+            per[cur] = set()
+            continue
+        m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", ln)
+        if m and cur:
+            per[cur].add(m.group(1).split(".")[0] + ("." + m.group(1).split(".")[1] if m.group(1).startswith(("LDGMC", "UBLK")) else ""))
+
+    def ops_of(fragment):
+        hits = [v for k, v in per.items() if fragment in k]
+        assert hits, f"no kernel matching {fragment}"
+        out = set()
+        for h in hits:
+            out |= h
+        return out
+
+    gemm = ops_of("gemm_nt_tcgen05_kernel")
+    assert {"UTCHMMA", "LDTM", "UTMALDG"} <= gemm, sorted(gemm)
+    assert "UTCQMMA" in gemm                                                     # fp8 (kind::f8f6f4) instantiation
+    pair = ops_of("gemm_nt_tcgen05_pair_kernel")
+    assert {"UTCHMMA", "LDTM", "UTMALDG", "UCGABAR_ARV", "UCGABAR_WAIT"} <= pair, sorted(pair)     # cta_group::2 + cluster
+    assert {"UTCHMMA", "LDTM"} <= ops_of("gather_gemm_kernel")
+    sgns = ops_of("sgns_step_tma_kernel")
+    assert {"UBLKCP.S", "UBLKRED.G", "SYNCS"} <= sgns, sorted(sgns)              # TMA ring in, TMA bulk reductions out
+    assert {"LDGMC.E"} <= ops_of("xbar_kernel")                                   # multimem.ld_reduce (NVLS)
+    ptx = subprocess.run(["cuobjdump", "-ptx", so[0]], capture_output=True, text=True).stdout
+    assert "multimem.st.release.sys.global" in ptx and "multimem.ld_reduce" in ptx
+    assert "tcgen05.mma.cta_group::2" in ptx and "cp.reduce.async.bulk" in ptx
