@@ -338,3 +338,75 @@ def test_prometheus_metrics_endpoint():
     moved = sum(float(l.split()[-1]) for r in res.values() for l in r[0].splitlines()
                 if l.startswith(("adapm_relocations_total", "adapm_replica_setups_total")))
     assert moved > 0                              # both ranks wanted all ten keys: relocated or replicated
+
+
+def _save_for_serving(kv, server, wid):
+    from adapm_b200.utils.checkpoint import save_store
+
+    d = 8
+    keys = torch.arange(server.num_keys(), dtype=torch.int64)
+    mine = keys[(keys % server.num_servers()) == server.my_rank()]
+    g = torch.Generator().manual_seed(1)
+    table = torch.randn(server.num_keys(), 2 * d, generator=g)
+    table[2] = table[0] * 3.0                      # key 2 is parallel to key 0 (syn0 keys are the even ones)
+    kv.wait(kv.set(mine, table[mine].reshape(-1)))
+    kv.barrier()
+    save_store(kv, server._ck)
+    kv.barrier()
+    kv.finalize()
+    return table[:4].tolist()
+
+
+def test_serving_from_a_store_checkpoint(tmp_path):
+    """adapm_b200.serve: a 2-rank job saves its store, a single-rank server loads it and answers /pull, /topk, /metrics."""
+    pytest.importorskip("fastapi")
+    pytest.importorskip("uvicorn")
+    import json
+    import threading
+    import time
+    import urllib.request
+
+    import uvicorn
+
+    from adapm_b200.serve import load_service, make_app
+
+    ck = str(tmp_path / "model")
+
+    def setup(server):
+        server._ck = ck
+
+    res = run_cluster(_save_for_serving, world=2, workers=1, mode="threads", setup_fn=setup, value_lengths=16, num_keys=40)
+    table4 = res[0][0]
+    svc = load_service(ck, embed_dim=8, backend="cpu", stride=2, offset=0)
+    import socket
+
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    srv = uvicorn.Server(uvicorn.Config(make_app(svc), host="127.0.0.1", port=port, log_level="error"))
+    th = threading.Thread(target=srv.run, daemon=True)
+    th.start()
+    try:
+        for _ in range(100):
+            if srv.started:
+                break
+            time.sleep(0.05)
+        get = lambda path: urllib.request.urlopen(f"http://127.0.0.1:{port}{path}", timeout=10).read().decode()  # noqa: E731
+        assert json.loads(get("/health"))["candidates"] == 20
+        got = json.loads(get("/pull?keys=0,3"))
+        assert got["keys"] == [0, 3]
+        assert all(abs(a - b) < 1e-6 for a, b in zip(got["values"][0], table4[0]))
+        assert all(abs(a - b) < 1e-6 for a, b in zip(got["values"][1], table4[3]))
+        nb = json.loads(get("/topk?key=0&k=3"))["neighbours"]
+        assert nb[0][0] == 2 and nb[0][1] > 0.999                   # the parallel row is the nearest neighbour
+        assert "adapm_pull_local_total" in get("/metrics")
+        try:
+            get("/pull?keys=9999")
+            assert False, "out-of-range key was served"
+        except urllib.error.HTTPError as e:
+            assert e.code == 400
+    finally:
+        srv.should_exit = True
+        th.join(10)
+        svc.worker.finalize()
+        svc.server.shutdown()
