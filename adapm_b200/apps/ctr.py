@@ -36,15 +36,25 @@ def main(argv=None) -> int:
     model = DeepFM(server, kv, cfg)
     model.init_model()
     rank = server.my_rank()
-    fut = [synthetic_ctr_batch(cfg, s, rank) for s in range(cfg.read_ahead)]
-    for s, (ids, _) in enumerate(fut):
-        model.signal_intent(ids, kv.current_clock() + s)
+    # look-ahead: while step s runs, the distinct feature ids of step s + read_ahead are signalled (parallel/schedules.py)
+    from ..parallel.schedules import LookaheadIntents
+
+    batches = {}
+
+    def batch(b):
+        if b not in batches:
+            batches[b] = synthetic_ctr_batch(cfg, b, rank)
+        return batches[b]
+
+    look = LookaheadIntents(kv, args.steps + cfg.read_ahead, cfg.read_ahead, lambda b: batch(b)[0]) if server.num_servers() > 1 else None
+    if look:
+        look.prime()
     t0, losses = time.time(), []
     for s in range(args.steps):
-        nxt = synthetic_ctr_batch(cfg, s + cfg.read_ahead, rank)
-        model.signal_intent(nxt[0], kv.current_clock() + cfg.read_ahead)
-        fut.append(nxt)
-        ids, y = fut.pop(0)
+        if look:
+            look.signal(s)
+        ids, y = batch(s)
+        batches.pop(s - 1, None)
         losses.append(model.step(ids, y))
         kv.advance_clock()
         if rank == 0 and (s + 1) % max(1, args.steps // 5) == 0:

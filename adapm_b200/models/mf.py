@@ -89,11 +89,7 @@ class SparseMatrix:
         return self.i[s:e], self.j[s:e], self.x[s:e]
 
 
-def wor_block_schedule(world: int, epoch: int, seed: int = 0) -> np.ndarray:
-    """schedule[subepoch, worker] = column block (a random Latin square: WOR block schedule)."""
-    rng = np.random.default_rng(seed * 7919 + epoch)
-    perm, shift = rng.permutation(world), rng.permutation(world)
-    return np.array([[perm[(w + shift[se]) % world] for w in range(world)] for se in range(world)])
+from ..parallel.schedules import column_intent_plan, wor_block_schedule  # noqa: E402,F401  (re-exported: tests, docs)
 
 
 class MatrixFactorization:
@@ -207,12 +203,7 @@ class MatrixFactorization:
                 # clocks during which the column's data points are processed): the points are sorted by column, so a
                 # column occupies a contiguous run of batches [first, last]; it is signalled ONCE, read_ahead batches before
                 # its first one, for last - first + 1 clocks - not again in every batch it spans.
-                js = data.j[order]
-                cols, first_idx = np.unique(js, return_index=True)
-                last_idx = np.r_[first_idx[1:], n] - 1
-                first_b, last_b = first_idx // cfg.batch_nnz, last_idx // cfg.batch_nnz
-                ptr = np.searchsorted(first_b, np.arange(len(starts) + 1))     # columns whose first batch is b: ptr[b]:ptr[b+1]
-                col_plan = (cols, last_b - first_b + 1, ptr)
+                col_plan = column_intent_plan(data.j[order], cfg.batch_nnz)
             for bi, s in enumerate(starts):
                 fut = bi + cfg.read_ahead
                 if W > 1 and fut < len(starts):

@@ -5,8 +5,9 @@
 * key-space sharding             - a key's home is ``key % world``; :func:`home_rank`, :func:`home_keys`.
 * relocation / replication       - decided per key and per sync round by the owner (``csrc/adapm/protocol.h``,
                                    ``sync_engine.cc``); steered by ``Worker.intent`` and ``sys.techniques``.
-* DSGD block schedule            - :func:`wor_block_schedule` (matrix factorisation: ranks own row blocks, column
-                                   blocks rotate; the rotation is expressed as intents).
+* schedules -> intents            - :mod:`adapm_b200.parallel.schedules`: :func:`wor_block_schedule` (DSGD: ranks own row
+                                   blocks, column blocks rotate), :func:`column_intent_plan` (column-wise: one ranged
+                                   intent per column), :class:`LookaheadIntents` (batched apps: signal batch s + k).
 * data partitioning              - :func:`partition_rows` (rank r gets rows r, r + world, ...: the apps' rule).
 * comparison arm                 - :mod:`adapm_b200.parallel.nccl_baseline` (stock PyTorch + NCCL all_to_all only).
 """
@@ -14,7 +15,7 @@ from __future__ import annotations
 
 import torch
 
-from ..models.mf import wor_block_schedule  # noqa: F401  (re-export)
+from .schedules import LookaheadIntents, column_intent_plan, wor_block_schedule  # noqa: F401
 
 
 def home_rank(keys: torch.Tensor, world: int) -> torch.Tensor:

@@ -410,3 +410,38 @@ def test_serving_from_a_store_checkpoint(tmp_path):
         th.join(10)
         svc.worker.finalize()
         svc.server.shutdown()
+
+
+def test_schedules_to_intents():
+    """parallel/schedules.py: the DSGD Latin square, the column-wise ranged-intent plan and the look-ahead helper."""
+    import numpy as np
+
+    from adapm_b200.parallel.schedules import LookaheadIntents, column_intent_plan, wor_block_schedule
+
+    s = wor_block_schedule(5, epoch=3, seed=7)
+    assert sorted(s[0].tolist()) == list(range(5)) and all(sorted(s[:, w].tolist()) == list(range(5)) for w in range(5))
+    cols, dur, ptr = column_intent_plan(np.array([0, 0, 0, 0, 0, 2, 2, 5, 5, 5, 5, 5, 5, 9]), batch=4)
+    assert cols.tolist() == [0, 2, 5, 9]
+    assert dur.tolist() == [2, 1, 3, 1]                       # column 0 spans batches 0-1, column 5 batches 1-3 ...
+    assert [cols[ptr[b]:ptr[b + 1]].tolist() for b in range(4)] == [[0], [2, 5], [], [9]]
+
+    class FakeWorker:
+        def __init__(self):
+            self.clock, self.calls = 10, []
+
+        def current_clock(self):
+            return self.clock
+
+        def intent(self, keys, start, end=0):
+            self.calls.append((sorted(keys.tolist()), start, end))
+
+    w = FakeWorker()
+    data = [torch.tensor([[3, 3, 1], [1, 7, 7]]) + 10 * b for b in range(5)]
+    look = LookaheadIntents(w, num_batches=5, read_ahead=2, keys_of=lambda b: data[b])
+    look.prime()
+    assert w.calls == [([1, 3, 7], 10, 11), ([11, 13, 17], 11, 12)]
+    for s_ in range(5):
+        look.signal(s_)
+        w.clock += 1
+    assert [c[0][0] for c in w.calls[2:]] == [21, 31, 41] and [c[1] for c in w.calls[2:]] == [12, 13, 14]
+    assert look.keys_signalled == 15
